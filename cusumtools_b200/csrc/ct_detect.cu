@@ -1,0 +1,271 @@
+// Baseline block statistics + threshold/hysteresis event detection with stream compaction.
+//
+// The reference has no implementation of this stage; the semantics are the consumer's
+// (plot-trace.py:379-414: start line = baseline - sign*threshold*stdev, end line =
+// baseline - sign*(threshold-hysteresis)*stdev, per baseline block) and the definition is
+// oracle/events_oracle.py (block_stats / detect_events).  Everything here is exact:
+// block sums are int64 sums of fixed-point samples (order independent), comparisons are
+// float32-vs-float32, so event indices are bit-identical to the oracle on the same input.
+//
+// Detection is a scan over a 2-state automaton (outside/inside) whose per-sample maps are
+// "set inside" (A), "set outside" (B) or identity.  Pass 1 reads the trace once
+// (4 B/sample), ballots A/B into bit masks (0.25 B/sample written) and emits one summary
+// per 4096-sample run; a single-CTA scan chains the run states and prefix-sums the event
+// counts; pass 2 reads only the masks and writes start/end indices in time order.
+// Inside a 32-sample word the automaton is evaluated with one 64-bit ADD (generate = A,
+// propagate = ~(A|B): the carry chain of the adder is the state).
+#include "ct_common.cuh"
+#include "cusumtools_b200.h"
+
+namespace {
+
+constexpr int kRun = 4096;           // samples per warp run (128 mask words)
+constexpr int kRunWords = kRun / 32;
+constexpr int kDetWarps = 8;
+
+struct RunSummary {                  // 16 bytes
+    unsigned first_last;             // first symbol (bits 0-1), last symbol (bits 2-3); 0 none, 1 in, 2 out
+    unsigned ns0;                    // starts assuming the run begins outside
+    unsigned ne0;                    // ends   assuming the run begins outside
+    unsigned pad;
+};
+
+// state after each bit given carry-in c (1 = inside): returns I mask, updates c
+__device__ __forceinline__ unsigned automaton_word(unsigned A, unsigned B, unsigned& c) {
+    unsigned P = ~(A | B);
+    unsigned long long X = (unsigned long long)(A | P), Y = (unsigned long long)A;
+    unsigned long long sum = X + Y + c;
+    unsigned long long cin = sum ^ X ^ Y;       // bit i = carry into bit i = state before sample i
+    unsigned I = (unsigned)(cin >> 1);          // state after sample i
+    c = I >> 31;
+    return I;
+}
+
+__global__ void __launch_bounds__(kDetWarps * 32)
+ct_detect_pass1(const float* __restrict__ y, long long n, long long block,
+                const int* __restrict__ sign, const float* __restrict__ t_start,
+                const float* __restrict__ t_end, uint2* __restrict__ masks,
+                RunSummary* __restrict__ summ, long long nruns) {
+    const int lane = ct_lane();
+    const long long run = (long long)blockIdx.x * kDetWarps + (threadIdx.x >> 5);
+    if (run >= nruns) return;
+    const long long base = run * kRun;
+    // block is a multiple of kRun, so a run never straddles two baseline blocks
+    const long long kb = base / block;
+    const bool pos = sign[kb] > 0;
+    const float ts = t_start[kb], te = t_end[kb];
+    unsigned c = 0, first = 0, last = 0, ns = 0, ne = 0;
+    for (int w0 = 0; w0 < kRunWords; w0 += 4) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            long long p = base + (long long)(w0 + j) * 32 + lane;
+            v[j] = p < n ? y[p] : (pos ? te : te);   // beyond the end: identity symbol (== te is neither)
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            long long p = base + (long long)(w0 + j) * 32 + lane;
+            bool a = pos ? v[j] < ts : v[j] > ts;
+            bool b = pos ? v[j] > te : v[j] < te;
+            if (p >= n) { a = false; b = false; }
+            unsigned A = __ballot_sync(CT_FULL, a);
+            unsigned B = __ballot_sync(CT_FULL, b);
+            if (lane == 0) masks[run * kRunWords + w0 + j] = make_uint2(A, B);
+            unsigned nz = A | B;
+            if (nz) {
+                if (!first) first = ((A >> (__ffs(nz) - 1)) & 1) ? 1u : 2u;
+                last = ((A >> (31 - __clz(nz))) & 1) ? 1u : 2u;
+            }
+            unsigned cprev = c;
+            unsigned I = automaton_word(A, B, c);
+            unsigned prev = (I << 1) | cprev;
+            ns += __popc(I & ~prev);
+            ne += __popc(~I & prev);
+        }
+    }
+    if (lane == 0) {
+        RunSummary s; s.first_last = first | (last << 2); s.ns0 = ns; s.ne0 = ne; s.pad = 0;
+        summ[run] = s;
+    }
+}
+
+// single-CTA chained scan over run summaries -> per-run (state_in, start offset, end offset)
+__global__ void __launch_bounds__(1024)
+ct_detect_scan(const RunSummary* __restrict__ summ, long long nruns, int state_in,
+               uint4* __restrict__ runinfo /* x=state_in, y=unused, (z,w) lo words of offsets */,
+               unsigned long long* __restrict__ offs /*[nruns][2]*/,
+               unsigned long long* __restrict__ counts /*[2]*/) {
+    __shared__ unsigned s_last[1024];
+    __shared__ unsigned long long s_ns[1024], s_ne[1024];
+    __shared__ unsigned s_statein[1024];
+    const int tid = threadIdx.x;
+    const long long per = (nruns + 1023) / 1024;
+    const long long r0 = tid * per, r1 = (r0 + per < nruns) ? r0 + per : nruns;
+    // pass A: thread-local last symbol
+    unsigned last = 0;
+    for (long long r = r0; r < r1; ++r) { unsigned l = (summ[r].first_last >> 2) & 3; if (l) last = l; }
+    s_last[tid] = last;
+    __syncthreads();
+    if (tid == 0) {   // serial chain over 1024 entries: state entering each thread's range
+        unsigned st = state_in ? 1u : 2u;
+        for (int i = 0; i < 1024; ++i) { s_statein[i] = st; if (s_last[i]) st = s_last[i]; }
+    }
+    __syncthreads();
+    // pass B: counts with the true incoming state
+    unsigned st = s_statein[tid];
+    unsigned long long ns = 0, ne = 0;
+    for (long long r = r0; r < r1; ++r) {
+        RunSummary s = summ[r];
+        unsigned f = s.first_last & 3, l = (s.first_last >> 2) & 3;
+        unsigned a = s.ns0, b = s.ne0;
+        if (st == 1) { if (f == 1) a -= 1; else if (f == 2) b += 1; }
+        ns += a; ne += b;
+        if (l) st = l;
+    }
+    s_ns[tid] = ns; s_ne[tid] = ne;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long a = 0, b = 0;
+        for (int i = 0; i < 1024; ++i) {
+            unsigned long long ta = s_ns[i], tb = s_ne[i];
+            s_ns[i] = a; s_ne[i] = b; a += ta; b += tb;
+        }
+        counts[0] = a; counts[1] = b;
+    }
+    __syncthreads();
+    // pass C: write per-run state_in and exclusive offsets
+    st = s_statein[tid]; ns = s_ns[tid]; ne = s_ne[tid];
+    for (long long r = r0; r < r1; ++r) {
+        RunSummary s = summ[r];
+        unsigned f = s.first_last & 3, l = (s.first_last >> 2) & 3;
+        unsigned a = s.ns0, b = s.ne0;
+        if (st == 1) { if (f == 1) a -= 1; else if (f == 2) b += 1; }
+        runinfo[r] = make_uint4(st == 1 ? 1u : 0u, 0u, 0u, 0u);
+        offs[2 * r] = ns; offs[2 * r + 1] = ne;
+        ns += a; ne += b;
+        if (l) st = l;
+    }
+}
+
+// pass 2: one thread per run, masks only
+__global__ void __launch_bounds__(128)
+ct_detect_pass2(const uint2* __restrict__ masks, const uint4* __restrict__ runinfo,
+                const unsigned long long* __restrict__ offs, long long nruns,
+                long long* __restrict__ starts, long long* __restrict__ ends, long long cap) {
+    const long long run = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (run >= nruns) return;
+    unsigned c = runinfo[run].x;
+    unsigned long long os = offs[2 * run], oe = offs[2 * run + 1];
+    const uint4* m4 = reinterpret_cast<const uint4*>(masks + run * kRunWords);
+    const long long base = run * kRun;
+    for (int w = 0; w < kRunWords; w += 2) {
+        uint4 q = m4[w >> 1];
+        unsigned AB[2][2] = {{q.x, q.y}, {q.z, q.w}};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            unsigned A = AB[j][0], B = AB[j][1];
+            if ((A | B) == 0) continue;                 // identity word: state unchanged
+            unsigned cprev = c;
+            unsigned I = automaton_word(A, B, c);
+            unsigned prev = (I << 1) | cprev;
+            unsigned S = I & ~prev, E = ~I & prev;
+            const long long wb = base + (long long)(w + j) * 32;
+            while (S) { int b = __ffs(S) - 1; S &= S - 1; if ((long long)os < cap) starts[os] = wb + b; ++os; }
+            while (E) { int b = __ffs(E) - 1; E &= E - 1; if ((long long)oe < cap) ends[oe] = wb + b; ++oe; }
+        }
+    }
+}
+
+// ---------------------------------- block statistics ---------------------------------
+constexpr int kStatChunk = 8192;
+__global__ void __launch_bounds__(256)
+ct_block_stats_kernel(const float* __restrict__ y, long long n, long long block, long long chunks_per_block,
+                      float bmin, float bmax, float c0, float scale,
+                      long long* __restrict__ cnt, long long* __restrict__ s1, long long* __restrict__ s2) {
+    const long long kb = blockIdx.x / chunks_per_block;
+    const long long ch = blockIdx.x % chunks_per_block;
+    const long long b0 = kb * block + ch * kStatChunk;
+    long long b1 = b0 + kStatChunk;
+    const long long bend = (kb + 1) * block < n ? (kb + 1) * block : n;
+    if (b1 > bend) b1 = bend;
+    long long c = 0, a = 0, b = 0;
+    for (long long p = b0 + threadIdx.x; p < b1; p += 256) {
+        float v = y[p];
+        if (v >= bmin && v <= bmax) {
+            float d = __fmul_rn(__fsub_rn(v, c0), scale);
+            long long q = (long long)__float2ll_rn(d);
+            c += 1; a += q; b += q * q;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(CT_FULL, c, o);
+        a += __shfl_xor_sync(CT_FULL, a, o);
+        b += __shfl_xor_sync(CT_FULL, b, o);
+    }
+    if (ct_lane() == 0 && c) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(cnt + kb), (unsigned long long)c);
+        atomicAdd(reinterpret_cast<unsigned long long*>(s1 + kb), (unsigned long long)a);
+        atomicAdd(reinterpret_cast<unsigned long long*>(s2 + kb), (unsigned long long)b);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ct_detect_run(void) { return kRun; }
+
+int64_t ct_detect_workspace_bytes(int64_t n) {
+    long long nruns = (n + kRun - 1) / kRun;
+    if (nruns < 1) nruns = 1;
+    // masks + summaries + runinfo + offsets, each 256-byte aligned
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    return al(nruns * kRunWords * 8) + al(nruns * 16) + al(nruns * 16) + al(nruns * 16);
+}
+
+int ct_block_stats_f32(const float* y, int64_t n, int64_t block, float bmin, float bmax, float c0,
+                       int shift, int64_t* cnt, int64_t* s1, int64_t* s2, void* stream) {
+    if (!y || !cnt || !s1 || !s2 || n < 0 || block <= 0) { ct_set_error("block_stats: bad argument"); return CT_ERR_ARG; }
+    long long nb = (n + block - 1) / block;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nb == 0) return CT_OK;
+    cudaMemsetAsync(cnt, 0, nb * 8, st); cudaMemsetAsync(s1, 0, nb * 8, st); cudaMemsetAsync(s2, 0, nb * 8, st);
+    long long cpb = (block + kStatChunk - 1) / kStatChunk;
+    long long grid = nb * cpb;
+    if (grid > 0x7fffffffLL) { ct_set_error("block_stats: trace too long for one launch"); return CT_ERR_UNSUPPORTED; }
+    CT_COUNT_LAUNCH();
+    ct_block_stats_kernel<<<(unsigned)grid, 256, 0, st>>>(y, n, block, cpb, bmin, bmax, c0, ldexpf(1.f, shift), (long long*)cnt, (long long*)s1, (long long*)s2);
+    return ct_check_launch("ct_block_stats_kernel");
+}
+
+int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign, const float* t_start,
+                  const float* t_end, int state_in, void* workspace, int64_t workspace_bytes,
+                  int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream) {
+    if (!y || !sign || !t_start || !t_end || !workspace || !starts || !ends || !counts2 || n < 0) {
+        ct_set_error("detect: bad argument"); return CT_ERR_ARG;
+    }
+    if (block <= 0 || block % kRun) { ct_set_error("detect: baseline block must be a multiple of %d samples", kRun); return CT_ERR_ARG; }
+    if (workspace_bytes < ct_detect_workspace_bytes(n)) { ct_set_error("detect: workspace too small"); return CT_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(counts2, 0, 16, st); return CT_OK; }
+    long long nruns = (n + kRun - 1) / kRun;
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    char* w = (char*)workspace;
+    uint2* masks = (uint2*)w;            w += al(nruns * kRunWords * 8);
+    RunSummary* summ = (RunSummary*)w;   w += al(nruns * 16);
+    uint4* runinfo = (uint4*)w;          w += al(nruns * 16);
+    unsigned long long* offs = (unsigned long long*)w;
+    long long g1 = (nruns + kDetWarps - 1) / kDetWarps;
+    CT_COUNT_LAUNCH();
+    ct_detect_pass1<<<(unsigned)g1, kDetWarps * 32, 0, st>>>(y, n, block, sign, t_start, t_end, masks, summ, nruns);
+    int rc = ct_check_launch("ct_detect_pass1"); if (rc) return rc;
+    CT_COUNT_LAUNCH();
+    ct_detect_scan<<<1, 1024, 0, st>>>(summ, nruns, state_in, runinfo, offs, (unsigned long long*)counts2);
+    rc = ct_check_launch("ct_detect_scan"); if (rc) return rc;
+    CT_COUNT_LAUNCH();
+    ct_detect_pass2<<<(unsigned)((nruns + 127) / 128), 128, 0, st>>>(masks, runinfo, offs, nruns, (long long*)starts, (long long*)ends, capacity);
+    return ct_check_launch("ct_detect_pass2");
+}
+
+}  // extern "C"

@@ -1,0 +1,442 @@
+// Fused dequantise + median-pad + zero-phase Bessel (filtfilt) for sm_100a.
+//
+// Replaces, for the hot path of reference plot-trace.py:
+//   scale_raw_data (:272-287)  ->  affine map folded into the load / the epilogue FMA
+//   np.pad(mode='median', 1000) (:318-319)  ->  "virtual" pad: the kernel works on
+//       x' = code - median_code, which is 0 in the pad, so the pad is never materialised
+//   filtfilt(b, a, padded, padtype=None) (:320)  ->  forward + backward cascade of
+//       all-pole second-order sections with (1+z^-1)^2 numerators, in ONE kernel:
+//       HBM sees one 2-byte read and one 4-byte write per sample.
+//
+// Parallelisation of the sequential IIR (DESIGN.md "filter kernel"):
+//   * a WARP owns a sub-segment of S output samples and sweeps it in tiles of 32*C
+//     samples (lane l holds C consecutive samples in registers);
+//   * per section: every lane runs the recursion over its chunk from zero state, the
+//     32 chunk-final states are combined by a warp-shuffle Kogge-Stone scan over the
+//     2x2 affine state maps (the matrices A^(C*2^k) are constants), the tile-to-tile
+//     carry is injected at lane 0, and the lanes re-run their chunk from the now exact
+//     incoming state, emitting the section output in place;
+//   * the forward result of the sub-segment (+ H warm-up samples to its right) stays
+//     in shared memory (bank-conflict-free XOR-swizzled 16-byte units); the backward
+//     sweep consumes it top-down and writes the final samples to global memory;
+//   * sub-segments are independent: each starts its recursions H samples early from
+//     zero state, H chosen on the host so the truncated natural response is < eps.
+//
+// Boundary semantics identical to the reference (scipy/_signaltools.py:4897-4913):
+// forward initial state = steady state of padded[0] (the median => zero in x'),
+// backward initial state = steady state of the last forward output.
+#include "ct_common.cuh"
+#include "cusumtools_b200.h"
+
+namespace {
+
+constexpr int kC = 16;              // samples per lane per tile
+constexpr int kT = 32 * kC;         // tile = 512 samples
+constexpr int kWarpsPerCta = 4;
+
+struct FilterArgs {
+    const void* in;
+    float* out;
+    long long n;          // samples
+    long long pad;        // reference's constant pad length (1000)
+    int S;                // sub-segment length (multiple of kT)
+    int H;                // warm-up halo (multiple of kT)
+    float sub;            // value subtracted from the input (median code / pad value)
+    unsigned mask2;       // ADC bitmask replicated in both halves (u16 input)
+    float out_scale;      // pA per code (alpha) or 1
+    float out_offset;     // pad value in output units
+    int in_aligned;       // input base 16-byte aligned
+    int out_aligned;      // output base 16-byte aligned
+};
+
+template <int C>
+__device__ __forceinline__ int swz(int lane) {
+    constexpr int U = C / 4;                 // 16-byte units per lane chunk
+    return (lane / (8 / U)) & (U - 1);
+}
+
+// ---- one cascade pass (all sections) over the C samples a lane holds ----------------
+template <int NSEC, int C>
+__device__ __forceinline__ void cascade_tile(float (&x)[C], float (&carry)[NSEC][2],
+                                             const CtFilterCoef& k, int lane) {
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        const float na1 = k.na1[s], na2 = k.na2[s];
+        // (1) zero-state run: only the chunk-final state is needed
+        float v1 = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            float v = fmaf(na1, v1, fmaf(na2, v2, x[e]));
+            v2 = v1; v1 = v;
+        }
+        // (2) inject the tile carry at lane 0: f_0 += A^C * carry
+        if (lane == 0) {
+            v1 = fmaf(k.AC[s][0], carry[s][0], fmaf(k.AC[s][1], carry[s][1], v1));
+            v2 = fmaf(k.AC[s][2], carry[s][0], fmaf(k.AC[s][3], carry[s][1], v2));
+        }
+        // (3) inclusive Kogge-Stone scan of the affine maps across lanes
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            const int d = 1 << st;
+            float t1 = __shfl_up_sync(CT_FULL, v1, d);
+            float t2 = __shfl_up_sync(CT_FULL, v2, d);
+            if (lane >= d) {
+                v1 = fmaf(k.M[s][st][0], t1, fmaf(k.M[s][st][1], t2, v1));
+                v2 = fmaf(k.M[s][st][2], t1, fmaf(k.M[s][st][3], t2, v2));
+            }
+        }
+        // (4) incoming state of this lane = end state of the previous lane
+        float i1 = __shfl_up_sync(CT_FULL, v1, 1);
+        float i2 = __shfl_up_sync(CT_FULL, v2, 1);
+        if (lane == 0) { i1 = carry[s][0]; i2 = carry[s][1]; }
+        carry[s][0] = __shfl_sync(CT_FULL, v1, 31);
+        carry[s][1] = __shfl_sync(CT_FULL, v2, 31);
+        // (5) exact run from the incoming state, numerator applied on the way out
+        const float n1 = k.n1[s], n2 = k.n2[s];
+        v1 = i1; v2 = i2;
+        if (s == NSEC - 1) {
+            const float g = k.gain, g1 = n1 * k.gain, g2 = n2 * k.gain;
+#pragma unroll
+            for (int e = 0; e < C; ++e) {
+                float v = fmaf(na1, v1, fmaf(na2, v2, x[e]));
+                x[e] = fmaf(g1, v1, fmaf(g2, v2, g * v));
+                v2 = v1; v1 = v;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < C; ++e) {
+                float v = fmaf(na1, v1, fmaf(na2, v2, x[e]));
+                x[e] = fmaf(n1, v1, fmaf(n2, v2, v));
+                v2 = v1; v1 = v;
+            }
+        }
+    }
+}
+
+// ---- input tile: positions p0 .. p0+C-1 of the virtual (median-subtracted) signal ---
+template <int C>
+__device__ __forceinline__ void load_chunk(const FilterArgs& a, const uint16_t* in, long long p0,
+                                           float (&x)[C]) {
+    if (a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
+#pragma unroll
+        for (int u = 0; u < C / 8; ++u) {
+            uint4 w = ct_ldg_stream(in + p0 + u * 8);
+            unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned m = ww[j] & a.mask2;
+                x[u * 8 + 2 * j]     = (float)(int)(m & 0xffffu) - a.sub;
+                x[u * 8 + 2 * j + 1] = (float)(int)(m >> 16) - a.sub;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            long long p = p0 + e;
+            x[e] = (p >= 0 && p < a.n) ? (float)(int)(in[p] & (a.mask2 & 0xffffu)) - a.sub : 0.f;
+        }
+    }
+}
+template <int C>
+__device__ __forceinline__ void load_chunk(const FilterArgs& a, const float* in, long long p0,
+                                           float (&x)[C]) {
+    if (a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
+#pragma unroll
+        for (int u = 0; u < C / 4; ++u) {
+            uint4 w = ct_ldg_stream(in + p0 + u * 4);
+            x[u * 4 + 0] = __uint_as_float(w.x) - a.sub;
+            x[u * 4 + 1] = __uint_as_float(w.y) - a.sub;
+            x[u * 4 + 2] = __uint_as_float(w.z) - a.sub;
+            x[u * 4 + 3] = __uint_as_float(w.w) - a.sub;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            long long p = p0 + e;
+            x[e] = (p >= 0 && p < a.n) ? in[p] - a.sub : 0.f;
+        }
+    }
+}
+
+// output chunk for positions p0..p0+C-1, values given in position order
+template <int C>
+__device__ __forceinline__ void store_chunk(const FilterArgs& a, long long p0, const float (&y)[C]) {
+    if (a.out_aligned && p0 >= 0 && p0 + C <= a.n) {
+#pragma unroll
+        for (int u = 0; u < C / 4; ++u) {
+            float4 v;
+            v.x = fmaf(y[u * 4 + 0], a.out_scale, a.out_offset);
+            v.y = fmaf(y[u * 4 + 1], a.out_scale, a.out_offset);
+            v.z = fmaf(y[u * 4 + 2], a.out_scale, a.out_offset);
+            v.w = fmaf(y[u * 4 + 3], a.out_scale, a.out_offset);
+            ct_stg_stream(a.out + p0 + u * 4, v);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            long long p = p0 + e;
+            if (p >= 0 && p < a.n) a.out[p] = fmaf(y[e], a.out_scale, a.out_offset);
+        }
+    }
+}
+
+// swizzled shared-memory index of relative position r (>= 0) inside the warp's y1 store
+template <int C>
+__device__ __forceinline__ int y1_index(int r) {
+    constexpr int T = 32 * C;
+    int tile = r / T, w = r % T, l = w / C, e = w % C;
+    return tile * T + l * C + (((e >> 2) ^ swz<C>(l)) << 2) + (e & 3);
+}
+
+template <int NSEC, int C, typename InT, bool FWD_ONLY>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ct_filtfilt_kernel(FilterArgs a, CtFilterCoef k, long long nseg) {
+    constexpr int T = 32 * C;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = ct_lane();
+    const int wib = threadIdx.x >> 5;
+    float* y1 = smem + (size_t)wib * (size_t)(a.S + a.H);
+    const InT* in = reinterpret_cast<const InT*>(a.in);
+    const long long gw = (long long)blockIdx.x * kWarpsPerCta + wib;
+    const long long nw = (long long)gridDim.x * kWarpsPerCta;
+    const long long top = ((a.n + a.pad + T - 1) / T) * T;
+    const int sw = swz<C>(lane);
+
+    for (long long seg = gw; seg < nseg; seg += nw) {
+        const long long s0 = seg * a.S, s1 = s0 + a.S;
+        long long q0 = s0 - a.H; if (q0 < 0) q0 = 0;
+        long long q1 = FWD_ONLY ? s1 : (s1 + a.H < top ? s1 + a.H : top);
+        if (FWD_ONLY && q1 > top) q1 = top;
+
+        float carry[NSEC][2];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) { carry[s][0] = 0.f; carry[s][1] = 0.f; }
+
+        // ------------------------------ forward sweep ------------------------------
+        for (long long t = q0; t < q1; t += T) {
+            float x[C];
+            load_chunk<C>(a, in, t + (long long)lane * C, x);
+            cascade_tile<NSEC, C>(x, carry, k, lane);
+            if (FWD_ONLY) {
+                if (t >= s0) store_chunk<C>(a, t + (long long)lane * C, x);
+            } else if (t >= s0) {
+                float* dst = y1 + (size_t)(t - s0) + lane * C;
+#pragma unroll
+                for (int u = 0; u < C / 4; ++u)
+                    *reinterpret_cast<float4*>(dst + ((u ^ sw) << 2)) =
+                        make_float4(x[u * 4], x[u * 4 + 1], x[u * 4 + 2], x[u * 4 + 3]);
+            }
+        }
+        if (FWD_ONLY) continue;
+
+        // ---- right end: the forward output is held constant beyond the pad (that is
+        // ---- what "steady-state initial condition zi*y[-1]" means for the backward pass)
+        __syncwarp();
+        float c = 0.f;
+        const long long last = a.n + a.pad - 1;
+        if (q1 > last + 1) {
+            c = y1[y1_index<C>((int)(last - s0))];
+            __syncwarp();
+            for (long long p = last + 1 + lane; p < q1; p += 32) y1[y1_index<C>((int)(p - s0))] = c;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) { carry[s][0] = c * k.ss[s]; carry[s][1] = carry[s][0]; }
+
+        // ------------------------------ backward sweep -----------------------------
+        for (long long t = q1 - T; t >= s0; t -= T) {
+            // lane j walks the chunk of forward lane 31-j in decreasing time
+            const int fl = 31 - lane;
+            const int fsw = swz<C>(fl);
+            const float* src = y1 + (size_t)(t - s0) + fl * C;
+            float x[C];
+#pragma unroll
+            for (int u = 0; u < C / 4; ++u) {
+                float4 v = *reinterpret_cast<const float4*>(src + ((u ^ fsw) << 2));
+                x[C - 1 - (u * 4 + 0)] = v.x;
+                x[C - 1 - (u * 4 + 1)] = v.y;
+                x[C - 1 - (u * 4 + 2)] = v.z;
+                x[C - 1 - (u * 4 + 3)] = v.w;
+            }
+            cascade_tile<NSEC, C>(x, carry, k, lane);
+            if (t < a.n) {
+                float y[C];
+#pragma unroll
+                for (int e = 0; e < C; ++e) y[e] = x[C - 1 - e];
+                store_chunk<C>(a, t + (long long)fl * C, y);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------ exact median of u16 codes ----------------------------
+// Sampled histogram (estimate) + exact window count (verification); the host replays the
+// reference's scale_raw_data on the selected code(s) so the pad value is bit-identical
+// to np.median(scale_raw_data(raw)).
+__global__ void ct_hist_sampled_kernel(const uint16_t* __restrict__ raw, long long n, long long stride,
+                                       unsigned mask, unsigned* __restrict__ hist) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    const long long step = (long long)gridDim.x * blockDim.x * stride;
+    for (; i < n; i += step) atomicAdd(&hist[raw[i] & mask], 1u);
+}
+
+constexpr int kWin = 8;
+__global__ void __launch_bounds__(256)
+ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned mask, unsigned lo,
+                       unsigned step, unsigned long long* __restrict__ out /*[1+kWin]*/) {
+    // out[0] = #codes < lo ; out[1+i] = #codes == lo + i*step
+    unsigned below = 0, w[kWin];
+#pragma unroll
+    for (int i = 0; i < kWin; ++i) w[i] = 0;
+    const long long nvec = n / 8;
+    const uint4* v = reinterpret_cast<const uint4*>(raw);
+    const bool aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    auto tally = [&](unsigned code) {
+        code &= mask;
+        below += code < lo;
+        unsigned d = code - lo;
+#pragma unroll
+        for (int i = 0; i < kWin; ++i) w[i] += (d == i * step);
+    };
+    if (aligned) {
+        for (long long i = tid; i < nvec; i += nth) {
+            uint4 q = ct_ldg_stream(v + i);
+            unsigned ww[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tally(ww[j] & 0xffffu); tally(ww[j] >> 16); }
+        }
+        for (long long i = nvec * 8 + tid; i < n; i += nth) tally(raw[i]);
+    } else {
+        for (long long i = tid; i < n; i += nth) tally(raw[i]);
+    }
+    // warp reduce, then one atomic per warp per counter
+    unsigned vals[1 + kWin];
+    vals[0] = below;
+#pragma unroll
+    for (int i = 0; i < kWin; ++i) vals[1 + i] = w[i];
+#pragma unroll
+    for (int i = 0; i < 1 + kWin; ++i) {
+        unsigned long long s = vals[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CT_FULL, s, o);
+        if (ct_lane() == 0 && s) atomicAdd(&out[i], s);
+    }
+}
+
+template <int NSEC, typename InT, bool FWD>
+int launch_filter(const FilterArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    auto kern = ct_filtfilt_kernel<NSEC, kC, InT, FWD>;
+    size_t smem = FWD ? 0 : (size_t)kWarpsPerCta * (size_t)(a.S + a.H) * sizeof(float);
+    if (smem > (size_t)ct_max_smem_optin()) {
+        ct_set_error("filter: sub-segment + halo (%d + %d samples) does not fit in shared memory", a.S, a.H);
+        return CT_ERR_UNSUPPORTED;
+    }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem);
+    if (occ < 1) occ = 1;
+    long long nseg = (a.n + a.S - 1) / a.S;
+    long long want = (nseg + kWarpsPerCta - 1) / kWarpsPerCta;
+    long long grid = (long long)ct_sm_count() * occ;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CT_COUNT_LAUNCH();
+    kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(a, k, nseg);
+    return ct_check_launch("ct_filtfilt_kernel");
+}
+
+template <typename InT, bool FWD>
+int dispatch_nsec(const FilterArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    switch (k.nsec) {
+        case 1: return launch_filter<1, InT, FWD>(a, k, st);
+        case 2: return launch_filter<2, InT, FWD>(a, k, st);
+        case 3: return launch_filter<3, InT, FWD>(a, k, st);
+        case 4: return launch_filter<4, InT, FWD>(a, k, st);
+        case 5: return launch_filter<5, InT, FWD>(a, k, st);
+    }
+    ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
+    return CT_ERR_ARG;
+}
+
+int check_common(const void* in, const float* out, long long n, long long pad, int S, int H,
+                 const CtFilterCoef* k) {
+    if (!in || !out || !k) { ct_set_error("filter: null pointer"); return CT_ERR_ARG; }
+    if (n < 0 || pad < 0) { ct_set_error("filter: negative length"); return CT_ERR_ARG; }
+    if (S <= 0 || H < 0 || S % kT || H % kT) {
+        ct_set_error("filter: S and H must be multiples of %d (got %d, %d)", kT, S, H);
+        return CT_ERR_ARG;
+    }
+    if (k->tile_c != kC) { ct_set_error("filter: coefficients built for C=%d, kernel uses %d", k->tile_c, kC); return CT_ERR_ARG; }
+    return CT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ct_filter_tile(void) { return kT; }
+int ct_filter_chunk(void) { return kC; }
+
+int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_code, uint16_t mask,
+                    float alpha, float pad_value, const CtFilterCoef* coef, int S, int H,
+                    int forward_only, float* out, void* stream) {
+    int rc = check_common(raw, out, n, pad, S, H, coef);
+    if (rc) return rc;
+    if (n == 0) return CT_OK;
+    FilterArgs a;
+    a.in = raw; a.out = out; a.n = n; a.pad = pad; a.S = S; a.H = H;
+    a.sub = median_code; a.mask2 = (unsigned)mask | ((unsigned)mask << 16);
+    a.out_scale = alpha; a.out_offset = pad_value;
+    a.in_aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
+    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    return forward_only ? dispatch_nsec<uint16_t, true>(a, *coef, st)
+                        : dispatch_nsec<uint16_t, false>(a, *coef, st);
+}
+
+int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, const CtFilterCoef* coef,
+                    int S, int H, int forward_only, float* out, void* stream) {
+    int rc = check_common(x, out, n, pad, S, H, coef);
+    if (rc) return rc;
+    if (n == 0) return CT_OK;
+    FilterArgs a;
+    a.in = x; a.out = out; a.n = n; a.pad = pad; a.S = S; a.H = H;
+    a.sub = pad_value; a.mask2 = 0xffffffffu; a.out_scale = 1.f; a.out_offset = pad_value;
+    a.in_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    return forward_only ? dispatch_nsec<float, true>(a, *coef, st)
+                        : dispatch_nsec<float, false>(a, *coef, st);
+}
+
+int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t mask,
+                        uint32_t* hist65536, void* stream) {
+    if (!raw || !hist65536 || n < 0 || stride < 1) { ct_set_error("hist: bad argument"); return CT_ERR_ARG; }
+    if (n == 0) return CT_OK;
+    long long ns = (n + stride - 1) / stride;
+    int threads = 256;
+    long long blocks = (ns + threads - 1) / threads;
+    long long cap = (long long)ct_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    CT_COUNT_LAUNCH();
+    ct_hist_sampled_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(raw, n, stride, mask, hist65536);
+    return ct_check_launch("ct_hist_sampled_kernel");
+}
+
+int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
+                        uint64_t* counts9, void* stream) {
+    if (!raw || !counts9 || n < 0 || step < 1) { ct_set_error("count_window: bad argument"); return CT_ERR_ARG; }
+    if (n == 0) return CT_OK;
+    long long blocks = (long long)ct_sm_count() * 8;
+    long long want = (n / 8 + 255) / 256 + 1;
+    if (blocks > want) blocks = want;
+    CT_COUNT_LAUNCH();
+    ct_count_window_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        raw, n, mask, lo, step, reinterpret_cast<unsigned long long*>(counts9));
+    return ct_check_launch("ct_count_window_kernel");
+}
+
+}  // extern "C"

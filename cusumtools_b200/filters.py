@@ -1,0 +1,251 @@
+"""Stage 1 of the hot path: dequantise + median pad + zero-phase Bessel low-pass.
+
+Python entry points over the C ABI (include/cusumtools_b200.h).  They mirror the
+reference call sites `App.scale_raw_data` / `App.filter_data`
+(plot-trace.py:272-287, 313-320) and `scipy.signal.lfilter`/`filtfilt` as used there;
+torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .design import BesselDesign, bessel_lowpass
+
+DEFAULT_HALO_EPS = 1e-7      # truncated natural response relative to max |x - median|
+DEFAULT_SUBSEGMENT = 4096    # output samples per warp sub-segment
+
+
+# ------------------------------------------------------------------ coefficient packing
+def _mat_pow(A: np.ndarray, p: int) -> np.ndarray:
+    R = np.eye(2)
+    B = A.copy()
+    while p:
+        if p & 1:
+            R = R @ B
+        B = B @ B
+        p >>= 1
+    return R
+
+
+def make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
+    """Pack a design for the kernel: per-section taps, the constant state-transition
+    powers A^C and A^(C*2^k) used by the warp scan, steady-state factors, gain."""
+    Cc = _lib.lib().ct_filter_chunk()
+    k = _lib.CtFilterCoef()
+    k.nsec = design.nsec
+    k.tile_c = Cc
+    dc = 1.0  # DC gain of the cascade up to (not including) the current section
+    for s in range(design.nsec):
+        a1, a2 = design.sections[s]
+        fo = bool(design.first_order[s])
+        n1, n2 = (1.0, 0.0) if fo else (2.0, 1.0)
+        k.na1[s], k.na2[s], k.n1[s], k.n2[s] = -a1, -a2, n1, n2
+        A = np.array([[-a1, -a2], [1.0, 0.0]])
+        AC = _mat_pow(A, Cc)
+        for i in range(4):
+            k.AC[s][i] = AC.flat[i]
+        for st in range(_lib.CT_SCAN_STEPS):
+            M = _mat_pow(A, Cc * (1 << st))
+            for i in range(4):
+                k.M[s][st][i] = M.flat[i]
+        k.ss[s] = dc / (1.0 + a1 + a2)
+        dc *= (1.0 + n1 + n2) / (1.0 + a1 + a2)
+    k.gain = design.gain
+    peak = 65536.0 * dc  # largest un-normalised intermediate for a full-scale step
+    if not math.isfinite(peak) or peak > 1e36:
+        raise ValueError("cutoff/samplerate too low for the float32 cascade (intermediate overflow)")
+    return k
+
+
+_halo_cache: dict[tuple[int, float, float], int] = {}
+
+
+def halo_samples(design: BesselDesign, eps: float = DEFAULT_HALO_EPS) -> int:
+    """IIR warm-up halo H, rounded up to the kernel tile."""
+    key = (design.order, design.wn, float(eps))
+    if key not in _halo_cache:
+        T = _lib.lib().ct_filter_tile()
+        h = design.impulse_tail(eps)
+        _halo_cache[key] = max(T, (h + T - 1) // T * T)
+    return _halo_cache[key]
+
+
+def _plan(design: BesselDesign, halo_eps: float, subsegment: int | None):
+    T = _lib.lib().ct_filter_tile()
+    H = halo_samples(design, halo_eps)
+    S = subsegment or DEFAULT_SUBSEGMENT
+    S = max(T, (S + T - 1) // T * T)
+    return S, H
+
+
+def _stream_ptr(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str, dtype) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: cusumtools_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+# ------------------------------------------------------------------- Chimera scaling
+def chimera_bitmask(settings) -> int:
+    """plot-trace.py:281: bitmask = (2**16 - 1) - (2**(16-ADCbits) - 1)."""
+    bits = int(np.squeeze(settings["SETUP_ADCBITS"]))
+    return (2 ** 16 - 1) - (2 ** (16 - bits) - 1)
+
+
+def scale_codes_host(codes, settings) -> np.ndarray:
+    """The reference's own operation sequence (plot-trace.py:280-287) applied on the host
+    to a handful of codes: used for the pad value so it is bit-identical to
+    np.median(scale_raw_data(raw))."""
+    TIAgain = np.squeeze(settings["SETUP_TIAgain"])
+    preADCgain = np.squeeze(settings["SETUP_preADCgain"])
+    currentoffset = np.squeeze(settings["SETUP_pAoffset"])
+    ADCvref = np.squeeze(settings["SETUP_ADCVREF"])
+    closedloop_gain = TIAgain * preADCgain
+    t = np.asarray(codes).astype(np.uint16) & chimera_bitmask(settings)
+    t = ADCvref - (2 * ADCvref) * t.astype(float) / float(2 ** 16)
+    t = -t / float(closedloop_gain) + float(currentoffset)
+    return t * 1e12
+
+
+def chimera_affine(settings) -> tuple[float, float]:
+    """pA = alpha * (code & mask) + beta, the closed form of plot-trace.py:283-287."""
+    b0, b1 = scale_codes_host(np.array([0, 32768], dtype=np.uint16), settings)
+    return float((b1 - b0) / 32768.0), float(b0)
+
+
+# ----------------------------------------------------------------------- exact median
+def code_median(raw: torch.Tensor, mask: int = 0xFFFF) -> tuple[int, int]:
+    """The two middle order statistics (equal for odd n) of the masked codes, exactly.
+
+    A strided sample histogram locates the median; an exact counting pass over a window
+    of 8 adjacent codes verifies the ranks (and is repeated if the window missed)."""
+    if raw.dtype not in (torch.uint16, torch.int16):
+        raise TypeError("raw must hold the 16-bit ADC codes (torch.uint16 or the int16 view)")
+    _require_cuda(raw, "raw", raw.dtype)
+    L = _lib.lib()
+    n = raw.numel()
+    if n == 0:
+        raise ValueError("median of an empty trace")
+    shift = 0
+    while shift < 16 and not (mask >> shift) & 1:
+        shift += 1
+    step = 1 << shift
+    k1, k2 = (n - 1) // 2, n // 2
+    st = _stream_ptr(raw)
+
+    def sampled_hist(stride):
+        h = torch.zeros(65536, dtype=torch.int32, device=raw.device)
+        _lib.check(L.ct_hist_sampled_u16(raw.data_ptr(), n, stride, mask, h.data_ptr(), st), "ct_hist_sampled_u16")
+        return h.cpu().numpy().astype(np.int64)
+
+    stride = max(1, n // (1 << 22))
+    hist = sampled_hist(stride)
+    if stride == 1:
+        cdf = np.cumsum(hist)
+        return int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
+    cdf = np.cumsum(hist)
+    est = int(np.searchsorted(cdf, (cdf[-1] + 1) // 2))
+    lo = max(0, (est >> shift) * step - 3 * step)
+    for _ in range(6):
+        cnt = torch.zeros(9, dtype=torch.int64, device=raw.device)
+        _lib.check(L.ct_count_window_u16(raw.data_ptr(), n, mask, lo, step, cnt.data_ptr(), st), "ct_count_window_u16")
+        c = cnt.cpu().numpy().astype(np.int64)
+        below, w = int(c[0]), c[1:]
+        cw = below + np.cumsum(w)
+        if below <= k1 and k2 < cw[-1]:
+            i1 = int(np.searchsorted(cw, k1 + 1))
+            i2 = int(np.searchsorted(cw, k2 + 1))
+            return lo + i1 * step, lo + i2 * step
+        lo = max(0, lo - 6 * step) if k1 < below else lo + 6 * step
+    # pathological distribution: exact full histogram
+    cdf = np.cumsum(sampled_hist(1))
+    return int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
+
+
+# ------------------------------------------------------------------------ entry points
+def filtfilt_codes(raw: torch.Tensor, *, alpha: float, pad_value: float, median_code: float, mask: int,
+                   design: BesselDesign, padding: int = 1000, forward_only: bool = False,
+                   halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = pad_value + alpha * filtfilt((raw & mask) - median_code) with the reference's
+    boundary handling; one fused kernel, 2 B read + 4 B written per sample."""
+    if raw.dtype not in (torch.uint16, torch.int16):
+        raise TypeError("raw must hold the 16-bit ADC codes (torch.uint16 or the int16 view)")
+    _require_cuda(raw, "raw", raw.dtype)
+    n = raw.numel()
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=raw.device)
+    _require_cuda(out, "out", torch.float32)
+    if out.numel() != n:
+        raise ValueError("out has the wrong length")
+    coef = make_coef(design)
+    S, H = _plan(design, halo_eps, subsegment)
+    rc = _lib.lib().ct_filtfilt_u16(raw.data_ptr(), n, int(padding), float(median_code), int(mask),
+                                    float(alpha), float(pad_value), C.byref(coef), S, H,
+                                    int(bool(forward_only)), out.data_ptr(), _stream_ptr(raw))
+    _lib.check(rc, "ct_filtfilt_u16")
+    return out
+
+
+def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8, *,
+                     samplerate: float | None = None, padding: int = 1000, forward_only: bool = False,
+                     halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
+                     median_codes: tuple[int, int] | None = None,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+    """`App.scale_raw_data` + `App.filter_data` (plot-trace.py:272-287, 313-320) fused:
+    raw Chimera codes on the GPU -> filtered pA (float32) on the GPU.
+
+    `settings` is the dict `scipy.io.loadmat` returns for the `.mat` next to the `.log`
+    (or any mapping with the same keys).  `median_codes` lets a multi-GPU caller pass the
+    globally reduced median instead of this shard's."""
+    fs = float(np.floor(np.squeeze(settings["ADCSAMPLERATE"]))) if samplerate is None else float(samplerate)
+    design = bessel_lowpass(int(order), 2.0 * float(cutoff) / fs)
+    mask = chimera_bitmask(settings)
+    alpha, _ = chimera_affine(settings)
+    c1, c2 = median_codes if median_codes is not None else code_median(raw, mask)
+    vals = scale_codes_host(np.array([c1, c2], dtype=np.uint16), settings)
+    pad_value = float(np.median(vals))
+    return filtfilt_codes(raw, alpha=alpha, pad_value=pad_value, median_code=0.5 * (c1 + c2), mask=mask,
+                          design=design, padding=padding, forward_only=forward_only, halo_eps=halo_eps,
+                          subsegment=subsegment, out=out)
+
+
+def bessel_filtfilt(x: torch.Tensor, samplerate: float, cutoff: float, order: int = 8, *,
+                    pad_value: float, padding: int = 1000, forward_only: bool = False,
+                    halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+    """Zero-phase Bessel of an already-dequantised float32 trace (e.g. `.bin` data,
+    print_trace.py:33): out = pad_value + filtfilt(x - pad_value) with `padding` samples
+    of constant pad, i.e. filtfilt(b, a, np.pad(x, padding, constant=pad_value),
+    padtype=None)[padding:-padding]."""
+    _require_cuda(x, "x", torch.float32)
+    n = x.numel()
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+    _require_cuda(out, "out", torch.float32)
+    design = bessel_lowpass(int(order), 2.0 * float(cutoff) / float(samplerate))
+    coef = make_coef(design)
+    S, H = _plan(design, halo_eps, subsegment)
+    rc = _lib.lib().ct_filtfilt_f32(x.data_ptr(), n, int(padding), float(pad_value), C.byref(coef), S, H,
+                                    int(bool(forward_only)), out.data_ptr(), _stream_ptr(x))
+    _lib.check(rc, "ct_filtfilt_f32")
+    return out
+
+
+def bessel_lfilter(x: torch.Tensor, samplerate: float, cutoff: float, order: int = 8, *,
+                   initial: float = 0.0, **kw) -> torch.Tensor:
+    """Causal pass only: scipy.signal.lfilter(b, a, x, zi=lfilter_zi(b, a)*initial)[0]
+    (`initial = 0` is the plain zero-state lfilter)."""
+    return bessel_filtfilt(x, samplerate, cutoff, order, pad_value=float(initial), padding=0,
+                           forward_only=True, **kw)

@@ -1,0 +1,100 @@
+/* cusumtools_b200 — C ABI of the B200-native raw-trace hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (shadowk29/cusumtools) is pure Python with no FFI of its own; its de-facto operator
+ * boundary for this path is four library calls plus file formats.
+ * Each entry point below names the reference call site it replaces.  A maintainer binds
+ * these with ctypes (cusumtools_b200/_lib.py is that binding).
+ *
+ * Conventions
+ *   - every pointer except `coef`, `sign`-less scalars and `ct_last_error` results is a
+ *     DEVICE pointer owned by the caller; the library never frees or retains it;
+ *   - `stream` is a cudaStream_t (0 = default stream); all work is enqueued on it and no
+ *     entry point synchronises the device;
+ *   - return value 0 = ok, negative = error (CT_ERR_*), message via ct_last_error();
+ *   - 64-bit sample counts everywhere (a 1-hour trace has 1.5e10 samples).
+ */
+#ifndef CUSUMTOOLS_B200_H
+#define CUSUMTOOLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CT_ABI_VERSION 1
+#define CT_MAX_SECTIONS 5
+#define CT_SCAN_STEPS 5
+
+/* Filter coefficients as the kernel consumes them (built on the host in float64 by
+ * cusumtools_b200/design.py from the same Bessel design the reference requests with
+ * scipy.signal.bessel(order, Wn, 'low') at plot-trace.py:317).
+ *   section s: v[n] = x[n] + na1*v[n-1] + na2*v[n-2];  y[n] = v[n] + n1*v[n-1] + n2*v[n-2]
+ *   AC  = A^C,  M[k] = A^(C*2^k)  with A = [[na1, na2], [1, 0]] (row-major 2x2)
+ *   ss  = steady-state value of v for a unit constant at the cascade input
+ *   gain = overall scale making the DC gain exactly 1 (applied in the last section)   */
+typedef struct CtFilterCoef {
+    int32_t nsec;
+    int32_t tile_c;                               /* must equal ct_filter_chunk() */
+    float na1[CT_MAX_SECTIONS], na2[CT_MAX_SECTIONS];
+    float n1[CT_MAX_SECTIONS], n2[CT_MAX_SECTIONS];
+    float AC[CT_MAX_SECTIONS][4];
+    float M[CT_MAX_SECTIONS][CT_SCAN_STEPS][4];
+    float ss[CT_MAX_SECTIONS];
+    float gain;
+} CtFilterCoef;
+
+int ct_version(void);
+const char* ct_last_error(void);                  /* thread-local, never NULL */
+uint64_t ct_launch_count(void);                   /* kernels launched by this library so far */
+void ct_launch_count_reset(void);
+int ct_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin);
+
+/* ---- stage 1: dequantise + median pad + zero-phase Bessel -------------------------
+ * Replaces App.scale_raw_data + App.filter_data (plot-trace.py:272-287, 313-320):
+ *   out[i] = pad_value + alpha * filtfilt(code - median_code)[i],  i in [0, n)
+ * with the reference's boundary semantics (constant pad of `pad` samples each side,
+ * steady-state initial conditions).  raw codes are masked with `mask` first
+ * (plot-trace.py:281-282).  S (sub-segment) and H (IIR warm-up halo) are multiples of
+ * ct_filter_tile(); forward_only != 0 gives the causal pass only (scipy.signal.lfilter
+ * with zi = lfilter_zi*pad_value), the primitive filtfilt is built from.               */
+int ct_filter_tile(void);
+int ct_filter_chunk(void);
+int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_code, uint16_t mask,
+                    float alpha, float pad_value, const CtFilterCoef* coef, int S, int H,
+                    int forward_only, float* out, void* stream);
+/* Same for already-dequantised float32 input (.bin traces, print_trace.py:33,
+ * noise-fit.py:90; multi-gain file series, plot-trace.py:252-269):
+ *   out = pad_value + filtfilt(x - pad_value).                                         */
+int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, const CtFilterCoef* coef,
+                    int S, int H, int forward_only, float* out, void* stream);
+
+/* Exact global median of the masked codes, the value np.pad(mode='median') needs
+ * (plot-trace.py:319): a strided-sample histogram to locate it and an exact count of
+ * the codes below / inside a window of 8 codes {lo + i*step} to verify it.
+ *   hist65536: uint32[65536], caller-zeroed; counts9: uint64[9], caller-zeroed.        */
+int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t mask,
+                        uint32_t* hist65536, void* stream);
+int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
+                        uint64_t* counts9, void* stream);
+
+/* ---- stage 2: baseline statistics + threshold/hysteresis detection ---------------
+ * No reference implementation exists; semantics per plot-trace.py:379-414, definition in
+ * oracle/events_oracle.py.  Block sums are exact int64 sums of
+ * q = rint((y - c0) * 2^shift) over samples with bmin <= y <= bmax.                   */
+int ct_block_stats_f32(const float* y, int64_t n, int64_t block, float bmin, float bmax, float c0,
+                       int shift, int64_t* cnt, int64_t* s1, int64_t* s2, void* stream);
+int ct_detect_run(void);                          /* `block` must be a multiple of this */
+int64_t ct_detect_workspace_bytes(int64_t n);
+/* starts/ends: int64[capacity] in time order; counts2 = {n_starts, n_ends} (may exceed
+ * capacity: nothing is written past it).  With state_in == 0 event i is
+ * [starts[i], ends[i]) for i < n_ends and starts[n_ends] (if any) is still open.       */
+int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign, const float* t_start,
+                  const float* t_end, int state_in, void* workspace, int64_t workspace_bytes,
+                  int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

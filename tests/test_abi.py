@@ -1,0 +1,71 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/*.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cusumtools_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ct_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    syms = declared_symbols()
+    for must in ("ct_filtfilt_u16", "ct_filtfilt_f32", "ct_detect_f32", "ct_block_stats_f32", "ct_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from cusumtools_b200 import _lib
+    _lib.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_binding_covers_header():
+    from cusumtools_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_version_and_struct_layout():
+    from cusumtools_b200 import _lib
+    L = _lib.lib()
+    assert L.ct_version() == 1
+    assert L.ct_filter_tile() == 32 * L.ct_filter_chunk()
+    # struct: 2 int32 + (4*5 + 20 + 100 + 5 + 1) floats
+    assert ctypes.sizeof(_lib.CtFilterCoef) == 8 + 4 * (20 + 20 + 100 + 5 + 1)
+
+
+def test_argument_errors_are_reported_without_gpu():
+    from cusumtools_b200 import _lib
+    L = _lib.lib()
+    coef = _lib.CtFilterCoef()
+    coef.nsec, coef.tile_c = 4, L.ct_filter_chunk()
+    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 4096, 512, 0, None, None)
+    assert rc == -1 and b"null" in L.ct_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "ct_filtfilt_u16")
+
+
+def test_product_refuses_cpu_tensors():
+    import torch
+    from cusumtools_b200 import filters, synth
+    raw = torch.zeros(1024, dtype=torch.uint16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        filters.dequant_filtfilt(raw, synth.CHIMERA_SETTINGS, 1e5, 8, median_codes=(0, 0))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cusumtools_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
+                assert "scipy.signal" not in txt or fn == "design.py" or "import scipy" not in txt, fn
