@@ -259,7 +259,7 @@ ct_filtfilt_kernel(FilterArgs a, CtFilterCoef k, long long nseg) {
                 x[C - 1 - (u * 4 + 3)] = v.w;
             }
             cascade_tile<NSEC, C>(x, carry, k, lane);
-            if (t < a.n) {
+            if (t < s1 && t < a.n) {      // halo tiles (t >= s1) only warm the recursion up
                 float y[C];
 #pragma unroll
                 for (int e = 0; e < C; ++e) y[e] = x[C - 1 - e];

@@ -78,11 +78,11 @@ def test_unaligned_views():
 
 def test_halo_sharding_is_invisible():
     """Sub-segments are filtered independently with an H-sample warm-up: the result must
-    not depend on the sub-segment length (512 vs 4096 vs 16384)."""
+    not depend on the sub-segment length (512 vs 4096 vs 8192)."""
     codes, _ = synth.c1_trace(n=300000, n_events=70, seed=9)
     a = gpu_filter(codes, 1e5, 8, subsegment=512)
     b = gpu_filter(codes, 1e5, 8, subsegment=4096)
-    c = gpu_filter(codes, 1e5, 8, subsegment=16384)
+    c = gpu_filter(codes, 1e5, 8, subsegment=8192)
     assert np.abs(a - b).max() < 0.02 and np.abs(b - c).max() < 0.02
 
 
