@@ -270,6 +270,288 @@ ct_filtfilt_kernel(FilterArgs a, CtFilterCoef k, long long nseg) {
     }
 }
 
+// =====================================================================================
+// Dual-stream zero-phase kernel (the production filtfilt path).
+//
+// A warp walks its contiguous run of sub-segments as a software pipeline: in phase k it
+// runs the FORWARD sweep of segment k and the BACKWARD sweep of segment k-1 in lock step,
+// one tile of each per super-step.  The two sweeps execute the same cascade, so they are
+// packed into the two halves of float2 registers and issued as FFMA2 (fma.rn.f32x2, new
+// in sm_100): half the issue slots for the same work, and two independent dependency
+// chains per warp.  They also run in anti-phase on the shared-memory store of forward
+// results: the backward sweep drains slot i in the same super-step in which the forward
+// sweep refills it, so ONE (S+H)-float buffer serves both segments (twice as many
+// streams per SM as buffer-per-segment).
+// Global traffic uses 256-bit LDG/STG (32 B = one sector per lane per instruction).
+// =====================================================================================
+typedef float2 f2;
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ f2 shfl_up2(f2 v, int d) {
+    return make_float2(__shfl_up_sync(CT_FULL, v.x, d), __shfl_up_sync(CT_FULL, v.y, d));
+}
+__device__ __forceinline__ f2 shfl_idx2(f2 v, int l) {
+    return make_float2(__shfl_sync(CT_FULL, v.x, l), __shfl_sync(CT_FULL, v.y, l));
+}
+
+struct u8x { unsigned w[8]; };
+static __device__ __forceinline__ u8x ldg256(const void* p) {
+    u8x r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
+                   "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    return r;
+}
+static __device__ __forceinline__ void stg256(void* p, const float* f) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+                 : "memory");
+}
+
+// Per-lane masked scan matrices: entry [s][st][0] is zero, [s][st][1] is A^(C*2^st) (st < 5)
+// or A^C (st == 5, the tile-carry injection).  A lane reads [lane >= 2^st] (or [lane == 0]),
+// so the Kogge-Stone update "v += M t for lanes >= d" becomes four UNCONDITIONAL FFMA2 with
+// no predicate, select or move, and the coefficients arrive with one LDS.128.
+struct ScanTab { float4 m[CT_MAX_SECTIONS][6][2]; };
+
+__device__ __forceinline__ void scan_fma(f2& v1, f2& v2, f2 t1, f2 t2, float4 m) {
+    v1 = fma2(splat(m.x), t1, fma2(splat(m.y), t2, v1));
+    v2 = fma2(splat(m.z), t1, fma2(splat(m.w), t2, v2));
+}
+
+template <int NSEC, int C>
+__device__ __forceinline__ void cascade_tile2(f2 (&x)[C], f2 (&carry)[NSEC][2], const CtFilterCoef& k,
+                                              int lane, const float4* const (&tp)[6]) {
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        const f2 na1 = splat(k.na1[s]), na2 = splat(k.na2[s]);
+        // zero-state run (the first two steps have no history)
+        f2 v2 = x[0], v1 = fma2(na1, x[0], x[1]);
+#pragma unroll
+        for (int e = 2; e < C; ++e) {
+            f2 v = fma2(na1, v1, fma2(na2, v2, x[e]));
+            v2 = v1; v1 = v;
+        }
+        scan_fma(v1, v2, carry[s][0], carry[s][1], tp[5][s * 12]);
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+            f2 t1 = shfl_up2(v1, 1 << st), t2 = shfl_up2(v2, 1 << st);
+            scan_fma(v1, v2, t1, t2, tp[st][s * 12]);
+        }
+        f2 i1 = shfl_up2(v1, 1), i2 = shfl_up2(v2, 1);
+        if (lane == 0) { i1 = carry[s][0]; i2 = carry[s][1]; }
+        carry[s][0] = shfl_idx2(v1, 31);
+        carry[s][1] = shfl_idx2(v2, 31);
+        v1 = i1; v2 = i2;
+        if (s == NSEC - 1) {
+            const f2 g = splat(k.gain), g1 = splat(k.n1[s] * k.gain), g2 = splat(k.n2[s] * k.gain);
+#pragma unroll
+            for (int e = 0; e < C; ++e) {
+                f2 v = fma2(na1, v1, fma2(na2, v2, x[e]));
+                x[e] = fma2(g1, v1, fma2(g2, v2, mul2(g, v)));
+                v2 = v1; v1 = v;
+            }
+        } else {
+            const f2 n1 = splat(k.n1[s]), n2 = splat(k.n2[s]);
+#pragma unroll
+            for (int e = 0; e < C; ++e) {
+                f2 v = fma2(na1, v1, fma2(na2, v2, x[e]));
+                x[e] = fma2(n1, v1, fma2(n2, v2, v));
+                v2 = v1; v1 = v;
+            }
+        }
+    }
+}
+
+// raw (unconverted) input chunk of a lane, so the next tile can be prefetched cheaply
+template <int C, typename InT> struct Raw;
+template <int C> struct Raw<C, uint16_t> { u8x v[C / 16]; unsigned valid; };
+template <int C> struct Raw<C, float> { u8x v[C / 8]; unsigned valid; };
+
+template <int C>
+__device__ __forceinline__ void fetch(const FilterArgs& a, const uint16_t* in, long long p0, bool active,
+                                      Raw<C, uint16_t>& r) {
+    if (active && a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
+#pragma unroll
+        for (int u = 0; u < C / 16; ++u) r.v[u] = ldg256(in + p0 + u * 16);
+        r.valid = 0xffffffffu;
+    } else {
+        unsigned valid = 0;
+#pragma unroll
+        for (int u = 0; u < C / 16; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                long long pa = p0 + u * 16 + 2 * j, pb = pa + 1;
+                bool oa = active && pa >= 0 && pa < a.n, ob = active && pb >= 0 && pb < a.n;
+                unsigned ca = oa ? in[pa] : 0u, cb = ob ? in[pb] : 0u;
+                r.v[u].w[j] = ca | (cb << 16);
+                valid |= (oa ? 1u : 0u) << (u * 16 + 2 * j);
+                valid |= (ob ? 1u : 0u) << (u * 16 + 2 * j + 1);
+            }
+        r.valid = valid;
+    }
+}
+template <int C>
+__device__ __forceinline__ void fetch(const FilterArgs& a, const float* in, long long p0, bool active,
+                                      Raw<C, float>& r) {
+    if (active && a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
+#pragma unroll
+        for (int u = 0; u < C / 8; ++u) r.v[u] = ldg256(in + p0 + u * 8);
+        r.valid = 0xffffffffu;
+    } else {
+        unsigned valid = 0;
+#pragma unroll
+        for (int u = 0; u < C / 8; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                long long p = p0 + u * 8 + j;
+                bool ok = active && p >= 0 && p < a.n;
+                r.v[u].w[j] = ok ? __float_as_uint(in[p]) : 0u;
+                valid |= (ok ? 1u : 0u) << (u * 8 + j);
+            }
+        r.valid = valid;
+    }
+}
+// converted, median-subtracted samples into the .x halves
+template <int C>
+__device__ __forceinline__ void unpack(const FilterArgs& a, const Raw<C, uint16_t>& r, f2 (&x)[C]) {
+#pragma unroll
+    for (int u = 0; u < C / 16; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            unsigned m = r.v[u].w[j] & a.mask2;
+            const int e = u * 16 + 2 * j;
+            x[e].x = (float)(int)(m & 0xffffu) - a.sub;
+            x[e + 1].x = (float)(int)(m >> 16) - a.sub;
+        }
+    if (r.valid != 0xffffffffu) {            // trace edges only
+#pragma unroll
+        for (int e = 0; e < C; ++e) if (!((r.valid >> e) & 1)) x[e].x = 0.f;
+    }
+}
+template <int C>
+__device__ __forceinline__ void unpack(const FilterArgs& a, const Raw<C, float>& r, f2 (&x)[C]) {
+#pragma unroll
+    for (int u = 0; u < C / 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[u * 8 + j].x = __uint_as_float(r.v[u].w[j]) - a.sub;
+    if (r.valid != 0xffffffffu) {
+#pragma unroll
+        for (int e = 0; e < C; ++e) if (!((r.valid >> e) & 1)) x[e].x = 0.f;
+    }
+}
+
+// forward results live in shared memory element-major ([e][lane]) so that every scalar
+// LDS/STS of a warp is bank-conflict free and lands directly in the right register half
+template <int C>
+__device__ __forceinline__ int buf_index(int r, int par, int NB) {
+    constexpr int T = 32 * C;
+    int tile = r / T, w = r % T, l = w / C, e = w % C;
+    int slot = par ? NB - 1 - tile : tile;
+    return slot * T + e * 32 + l;
+}
+
+template <int NSEC, int C, typename InT>
+__global__ void __launch_bounds__(128)
+ct_filtfilt2_kernel(FilterArgs a, CtFilterCoef k, long long nseg) {
+    static_assert(C == 16, "the lane chunk is 16 samples (one 256-bit load of codes)");
+    constexpr int T = 32 * C;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = ct_lane();
+    // warp-uniform by construction: the shuffle lets the compiler keep everything derived
+    // from it (loop bounds, coefficients) in uniform registers
+    const int wib = __shfl_sync(CT_FULL, threadIdx.x >> 5, 0);
+    const int wpc = blockDim.x >> 5;
+    float* buf = smem + (size_t)wib * (size_t)(a.S + a.H);
+    const InT* in = reinterpret_cast<const InT*>(a.in);
+    const long long gw = (long long)blockIdx.x * wpc + wib;
+    const long long nw = (long long)gridDim.x * wpc;
+    const long long per = (nseg + nw - 1) / nw;
+    const long long sb = gw * per;
+    const long long cnt = (sb + per <= nseg ? per : nseg - sb);
+    const int HT = a.H / T, NB = (a.S + a.H) / T, NF = NB + HT;
+    const int fl = 31 - lane;
+    const long long last = a.n + a.pad - 1;
+    float cB = 0.f;   // constant the forward output of the backward stream's segment is held at
+
+    __shared__ ScanTab tab;
+    if (threadIdx.x < NSEC * 6) {
+        const int s = threadIdx.x / 6, st = threadIdx.x % 6;
+        const float* M = st < 5 ? k.M[s][st] : k.AC[s];
+        tab.m[s][st][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tab.m[s][st][1] = make_float4(M[0], M[1], M[2], M[3]);
+    }
+    __syncthreads();
+    const float4* tp[6];
+#pragma unroll
+    for (int st = 0; st < 5; ++st) tp[st] = &tab.m[0][st][lane >= (1 << st) ? 1 : 0];
+    tp[5] = &tab.m[0][5][lane == 0 ? 1 : 0];
+    if (cnt <= 0) return;
+
+    for (long long ph = 0; ph <= cnt; ++ph) {
+        const bool vF = ph < cnt, vB = ph >= 1;
+        const long long s0F = (sb + ph) * (long long)a.S;
+        const long long s0B = s0F - a.S;
+        const int par = (int)(ph & 1);
+        f2 carry[NSEC][2];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) { carry[s][0] = make_float2(0.f, cB * k.ss[s]); carry[s][1] = carry[s][0]; }
+
+        Raw<C, InT> pre;
+        fetch<C>(a, in, s0F - a.H + (long long)lane * C, vF, pre);
+        for (int u = 0; u < NF; ++u) {
+            f2 x[C];
+            unpack<C>(a, pre, x);
+            if (u + 1 < NF) fetch<C>(a, in, s0F - a.H + (long long)(u + 1) * T + (long long)lane * C, vF, pre);
+            const int ai = u - HT;                       // stored forward tile == backward tile index
+            const bool st = ai >= 0;
+            float* tb = buf + (size_t)(par ? NB - 1 - ai : ai) * T;
+            if (st && vB) {
+#pragma unroll
+                for (int e = 0; e < C; ++e) x[C - 1 - e].y = tb[e * 32 + fl];
+            } else {
+#pragma unroll
+                for (int e = 0; e < C; ++e) x[e].y = 0.f;
+            }
+            __syncwarp();
+            cascade_tile2<NSEC, C>(x, carry, k, lane, tp);
+            if (st && vF) {
+#pragma unroll
+                for (int e = 0; e < C; ++e) tb[e * 32 + lane] = x[e].x;
+            }
+            if (st && vB) {
+                const long long tB = s0B + a.S + a.H - (long long)(ai + 1) * T;
+                if (tB < s0B + a.S && tB < a.n) {          // owned tile (halo tiles only warm up)
+                    const long long p0 = tB + (long long)fl * C;
+                    float y[C];
+#pragma unroll
+                    for (int e = 0; e < C; ++e) y[e] = fmaf(x[C - 1 - e].y, a.out_scale, a.out_offset);
+                    if (a.out_aligned && p0 + C <= a.n) {
+                        stg256(a.out + p0, y);
+                        stg256(a.out + p0 + 8, y + 8);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < C; ++e) if (p0 + e < a.n) a.out[p0 + e] = y[e];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // right end of the trace: hold the forward output constant beyond the pad, which is
+        // what the steady-state initial condition zi*y[-1] of the backward pass means
+        cB = 0.f;
+        if (vF && s0F + a.S + a.H > last + 1) {
+            float c = buf[buf_index<C>((int)(last - s0F), par, NB)];
+            __syncwarp();
+            for (long long p = last + 1 + lane; p < s0F + a.S + a.H; p += 32)
+                buf[buf_index<C>((int)(p - s0F), par, NB)] = c;
+            __syncwarp();
+            cB = c;
+        }
+    }
+}
+
 // ------------------------------ exact median of u16 codes ----------------------------
 // Sampled histogram (estimate) + exact window count (verification); the host replays the
 // reference's scale_raw_data on the selected code(s) so the pad value is bit-identical
@@ -328,24 +610,45 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
 
 template <int NSEC, typename InT, bool FWD>
 int launch_filter(const FilterArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    auto kern = ct_filtfilt_kernel<NSEC, kC, InT, FWD>;
-    size_t smem = FWD ? 0 : (size_t)kWarpsPerCta * (size_t)(a.S + a.H) * sizeof(float);
-    if (smem > (size_t)ct_max_smem_optin()) {
+    long long nseg = (a.n + a.S - 1) / a.S;
+    if (FWD) {
+        auto kern = ct_filtfilt_kernel<NSEC, kC, InT, true>;
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, 0);
+        if (occ < 1) occ = 1;
+        long long want = (nseg + kWarpsPerCta - 1) / kWarpsPerCta;
+        long long grid = (long long)ct_sm_count() * occ;
+        if (grid > want) grid = want;
+        if (grid < 1) grid = 1;
+        CT_COUNT_LAUNCH();
+        kern<<<(unsigned)grid, kWarpsPerCta * 32, 0, st>>>(a, k, nseg);
+        return ct_check_launch("ct_filtfilt_kernel");
+    }
+    auto kern = ct_filtfilt2_kernel<NSEC, kC, InT>;
+    // warps per CTA: as many resident warps per SM as the shared-memory buffers allow
+    const size_t per_warp = (size_t)(a.S + a.H) * sizeof(float);
+    int best_w = 0, best_occ = 0, best_total = 0;
+    for (int w = 4; w >= 1; w >>= 1) {
+        size_t smem = per_warp * w;
+        if (smem > (size_t)ct_max_smem_optin()) continue;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, smem);
+        if (occ * w > best_total) { best_total = occ * w; best_w = w; best_occ = occ; }
+    }
+    if (!best_w) {
         ct_set_error("filter: sub-segment + halo (%d + %d samples) does not fit in shared memory", a.S, a.H);
         return CT_ERR_UNSUPPORTED;
     }
+    size_t smem = per_warp * best_w;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem);
-    if (occ < 1) occ = 1;
-    long long nseg = (a.n + a.S - 1) / a.S;
-    long long want = (nseg + kWarpsPerCta - 1) / kWarpsPerCta;
-    long long grid = (long long)ct_sm_count() * occ;
+    long long grid = (long long)ct_sm_count() * best_occ;
+    long long want = (nseg + best_w - 1) / best_w;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     CT_COUNT_LAUNCH();
-    kern<<<(unsigned)grid, kWarpsPerCta * 32, smem, st>>>(a, k, nseg);
-    return ct_check_launch("ct_filtfilt_kernel");
+    kern<<<(unsigned)grid, best_w * 32, smem, st>>>(a, k, nseg);
+    return ct_check_launch("ct_filtfilt2_kernel");
 }
 
 template <typename InT, bool FWD>
@@ -390,8 +693,8 @@ int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_co
     a.in = raw; a.out = out; a.n = n; a.pad = pad; a.S = S; a.H = H;
     a.sub = median_code; a.mask2 = (unsigned)mask | ((unsigned)mask << 16);
     a.out_scale = alpha; a.out_offset = pad_value;
-    a.in_aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
-    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    a.in_aligned = (reinterpret_cast<uintptr_t>(raw) & 31) == 0;
+    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     cudaStream_t st = (cudaStream_t)stream;
     return forward_only ? dispatch_nsec<uint16_t, true>(a, *coef, st)
                         : dispatch_nsec<uint16_t, false>(a, *coef, st);
@@ -405,8 +708,8 @@ int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, con
     FilterArgs a;
     a.in = x; a.out = out; a.n = n; a.pad = pad; a.S = S; a.H = H;
     a.sub = pad_value; a.mask2 = 0xffffffffu; a.out_scale = 1.f; a.out_offset = pad_value;
-    a.in_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    a.in_aligned = (reinterpret_cast<uintptr_t>(x) & 31) == 0;
+    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
     cudaStream_t st = (cudaStream_t)stream;
     return forward_only ? dispatch_nsec<float, true>(a, *coef, st)
                         : dispatch_nsec<float, false>(a, *coef, st);
