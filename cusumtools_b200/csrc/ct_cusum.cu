@@ -1,0 +1,280 @@
+// Batched per-event CUSUM+ level segmentation, one warp per event.
+//
+// No reference implementation exists (readevents.py only consumes level_current_pA /
+// level_duration_us / blockages_pA / stdev_pA / n_levels, :843-846,1297-1306); the
+// definition of record is oracle/events_oracle.py::cusum_event, the two-sided CUSUM of
+// SURVEY.md Appendix C with every reduction in exact integer arithmetic, so changepoints
+// are bit-identical to the sequential definition whatever the scan order:
+//   q_k  = rint((x_k - x_0) * 64)                      (int32, |q| < 2^22)
+//   Sq, Sqq = prefix sums of q, q^2 from the anchor    (warp scans: int32 / int64)
+//   m, v = running mean / population variance          (float64 from the exact sums)
+//   s+-  = rint(1024 * (+-delta/v) (q - m -+ delta/2)) (float32 ops, individually rounded)
+//   S+-  = prefix sums of s+-, g+- = S+- - running min (warp sum scan + warp min scan)
+// A jump is detected at the first k with g+ > H or g- > H; the new level starts after the
+// last index at which the winning g was 0; the anchor moves to k and the block is redone
+// with the new anchor.  Work per block of 256 samples: lane l holds 8 consecutive samples.
+#include "ct_common.cuh"
+#include "cusumtools_b200.h"
+
+namespace {
+
+constexpr int kE = 8;                 // samples per lane per block
+constexpr int kBlk = 32 * kE;         // 256
+constexpr float kQ = 64.0f, kQMax = 4194303.0f, kSScale = 1024.0f, kSMax = 2097152.0f;
+constexpr int kBig = 0x3fffffff;
+
+struct CusumArgs {
+    const float* y; long long ntot;
+    const long long* w0; const long long* w1; const int* type; long long nev;
+    float delta, h; int max_levels;
+    int* n_levels; int* edges; double* mean; double* sd; unsigned char* overflow;
+    unsigned long long* counter;
+};
+
+__device__ __forceinline__ int warp_excl_add(int v, int lane, int& total) {
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(CT_FULL, inc, d); if (lane >= d) inc += t; }
+    total = __shfl_sync(CT_FULL, inc, 31);
+    return inc - v;
+}
+__device__ __forceinline__ long long warp_excl_add(long long v, int lane, long long& total) {
+    long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { long long t = __shfl_up_sync(CT_FULL, inc, d); if (lane >= d) inc += t; }
+    total = __shfl_sync(CT_FULL, inc, 31);
+    return inc - v;
+}
+__device__ __forceinline__ int warp_excl_min(int v, int lane, int& total) {
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(CT_FULL, inc, d); if (lane >= d) inc = min(inc, t); }
+    total = __shfl_sync(CT_FULL, inc, 31);
+    int ex = __shfl_up_sync(CT_FULL, inc, 1);
+    return lane == 0 ? kBig : ex;
+}
+__device__ __forceinline__ int quantise(float x, float x0) {
+    float d = __fmul_rn(__fsub_rn(x, x0), kQ);
+    d = fminf(fmaxf(d, -kQMax), kQMax);
+    return __float2int_rn(d);
+}
+// highest index k in [lo, hi] among the lane-held candidates (cand = per-lane best or -1)
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(CT_FULL, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(128) ct_cusum_kernel(CusumArgs a) {
+    const int lane = ct_lane();
+    const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
+    const float dq = __fmul_rn(a.delta, kQ);
+    const float hq = __fmul_rn(dq, 0.5f);
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
+
+    for (;;) {
+        long long ev = 0;
+        if (lane == 0) ev = (long long)atomicAdd(a.counter, 1ULL);
+        ev = __shfl_sync(CT_FULL, ev, 0);
+        if (ev >= a.nev) break;
+        int* ed = a.edges + ev * (a.max_levels + 1);
+        for (int i = lane; i <= a.max_levels; i += 32) ed[i] = -1;
+        const long long p0 = a.w0[ev];
+        const long long nn = a.w1[ev] - p0;
+        if (nn <= 0 || p0 < 0 || a.w1[ev] > a.ntot || nn > 0x3fffffffLL || (a.type && a.type[ev] != 0)) {
+            if (lane == 0) { a.n_levels[ev] = 0; a.overflow[ev] = 0; }
+            continue;
+        }
+        const int n = (int)nn;
+        const float x0 = a.y[p0];
+        __syncwarp();
+        if (lane == 0) ed[0] = 0;
+        int nedge = 1, overflow = 0;
+        int k0 = 0;
+        long long cSq = 0, cSqq = 0;
+        int mp = kBig, mn = kBig;           // running min of S+-, relative to the block start
+        int argp = 0, argn = 0;             // last index at which g+- was 0
+        const long long abase = p0 & ~7LL;  // 32-byte aligned block grid
+        int rs = (int)(abase - p0);         // relative index of the block's first sample (<= 0)
+        bool fresh = true;
+        int q[kE];
+
+        while (rs < n && !overflow) {
+            const int r0 = rs + lane * kE;
+            if (fresh) {                    // (re)load and quantise this block's samples
+                const long long pa = p0 + r0;
+                float xv[kE];
+                if (aligned && pa >= 0 && pa + kE <= a.ntot) {
+                    const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
+                    uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
+                    xv[0] = __uint_as_float(lo.x); xv[1] = __uint_as_float(lo.y); xv[2] = __uint_as_float(lo.z); xv[3] = __uint_as_float(lo.w);
+                    xv[4] = __uint_as_float(hi.x); xv[5] = __uint_as_float(hi.y); xv[6] = __uint_as_float(hi.z); xv[7] = __uint_as_float(hi.w);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kE; ++e) { long long p = pa + e; xv[e] = (p >= 0 && p < a.ntot) ? a.y[p] : x0; }
+                }
+#pragma unroll
+                for (int e = 0; e < kE; ++e) q[e] = quantise(xv[e], x0);
+            }
+            // ---- exact prefix sums of q, q^2 over [k0, k]
+            int pq[kE]; long long pqq[kE];
+            {
+                int aq = 0; long long aqq = 0;
+#pragma unroll
+                for (int e = 0; e < kE; ++e) {
+                    const int k = r0 + e;
+                    const int qv = (k >= k0 && k < n) ? q[e] : 0;
+                    aq += qv; aqq += (long long)qv * qv;
+                    pq[e] = aq; pqq[e] = aqq;
+                }
+            }
+            int totq; long long totqq;
+            const int exq = warp_excl_add(pq[kE - 1], lane, totq);
+            const long long exqq = warp_excl_add(pqq[kE - 1], lane, totqq);
+            // ---- log-likelihood increments (fixed point) and their local prefix sums
+            int lp[kE], ln[kE];
+            {
+                int ap = 0, an = 0;
+#pragma unroll
+                for (int e = 0; e < kE; ++e) {
+                    const int k = r0 + e;
+                    int sp = 0, sn = 0;
+                    if (k > k0 && k < n) {
+                        const int cnt = k - k0 + 1;
+                        const double Sq = (double)(cSq + exq + pq[e]);
+                        const double Sqq = (double)(cSqq + exqq + pqq[e]);
+                        double rc = (double)__fdiv_rn(1.0f, (float)cnt);
+                        rc = __dmul_rn(rc, __dsub_rn(2.0, __dmul_rn((double)cnt, rc)));
+                        const double m = __dmul_rn(Sq, rc);
+                        const double vv = __dmul_rn(__dsub_rn(Sqq, __dmul_rn(Sq, m)), rc);
+                        const float v = __double2float_rn(vv);
+                        if (v > 0.f) {
+                            const float r = __fdiv_rn(dq, v);
+                            const float t = __fsub_rn((float)q[e], __double2float_rn(m));
+                            float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
+                            float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
+                            fa = fminf(fmaxf(fa, -kSMax), kSMax);
+                            fb = fminf(fmaxf(fb, -kSMax), kSMax);
+                            sp = __float2int_rn(fa);
+                            sn = __float2int_rn(fb);
+                        }
+                    }
+                    ap += sp; an += sn;
+                    lp[e] = ap; ln[e] = an;
+                }
+            }
+            int totp, totn;
+            const int exp_ = warp_excl_add(lp[kE - 1], lane, totp);
+            const int exn_ = warp_excl_add(ln[kE - 1], lane, totn);
+            // ---- running minima (block-relative S; positions before the anchor hold S = 0)
+            int lmp = kBig, lmn = kBig;
+#pragma unroll
+            for (int e = 0; e < kE; ++e) { lp[e] += exp_; ln[e] += exn_; lmp = min(lmp, lp[e]); lmn = min(lmn, ln[e]); }
+            int bminp, bminn;
+            const int exmp = min(warp_excl_min(lmp, lane, bminp), mp);
+            const int exmn = min(warp_excl_min(lmn, lane, bminn), mn);
+            // ---- g = S - running min; first detection; last zero of g
+            int firste = kE, zp = -1, zn = -1;
+            int gpd[kE], gnd[kE];
+            {
+                int rp = exmp, rn = exmn;
+#pragma unroll
+                for (int e = 0; e < kE; ++e) {
+                    const int k = r0 + e;
+                    rp = min(rp, lp[e]); rn = min(rn, ln[e]);
+                    gpd[e] = lp[e] - rp; gnd[e] = ln[e] - rn;
+                    const bool valid = k > k0 && k < n;
+                    if (valid && firste == kE && (gpd[e] > H || gnd[e] > H)) firste = e;
+                }
+            }
+            const unsigned hit = __ballot_sync(CT_FULL, firste < kE);
+            int limit = min(rs + kBlk, n) - 1;      // last index to consider for "last zero"
+            int kdet = -1, gp_d = 0, gn_d = 0;
+            if (hit) {
+                const int ld = __ffs(hit) - 1;
+                const int ef = __shfl_sync(CT_FULL, firste, ld);
+                kdet = rs + ld * kE + ef;
+                int mygp = 0, mygn = 0;
+#pragma unroll
+                for (int e = 0; e < kE; ++e) if (e == ef) { mygp = gpd[e]; mygn = gnd[e]; }
+                gp_d = __shfl_sync(CT_FULL, mygp, ld);
+                gn_d = __shfl_sync(CT_FULL, mygn, ld);
+                limit = kdet;
+            }
+#pragma unroll
+            for (int e = 0; e < kE; ++e) {
+                const int k = r0 + e;
+                if (k >= k0 && k <= limit) { if (gpd[e] == 0) zp = k; if (gnd[e] == 0) zn = k; }
+            }
+            zp = warp_max(zp); zn = warp_max(zn);
+            if (zp >= 0) argp = zp;
+            if (zn >= 0) argn = zn;
+            if (hit) {
+                const int jmin = (gp_d >= gn_d) ? argp : argn;
+                if (nedge >= a.max_levels) { overflow = 1; break; }
+                if (lane == 0) ed[nedge] = jmin + 1;
+                ++nedge;
+                k0 = kdet; cSq = 0; cSqq = 0; mp = kBig; mn = kBig; argp = kdet; argn = kdet;
+                fresh = false;                      // redo this block with the new anchor
+            } else {
+                cSq += totq; cSqq += totqq;
+                const long long nmp = (long long)min(mp, bminp) - totp, nmn = (long long)min(mn, bminn) - totn;
+                mp = (int)max(min(nmp, (long long)kBig), -(long long)kBig);
+                mn = (int)max(min(nmn, (long long)kBig), -(long long)kBig);
+                rs += kBlk;
+                fresh = true;
+            }
+        }
+        if (lane == 0) { ed[nedge] = n; a.n_levels[ev] = nedge; a.overflow[ev] = (unsigned char)overflow; }
+        __syncwarp();
+        // ---- level statistics from exact integer sums (second, cheap pass; L1/L2 resident)
+        for (int i = 0; i < nedge; ++i) {
+            const int e0 = ed[i], e1 = ed[i + 1];
+            long long sq = 0, sqq = 0;
+            for (int k = e0 + lane; k < e1; k += 32) {
+                const long long qv = quantise(a.y[p0 + k], x0);
+                sq += qv; sqq += qv * qv;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(CT_FULL, sq, o); sqq += __shfl_xor_sync(CT_FULL, sqq, o); }
+            if (lane == 0) {
+                const double len = (double)(e1 - e0), ad = (double)sq, bd = (double)sqq;
+                a.mean[ev * a.max_levels + i] = __dadd_rn((double)x0, __ddiv_rn(__ddiv_rn(ad, len), 64.0));
+                double var = __dsub_rn(bd, __ddiv_rn(__dmul_rn(ad, ad), len));
+                if (var < 0.0) var = 0.0;
+                a.sd[ev * a.max_levels + i] = __ddiv_rn(__dsqrt_rn(__ddiv_rn(var, len)), 64.0);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+extern "C" int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                              const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
+                              int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
+                              uint8_t* overflow, uint64_t* work_counter, void* stream) {
+    if (!y || !win_start || !win_end || !n_levels || !edges || !level_mean || !level_std || !overflow || !work_counter) {
+        ct_set_error("cusum: null pointer"); return CT_ERR_ARG;
+    }
+    if (n_events < 0 || max_levels < 2 || max_levels > 1024 || !(delta > 0.f) || !(h > 0.f) || h > 262144.f) {
+        ct_set_error("cusum: bad argument (need delta > 0, 0 < h <= 2^18, 2 <= max_levels <= 1024)"); return CT_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(work_counter, 0, 8, st);
+    if (n_events == 0) return CT_OK;
+    CusumArgs a;
+    a.y = y; a.ntot = n_total; a.w0 = (const long long*)win_start; a.w1 = (const long long*)win_end; a.type = type;
+    a.nev = n_events; a.delta = delta; a.h = h; a.max_levels = max_levels; a.n_levels = n_levels; a.edges = edges;
+    a.mean = level_mean; a.sd = level_std; a.overflow = overflow; a.counter = (unsigned long long*)work_counter;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_cusum_kernel, 128, 0);
+    if (occ < 1) occ = 1;
+    long long grid = (long long)ct_sm_count() * occ;
+    long long want = (n_events + 3) / 4;
+    if (grid > want) grid = want;
+    CT_COUNT_LAUNCH();
+    ct_cusum_kernel<<<(unsigned)grid, 128, 0, st>>>(a);
+    return ct_check_launch("ct_cusum_kernel");
+}

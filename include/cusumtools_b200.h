@@ -94,6 +94,20 @@ int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign,
                   const float* t_end, int state_in, void* workspace, int64_t workspace_bytes,
                   int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream);
 
+/* ---- stage 3: batched per-event CUSUM+ level segmentation -----------------------
+ * No reference implementation exists (readevents.py:843-846,1297-1306 only consumes the
+ * level lists); definition in oracle/events_oracle.py::cusum_event (two-sided CUSUM,
+ * SURVEY.md Appendix C, all reductions in exact integers).  Event e is the window
+ * y[win_start[e] : win_end[e]) of the filtered trace; events with type[e] != 0 are
+ * skipped (type may be NULL).  Outputs per event: n_levels, edges[max_levels+1] (sample
+ * offsets inside the window, edges[0] = 0, edges[n_levels] = length, unused = -1),
+ * level mean / population std in pA (float64), overflow flag (more jumps than
+ * max_levels-1).  work_counter: 8 bytes of device scratch.                             */
+int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                   const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
+                   int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
+                   uint8_t* overflow, uint64_t* work_counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

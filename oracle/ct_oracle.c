@@ -79,7 +79,7 @@ int64_t orc_detect(const float *y, int64_t n, int64_t block, const int32_t *sign
 #define CQ 64.0f
 #define CQMAX 4194303.0f
 #define CSSCALE 1024.0f
-#define CSMAX 268435456.0f
+#define CSMAX 2097152.0f
 
 static inline int64_t quantise(float x, float x0)
 {

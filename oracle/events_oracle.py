@@ -174,7 +174,7 @@ def event_windows(starts, ends, n, padding, minpoints, maxpoints):
 CUSUM_Q = np.float32(64.0)          # samples are quantised to 1/64 pA
 CUSUM_QMAX = np.float32(4194303.0)  # |q| <= 2^22 - 1
 CUSUM_SSCALE = np.float32(1024.0)   # log-likelihood increments quantised to 2^-10
-CUSUM_SMAX = np.float32(1073741824.0 / 4)  # |s| <= 2^28 (fixed point)
+CUSUM_SMAX = np.float32(2097152.0)   # |s| <= 2^21 fixed-point units (2048 nats per sample)
 
 
 def cusum_quantise(x):

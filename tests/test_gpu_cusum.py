@@ -1,0 +1,110 @@
+"""GPU parity: batched CUSUM+ kernel vs the oracle definition (NumPy / its plain-C twin)
+on identical float32 samples: n_levels, changepoint edges, overflow flags AND the level
+means / standard deviations are bit-exact (all reductions are over exact integers)."""
+import numpy as np
+import pytest
+import torch
+
+from cusumtools_b200 import cusum, synth
+from oracle import c_twin, events_oracle as eo
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(x, offsets, delta, h, max_levels=16, types=None):
+    t = cusum.cusum_flat(torch.from_numpy(x).cuda(), torch.from_numpy(offsets).cuda(), delta=delta, h=h,
+                         max_levels=max_levels, types=types)
+    torch.cuda.synchronize()
+    return [v.cpu().numpy() for v in (t.n_levels, t.edges, t.mean, t.std, t.overflow)]
+
+
+def assert_same(got, want):
+    for name, a, b in zip(("n_levels", "edges", "mean", "std", "overflow"), got, want):
+        assert np.array_equal(a, b), name
+
+
+def test_c3_sample_bit_exact():
+    x, offsets, nlev = synth.c3_events(3000, seed=2024)
+    got = run_gpu(x, offsets, 400.0, 10.0)
+    want = c_twin.cusum_batch(x, offsets, 400.0, 10.0, 16)
+    assert_same(got, want)
+    assert np.mean(got[0] == nlev + 2) > 0.9
+    # the numpy definition itself on a subset
+    sub = slice(0, 40)
+    w = eo.cusum_batch(x[:offsets[40]], offsets[:41], 400.0, 10.0, 16)
+    for a, b in zip(got, w):
+        assert np.array_equal(a[sub], b)
+
+
+@pytest.mark.parametrize("delta,h", [(200.0, 5.0), (400.0, 10.0), (800.0, 40.0), (50.0, 2.0)])
+def test_parameter_sweep(delta, h):
+    x, offsets, _ = synth.c3_events(400, seed=int(delta), max_len=3000)
+    assert_same(run_gpu(x, offsets, delta, h), c_twin.cusum_batch(x, offsets, delta, h, 16))
+
+
+def test_edge_cases():
+    rng = np.random.default_rng(3)
+    parts = [np.full(50, 7.0, np.float32),                       # zero variance: no information
+             np.array([1.0], np.float32),                         # single sample
+             np.array([1.0, 900.0], np.float32),                  # two samples
+             (24 * rng.standard_normal(255)).astype(np.float32),  # one block minus one
+             (24 * rng.standard_normal(256)).astype(np.float32),
+             (24 * rng.standard_normal(257)).astype(np.float32)]
+    y = (24 * rng.standard_normal(4000)).astype(np.float32)       # overflow: 19 jumps, max_levels 8
+    for k in range(1, 20):
+        y[k * 200:] += np.float32(1000 * (-1) ** k)
+    parts.append(y)
+    parts.append(np.zeros(0, np.float32))                         # empty window
+    big = (5000 + 24 * rng.standard_normal(70000)).astype(np.float32)   # long event, many blocks
+    big[30000:50000] -= 900
+    parts.append(big)
+    offsets = np.concatenate(([0], np.cumsum([len(p) for p in parts]))).astype(np.int64)
+    x = np.concatenate(parts)
+    got = run_gpu(x, offsets, 400.0, 10.0, max_levels=8)
+    want = c_twin.cusum_batch(x, offsets, 400.0, 10.0, 8)
+    assert_same(got, want)
+    assert got[4][6] == 1 and got[0][7] == 0 and got[0][8] == 3
+
+
+def test_unaligned_windows_inside_a_trace():
+    """Windows into a long trace at arbitrary offsets (the detection -> CUSUM path)."""
+    rng = np.random.default_rng(8)
+    y = (5000 + 24 * rng.standard_normal(300000)).astype(np.float32)
+    w0, w1 = [], []
+    for k in range(60):
+        s = 1000 + 4777 * k + int(rng.integers(0, 9))
+        L = int(rng.integers(300, 2500))
+        y[s:s + L // 2] -= 800
+        y[s + L // 2:s + L] -= 1500
+        w0.append(s - 100); w1.append(s + L + 100)
+    w0 = np.array(w0, np.int64); w1 = np.array(w1, np.int64)
+    typ = np.zeros(60, np.int32); typ[5] = 3
+    t = cusum.cusum_levels(torch.from_numpy(y).cuda(), torch.from_numpy(w0).cuda(), torch.from_numpy(w1).cuda(),
+                           delta=400.0, h=10.0, types=torch.from_numpy(typ).cuda())
+    torch.cuda.synchronize()
+    flat = np.concatenate([y[a:b] for a, b in zip(w0, w1)])
+    offs = np.concatenate(([0], np.cumsum(w1 - w0)))
+    want = c_twin.cusum_batch(flat, offs, 400.0, 10.0, 16)
+    nl = t.n_levels.cpu().numpy()
+    assert nl[5] == 0
+    keep = typ == 0
+    assert np.array_equal(nl[keep], want[0][keep])
+    assert np.array_equal(t.edges.cpu().numpy()[keep], want[1][keep])
+    assert np.array_equal(t.mean.cpu().numpy()[keep], want[2][keep])
+    assert np.array_equal(t.std.cpu().numpy()[keep], want[3][keep])
+    assert np.all(nl[keep] == 4)
+
+
+def test_full_c3_checksum_properties():
+    """1M-event config at reduced event count on the device: order invariance (shuffling
+    the event order permutes the outputs) and agreement with the C twin on a slice."""
+    x, offsets, _ = synth.c3_events(100000, seed=99)
+    xt = torch.from_numpy(x).cuda()
+    w0 = torch.from_numpy(offsets[:-1].copy()).cuda(); w1 = torch.from_numpy(offsets[1:].copy()).cuda()
+    a = cusum.cusum_levels(xt, w0, w1, delta=400.0, h=10.0)
+    perm = torch.randperm(w0.numel(), device="cuda")
+    b = cusum.cusum_levels(xt, w0[perm].contiguous(), w1[perm].contiguous(), delta=400.0, h=10.0)
+    assert torch.equal(a.edges[perm], b.edges) and torch.equal(a.mean[perm], b.mean)
+    want = c_twin.cusum_batch(x[:offsets[5000]], offsets[:5001], 400.0, 10.0, 16)
+    assert np.array_equal(a.edges[:5000].cpu().numpy(), want[1])
+    assert np.array_equal(a.std[:5000].cpu().numpy(), want[3])
