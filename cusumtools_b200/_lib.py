@@ -53,6 +53,8 @@ SIGNATURES = {
     "ct_detect_run": (C.c_int, []),
     "ct_detect_workspace_bytes": (_i64, [_i64]),
     "ct_detect_f32": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "ct_welch_workspace_bytes": (_i64, [_i32, _i32]),
+    "ct_welch_f32": (C.c_int, [_vp, _i64, _i32, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "ct_cusum_batch": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _f32, _f32, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -1,0 +1,112 @@
+"""Stage 4 of the hot path: Welch PSD and the noise integrals built on it.
+
+Mirrors `scipy.signal.welch(x, fs, nperseg=L)` exactly as the reference calls it
+(plot-trace.py:432-448, noise-fit.py:92-99, legacy/minimal_psd.py:250-255) plus
+`App.integrate_noise` (plot-trace.py:309-311).  The periodogram sums come from the
+hand-written FFT kernels (ct_welch_f32); the O(L) scaling / cumulative sum runs on the host
+in float64 like the reference's."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .filters import _require_cuda, _stream_ptr
+
+L2_BUDGET_BYTES = 64 << 20     # intermediate of one batch of segments (stays in the 126 MB L2)
+
+
+def psd_length(n: int, samplerate: float, psd_length_s: float | None = None) -> int:
+    """plot-trace.py:432-437: segment length from the GUI entry (seconds) or min(2^20, n)."""
+    if psd_length_s is not None:
+        length = 2 ** np.ceil(np.log2(float(psd_length_s) * samplerate))
+        if length > n:
+            length = n
+    else:
+        length = np.minimum(2 ** 20, n)
+    return int(length)
+
+
+def welch_sums(x: torch.Tensor, nperseg: int, *, use_abs: bool = False, shift: float | None = None):
+    """Raw periodogram sums on the device: (acc float64[L/2+1] CUDA tensor, nseg).  A
+    multi-GPU caller reduces `acc` and `nseg` over ranks before scaling."""
+    _require_cuda(x, "x", torch.float32)
+    L = int(nperseg)
+    if L != nperseg or L & (L - 1) or L < 256:
+        raise NotImplementedError(
+            f"nperseg={nperseg}: the GPU Welch path needs a power-of-two segment >= 256 (the reference's default "
+            "2**20 and its 2**ceil(log2(.)) lengths are; a window shorter than the segment is not)")
+    lib = _lib.lib()
+    batch = max(1, min(64, L2_BUDGET_BYTES // (L // 2 * 8)))
+    wsb = int(lib.ct_welch_workspace_bytes(L, batch))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    acc = torch.empty(L // 2 + 1, dtype=torch.float64, device=x.device)
+    if shift is None:
+        shift = float(x[: min(x.numel(), 1 << 16)].abs().mean().item() if use_abs else x[: min(x.numel(), 1 << 16)].mean().item()) if x.numel() else 0.0
+    nseg = C.c_int64(0)
+    rc = lib.ct_welch_f32(x.data_ptr(), x.numel(), L, float(shift), int(bool(use_abs)), batch, ws.data_ptr(), wsb,
+                          acc.data_ptr(), C.byref(nseg), _stream_ptr(x))
+    _lib.check(rc, "ct_welch_f32")
+    return acc, int(nseg.value)
+
+
+def scale_sums(acc: np.ndarray, nseg: int, samplerate: float, nperseg: int):
+    """Density scaling of scipy's welch: / (fs * sum(w^2)), mean over segments, one-sided
+    doubling of bins 1..L/2-1.  sum(w^2) = 3L/8 exactly for the periodic Hann window."""
+    L = int(nperseg)
+    if nseg <= 0:
+        raise ValueError("trace shorter than one segment")
+    P = np.asarray(acc, dtype=np.float64) / (float(nseg) * float(samplerate) * (3.0 * L / 8.0))
+    P[1:-1] *= 2.0
+    f = np.arange(L // 2 + 1, dtype=np.float64) * (float(samplerate) / L)
+    return f, P
+
+
+def welch(x: torch.Tensor, samplerate: float, nperseg, *, use_abs: bool = False):
+    """`f, Pxx = welch(x, fs, nperseg=L)` with x a float32 CUDA tensor; returns numpy
+    float64 arrays of length L/2+1 like scipy.  `nperseg` may be a float (the reference
+    passes 2**np.ceil(...), plot-trace.py:433, noise-fit.py:138)."""
+    L = int(nperseg)
+    acc, nseg = welch_sums(x, L, use_abs=use_abs)
+    return scale_sums(acc.cpu().numpy(), nseg, samplerate, L)
+
+
+def integrate_noise(f: np.ndarray, Pxx: np.ndarray) -> np.ndarray:
+    """plot-trace.py:309-311."""
+    df = f[1] - f[0]
+    return np.sqrt(np.cumsum(Pxx * df))
+
+
+def update_psd(filtered: torch.Tensor, samplerate: float, *, psd_length_s: float | None = None,
+               normalize: bool = False, cutoff: float | None = None):
+    """`App.update_psd` without the plotting (plot-trace.py:418-451): returns
+    (f, Pxx, rms, current).  `cutoff` None means the trace was not filtered (bandwidth 1 MHz)."""
+    _require_cuda(filtered, "filtered", torch.float32)
+    n = filtered.numel()
+    bandwidth = 1.0e6 if cutoff is None else float(cutoff)
+    length = psd_length(n, samplerate, psd_length_s)
+    end_index = int(np.floor(n / length) * length)
+    current = float(filtered[:end_index].to(torch.float64).mean().item())
+    f, Pxx = welch(filtered, samplerate, length)
+    rms = integrate_noise(f, Pxx)
+    if normalize:
+        Pxx = Pxx / current ** 2 * bandwidth
+        rms = rms / np.absolute(current)
+    return f, Pxx, rms, current
+
+
+def spectrum_sample(raw: torch.Tensor, samplerate: float, psdlength, cutoff: float):
+    """`SpectrumSample.__init__` (noise-fit.py:92-99): welch(|raw|), crop to f <= cutoff,
+    scale by cutoff / I^2 and by f.  Returns (f, Pxx, current)."""
+    _require_cuda(raw, "raw", torch.float32)
+    f, Pxx = welch(raw, samplerate, psdlength, use_abs=True)
+    inds = f <= cutoff
+    length = int(np.sum(inds)) - 1
+    f = f[1:length]
+    Pxx = Pxx[1:length].copy()
+    current = abs(float(raw.to(torch.float64).mean().item()))
+    Pxx *= cutoff / current ** 2
+    Pxx *= f
+    return f, Pxx, current

@@ -108,6 +108,19 @@ int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, co
                    int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
                    uint8_t* overflow, uint64_t* work_counter, void* stream);
 
+/* ---- stage 4: Welch PSD ------------------------------------------------------------
+ * Replaces scipy.signal.welch(x, fs, nperseg=L) as called at plot-trace.py:442,
+ * noise-fit.py:92 (use_abs != 0: welch(|x|)), legacy/minimal_psd.py:255: periodic Hann,
+ * hop L/2, tail dropped, per-segment mean removal.  L = nperseg must be a power of two.
+ * acc[k] (float64, k = 0..L/2) receives sum over segments of |rfft(w (x_s - mean x_s))[k]|^2;
+ * the caller divides by nseg * fs * sum(w^2) = nseg * fs * 3L/8 and doubles bins 1..L/2-1.
+ * `shift` is any constant near the signal mean (subtracted before the float32 FFT, exactly
+ * compensated); `batch` segments are transformed per launch pair (intermediate
+ * batch * L/2 * 8 bytes, meant to stay in L2).                                          */
+int64_t ct_welch_workspace_bytes(int32_t nperseg, int32_t batch);
+int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_t use_abs, int32_t batch,
+                 void* workspace, int64_t workspace_bytes, double* acc, int64_t* nseg_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
