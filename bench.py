@@ -56,7 +56,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -184,26 +184,43 @@ def run_ours(args):
     raw = synth.device_trace(n_own + lo_h + hi_h, dev, seed=1234 + rank, start_index=rank * n_own - lo_h)
     have_cusum = hasattr(cusum, "cusum_levels")
     stage_ev = []
+    host_ev = []
+
+    stage_names = ("median", "filter", "baseline", "detect", "cusum")
 
     def step(record=False):
+        marks = []
+        hmarks = []
+
+        def mark():
+            if record:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+                hmarks.append(time.perf_counter())
+
         mask = filters.chimera_bitmask(S)
         owned = raw[lo_h:lo_h + n_own]
+        mark()
         med = pipeline.global_code_median(owned, mask, group)
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
+        mark()
         y = filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med)
-        e1.record()
-        if record:
-            stage_ev.append((e0, e1))
+        mark()
         yd = y[lo_h:]
         bl = detect.baseline_blocks(yd, BASELINE_BLOCK, BASELINE_MIN, BASELINE_MAX).with_thresholds(THRESHOLD, HYSTERESIS)
+        mark()
         ev = detect.detect_events(yd, bl)
         keep = int((ev.starts < n_own).sum().item()) if len(ev) else 0
         starts, ends = ev.starts[:keep], ev.ends[:keep]
+        mark()
         out = {"starts": starts, "ends": ends, "levels": None}
         if have_cusum and keep:
             w0, w1, typ = detect.event_windows(starts, ends, yd.numel(), EVENT_PAD, MINPOINTS, MAXPOINTS)
             out["levels"] = cusum.cusum_levels(yd, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H, types=typ)
+        mark()
+        if record:
+            stage_ev.append(marks)
+            host_ev.append(hmarks)
         if group is not None:
             c = torch.zeros(world, dtype=torch.int64, device=dev); c[rank] = keep
             dist.all_reduce(c, group=group)
@@ -231,9 +248,9 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
         return float(ms[0]), float(ms[1]), r
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local) if rank == 0 else None
     _lib.reset_launch_count()
     tm0 = time.time()
     dev_ms, wall_ms, res = timed(lambda: step(True), args.steps)
@@ -244,7 +261,8 @@ def run_ours(args):
     ev_all = torch.tensor([n_events], dtype=torch.int64, device=dev)
     if group is not None:
         dist.all_reduce(ev_all, group=group)
-    filt_ms = float(np.mean([a.elapsed_time(b) for a, b in stage_ev]))
+    stage_ms = {nm: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in stage_ev])) for i, nm in enumerate(stage_names)}
+    filt_ms = stage_ms["filter"]
     ms_per_step = dev_ms / args.steps
     total = n_own * world
     value = total / (ms_per_step / 1e3) / 1e6
@@ -295,6 +313,8 @@ def run_ours(args):
                    "l2": "inputs (5 GB/GPU) larger than L2; no flush needed", "parallelism": f"time-sharded x{world}"},
         "events_per_s": int(ev_all.item()) / (ms_per_step / 1e3),
         "wall_ms_per_step": wall_ms / args.steps,
+        "stage_ms": stage_ms,
+        "stage_host_ms": {nm: float(np.mean([1e3 * (h[i + 1] - h[i]) for h in host_ev])) for i, nm in enumerate(stage_names)},
         "roofline": {"kernel": "ct_filtfilt_kernel (fused dequantise + median pad + filtfilt)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "kernel_ms": filt_ms,
