@@ -23,7 +23,24 @@ constexpr int kBlk = 32 * kE;         // 256
 constexpr float kQ = 64.0f, kQMax = 4194303.0f, kSScale = 1024.0f, kSMax = 2097152.0f;
 constexpr int kBig = 0x3fffffff;
 
+// rc[cnt] = the oracle's refined reciprocal of the sample count: rc32 = 1.0f/(float)cnt (IEEE
+// float32 division), rc = (double)rc32, rc = rc * (2.0 - (double)cnt * rc).  It only depends
+// on cnt, so it is tabulated once per device with the very same operations and the hot loop
+// replaces a division and four float64 operations per sample by one (L1-resident) load.
+constexpr int kRcTab = 1 << 16;
+__global__ void ct_cusum_rc_table(double* tab) {
+    const int cnt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cnt >= kRcTab) return;
+    double rc = 0.0;
+    if (cnt > 0) {
+        rc = (double)__fdiv_rn(1.0f, (float)cnt);
+        rc = __dmul_rn(rc, __dsub_rn(2.0, __dmul_rn((double)cnt, rc)));
+    }
+    tab[cnt] = rc;
+}
+
 struct CusumArgs {
+    const double* rctab;
     const float* y; long long ntot;
     const long long* w0; const long long* w1; const int* type; long long nev;
     float delta, h; int max_levels;
@@ -53,6 +70,36 @@ __device__ __forceinline__ int warp_excl_min(int v, int lane, int& total) {
     int ex = __shfl_up_sync(CT_FULL, inc, 1);
     return lane == 0 ? kBig : ex;
 }
+// fused exclusive scan of an int32 and an int64 lane total (one shuffle round trip per step)
+__device__ __forceinline__ void warp_excl_add2(int v, long long w, int lane, int& exv, long long& exw, int& totv,
+                                               long long& totw) {
+    int iv = v; long long iw = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int tv = __shfl_up_sync(CT_FULL, iv, d);
+        long long tw = __shfl_up_sync(CT_FULL, iw, d);
+        if (lane >= d) { iv += tv; iw += tw; }
+    }
+    totv = __shfl_sync(CT_FULL, iv, 31); totw = __shfl_sync(CT_FULL, iw, 31);
+    exv = iv - v; exw = iw - w;
+}
+// fused exclusive (sum, running-min) scan for both tests: lane aggregates (s, m) with
+// m = min over the lane's local prefix; (l) + (r) = (sl + sr, min(ml, sl + mr)).
+__device__ __forceinline__ void warp_excl_summin2(int sp, int mp, int sn, int mn, int lane, int& exsp, int& exmp,
+                                                  int& exsn, int& exmn, int& totp, int& bminp, int& totn, int& bminn) {
+    int a = sp, b = mp, c = sn, d_ = mn;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int ta = __shfl_up_sync(CT_FULL, a, d), tb = __shfl_up_sync(CT_FULL, b, d);
+        int tc = __shfl_up_sync(CT_FULL, c, d), td = __shfl_up_sync(CT_FULL, d_, d);
+        if (lane >= d) { b = min(tb, ta + b); a += ta; d_ = min(td, tc + d_); c += tc; }
+    }
+    totp = __shfl_sync(CT_FULL, a, 31); bminp = __shfl_sync(CT_FULL, b, 31);
+    totn = __shfl_sync(CT_FULL, c, 31); bminn = __shfl_sync(CT_FULL, d_, 31);
+    exsp = __shfl_up_sync(CT_FULL, a, 1); exmp = __shfl_up_sync(CT_FULL, b, 1);
+    exsn = __shfl_up_sync(CT_FULL, c, 1); exmn = __shfl_up_sync(CT_FULL, d_, 1);
+    if (lane == 0) { exsp = 0; exmp = kBig; exsn = 0; exmn = kBig; }
+}
 __device__ __forceinline__ int quantise(float x, float x0) {
     float d = __fmul_rn(__fsub_rn(x, x0), kQ);
     d = fminf(fmaxf(d, -kQMax), kQMax);
@@ -65,7 +112,7 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
-__global__ void __launch_bounds__(128) ct_cusum_kernel(CusumArgs a) {
+__global__ void __launch_bounds__(128, 4) ct_cusum_kernel(CusumArgs a) {
     const int lane = ct_lane();
     const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
     const float dq = __fmul_rn(a.delta, kQ);
@@ -98,21 +145,32 @@ __global__ void __launch_bounds__(128) ct_cusum_kernel(CusumArgs a) {
         int rs = (int)(abase - p0);         // relative index of the block's first sample (<= 0)
         bool fresh = true;
         int q[kE];
+        float xn[kE];                       // prefetched samples of the next block
+        int pref_rs = -0x7fffffff;
+        auto load_block = [&](int rsb, float (&xv)[kE]) {
+            const long long pa = p0 + rsb + lane * kE;
+            if (aligned && pa >= 0 && pa + kE <= a.ntot) {
+                const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
+                uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
+                xv[0] = __uint_as_float(lo.x); xv[1] = __uint_as_float(lo.y); xv[2] = __uint_as_float(lo.z); xv[3] = __uint_as_float(lo.w);
+                xv[4] = __uint_as_float(hi.x); xv[5] = __uint_as_float(hi.y); xv[6] = __uint_as_float(hi.z); xv[7] = __uint_as_float(hi.w);
+            } else {
+#pragma unroll
+                for (int e = 0; e < kE; ++e) { long long p = pa + e; xv[e] = (p >= 0 && p < a.ntot) ? a.y[p] : x0; }
+            }
+        };
 
         while (rs < n && !overflow) {
             const int r0 = rs + lane * kE;
-            if (fresh) {                    // (re)load and quantise this block's samples
-                const long long pa = p0 + r0;
+            if (fresh) {                    // quantise this block's samples, prefetch the next block
                 float xv[kE];
-                if (aligned && pa >= 0 && pa + kE <= a.ntot) {
-                    const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
-                    uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
-                    xv[0] = __uint_as_float(lo.x); xv[1] = __uint_as_float(lo.y); xv[2] = __uint_as_float(lo.z); xv[3] = __uint_as_float(lo.w);
-                    xv[4] = __uint_as_float(hi.x); xv[5] = __uint_as_float(hi.y); xv[6] = __uint_as_float(hi.z); xv[7] = __uint_as_float(hi.w);
-                } else {
+                if (pref_rs == rs) {
 #pragma unroll
-                    for (int e = 0; e < kE; ++e) { long long p = pa + e; xv[e] = (p >= 0 && p < a.ntot) ? a.y[p] : x0; }
+                    for (int e = 0; e < kE; ++e) xv[e] = xn[e];
+                } else {
+                    load_block(rs, xv);
                 }
+                if (rs + kBlk < n) { load_block(rs + kBlk, xn); pref_rs = rs + kBlk; }
 #pragma unroll
                 for (int e = 0; e < kE; ++e) q[e] = quantise(xv[e], x0);
             }
@@ -128,9 +186,8 @@ __global__ void __launch_bounds__(128) ct_cusum_kernel(CusumArgs a) {
                     pq[e] = aq; pqq[e] = aqq;
                 }
             }
-            int totq; long long totqq;
-            const int exq = warp_excl_add(pq[kE - 1], lane, totq);
-            const long long exqq = warp_excl_add(pqq[kE - 1], lane, totqq);
+            int totq, exq; long long totqq, exqq;
+            warp_excl_add2(pq[kE - 1], pqq[kE - 1], lane, exq, exqq, totq, totqq);
             // ---- log-likelihood increments (fixed point) and their local prefix sums
             int lp[kE], ln[kE];
             {
@@ -143,8 +200,12 @@ __global__ void __launch_bounds__(128) ct_cusum_kernel(CusumArgs a) {
                         const int cnt = k - k0 + 1;
                         const double Sq = (double)(cSq + exq + pq[e]);
                         const double Sqq = (double)(cSqq + exqq + pqq[e]);
-                        double rc = (double)__fdiv_rn(1.0f, (float)cnt);
-                        rc = __dmul_rn(rc, __dsub_rn(2.0, __dmul_rn((double)cnt, rc)));
+                        double rc;
+                        if (cnt < kRcTab) rc = __ldg(a.rctab + cnt);
+                        else {
+                            rc = (double)__fdiv_rn(1.0f, (float)cnt);
+                            rc = __dmul_rn(rc, __dsub_rn(2.0, __dmul_rn((double)cnt, rc)));
+                        }
                         const double m = __dmul_rn(Sq, rc);
                         const double vv = __dmul_rn(__dsub_rn(Sqq, __dmul_rn(Sq, m)), rc);
                         const float v = __double2float_rn(vv);
@@ -163,16 +224,15 @@ __global__ void __launch_bounds__(128) ct_cusum_kernel(CusumArgs a) {
                     lp[e] = ap; ln[e] = an;
                 }
             }
-            int totp, totn;
-            const int exp_ = warp_excl_add(lp[kE - 1], lane, totp);
-            const int exn_ = warp_excl_add(ln[kE - 1], lane, totn);
-            // ---- running minima (block-relative S; positions before the anchor hold S = 0)
+            // ---- block-relative S and running minima (positions before the anchor hold S = 0)
             int lmp = kBig, lmn = kBig;
 #pragma unroll
-            for (int e = 0; e < kE; ++e) { lp[e] += exp_; ln[e] += exn_; lmp = min(lmp, lp[e]); lmn = min(lmn, ln[e]); }
-            int bminp, bminn;
-            const int exmp = min(warp_excl_min(lmp, lane, bminp), mp);
-            const int exmn = min(warp_excl_min(lmn, lane, bminn), mn);
+            for (int e = 0; e < kE; ++e) { lmp = min(lmp, lp[e]); lmn = min(lmn, ln[e]); }
+            int totp, totn, bminp, bminn, exp_, exn_, exmp, exmn;
+            warp_excl_summin2(lp[kE - 1], lmp, ln[kE - 1], lmn, lane, exp_, exmp, exn_, exmn, totp, bminp, totn, bminn);
+#pragma unroll
+            for (int e = 0; e < kE; ++e) { lp[e] += exp_; ln[e] += exn_; }
+            exmp = min(exmp, mp); exmn = min(exmn, mn);
             // ---- g = S - running min; first detection; last zero of g
             int firste = kE, zp = -1, zn = -1;
             int gpd[kE], gnd[kE];
@@ -264,7 +324,22 @@ extern "C" int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* wi
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(work_counter, 0, 8, st);
     if (n_events == 0) return CT_OK;
+    // library-owned per-device reciprocal table (built once with the oracle's operations)
+    static double* tabs[64] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) { ct_set_error("cusum: unsupported device ordinal"); return CT_ERR_UNSUPPORTED; }
+    if (!tabs[dev]) {
+        double* t = nullptr;
+        if (cudaMalloc(&t, sizeof(double) * kRcTab) != cudaSuccess) { ct_set_error("cusum: table allocation failed"); return CT_ERR_CUDA; }
+        CT_COUNT_LAUNCH();
+        ct_cusum_rc_table<<<kRcTab / 256, 256, 0, st>>>(t);
+        int rc0 = ct_check_launch("ct_cusum_rc_table"); if (rc0) return rc0;
+        cudaStreamSynchronize(st);          // one-time: other streams may use the table next
+        tabs[dev] = t;
+    }
     CusumArgs a;
+    a.rctab = tabs[dev];
     a.y = y; a.ntot = n_total; a.w0 = (const long long*)win_start; a.w1 = (const long long*)win_end; a.type = type;
     a.nev = n_events; a.delta = delta; a.h = h; a.max_levels = max_levels; a.n_levels = n_levels; a.edges = edges;
     a.mean = level_mean; a.sd = level_std; a.overflow = overflow; a.counter = (unsigned long long*)work_counter;

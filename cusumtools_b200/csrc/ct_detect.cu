@@ -41,6 +41,11 @@ __device__ __forceinline__ unsigned automaton_word(unsigned A, unsigned B, unsig
     return I;
 }
 
+// Pass 1: one warp per run of 4096 samples, 1024 samples (32 mask words) per batch.  The 32
+// coalesced loads of a batch are independent (deep memory-level parallelism); lane w keeps
+// the ballots of row w, so the automaton of all 32 words is evaluated in parallel, one word
+// per lane, after a ballot-based resolution of the word-to-word carry (a word is either the
+// identity or a constant map on the state).
 __global__ void __launch_bounds__(kDetWarps * 32)
 ct_detect_pass1(const float* __restrict__ y, long long n, long long block,
                 const int* __restrict__ sign, const float* __restrict__ t_start,
@@ -54,38 +59,101 @@ ct_detect_pass1(const float* __restrict__ y, long long n, long long block,
     const long long kb = base / block;
     const bool pos = sign[kb] > 0;
     const float ts = t_start[kb], te = t_end[kb];
-    unsigned c = 0, first = 0, last = 0, ns = 0, ne = 0;
-    for (int w0 = 0; w0 < kRunWords; w0 += 4) {
-        float v[4];
+    const bool full = base + kRun <= n;
+    unsigned cin = 0, first = 0, last = 0, ns = 0, ne = 0;
+    for (int b = 0; b < kRun / 1024; ++b) {
+        const long long bb = base + b * 1024;
+        unsigned myA = 0, myB = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            long long p = base + (long long)(w0 + j) * 32 + lane;
-            v[j] = p < n ? y[p] : (pos ? te : te);   // beyond the end: identity symbol (== te is neither)
-        }
+        for (int w0 = 0; w0 < 32; w0 += 8) {
+            float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            long long p = base + (long long)(w0 + j) * 32 + lane;
-            bool a = pos ? v[j] < ts : v[j] > ts;
-            bool b = pos ? v[j] > te : v[j] < te;
-            if (p >= n) { a = false; b = false; }
-            unsigned A = __ballot_sync(CT_FULL, a);
-            unsigned B = __ballot_sync(CT_FULL, b);
-            if (lane == 0) masks[run * kRunWords + w0 + j] = make_uint2(A, B);
-            unsigned nz = A | B;
-            if (nz) {
-                if (!first) first = ((A >> (__ffs(nz) - 1)) & 1) ? 1u : 2u;
-                last = ((A >> (31 - __clz(nz))) & 1) ? 1u : 2u;
+            for (int j = 0; j < 8; ++j) {
+                const long long p = bb + (w0 + j) * 32 + lane;
+                v[j] = (full || p < n) ? y[p] : te;          // == te is neither symbol
             }
-            unsigned cprev = c;
-            unsigned I = automaton_word(A, B, c);
-            unsigned prev = (I << 1) | cprev;
-            ns += __popc(I & ~prev);
-            ne += __popc(~I & prev);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool sa = pos ? v[j] < ts : v[j] > ts;
+                const bool sb = pos ? v[j] > te : v[j] < te;
+                const unsigned A = __ballot_sync(CT_FULL, sa);
+                const unsigned B = __ballot_sync(CT_FULL, sb);
+                if (lane == w0 + j) { myA = A; myB = B; }
+            }
+        }
+        masks[run * kRunWords + b * 32 + lane] = make_uint2(myA, myB);
+        const unsigned nz = myA | myB;
+        const unsigned lastIn = nz ? ((myA >> (31 - __clz(nz))) & 1u) : 0u;
+        const unsigned firstIn = nz ? ((myA >> (__ffs(nz) - 1)) & 1u) : 0u;
+        const unsigned nzmask = __ballot_sync(CT_FULL, nz != 0);
+        const unsigned lastmask = __ballot_sync(CT_FULL, lastIn != 0);
+        const unsigned firstmask = __ballot_sync(CT_FULL, firstIn != 0);
+        const unsigned lower = nzmask & ((1u << lane) - 1u);
+        unsigned c = lower ? ((lastmask >> (31 - __clz(lower))) & 1u) : cin;
+        const unsigned cprev = c;
+        const unsigned I = automaton_word(myA, myB, c);
+        const unsigned prev = (I << 1) | cprev;
+        ns += __popc(I & ~prev);
+        ne += __popc(~I & prev);
+        if (nzmask) {
+            if (!first) first = ((firstmask >> (__ffs(nzmask) - 1)) & 1u) ? 1u : 2u;
+            const unsigned hi = 31 - __clz(nzmask);
+            cin = (lastmask >> hi) & 1u;
+            last = cin ? 1u : 2u;
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(CT_FULL, ns, o); ne += __shfl_xor_sync(CT_FULL, ne, o); }
     if (lane == 0) {
         RunSummary s; s.first_last = first | (last << 2); s.ns0 = ns; s.ne0 = ne; s.pad = 0;
         summ[run] = s;
+    }
+}
+
+// ---- hierarchical chained scan over run summaries -----------------------------------
+// counts of a summary given the true incoming state (1 = inside)
+__device__ __forceinline__ void adjusted(const RunSummary& s, unsigned st, unsigned& a, unsigned& b) {
+    const unsigned f = s.first_last & 3;
+    a = s.ns0; b = s.ne0;
+    if (st == 1) { if (f == 1) a -= 1; else if (f == 2) b += 1; }
+}
+constexpr int kGroup = 64;
+// level 1: one thread per group of 64 runs -> group summary (assuming the group starts outside)
+__global__ void ct_detect_scan_groups(const RunSummary* __restrict__ summ, long long nruns,
+                                      RunSummary* __restrict__ gsum, long long ngroups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const long long r0 = g * kGroup, r1 = (r0 + kGroup < nruns) ? r0 + kGroup : nruns;
+    unsigned st = 2, first = 0, last = 0, ns = 0, ne = 0;
+    for (long long r = r0; r < r1; ++r) {
+        const RunSummary s = summ[r];
+        unsigned a, b; adjusted(s, st, a, b);
+        ns += a; ne += b;
+        const unsigned f = s.first_last & 3, l = (s.first_last >> 2) & 3;
+        if (!first) first = f;
+        if (l) { last = l; st = l; }
+    }
+    RunSummary o; o.first_last = first | (last << 2); o.ns0 = ns; o.ne0 = ne; o.pad = 0;
+    gsum[g] = o;
+}
+// level 3: one thread per group expands the group's state/offsets to its runs
+__global__ void ct_detect_scan_expand(const RunSummary* __restrict__ summ, long long nruns,
+                                      const uint4* __restrict__ ginfo, const unsigned long long* __restrict__ goffs,
+                                      long long ngroups, uint4* __restrict__ runinfo,
+                                      unsigned long long* __restrict__ offs) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const long long r0 = g * kGroup, r1 = (r0 + kGroup < nruns) ? r0 + kGroup : nruns;
+    unsigned st = ginfo[g].x ? 1u : 2u;
+    unsigned long long ns = goffs[2 * g], ne = goffs[2 * g + 1];
+    for (long long r = r0; r < r1; ++r) {
+        const RunSummary s = summ[r];
+        unsigned a, b; adjusted(s, st, a, b);
+        runinfo[r] = make_uint4(st == 1 ? 1u : 0u, 0u, 0u, 0u);
+        offs[2 * r] = ns; offs[2 * r + 1] = ne;
+        ns += a; ne += b;
+        const unsigned l = (s.first_last >> 2) & 3;
+        if (l) st = l;
     }
 }
 
@@ -189,13 +257,26 @@ ct_block_stats_kernel(const float* __restrict__ y, long long n, long long block,
     const long long bend = (kb + 1) * block < n ? (kb + 1) * block : n;
     if (b1 > bend) b1 = bend;
     long long c = 0, a = 0, b = 0;
-    for (long long p = b0 + threadIdx.x; p < b1; p += 256) {
-        float v = y[p];
+    auto tally = [&](float v) {
         if (v >= bmin && v <= bmax) {
             float d = __fmul_rn(__fsub_rn(v, c0), scale);
             long long q = (long long)__float2ll_rn(d);
             c += 1; a += q; b += q * q;
         }
+    };
+    if ((reinterpret_cast<uintptr_t>(y + b0) & 15) == 0 && b1 - b0 == kStatChunk) {
+        // 8192 samples = 2048 float4 = 8 independent 16-byte loads per thread
+        const uint4* y4 = reinterpret_cast<const uint4*>(y + b0);
+        uint4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = ct_ldg_stream(y4 + threadIdx.x + u * 256);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            tally(__uint_as_float(q[u].x)); tally(__uint_as_float(q[u].y));
+            tally(__uint_as_float(q[u].z)); tally(__uint_as_float(q[u].w));
+        }
+    } else {
+        for (long long p = b0 + threadIdx.x; p < b1; p += 256) tally(y[p]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -221,7 +302,8 @@ int64_t ct_detect_workspace_bytes(int64_t n) {
     if (nruns < 1) nruns = 1;
     // masks + summaries + runinfo + offsets, each 256-byte aligned
     auto al = [](long long b) { return (b + 255) / 256 * 256; };
-    return al(nruns * kRunWords * 8) + al(nruns * 16) + al(nruns * 16) + al(nruns * 16);
+    long long ng = (nruns + kGroup - 1) / kGroup;
+    return al(nruns * kRunWords * 8) + al(nruns * 16) + al(nruns * 16) + al(nruns * 16) + 3 * al(ng * 16);
 }
 
 int ct_block_stats_f32(const float* y, int64_t n, int64_t block, float bmin, float bmax, float c0,
@@ -255,14 +337,24 @@ int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign,
     uint2* masks = (uint2*)w;            w += al(nruns * kRunWords * 8);
     RunSummary* summ = (RunSummary*)w;   w += al(nruns * 16);
     uint4* runinfo = (uint4*)w;          w += al(nruns * 16);
-    unsigned long long* offs = (unsigned long long*)w;
+    unsigned long long* offs = (unsigned long long*)w;  w += al(nruns * 16);
+    const long long ng = (nruns + kGroup - 1) / kGroup;
+    RunSummary* gsum = (RunSummary*)w;   w += al(ng * 16);
+    uint4* ginfo = (uint4*)w;            w += al(ng * 16);
+    unsigned long long* goffs = (unsigned long long*)w;
     long long g1 = (nruns + kDetWarps - 1) / kDetWarps;
     CT_COUNT_LAUNCH();
     ct_detect_pass1<<<(unsigned)g1, kDetWarps * 32, 0, st>>>(y, n, block, sign, t_start, t_end, masks, summ, nruns);
     int rc = ct_check_launch("ct_detect_pass1"); if (rc) return rc;
     CT_COUNT_LAUNCH();
-    ct_detect_scan<<<1, 1024, 0, st>>>(summ, nruns, state_in, runinfo, offs, (unsigned long long*)counts2);
+    ct_detect_scan_groups<<<(unsigned)((ng + 127) / 128), 128, 0, st>>>(summ, nruns, gsum, ng);
+    rc = ct_check_launch("ct_detect_scan_groups"); if (rc) return rc;
+    CT_COUNT_LAUNCH();
+    ct_detect_scan<<<1, 1024, 0, st>>>(gsum, ng, state_in, ginfo, goffs, (unsigned long long*)counts2);
     rc = ct_check_launch("ct_detect_scan"); if (rc) return rc;
+    CT_COUNT_LAUNCH();
+    ct_detect_scan_expand<<<(unsigned)((ng + 127) / 128), 128, 0, st>>>(summ, nruns, ginfo, goffs, ng, runinfo, offs);
+    rc = ct_check_launch("ct_detect_scan_expand"); if (rc) return rc;
     CT_COUNT_LAUNCH();
     ct_detect_pass2<<<(unsigned)((nruns + 127) / 128), 128, 0, st>>>(masks, runinfo, offs, nruns, (long long*)starts, (long long*)ends, capacity);
     return ct_check_launch("ct_detect_pass2");

@@ -564,27 +564,53 @@ __global__ void ct_hist_sampled_kernel(const uint16_t* __restrict__ raw, long lo
 }
 
 constexpr int kWin = 8;
+// out[0] = #codes < lo ; out[1+i] = #codes == lo + i*step (step = power of two).  Eight
+// 16-bit in-register counters packed in two 64-bit words keep the tally at ~8 integer ops
+// per sample, so the pass runs at HBM speed (2 B/sample).
 __global__ void __launch_bounds__(256)
 ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned mask, unsigned lo,
                        unsigned step, unsigned long long* __restrict__ out /*[1+kWin]*/) {
-    // out[0] = #codes < lo ; out[1+i] = #codes == lo + i*step
-    unsigned below = 0, w[kWin];
+    const int sh = __ffs(step) - 1;
+    unsigned long long tot[1 + kWin];
 #pragma unroll
-    for (int i = 0; i < kWin; ++i) w[i] = 0;
+    for (int i = 0; i <= kWin; ++i) tot[i] = 0;
+    unsigned below = 0;
+    unsigned long long p0 = 0, p1 = 0;
+    auto tally = [&](unsigned code) {
+        code &= mask;
+        below += code < lo;
+        const unsigned idx = (code - lo) >> sh;            // wraps to a huge value below lo
+        const unsigned long long one = 1ULL << ((idx & 3) * 16);
+        p0 += idx < 4 ? one : 0ULL;
+        p1 += (idx - 4) < 4 ? one : 0ULL;
+    };
+    auto flush = [&]() {
+        tot[0] += below; below = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { tot[1 + i] += (p0 >> (16 * i)) & 0xffff; tot[5 + i] += (p1 >> (16 * i)) & 0xffff; }
+        p0 = 0; p1 = 0;
+    };
     const long long nvec = n / 8;
     const uint4* v = reinterpret_cast<const uint4*>(raw);
     const bool aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
-    auto tally = [&](unsigned code) {
-        code &= mask;
-        below += code < lo;
-        unsigned d = code - lo;
-#pragma unroll
-        for (int i = 0; i < kWin; ++i) w[i] += (d == i * step);
-    };
     if (aligned) {
-        for (long long i = tid; i < nvec; i += nth) {
+        int since = 0;
+        long long i = tid;
+        for (; i + 3 * nth < nvec; i += 4 * nth) {          // four independent 16-byte loads in flight
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = ct_ldg_stream(v + i + u * nth);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                unsigned ww[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { tally(ww[j] & 0xffffu); tally(ww[j] >> 16); }
+            }
+            if (++since == 1024) { flush(); since = 0; }
+        }
+        for (; i < nvec; i += nth) {
             uint4 q = ct_ldg_stream(v + i);
             unsigned ww[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -592,19 +618,16 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
         }
         for (long long i = nvec * 8 + tid; i < n; i += nth) tally(raw[i]);
     } else {
-        for (long long i = tid; i < n; i += nth) tally(raw[i]);
+        int since = 0;
+        for (long long i = tid; i < n; i += nth) { tally(raw[i]); if (++since == 32768) { flush(); since = 0; } }
     }
-    // warp reduce, then one atomic per warp per counter
-    unsigned vals[1 + kWin];
-    vals[0] = below;
-#pragma unroll
-    for (int i = 0; i < kWin; ++i) vals[1 + i] = w[i];
+    flush();
 #pragma unroll
     for (int i = 0; i < 1 + kWin; ++i) {
-        unsigned long long s = vals[i];
+        unsigned long long sum = tot[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CT_FULL, s, o);
-        if (ct_lane() == 0 && s) atomicAdd(&out[i], s);
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(CT_FULL, sum, o);
+        if (ct_lane() == 0 && sum) atomicAdd(&out[i], sum);
     }
 }
 
