@@ -221,16 +221,47 @@ def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8,
                           subsegment=subsegment, out=out)
 
 
+def float_median(x: torch.Tensor, *, use_abs: bool = False) -> float:
+    """Exact np.median of a float32 device vector (float64 mean of the two middle values
+    for even n) by a 4-pass most-significant-digit radix select on the GPU."""
+    _require_cuda(x, "x", torch.float32)
+    n = x.numel()
+    if n == 0:
+        raise ValueError("median of an empty trace")
+    L = _lib.lib()
+    st = _stream_ptr(x)
+
+    def select(rank: int) -> float:
+        prefix, bits = 0, 0
+        for _ in range(4):
+            h = torch.zeros(256, dtype=torch.int64, device=x.device)
+            _lib.check(L.ct_radix_hist_f32(x.data_ptr(), n, prefix, bits, int(use_abs), h.data_ptr(), st), "ct_radix_hist_f32")
+            c = np.cumsum(h.cpu().numpy())
+            d = int(np.searchsorted(c, rank + 1))
+            rank -= int(c[d - 1]) if d else 0
+            prefix, bits = (prefix << 8) | d, bits + 8
+        key = np.uint32(prefix)
+        b = key ^ (np.uint32(0x80000000) if key & np.uint32(0x80000000) else np.uint32(0xFFFFFFFF))
+        return float(np.array([b], dtype=np.uint32).view(np.float32)[0])
+
+    lo = select((n - 1) // 2)
+    hi = lo if n % 2 else select(n // 2)
+    return float(np.mean(np.array([lo, hi], dtype=np.float64)))
+
+
 def bessel_filtfilt(x: torch.Tensor, samplerate: float, cutoff: float, order: int = 8, *,
-                    pad_value: float, padding: int = 1000, forward_only: bool = False,
+                    pad_value: float | None = None, padding: int = 1000, forward_only: bool = False,
                     halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
                     out: torch.Tensor | None = None) -> torch.Tensor:
     """Zero-phase Bessel of an already-dequantised float32 trace (e.g. `.bin` data,
     print_trace.py:33): out = pad_value + filtfilt(x - pad_value) with `padding` samples
     of constant pad, i.e. filtfilt(b, a, np.pad(x, padding, constant=pad_value),
-    padtype=None)[padding:-padding]."""
+    padtype=None)[padding:-padding]; pad_value=None takes the median (the reference's
+    `filter_data` on float data)."""
     _require_cuda(x, "x", torch.float32)
     n = x.numel()
+    if pad_value is None:            # np.pad(mode='median'), plot-trace.py:319
+        pad_value = float_median(x)
     if out is None:
         out = torch.empty(n, dtype=torch.float32, device=x.device)
     _require_cuda(out, "out", torch.float32)
@@ -249,3 +280,22 @@ def bessel_lfilter(x: torch.Tensor, samplerate: float, cutoff: float, order: int
     (`initial = 0` is the plain zero-state lfilter)."""
     return bessel_filtfilt(x, samplerate, cutoff, order, pad_value=float(initial), padding=0,
                            forward_only=True, **kw)
+
+
+def bessel_filtfilt_odd(x: torch.Tensor, samplerate: float, cutoff: float, poles: int) -> torch.Tensor:
+    """legacy/bessel-filter.py:124-131: np.pad(x, poles, mode='edge') followed by scipy's
+    default filtfilt (padtype='odd', padlen = 3*ntaps = 3*(poles+1)).  The odd extension is a
+    few dozen samples and is built on the device with torch; the kernel then runs without a
+    constant pad, its steady-state initial conditions being exactly scipy's zi*ext[0] and
+    zi*y[-1].  Returns the edge-padded length like the reference."""
+    _require_cuda(x, "x", torch.float32)
+    p = int(poles)
+    xe = torch.cat((x[:1].expand(p), x, x[-1:].expand(p)))
+    edge = 3 * (p + 1)
+    if xe.numel() <= edge:
+        raise ValueError("The length of the input vector x must be greater than padlen")
+    left = 2 * xe[0] - torch.flip(xe[1:edge + 1], [0])
+    right = 2 * xe[-1] - torch.flip(xe[-edge - 1:-1], [0])
+    ext = torch.cat((left, xe, right)).contiguous()
+    y = bessel_filtfilt(ext, samplerate, cutoff, p, pad_value=float(ext[0].item()), padding=0)
+    return y[edge:-edge]
