@@ -182,49 +182,47 @@ def run_ours(args):
     lo_h = halo if rank > 0 else 0
     hi_h = halo if rank < world - 1 else 0
     raw = synth.device_trace(n_own + lo_h + hi_h, dev, seed=1234 + rank, start_index=rank * n_own - lo_h)
-    have_cusum = hasattr(cusum, "cusum_levels")
+    have_cusum = True
     stage_ev = []
-    host_ev = []
+    stage_names = ("median", "filter", "baseline", "detect", "windows+cusum")
+    an = pipeline.TraceAnalyzer(raw.numel(), S, CUTOFF, ORDER, lo_halo=lo_h, hi_halo=hi_h, threshold=THRESHOLD,
+                                hysteresis=HYSTERESIS, baseline_block=BASELINE_BLOCK, baseline_min=BASELINE_MIN,
+                                baseline_max=BASELINE_MAX, event_padding=EVENT_PAD, minpoints=MINPOINTS,
+                                maxpoints=MAXPOINTS, cusum_delta=CUSUM_DELTA, cusum_h=CUSUM_H, group=group, device=dev)
 
-    stage_names = ("median", "filter", "baseline", "detect", "cusum")
+    def step():
+        """One pass of the hot path through the public API (pipeline.TraceAnalyzer.run)."""
+        r = an.run(raw)
+        return {"starts": r.events.starts, "ends": r.events.ends, "levels": r.levels}
 
-    def step(record=False):
+    def staged_step():
+        """The same kernels launched stage by stage with CUDA events between them (only
+        for the per-stage breakdown; not part of the timed region)."""
         marks = []
-        hmarks = []
 
         def mark():
-            if record:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append(e)
-                hmarks.append(time.perf_counter())
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
 
         mask = filters.chimera_bitmask(S)
         owned = raw[lo_h:lo_h + n_own]
+        torch.cuda.synchronize()
         mark()
         med = pipeline.global_code_median(owned, mask, group)
         mark()
-        y = filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med)
+        y = filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y)
         mark()
         yd = y[lo_h:]
-        bl = detect.baseline_blocks(yd, BASELINE_BLOCK, BASELINE_MIN, BASELINE_MAX).with_thresholds(THRESHOLD, HYSTERESIS)
+        bl = detect.baseline_blocks(yd, BASELINE_BLOCK, BASELINE_MIN, BASELINE_MAX, threshold=THRESHOLD, hysteresis=HYSTERESIS)
         mark()
         ev = detect.detect_events(yd, bl)
-        keep = int((ev.starts < n_own).sum().item()) if len(ev) else 0
-        starts, ends = ev.starts[:keep], ev.ends[:keep]
         mark()
-        out = {"starts": starts, "ends": ends, "levels": None}
-        if have_cusum and keep:
-            w0, w1, typ = detect.event_windows(starts, ends, yd.numel(), EVENT_PAD, MINPOINTS, MAXPOINTS)
-            out["levels"] = cusum.cusum_levels(yd, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H, types=typ)
+        w0, w1, typ = detect.event_windows(ev.starts, ev.ends, yd.numel(), EVENT_PAD, MINPOINTS, MAXPOINTS)
+        cusum.cusum_levels(yd, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H, types=typ)
         mark()
-        if record:
-            stage_ev.append(marks)
-            host_ev.append(hmarks)
-        if group is not None:
-            c = torch.zeros(world, dtype=torch.int64, device=dev); c[rank] = keep
-            dist.all_reduce(c, group=group)
-        return out
+        torch.cuda.synchronize()
+        stage_ev.append(marks)
 
     def fence():
         torch.cuda.synchronize()
@@ -253,9 +251,15 @@ def run_ours(args):
         step()
     _lib.reset_launch_count()
     tm0 = time.time()
-    dev_ms, wall_ms, res = timed(lambda: step(True), args.steps)
+    if args.profile_range:
+        torch.cuda.profiler.start()
+    dev_ms, wall_ms, res = timed(step, args.steps)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     tm1 = time.time()
     launches = _lib.launch_count()
+    for _ in range(2):
+        staged_step()
     clocks = sampler.summary(tm0, tm1) if sampler else None
     n_events = int(res["starts"].numel())
     ev_all = torch.tensor([n_events], dtype=torch.int64, device=dev)
@@ -275,14 +279,10 @@ def run_ours(args):
 
     def e2e_step():
         raw.copy_(host, non_blocking=True)
-        r = step()
-        tabs = [r["starts"], r["ends"]]
-        if r["levels"] is not None:
-            lv = r["levels"]
-            tabs += [lv.n_levels, lv.edges, lv.mean, lv.std]
-        outs = [t.to("cpu", non_blocking=True) for t in tabs]
-        d2h[0] = sum(t.numel() * t.element_size() for t in tabs)
-        return outs
+        r = an.run(raw)
+        tabs = an.tables_to_host(r)          # pinned D2H of the event + level tables, then sync
+        d2h[0] = sum(v.nbytes for v in tabs.values())
+        return tabs
 
     e2e_step()
     e_dev_ms, e_wall_ms, _ = timed(e2e_step, max(2, args.steps // 2))
@@ -314,7 +314,6 @@ def run_ours(args):
         "events_per_s": int(ev_all.item()) / (ms_per_step / 1e3),
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms": stage_ms,
-        "stage_host_ms": {nm: float(np.mean([1e3 * (h[i + 1] - h[i]) for h in host_ev])) for i, nm in enumerate(stage_names)},
         "roofline": {"kernel": "ct_filtfilt_kernel (fused dequantise + median pad + filtfilt)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "kernel_ms": filt_ms,
@@ -340,6 +339,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=C2_SAMPLES, help="samples per GPU (default: config C2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

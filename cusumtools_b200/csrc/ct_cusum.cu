@@ -43,6 +43,7 @@ struct CusumArgs {
     const double* rctab;
     const float* y; long long ntot;
     const long long* w0; const long long* w1; const int* type; long long nev;
+    const long long* nev_dev;          // event count read from device memory (NULL: use nev)
     float delta, h; int max_levels;
     int* n_levels; int* edges; double* mean; double* sd; unsigned char* overflow;
     unsigned long long* counter;
@@ -118,12 +119,14 @@ __global__ void __launch_bounds__(128, 4) ct_cusum_kernel(CusumArgs a) {
     const float dq = __fmul_rn(a.delta, kQ);
     const float hq = __fmul_rn(dq, 0.5f);
     const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
+    long long nev = a.nev;
+    if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
 
     for (;;) {
         long long ev = 0;
         if (lane == 0) ev = (long long)atomicAdd(a.counter, 1ULL);
         ev = __shfl_sync(CT_FULL, ev, 0);
-        if (ev >= a.nev) break;
+        if (ev >= nev) break;
         int* ed = a.edges + ev * (a.max_levels + 1);
         for (int i = lane; i <= a.max_levels; i += 32) ed[i] = -1;
         const long long p0 = a.w0[ev];
@@ -275,7 +278,11 @@ __global__ void __launch_bounds__(128, 4) ct_cusum_kernel(CusumArgs a) {
                 if (lane == 0) ed[nedge] = jmin + 1;
                 ++nedge;
                 k0 = kdet; cSq = 0; cSqq = 0; mp = kBig; mn = kBig; argp = kdet; argn = kdet;
-                fresh = false;                      // redo this block with the new anchor
+                // restart at the lane chunk (32-byte grid) that holds the new anchor: nothing before
+                // it is needed again, so no block position is spent on samples behind the anchor
+                const int nrs = rs + ((kdet - rs) & ~(kE - 1));
+                fresh = nrs != rs;                  // same chunk: redo this block with the new anchor
+                rs = nrs;
             } else {
                 cSq += totq; cSqq += totqq;
                 const long long nmp = (long long)min(mp, bminp) - totp, nmn = (long long)min(mn, bminn) - totn;
@@ -311,10 +318,10 @@ __global__ void __launch_bounds__(128, 4) ct_cusum_kernel(CusumArgs a) {
 
 }  // namespace
 
-extern "C" int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
-                              const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
-                              int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
-                              uint8_t* overflow, uint64_t* work_counter, void* stream) {
+static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                        const int32_t* type, int64_t n_events, const int64_t* n_events_dev, float delta, float h,
+                        int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
+                        uint8_t* overflow, uint64_t* work_counter, void* stream) {
     if (!y || !win_start || !win_end || !n_levels || !edges || !level_mean || !level_std || !overflow || !work_counter) {
         ct_set_error("cusum: null pointer"); return CT_ERR_ARG;
     }
@@ -341,7 +348,7 @@ extern "C" int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* wi
     CusumArgs a;
     a.rctab = tabs[dev];
     a.y = y; a.ntot = n_total; a.w0 = (const long long*)win_start; a.w1 = (const long long*)win_end; a.type = type;
-    a.nev = n_events; a.delta = delta; a.h = h; a.max_levels = max_levels; a.n_levels = n_levels; a.edges = edges;
+    a.nev = n_events; a.nev_dev = (const long long*)n_events_dev; a.delta = delta; a.h = h; a.max_levels = max_levels; a.n_levels = n_levels; a.edges = edges;
     a.mean = level_mean; a.sd = level_std; a.overflow = overflow; a.counter = (unsigned long long*)work_counter;
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_cusum_kernel, 128, 0);
@@ -352,4 +359,21 @@ extern "C" int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* wi
     CT_COUNT_LAUNCH();
     ct_cusum_kernel<<<(unsigned)grid, 128, 0, st>>>(a);
     return ct_check_launch("ct_cusum_kernel");
+}
+
+extern "C" int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                              const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
+                              int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
+                              uint8_t* overflow, uint64_t* work_counter, void* stream) {
+    return cusum_launch(y, n_total, win_start, win_end, type, n_events, nullptr, delta, h, max_levels, n_levels, edges,
+                        level_mean, level_std, overflow, work_counter, stream);
+}
+
+extern "C" int ct_cusum_batch_dev(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                                  const int32_t* type, const int64_t* n_events_dev, int64_t capacity, float delta,
+                                  float h, int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean,
+                                  double* level_std, uint8_t* overflow, uint64_t* work_counter, void* stream) {
+    if (!n_events_dev) { ct_set_error("cusum: null event count pointer"); return CT_ERR_ARG; }
+    return cusum_launch(y, n_total, win_start, win_end, type, capacity, n_events_dev, delta, h, max_levels, n_levels,
+                        edges, level_mean, level_std, overflow, work_counter, stream);
 }

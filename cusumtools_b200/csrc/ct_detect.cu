@@ -291,6 +291,95 @@ ct_block_stats_kernel(const float* __restrict__ y, long long n, long long block,
     }
 }
 
+
+// ---------------------------- baseline table + thresholds ----------------------------
+// oracle/events_oracle.py::baseline_from_stats + thresholds, evaluated on the device with the
+// same individually rounded float64 operations (no FMA contraction), so the thresholds the
+// detector compares against never leave the GPU:
+//   ma = Sq / cnt ; mean = c0 + ma * 2^-shift ; var = Sqq / cnt - ma * ma ;
+//   std = sqrt(max(var, 0)) * 2^-shift ; blocks with cnt < min_count inherit the nearest
+//   earlier valid block (the first valid one for leading blocks) ;
+//   sign = mean >= 0 ? +1 : -1 ; t_start = (float)(mean - (sign*thr) * std) ;
+//   t_end = (float)(mean - (sign*(thr - hyst)) * std)           (plot-trace.py:408-411)
+__global__ void __launch_bounds__(1024)
+ct_baseline_finalize_kernel(const long long* __restrict__ cnt, const long long* __restrict__ s1,
+                            const long long* __restrict__ s2, long long nb, double c0, double inv_sc,
+                            long long min_count, double thr, double thr_end, double* __restrict__ mean,
+                            double* __restrict__ sd, int* __restrict__ sign, float* __restrict__ t_start,
+                            float* __restrict__ t_end, int* __restrict__ status) {
+    __shared__ long long s_first;
+    if (threadIdx.x == 0) s_first = -1;
+    __syncthreads();
+    for (long long k = threadIdx.x; k < nb; k += blockDim.x) {
+        const long long c = cnt[k];
+        double m = __longlong_as_double(0x7ff8000000000000LL), s = m;
+        if (c >= min_count) {
+            const double cd = (double)c;
+            const double ma = __ddiv_rn((double)s1[k], cd);
+            m = __dadd_rn(c0, __dmul_rn(ma, inv_sc));
+            double var = __dsub_rn(__ddiv_rn((double)s2[k], cd), __dmul_rn(ma, ma));
+            if (!(var > 0.0)) var = 0.0;
+            s = __dmul_rn(__dsqrt_rn(var), inv_sc);
+        }
+        mean[k] = m; sd[k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                       // inheritance is a sequential fill (nb is small)
+        long long first = -1;
+        for (long long k = 0; k < nb; ++k) if (mean[k] == mean[k]) { first = k; break; }
+        s_first = first;
+        if (first >= 0) {
+            long long last = first;
+            for (long long k = 0; k < nb; ++k) {
+                if (mean[k] == mean[k]) last = k;
+                else { mean[k] = mean[last]; sd[k] = sd[last]; }
+            }
+        }
+        *status = first < 0 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_first < 0) return;
+    for (long long k = threadIdx.x; k < nb; k += blockDim.x) {
+        const double m = mean[k], s = sd[k];
+        const int sg = m >= 0.0 ? 1 : -1;
+        sign[k] = sg;
+        t_start[k] = __double2float_rn(__dsub_rn(m, __dmul_rn(sg > 0 ? thr : -thr, s)));
+        t_end[k] = __double2float_rn(__dsub_rn(m, __dmul_rn(sg > 0 ? thr_end : -thr_end, s)));
+    }
+}
+
+// ------------------------------ event windows / type codes ---------------------------
+// oracle/events_oracle.py::event_windows on the device, with the event count read from
+// device memory (counts2 of ct_detect_f32) so no host round trip separates detection from
+// CUSUM+.  Events are [starts[i], ends[i]) for i < min(n_starts, n_ends, capacity); only
+// events starting before n_keep are kept (time shards: the owner is the rank containing the
+// start).  n_events_out[0] = number kept.
+__global__ void ct_event_windows_kernel(const long long* __restrict__ starts, const long long* __restrict__ ends,
+                                        const unsigned long long* __restrict__ counts2, long long capacity,
+                                        long long n_total, long long n_keep, long long padding, long long minpoints,
+                                        long long maxpoints, long long* __restrict__ w0, long long* __restrict__ w1,
+                                        int* __restrict__ type, long long* __restrict__ n_events_out) {
+    long long ne = (long long)min(counts2[0], counts2[1]);
+    if (ne > capacity) ne = capacity;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (i0 == 0 && (ne == 0 || starts[0] >= n_keep)) n_events_out[0] = 0;
+    for (long long i = i0; i < ne; i += stride) {
+        const long long s = starts[i], e = ends[i];
+        if (s >= n_keep) continue;
+        const bool lastkept = (i + 1 == ne) || starts[i + 1] >= n_keep;
+        if (lastkept) n_events_out[0] = i + 1;
+        const long long a = s - padding, b = e + padding, len = e - s;
+        const long long prev_end = i ? ends[i - 1] : 0;
+        const long long next_start = lastkept ? n_total : starts[i + 1];
+        int t = 0;
+        if (a < prev_end || b > next_start || a < 0 || b > n_total) t = 4;
+        if (len > maxpoints) t = 3;
+        if (len < minpoints) t = 2;
+        w0[i] = a; w1[i] = b; type[i] = t;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -358,6 +447,39 @@ int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign,
     CT_COUNT_LAUNCH();
     ct_detect_pass2<<<(unsigned)((nruns + 127) / 128), 128, 0, st>>>(masks, runinfo, offs, nruns, (long long*)starts, (long long*)ends, capacity);
     return ct_check_launch("ct_detect_pass2");
+}
+
+int ct_baseline_finalize(const int64_t* cnt, const int64_t* s1, const int64_t* s2, int64_t nb, float c0, int shift,
+                         int64_t min_count, double threshold, double hysteresis, double* mean, double* stdev,
+                         int32_t* sign, float* t_start, float* t_end, int32_t* status, void* stream) {
+    if (!cnt || !s1 || !s2 || !mean || !stdev || !sign || !t_start || !t_end || !status || nb < 0) {
+        ct_set_error("baseline_finalize: bad argument"); return CT_ERR_ARG;
+    }
+    if (nb == 0) return CT_OK;
+    CT_COUNT_LAUNCH();
+    ct_baseline_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+        (const long long*)cnt, (const long long*)s1, (const long long*)s2, nb, (double)c0, ldexp(1.0, -shift), min_count,
+        threshold, threshold - hysteresis, mean, stdev, sign, t_start, t_end, status);
+    return ct_check_launch("ct_baseline_finalize_kernel");
+}
+
+int ct_event_windows(const int64_t* starts, const int64_t* ends, const uint64_t* counts2, int64_t capacity,
+                     int64_t n_total, int64_t n_keep, int64_t padding, int64_t minpoints, int64_t maxpoints,
+                     int64_t* win_start, int64_t* win_end, int32_t* type, int64_t* n_events_out, void* stream) {
+    if (!starts || !ends || !counts2 || !win_start || !win_end || !type || !n_events_out || capacity < 0) {
+        ct_set_error("event_windows: bad argument"); return CT_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(n_events_out, 0, 8, st);
+    if (capacity == 0) return CT_OK;
+    long long grid = (capacity + 255) / 256;
+    const long long cap = (long long)ct_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    CT_COUNT_LAUNCH();
+    ct_event_windows_kernel<<<(unsigned)grid, 256, 0, st>>>(
+        (const long long*)starts, (const long long*)ends, (const unsigned long long*)counts2, capacity, n_total, n_keep,
+        padding, minpoints, maxpoints, (long long*)win_start, (long long*)win_end, type, (long long*)n_events_out);
+    return ct_check_launch("ct_event_windows_kernel");
 }
 
 }  // extern "C"

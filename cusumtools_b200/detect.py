@@ -32,31 +32,103 @@ def stats_shift(half_width: float, block: int) -> int:
     return s
 
 
-@dataclass
 class Baseline:
     """Per-block baseline table (the rows of baseline.csv) plus the float32 lines the
-    detector compares against."""
-    block: int
-    mean: np.ndarray      # float64 [nb]  baseline_pA
-    std: np.ndarray       # float64 [nb]  stdev_pA
-    count: np.ndarray     # int64   [nb]  samples inside the baseline window
-    sign: np.ndarray | None = None      # int32 [nb]
-    t_start: np.ndarray | None = None   # float32 [nb]
-    t_end: np.ndarray | None = None     # float32 [nb]
+    detector compares against.  When produced by `baseline_blocks` everything lives on the
+    device (`dev` holds the tensors the detector reads) and the numpy views are fetched on
+    first access; a table can also be built from host arrays (tests, restored tables)."""
+
+    def __init__(self, block: int, mean=None, std=None, count=None, sign=None, t_start=None, t_end=None, dev=None):
+        self.block = int(block)
+        self._mean, self._std, self._count = mean, std, count
+        self._sign, self._t_start, self._t_end = sign, t_start, t_end
+        self.dev = dev              # dict of device tensors: cnt s1 s2 mean std sign t_start t_end status (+ c0, shift)
+        self._checked = False
+
+    # -- host views ----------------------------------------------------------------
+    def _fetch(self, name):
+        self.check()
+        return self.dev[name].cpu().numpy()
+
+    def check(self) -> None:
+        """Raise if no block had enough samples inside the baseline window (one device read)."""
+        if self.dev is not None and not self._checked:
+            if int(self.dev["status"].item()) != 0:
+                raise ValueError("no baseline block has enough samples inside [baseline_min, baseline_max]")
+            self._checked = True
+
+    @property
+    def mean(self):
+        if self._mean is None:
+            self._mean = self._fetch("mean")
+        return self._mean
+
+    @property
+    def std(self):
+        if self._std is None:
+            self._std = self._fetch("std")
+        return self._std
+
+    @property
+    def count(self):
+        if self._count is None:
+            self._count = self._fetch("cnt")
+        return self._count
+
+    def _line(self, name):
+        v = getattr(self, "_" + name)
+        if v is None and self.dev is not None and self.dev.get("have_thresholds"):
+            v = self._fetch(name)
+            setattr(self, "_" + name, v)
+        return v
+
+    sign = property(lambda self: self._line("sign"), lambda self, v: setattr(self, "_sign", v))
+    t_start = property(lambda self: self._line("t_start"), lambda self, v: setattr(self, "_t_start", v))
+    t_end = property(lambda self: self._line("t_end"), lambda self, v: setattr(self, "_t_end", v))
+
+    def __len__(self):
+        return int(self.dev["mean"].numel()) if self.dev is not None else len(self._mean)
 
     def with_thresholds(self, threshold: float, hysteresis: float) -> "Baseline":
-        sign = np.where(self.mean >= 0, 1, -1).astype(np.int32)
-        self.sign = sign
-        self.t_start = (self.mean - sign * threshold * self.std).astype(np.float32)
-        self.t_end = (self.mean - sign * (threshold - hysteresis) * self.std).astype(np.float32)
+        """plot-trace.py:408-411: start line = baseline - sign*threshold*stdev, end line =
+        baseline - sign*(threshold - hysteresis)*stdev, rounded to float32."""
+        self.threshold, self.hysteresis = float(threshold), float(hysteresis)
+        if self.dev is not None:
+            d = self.dev
+            nb = d["mean"].numel()
+            rc = _lib.lib().ct_baseline_finalize(d["cnt"].data_ptr(), d["s1"].data_ptr(), d["s2"].data_ptr(), nb,
+                                                 float(d["c0"]), int(d["shift"]), int(d["min_count"]), float(threshold),
+                                                 float(hysteresis), d["mean"].data_ptr(), d["std"].data_ptr(),
+                                                 d["sign"].data_ptr(), d["t_start"].data_ptr(), d["t_end"].data_ptr(),
+                                                 d["status"].data_ptr(), _stream_ptr(d["mean"]))
+            _lib.check(rc, "ct_baseline_finalize")
+            d["have_thresholds"] = True
+            self._sign = self._t_start = self._t_end = None
+            return self
+        sign = np.where(self._mean >= 0, 1, -1).astype(np.int32)
+        self._sign = sign
+        self._t_start = (self._mean - sign * threshold * self._std).astype(np.float32)
+        self._t_end = (self._mean - sign * (threshold - hysteresis) * self._std).astype(np.float32)
         return self
+
+    def device_lines(self, device):
+        """(sign int32, t_start float32, t_end float32) device tensors for the detector."""
+        if self.dev is not None and self.dev.get("have_thresholds"):
+            return self.dev["sign"], self.dev["t_start"], self.dev["t_end"]
+        if self._t_start is None:
+            raise ValueError("call Baseline.with_thresholds(threshold, hysteresis) first")
+        return (torch.from_numpy(np.ascontiguousarray(self._sign, np.int32)).to(device),
+                torch.from_numpy(np.ascontiguousarray(self._t_start, np.float32)).to(device),
+                torch.from_numpy(np.ascontiguousarray(self._t_end, np.float32)).to(device))
 
 
 def baseline_blocks(y: torch.Tensor, block: int, baseline_min: float, baseline_max: float,
-                    min_count: int = 16) -> Baseline:
+                    min_count: int = 16, *, threshold: float | None = None, hysteresis: float | None = None) -> Baseline:
     """Mean / population std of the samples inside [baseline_min, baseline_max] for every
-    block of `block` samples.  The device produces exact integer sums; the (tiny) division
-    and square root run on the host in Python integers / float64."""
+    block of `block` samples.  The device produces exact integer sums and turns them into
+    the table (and, if `threshold` is given, the detector's lines) without a host round
+    trip; the arithmetic is oracle/events_oracle.py::baseline_from_stats, operation for
+    operation."""
     _require_cuda(y, "y", torch.float32)
     L = _lib.lib()
     n = y.numel()
@@ -65,31 +137,24 @@ def baseline_blocks(y: torch.Tensor, block: int, baseline_min: float, baseline_m
     c0 = np.float32(0.5 * (np.float32(baseline_min) + np.float32(baseline_max)))
     hw = max(float(c0) - float(np.float32(baseline_min)), float(np.float32(baseline_max)) - float(c0))
     shift = stats_shift(hw, block)
-    acc = torch.zeros((3, max(nb, 1)), dtype=torch.int64, device=y.device)
+    dev = y.device
+    m = max(nb, 1)
+    acc = torch.empty((3, m), dtype=torch.int64, device=dev)
+    f64 = torch.empty((2, m), dtype=torch.float64, device=dev)
+    lines = torch.empty((2, m), dtype=torch.float32, device=dev)
+    d = {"cnt": acc[0, :nb], "s1": acc[1, :nb], "s2": acc[2, :nb], "mean": f64[0, :nb], "std": f64[1, :nb],
+         "sign": torch.empty(m, dtype=torch.int32, device=dev)[:nb], "t_start": lines[0, :nb], "t_end": lines[1, :nb],
+         "status": torch.zeros(1, dtype=torch.int32, device=dev), "c0": float(c0), "shift": shift,
+         "min_count": int(min_count), "have_thresholds": False}
     rc = L.ct_block_stats_f32(y.data_ptr(), n, block, float(baseline_min), float(baseline_max), float(c0), shift,
                               acc[0].data_ptr(), acc[1].data_ptr(), acc[2].data_ptr(), _stream_ptr(y))
     _lib.check(rc, "ct_block_stats_f32")
-    cnt, s1, s2 = acc.cpu().numpy()
-    mean = np.full(nb, np.nan)
-    std = np.full(nb, np.nan)
-    sc = 2.0 ** shift
-    for k in range(nb):
-        c = int(cnt[k])
-        if c >= min_count:
-            a, b = int(s1[k]), int(s2[k])
-            mean[k] = float(c0) + (a / c) / sc
-            std[k] = math.sqrt(max(b * c - a * a, 0) / (c * c)) / sc
-    valid = np.nonzero(~np.isnan(mean))[0]
-    if nb and valid.size == 0:
-        raise ValueError("no baseline block has enough samples inside [baseline_min, baseline_max]")
-    if nb:
-        last = valid[0]
-        for k in range(nb):
-            if np.isnan(mean[k]):
-                mean[k], std[k] = mean[last], std[last]
-            else:
-                last = k
-    return Baseline(block=block, mean=mean, std=std, count=cnt[:nb].copy())
+    bl = Baseline(block, dev=d)
+    thr = float("nan") if threshold is None else float(threshold)
+    hys = 0.0 if hysteresis is None else float(hysteresis)
+    bl.with_thresholds(thr, hys)
+    d["have_thresholds"] = threshold is not None
+    return bl
 
 
 @dataclass
@@ -107,17 +172,13 @@ def detect_events(y: torch.Tensor, baseline: Baseline, *, state_in: bool = False
     """Threshold/hysteresis detection over the whole filtered trace `y` (device float32).
     Event i occupies samples [starts[i], ends[i])."""
     _require_cuda(y, "y", torch.float32)
-    if baseline.t_start is None:
-        raise ValueError("call Baseline.with_thresholds(threshold, hysteresis) first")
     L = _lib.lib()
     n = y.numel()
     run = L.ct_detect_run()
     if baseline.block % run:
         raise ValueError(f"baseline block must be a multiple of {run} samples")
     dev = y.device
-    sign = torch.from_numpy(np.ascontiguousarray(baseline.sign, np.int32)).to(dev)
-    ts = torch.from_numpy(np.ascontiguousarray(baseline.t_start, np.float32)).to(dev)
-    te = torch.from_numpy(np.ascontiguousarray(baseline.t_end, np.float32)).to(dev)
+    sign, ts, te = baseline.device_lines(dev)
     wsb = int(L.ct_detect_workspace_bytes(n))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     cap = int(capacity) if capacity else max(1024, n // 2048)

@@ -32,9 +32,19 @@ def _mat_pow(A: np.ndarray, p: int) -> np.ndarray:
     return R
 
 
+_coef_cache: dict[tuple[int, float], "_lib.CtFilterCoef"] = {}
+
+
 def make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
     """Pack a design for the kernel: per-section taps, the constant state-transition
     powers A^C and A^(C*2^k) used by the warp scan, steady-state factors, gain."""
+    key = (design.order, design.wn)
+    if key not in _coef_cache:
+        _coef_cache[key] = _make_coef(design)
+    return _coef_cache[key]
+
+
+def _make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
     Cc = _lib.lib().ct_filter_chunk()
     k = _lib.CtFilterCoef()
     k.nsec = design.nsec

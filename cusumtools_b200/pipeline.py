@@ -19,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _lib, detect, filters
+from . import _lib, cusum, detect, filters
 from .design import bessel_lowpass
 
 
@@ -88,42 +88,170 @@ def required_halo(cutoff: float, order: int, samplerate: float, max_event: int, 
     return 2 * filters.halo_samples(d, eps) + int(max_event)
 
 
+@dataclass
+class AnalysisResult:
+    """Everything one pass of the hot path over a (shard of a) trace produces; all tensors
+    are device-resident views into the analyzer's buffers (valid until its next run)."""
+    filtered: torch.Tensor          # float32, the rank's owned samples
+    detect_trace: torch.Tensor      # float32, owned + right halo: what event indices refer to
+    baseline: detect.Baseline
+    events: detect.EventList        # indices relative to the rank's first owned sample
+    win_start: torch.Tensor         # int64 [E]  CUSUM+ windows [start - padding, end + padding)
+    win_end: torch.Tensor           # int64 [E]
+    types: torch.Tensor             # int32 [E]  rate.csv type code (0 accepted, >1 rejected)
+    levels: "cusum.LevelTable | None"
+    pad_value: float
+    median_codes: tuple[int, int]
+    first_event_id: int = 0
+    total_events: int = 0
+
+
+class TraceAnalyzer:
+    """Stages 1-3 over a time shard with every buffer allocated once and a single host
+    synchronisation at the end of the step (the median needs two small ones up front).
+
+    `raw_ext` = [lo_halo | owned | hi_halo] codes.  The filter runs over the extended range
+    (its constant pad only matters at the true ends of the trace); detection and CUSUM+ run
+    over [owned | hi_halo] so an event that starts in the owned range and ends in the halo
+    is completed, and events starting in the halo are left to the next rank."""
+
+    def __init__(self, n_ext: int, settings, cutoff: float, order: int = 8, *, lo_halo: int = 0, hi_halo: int = 0,
+                 threshold: float = 5.0, hysteresis: float = 1.0, baseline_block: int = detect.DEFAULT_BASELINE_BLOCK,
+                 baseline_min: float, baseline_max: float, padding: int = 1000, event_padding: int = 100,
+                 minpoints: int = 8, maxpoints: int = 100_000, cusum_delta: float | None = None,
+                 cusum_h: float | None = None, max_levels: int = cusum.DEFAULT_MAX_LEVELS,
+                 event_capacity: int | None = None, group=None, device="cuda"):
+        self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
+        self.n_own = self.n_ext - self.lo_halo - self.hi_halo
+        self.n_det = self.n_ext - self.lo_halo
+        self.settings, self.cutoff, self.order, self.padding = settings, float(cutoff), int(order), int(padding)
+        self.threshold, self.hysteresis = float(threshold), float(hysteresis)
+        self.block, self.bmin, self.bmax = int(baseline_block), float(baseline_min), float(baseline_max)
+        self.event_padding, self.minpoints, self.maxpoints = int(event_padding), int(minpoints), int(maxpoints)
+        self.delta, self.h, self.max_levels = cusum_delta, cusum_h, int(max_levels)
+        self.group = group
+        self.device = torch.device(device)
+        self.mask = filters.chimera_bitmask(settings)
+        L = _lib.lib()
+        if self.block % L.ct_detect_run():
+            raise ValueError(f"baseline block must be a multiple of {L.ct_detect_run()} samples")
+        self.y = torch.empty(self.n_ext, dtype=torch.float32, device=self.device)
+        self.ws_bytes = int(L.ct_detect_workspace_bytes(self.n_det))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self._alloc_events(int(event_capacity) if event_capacity else max(1024, self.n_det // 2048))
+
+    def _alloc_events(self, cap: int) -> None:
+        dev, ML = self.device, self.max_levels
+        self.cap = cap
+        self.starts = torch.empty(cap, dtype=torch.int64, device=dev)
+        self.ends = torch.empty(cap, dtype=torch.int64, device=dev)
+        self.w0 = torch.empty(cap, dtype=torch.int64, device=dev)
+        self.w1 = torch.empty(cap, dtype=torch.int64, device=dev)
+        self.typ = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.scalars = torch.zeros(4, dtype=torch.int64, device=dev)     # n_starts, n_ends, n_kept, work counter
+        if self.delta is not None:
+            self.nl = torch.empty(cap, dtype=torch.int32, device=dev)
+            self.ed = torch.empty((cap, ML + 1), dtype=torch.int32, device=dev)
+            self.mu = torch.empty((cap, ML), dtype=torch.float64, device=dev)
+            self.sd = torch.empty((cap, ML), dtype=torch.float64, device=dev)
+            self.ov = torch.empty(cap, dtype=torch.uint8, device=dev)
+
+    def run(self, raw_ext: torch.Tensor) -> AnalysisResult:
+        if raw_ext.numel() != self.n_ext:
+            raise ValueError(f"analyzer was planned for {self.n_ext} samples, got {raw_ext.numel()}")
+        L = _lib.lib()
+        lo, n_own = self.lo_halo, self.n_own
+        owned = raw_ext[lo:lo + n_own]
+        c1, c2 = global_code_median(owned, self.mask, self.group)
+        y = filters.dequant_filtfilt(raw_ext, self.settings, self.cutoff, self.order, padding=self.padding,
+                                     median_codes=(c1, c2), out=self.y)
+        pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), self.settings)))
+        yd = y[lo:]
+        st = filters._stream_ptr(y)
+        bl = detect.baseline_blocks(yd, self.block, self.bmin, self.bmax, threshold=self.threshold,
+                                    hysteresis=self.hysteresis)
+        sign, ts, te = bl.device_lines(self.device)
+        while True:
+            sc = self.scalars
+            rc = L.ct_detect_f32(yd.data_ptr(), self.n_det, self.block, sign.data_ptr(), ts.data_ptr(), te.data_ptr(), 0,
+                                 self.ws.data_ptr(), self.ws_bytes, self.starts.data_ptr(), self.ends.data_ptr(),
+                                 self.cap, sc[0:].data_ptr(), st)
+            _lib.check(rc, "ct_detect_f32")
+            rc = L.ct_event_windows(self.starts.data_ptr(), self.ends.data_ptr(), sc[0:].data_ptr(), self.cap, self.n_det,
+                                    n_own, self.event_padding, self.minpoints, self.maxpoints, self.w0.data_ptr(),
+                                    self.w1.data_ptr(), self.typ.data_ptr(), sc[2:].data_ptr(), st)
+            _lib.check(rc, "ct_event_windows")
+            if self.delta is not None:
+                rc = L.ct_cusum_batch_dev(yd.data_ptr(), self.n_det, self.w0.data_ptr(), self.w1.data_ptr(),
+                                          self.typ.data_ptr(), sc[2:].data_ptr(), self.cap, float(self.delta),
+                                          float(self.h), self.max_levels, self.nl.data_ptr(), self.ed.data_ptr(),
+                                          self.mu.data_ptr(), self.sd.data_ptr(), self.ov.data_ptr(), sc[3:].data_ptr(), st)
+                _lib.check(rc, "ct_cusum_batch_dev")
+            host = torch.cat((sc[:3], bl.dev["status"].to(torch.int64))).cpu().numpy()   # the step's one sync
+            ns, ne, nk = int(host[0]), int(host[1]), int(host[2])
+            if max(ns, ne) <= self.cap:
+                break
+            self._alloc_events(max(ns, ne))          # more events than planned: grow and redo stages 2-3
+        if int(host[3]) != 0:
+            raise ValueError("no baseline block has enough samples inside [baseline_min, baseline_max]")
+        bl._checked = True
+        open_start = -1
+        if ns > ne:                                   # an event still open at the end of the data
+            o = int(self.starts[ne].item())
+            open_start = o if o < n_own else -1
+        ev = detect.EventList(self.starts[:nk], self.ends[:nk], open_start)
+        lv = None
+        if self.delta is not None:
+            lv = cusum.LevelTable(self.nl[:nk], self.ed[:nk], self.mu[:nk], self.sd[:nk], self.ov[:nk], self.max_levels)
+        first_id, total = 0, nk
+        if self.group is not None:
+            import torch.distributed as dist
+            ws, rk = dist.get_world_size(self.group), dist.get_rank(self.group)
+            counts = torch.zeros(ws, dtype=torch.int64, device=self.device)
+            counts[rk] = nk
+            _all_reduce_(counts, self.group)
+            c = counts.cpu().numpy()
+            first_id, total = int(c[:rk].sum()), int(c.sum())
+        return AnalysisResult(filtered=y[lo:lo + n_own], detect_trace=yd, baseline=bl, events=ev,
+                              win_start=self.w0[:nk], win_end=self.w1[:nk], types=self.typ[:nk], levels=lv,
+                              pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id, total_events=total)
+
+
+    def tables_to_host(self, r: AnalysisResult) -> dict:
+        """Event and level tables of `r` as numpy arrays: device -> pinned host buffers
+        (allocated once at capacity) with one synchronisation; the arrays alias the pinned
+        buffers and are valid until the next call."""
+        nk = int(r.events.starts.numel())
+        if getattr(self, "_pinned_cap", 0) < self.cap:
+            self._pinned = {}
+            self._pinned_cap = self.cap
+        src = {"starts": r.events.starts, "ends": r.events.ends, "types": r.types}
+        if r.levels is not None:
+            src.update(n_levels=r.levels.n_levels, edges=r.levels.edges, mean=r.levels.mean, std=r.levels.std,
+                       overflow=r.levels.overflow)
+        out = {}
+        for k, t in src.items():
+            if k not in self._pinned:
+                self._pinned[k] = torch.empty((self.cap,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True)
+            h = self._pinned[k][:nk]
+            h.copy_(t, non_blocking=True)
+            out[k] = h
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: v.numpy() for k, v in out.items()}
+
+
 def analyze_shard(raw_ext: torch.Tensor, settings, cutoff: float, order: int, *, lo_halo: int, hi_halo: int,
                   threshold: float, hysteresis: float, baseline_block: int, baseline_min: float,
                   baseline_max: float, group=None, is_first: bool = True, is_last: bool = True,
                   padding: int = 1000, keep_filtered: bool = True) -> TraceResult:
-    """Run stages 1-2 on a time shard.  `raw_ext` = [lo_halo | owned | hi_halo] codes.
-
-    The filter runs over the extended range (its constant pad only matters at the true
-    ends of the trace, i.e. on the first/last rank where the halo is 0); detection runs
-    over [owned | hi_halo] so an event that starts in the owned range and ends in the halo
-    is completed, and events starting in the halo are left to the next rank."""
-    n_ext = raw_ext.numel()
-    owned = raw_ext[lo_halo:n_ext - hi_halo]
-    mask = filters.chimera_bitmask(settings)
-    c1, c2 = global_code_median(owned, mask, group)
-    y_ext = filters.dequant_filtfilt(raw_ext, settings, cutoff, order, padding=padding, median_codes=(c1, c2))
-    pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), settings)))
-    n_own = owned.numel()
-    y_det = y_ext[lo_halo:]                      # owned + right halo
-    bl = detect.baseline_blocks(y_det, baseline_block, baseline_min, baseline_max).with_thresholds(threshold, hysteresis)
-    ev = detect.detect_events(y_det, bl)
-    keep = ev.starts < n_own
-    nk = int(keep.sum().item()) if len(ev) else 0
-    open_start = ev.open_start if (ev.open_start >= 0 and ev.open_start < n_own) else -1
-    ev = detect.EventList(ev.starts[:nk], ev.ends[:nk], open_start)
-    first_id, total = 0, nk
-    if group is not None:
-        import torch.distributed as dist
-        ws, rk = dist.get_world_size(group), dist.get_rank(group)
-        counts = torch.zeros(ws, dtype=torch.int64, device=raw_ext.device)
-        counts[rk] = nk
-        _all_reduce_(counts, group)
-        c = counts.cpu().numpy()
-        first_id, total = int(c[:rk].sum()), int(c.sum())
-    return TraceResult(filtered=y_ext[lo_halo:lo_halo + n_own] if keep_filtered else y_ext[:0], baseline=bl,
-                       events=ev, pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id,
-                       total_events=total)
+    """Run stages 1-2 on a time shard (see TraceAnalyzer; this is the one-shot form)."""
+    an = TraceAnalyzer(raw_ext.numel(), settings, cutoff, order, lo_halo=lo_halo, hi_halo=hi_halo, threshold=threshold,
+                       hysteresis=hysteresis, baseline_block=baseline_block, baseline_min=baseline_min,
+                       baseline_max=baseline_max, padding=padding, group=group, device=raw_ext.device)
+    r = an.run(raw_ext)
+    return TraceResult(filtered=r.filtered if keep_filtered else r.filtered[:0], baseline=r.baseline, events=r.events,
+                       pad_value=r.pad_value, median_codes=r.median_codes, first_event_id=r.first_event_id,
+                       total_events=r.total_events)
 
 
 def analyze_trace(raw: torch.Tensor, settings, cutoff: float, order: int = 8, *, threshold: float = 5.0,

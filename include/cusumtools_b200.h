@@ -85,6 +85,16 @@ int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t 
  * q = rint((y - c0) * 2^shift) over samples with bmin <= y <= bmax.                   */
 int ct_block_stats_f32(const float* y, int64_t n, int64_t block, float bmin, float bmax, float c0,
                        int shift, int64_t* cnt, int64_t* s1, int64_t* s2, void* stream);
+/* Baseline table + detector thresholds from the block sums, entirely on the device (the
+ * rows of baseline.csv and the two dashed lines of plot-trace.py:408-411):
+ *   mean = c0 + (s1/cnt) 2^-shift, std = sqrt(max(s2/cnt - (s1/cnt)^2, 0)) 2^-shift in
+ *   individually rounded float64 operations; blocks with cnt < min_count inherit the nearest
+ *   earlier valid block; sign = sign(mean); t_start = (float)(mean - sign*threshold*std);
+ *   t_end = (float)(mean - sign*(threshold - hysteresis)*std).  status[0] = 1 if no block
+ *   is valid (nothing else is written then).  All arrays have nb entries.                */
+int ct_baseline_finalize(const int64_t* cnt, const int64_t* s1, const int64_t* s2, int64_t nb, float c0, int shift,
+                         int64_t min_count, double threshold, double hysteresis, double* mean, double* stdev,
+                         int32_t* sign, float* t_start, float* t_end, int32_t* status, void* stream);
 int ct_detect_run(void);                          /* `block` must be a multiple of this */
 int64_t ct_detect_workspace_bytes(int64_t n);
 /* starts/ends: int64[capacity] in time order; counts2 = {n_starts, n_ends} (may exceed
@@ -93,6 +103,17 @@ int64_t ct_detect_workspace_bytes(int64_t n);
 int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign, const float* t_start,
                   const float* t_end, int state_in, void* workspace, int64_t workspace_bytes,
                   int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream);
+
+/* Event windows handed to CUSUM+ and the rate.csv `type` code (0 accepted, 2 shorter than
+ * minpoints, 3 longer than maxpoints, 4 padding leaves the trace or overlaps a neighbour;
+ * plot-trace.py:354-357 treats type > 1 as rejected), computed on the device from the
+ * detector's own counters so no host round trip separates detection from CUSUM+.
+ * Event i is [starts[i], ends[i]) for i < min(counts2[0], counts2[1], capacity); events
+ * starting at or beyond n_keep are dropped (time shards: the rank that holds the start owns
+ * the event).  win = [start - padding, end + padding); n_events_out[0] = events kept.      */
+int ct_event_windows(const int64_t* starts, const int64_t* ends, const uint64_t* counts2, int64_t capacity,
+                     int64_t n_total, int64_t n_keep, int64_t padding, int64_t minpoints, int64_t maxpoints,
+                     int64_t* win_start, int64_t* win_end, int32_t* type, int64_t* n_events_out, void* stream);
 
 /* ---- stage 3: batched per-event CUSUM+ level segmentation -----------------------
  * No reference implementation exists (readevents.py:843-846,1297-1306 only consumes the
@@ -107,6 +128,12 @@ int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, co
                    const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
                    int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
                    uint8_t* overflow, uint64_t* work_counter, void* stream);
+/* Same with the event count read from device memory (n_events_dev[0], clamped to capacity):
+ * the output arrays must hold `capacity` rows; rows at or beyond the count are not written. */
+int ct_cusum_batch_dev(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                       const int32_t* type, const int64_t* n_events_dev, int64_t capacity, float delta, float h,
+                       int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
+                       uint8_t* overflow, uint64_t* work_counter, void* stream);
 
 /* ---- stage 4: Welch PSD ------------------------------------------------------------
  * Replaces scipy.signal.welch(x, fs, nperseg=L) as called at plot-trace.py:442,

@@ -55,26 +55,30 @@ def block_stats(y, block, bmin, bmax, c0, shift):
 
 
 def baseline_from_stats(cnt, s1, s2, c0, shift, min_count=16):
-    """Block mean / population std from the exact integer sums (python ints, so the
-    result is independent of who computes it).  Blocks with fewer than `min_count`
-    in-window samples inherit the nearest earlier valid block (or the first valid one)."""
+    """Block mean / population std from the exact integer sums, as a fixed sequence of
+    individually rounded float64 operations (so numpy, C and CUDA agree bit for bit):
+      ma = s1/cnt ; mean = c0 + ma*2^-shift ; var = s2/cnt - ma*ma ;
+      std = sqrt(max(var, 0))*2^-shift.
+    Blocks with fewer than `min_count` in-window samples inherit the nearest earlier valid
+    block (or the first valid one)."""
+    cnt = np.asarray(cnt, np.int64)
     nb = len(cnt)
-    mean = np.full(nb, np.nan)
-    std = np.full(nb, np.nan)
-    sc = 2.0 ** shift
-    for k in range(nb):
-        c = int(cnt[k])
-        if c >= min_count:
-            a, b = int(s1[k]), int(s2[k])
-            mean[k] = float(np.float32(c0)) + (a / c) / sc
-            num = b * c - a * a
-            std[k] = math.sqrt(max(num, 0) / (c * c)) / sc
-    valid = np.nonzero(~np.isnan(mean))[0]
+    c = cnt.astype(np.float64)
+    ok = cnt >= min_count
+    cs = np.where(ok, c, 1.0)
+    inv = 2.0 ** (-shift)
+    ma = np.asarray(s1, np.int64).astype(np.float64) / cs
+    mean = float(np.float32(c0)) + ma * inv
+    var = np.asarray(s2, np.int64).astype(np.float64) / cs - ma * ma
+    std = np.sqrt(np.where(var > 0, var, 0.0)) * inv
+    mean = np.where(ok, mean, np.nan)
+    std = np.where(ok, std, np.nan)
+    valid = np.nonzero(ok)[0]
     if valid.size == 0:
         raise ValueError("no baseline block has enough samples inside [baseline_min, baseline_max]")
     last = valid[0]
     for k in range(nb):
-        if np.isnan(mean[k]):
+        if not ok[k]:
             mean[k], std[k] = mean[last], std[last]
         else:
             last = k

@@ -1,0 +1,86 @@
+"""GPU parity of the fused single-synchronisation path (pipeline.TraceAnalyzer): baseline
+table, detector lines, events, event windows / type codes and CUSUM+ levels against the
+oracle chain run on the SAME filtered samples.  Every integer and every float64 table entry
+is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from cusumtools_b200 import pipeline, synth
+from oracle import c_twin, events_oracle as eo
+
+pytestmark = pytest.mark.gpu
+S = synth.CHIMERA_SETTINGS
+KW = dict(threshold=5.0, hysteresis=1.0, baseline_min=4700.0, baseline_max=5300.0)
+
+
+def oracle_chain(y, n_keep, block, pad=100, minp=8, maxp=100000, delta=400.0, h=10.0, max_levels=16):
+    c0 = np.float32(5000.0)
+    sh = eo.stats_shift(300.0, block)
+    cnt, s1, s2 = c_twin.block_stats(y, block, 4700.0, 5300.0, c0, sh)
+    mean, std = eo.baseline_from_stats(cnt, s1, s2, c0, sh)
+    sign, ts, te = eo.thresholds(mean, std, 5.0, 1.0)
+    s, e, o = c_twin.detect_events(y, block, sign, ts, te)
+    keep = s < n_keep
+    s, e = s[keep], e[keep]
+    w0, w1, typ = eo.event_windows(s, e, len(y), pad, minp, maxp)
+    ok = typ == 0
+    offs = np.concatenate(([0], np.cumsum((w1 - w0)[ok])))
+    flat = np.concatenate([y[a:b] for a, b in zip(w0[ok], w1[ok])]) if ok.any() else np.zeros(0, np.float32)
+    lv = c_twin.cusum_batch(flat, offs, delta, h, max_levels)
+    return dict(mean=mean, std=std, sign=sign, ts=ts, te=te, s=s, e=e, o=o, w0=w0, w1=w1, typ=typ, ok=ok, lv=lv)
+
+
+def check(r, ref):
+    assert np.array_equal(r.baseline.mean, ref["mean"]) and np.array_equal(r.baseline.std, ref["std"])
+    assert np.array_equal(r.baseline.sign, ref["sign"])
+    assert np.array_equal(r.baseline.t_start, ref["ts"]) and np.array_equal(r.baseline.t_end, ref["te"])
+    assert np.array_equal(r.events.starts.cpu().numpy(), ref["s"])
+    assert np.array_equal(r.events.ends.cpu().numpy(), ref["e"])
+    assert np.array_equal(r.win_start.cpu().numpy(), ref["w0"]) and np.array_equal(r.win_end.cpu().numpy(), ref["w1"])
+    assert np.array_equal(r.types.cpu().numpy(), ref["typ"])
+    ok = ref["ok"]
+    nl, ed, mu, sd, ov = ref["lv"]
+    gnl = r.levels.n_levels.cpu().numpy()
+    assert np.array_equal(gnl[ok], nl) and np.all(gnl[~ok] == 0)
+    assert np.array_equal(r.levels.edges.cpu().numpy()[ok], ed)
+    L = r.levels.max_levels
+    gm, gs = r.levels.mean.cpu().numpy()[ok], r.levels.std.cpu().numpy()[ok]
+    for i in range(len(nl)):          # rows are only defined up to n_levels
+        assert np.array_equal(gm[i, :nl[i]], mu[i, :nl[i]]) and np.array_equal(gs[i, :nl[i]], sd[i, :nl[i]])
+    assert np.array_equal(r.levels.overflow.cpu().numpy()[ok], ov)
+
+
+@pytest.mark.parametrize("block,cap", [(65536, None), (4096, 5)])
+def test_analyzer_matches_oracle_chain(block, cap):
+    codes, true_starts = synth.c1_trace(n=600_000, n_events=140, seed=11)
+    raw = torch.from_numpy(codes).cuda()
+    an = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, baseline_block=block, cusum_delta=400.0, cusum_h=10.0,
+                                event_capacity=cap, **KW)
+    for _ in range(2):                       # the second run reuses every buffer
+        r = an.run(raw)
+        y = r.detect_trace.cpu().numpy()
+        ref = oracle_chain(y, len(codes), block)
+        check(r, ref)
+        assert len(true_starts) <= len(ref["s"]) <= len(true_starts) + 2
+        assert r.events.open_start == ref["o"]
+
+
+def test_analyzer_with_halos_keeps_only_owned_events():
+    codes, _ = synth.c1_trace(n=500_000, n_events=115, seed=12)
+    lo, hi = 8192, 12288
+    raw = torch.from_numpy(codes).cuda()
+    an = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=4096,
+                                cusum_delta=400.0, cusum_h=10.0, **KW)
+    r = an.run(raw)
+    y = r.detect_trace.cpu().numpy()
+    assert y.size == len(codes) - lo and r.filtered.numel() == len(codes) - lo - hi
+    check(r, oracle_chain(y, len(codes) - lo - hi, 4096))
+
+
+def test_no_valid_baseline_block_raises():
+    codes, _ = synth.c1_trace(n=100_000, n_events=10, seed=3)
+    an = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, baseline_block=4096, threshold=5.0, hysteresis=1.0,
+                                baseline_min=100.0, baseline_max=200.0)
+    with pytest.raises(ValueError):
+        an.run(torch.from_numpy(codes).cuda())
