@@ -46,7 +46,8 @@ struct CusumArgs {
     const long long* nev_dev;          // event count read from device memory (NULL: use nev)
     float delta, h; int max_levels;
     int* n_levels; int* edges; double* mean; double* sd; unsigned char* overflow;
-    unsigned long long* counter;
+    unsigned long long* counter;       // [0] event fetch counter, [1] pending count, [2] pending fetch counter
+    int* pending;                      // events left to the warp-cooperative kernel
 };
 
 __device__ __forceinline__ int warp_excl_add(int v, int lane, int& total) {
@@ -113,27 +114,18 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
-__global__ void __launch_bounds__(128, 4) ct_cusum_kernel(CusumArgs a) {
-    const int lane = ct_lane();
-    const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
-    const float dq = __fmul_rn(a.delta, kQ);
-    const float hq = __fmul_rn(dq, 0.5f);
-    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
-    long long nev = a.nev;
-    if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
-
-    for (;;) {
-        long long ev = 0;
-        if (lane == 0) ev = (long long)atomicAdd(a.counter, 1ULL);
-        ev = __shfl_sync(CT_FULL, ev, 0);
-        if (ev >= nev) break;
+// One event, one warp (windows longer than the thread-per-event limit, or batches too small
+// to fill the GPU with one event per lane).
+__device__ void warp_event(const CusumArgs& a, const long long ev, const int lane, const int H, const float dq,
+                           const float hq, const bool aligned) {
+    {
         int* ed = a.edges + ev * (a.max_levels + 1);
         for (int i = lane; i <= a.max_levels; i += 32) ed[i] = -1;
         const long long p0 = a.w0[ev];
         const long long nn = a.w1[ev] - p0;
         if (nn <= 0 || p0 < 0 || a.w1[ev] > a.ntot || nn > 0x3fffffffLL || (a.type && a.type[ev] != 0)) {
             if (lane == 0) { a.n_levels[ev] = 0; a.overflow[ev] = 0; }
-            continue;
+            return;
         }
         const int n = (int)nn;
         const float x0 = a.y[p0];
@@ -316,20 +308,224 @@ __global__ void __launch_bounds__(128, 4) ct_cusum_kernel(CusumArgs a) {
     }
 }
 
+// Events the thread-per-event kernel left to the warps (a.pending[0 .. counter[1])): persistent
+// warps pull them from an atomic counter, one event per warp at a time.
+__global__ void __launch_bounds__(128, 4) ct_cusum_warp_kernel(CusumArgs a) {
+    const int lane = ct_lane();
+    const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
+    const float dq = __fmul_rn(a.delta, kQ);
+    const float hq = __fmul_rn(dq, 0.5f);
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
+    const unsigned long long npend = a.counter[1];
+    for (;;) {
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(a.counter + 2, 1ULL);
+        i = __shfl_sync(CT_FULL, i, 0);
+        if (i >= npend) break;
+        warp_event(a, (long long)a.pending[i], lane, H, dq, hq, aligned);
+        __syncwarp();
+    }
+}
+
+// =====================================================================================
+// Thread-per-event kernel (the production path for windows up to kSeqMax samples).
+//
+// The definition (oracle/events_oracle.py::cusum_event_sequential) is a per-sample
+// recurrence; evaluating it literally, one event per LANE, needs no prefix scans, no
+// validity masks, no block re-runs after a detection and no second pass for the level
+// statistics: ~3x fewer instructions per sample than the warp-cooperative kernel above.
+// Lanes fetch their next event from the shared counter as soon as they finish one (warp
+// aggregated), so a warp stays full whatever the event lengths.  Each lane streams its own
+// event with 256-bit loads (one 32-byte sector per instruction; the L1 keeps the line for
+// the lane's next loads).  Level sums are exact integers: the sums of the samples between
+// the changepoint and the detection index are re-read at the (rare) detections, and the
+// float64 mean / std are produced by ct_cusum_finalize from the integer sums the lanes
+// leave (bit-cast) in the mean / std arrays.
+// =====================================================================================
+constexpr int kSeqMax = 16384;         // longest window a single lane takes
+constexpr int kSeqMinEvents = 16384;   // below this one event per lane cannot fill the GPU: warps take everything
+constexpr unsigned char kRawSums = 0x80;   // overflow[] bit: level rows hold raw integer sums (finalize pending)
+
+struct SeqOut { int sp, sn; };
+
+__device__ __forceinline__ SeqOut seq_increments(const double* __restrict__ rctab, long long Sq, long long Sqq,
+                                                 int cnt, int q, float dq, float hq) {
+    const double rc = __ldg(rctab + cnt);          // cnt <= kSeqMax < kRcTab
+    const double Sqd = (double)Sq;
+    const double m = __dmul_rn(Sqd, rc);
+    const double vv = __dmul_rn(__dsub_rn((double)Sqq, __dmul_rn(Sqd, m)), rc);
+    const float v = __double2float_rn(vv);
+    SeqOut o; o.sp = 0; o.sn = 0;
+    if (v > 0.f) {
+        const float r = __fdiv_rn(dq, v);
+        const float t = __fsub_rn((float)q, __double2float_rn(m));
+        float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
+        float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
+        fa = fminf(fmaxf(fa, -kSMax), kSMax);
+        fb = fminf(fmaxf(fb, -kSMax), kSMax);
+        o.sp = __float2int_rn(fa);
+        o.sn = __float2int_rn(fb);
+    }
+    return o;
+}
+
+__global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
+    const int lane = ct_lane();
+    const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
+    const float dq = __fmul_rn(a.delta, kQ);
+    const float hq = __fmul_rn(dq, 0.5f);
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
+    long long nev = a.nev;
+    if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
+    const int ML = a.max_levels;
+    const long long seq_limit = nev < kSeqMinEvents ? 0 : kSeqMax;
+
+    // per-lane event state
+    bool active = false, exhausted = false;
+    long long ev = 0, p0 = 0;
+    int n = 0, gk = 0;                   // window length; relative index of the current 8-sample group
+    float x0 = 0.f;
+    int k0 = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0, overflow = 0;
+    long long Sq = 0, Sqq = 0;           // sums over [k0, k]
+    long long Lp = 0, Lpp = 0;           // sums over [e0, k0): the part of the open level before the anchor
+
+    for (;;) {
+        // ---- lanes without an event fetch the next ones (one atomic per warp)
+        const unsigned need = __ballot_sync(CT_FULL, !active && !exhausted);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            long long base = 0;
+            if (lane == leader) base = (long long)atomicAdd(a.counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(CT_FULL, base, leader);
+            if (!active && !exhausted) {
+                ev = base + __popc(need & ((1u << lane) - 1u));
+                if (ev >= nev) exhausted = true;
+                else {
+                    p0 = a.w0[ev];
+                    const long long nn = a.w1[ev] - p0;
+                    const bool bad = nn <= 0 || p0 < 0 || a.w1[ev] > a.ntot || nn > 0x3fffffffLL || (a.type && a.type[ev] != 0);
+                    if (bad) { a.n_levels[ev] = 0; a.overflow[ev] = 0; }
+                    else if (nn > seq_limit) a.pending[atomicAdd(a.counter + 1, 1ULL)] = (int)ev;
+                    else {
+                        n = (int)nn;
+                        gk = -(int)(p0 & 7);
+                        k0 = 0; gp = gn = 0; rp = rn = 0; nedge = 1; e0 = 0; overflow = 0;
+                        Sq = Sqq = 0; Lp = Lpp = 0;
+                        a.edges[ev * (ML + 1)] = 0;
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(CT_FULL, active) == 0) {
+            if (__ballot_sync(CT_FULL, !exhausted) == 0) break;
+            continue;
+        }
+        if (active) {
+            // ---- one group of 8 consecutive samples of this lane's event
+            float xv[kE];
+            const long long pa = p0 + gk;
+            if (aligned && pa >= 0 && pa + kE <= a.ntot) {
+                const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
+                const uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
+                xv[0] = __uint_as_float(lo.x); xv[1] = __uint_as_float(lo.y); xv[2] = __uint_as_float(lo.z); xv[3] = __uint_as_float(lo.w);
+                xv[4] = __uint_as_float(hi.x); xv[5] = __uint_as_float(hi.y); xv[6] = __uint_as_float(hi.z); xv[7] = __uint_as_float(hi.w);
+            } else {
+#pragma unroll
+                for (int e = 0; e < kE; ++e) { const long long p = pa + e; xv[e] = (p >= 0 && p < a.ntot) ? a.y[p] : 0.f; }
+            }
+#pragma unroll
+            for (int e = 0; e < kE; ++e) {
+                const int k = gk + e;
+                if (k < 0 || k >= n || overflow) continue;
+                if (k == 0) x0 = xv[e];
+                const int q = quantise(xv[e], x0);
+                Sq += q; Sqq += (long long)q * q;
+                const SeqOut s = seq_increments(a.rctab, Sq, Sqq, k - k0 + 1, q, dq, hq);
+                gp += s.sp; if (gp <= 0) { gp = 0; rp = k; }
+                gn += s.sn; if (gn <= 0) { gn = 0; rn = k; }
+                if (gp > H || gn > H) {
+                    if (nedge >= ML) { overflow = 1; continue; }
+                    const int edge = ((gp >= gn) ? rp : rn) + 1;
+                    long long T = 0, TT = 0;             // sums over [edge, k]
+                    for (int j = edge; j <= k; ++j) {
+                        const long long qj = quantise(a.y[p0 + j], x0);
+                        T += qj; TT += qj * qj;
+                    }
+                    const long long row = ev * ML + (nedge - 1);
+                    reinterpret_cast<long long*>(a.mean)[row] = Lp + Sq - T;      // level [e0, edge)
+                    reinterpret_cast<long long*>(a.sd)[row] = Lpp + Sqq - TT;
+                    a.edges[ev * (ML + 1) + nedge] = edge;
+                    ++nedge;
+                    e0 = edge; Lp = T - q; Lpp = TT - (long long)q * q;
+                    k0 = k; Sq = q; Sqq = (long long)q * q; gp = gn = 0; rp = rn = k;
+                }
+            }
+            gk += kE;
+            if (gk >= n || overflow) {
+                if (overflow) {                          // the rest of the window belongs to the last level
+                    long long T = 0, TT = 0;
+                    for (int j = e0; j < n; ++j) { const long long qj = quantise(a.y[p0 + j], x0); T += qj; TT += qj * qj; }
+                    Lp = T; Lpp = TT; Sq = 0; Sqq = 0;
+                }
+                const long long row = ev * ML + (nedge - 1);
+                reinterpret_cast<long long*>(a.mean)[row] = Lp + Sq;              // level [e0, n)
+                reinterpret_cast<long long*>(a.sd)[row] = Lpp + Sqq;
+                a.edges[ev * (ML + 1) + nedge] = n;
+                a.n_levels[ev] = nedge;
+                a.overflow[ev] = (unsigned char)(overflow | kRawSums);
+                active = false;
+            }
+        }
+    }
+}
+
+// float64 level mean / population std from the integer sums the lanes left in the arrays
+// (oracle/events_oracle.py::level_stats, operation for operation); one thread per event.
+__global__ void ct_cusum_finalize_kernel(CusumArgs a) {
+    long long nev = a.nev;
+    if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
+    const int ML = a.max_levels;
+    for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < nev; ev += (long long)gridDim.x * blockDim.x) {
+        const unsigned char f = a.overflow[ev];
+        if (!(f & kRawSums)) continue;
+        const int* ed = a.edges + ev * (ML + 1);
+        const int nl = a.n_levels[ev];
+        const double x0 = (double)a.y[a.w0[ev]];
+        for (int lv = 0; lv < nl; ++lv) {
+            const long long i = ev * ML + lv;
+            const double len = (double)(ed[lv + 1] - ed[lv]);
+            const double ad = (double)reinterpret_cast<const long long*>(a.mean)[i];
+            const double bd = (double)reinterpret_cast<const long long*>(a.sd)[i];
+            a.mean[i] = __dadd_rn(x0, __ddiv_rn(__ddiv_rn(ad, len), 64.0));
+            double var = __dsub_rn(bd, __ddiv_rn(__dmul_rn(ad, ad), len));
+            if (var < 0.0) var = 0.0;
+            a.sd[i] = __ddiv_rn(__dsqrt_rn(__ddiv_rn(var, len)), 64.0);
+        }
+        a.overflow[ev] = f & (unsigned char)~kRawSums;
+    }
+}
+
 }  // namespace
+
+extern "C" int64_t ct_cusum_workspace_bytes(int64_t n_events) { return 24 + 4 * (n_events > 0 ? n_events : 0) + 8; }
 
 static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                         const int32_t* type, int64_t n_events, const int64_t* n_events_dev, float delta, float h,
                         int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
-                        uint8_t* overflow, uint64_t* work_counter, void* stream) {
-    if (!y || !win_start || !win_end || !n_levels || !edges || !level_mean || !level_std || !overflow || !work_counter) {
+                        uint8_t* overflow, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!y || !win_start || !win_end || !n_levels || !edges || !level_mean || !level_std || !overflow || !workspace) {
         ct_set_error("cusum: null pointer"); return CT_ERR_ARG;
     }
     if (n_events < 0 || max_levels < 2 || max_levels > 1024 || !(delta > 0.f) || !(h > 0.f) || h > 262144.f) {
         ct_set_error("cusum: bad argument (need delta > 0, 0 < h <= 2^18, 2 <= max_levels <= 1024)"); return CT_ERR_ARG;
     }
+    if (n_events > 0x7fffffffLL) { ct_set_error("cusum: more than 2^31-1 events in one batch"); return CT_ERR_UNSUPPORTED; }
+    if (workspace_bytes < ct_cusum_workspace_bytes(n_events) || (reinterpret_cast<uintptr_t>(workspace) & 7)) {
+        ct_set_error("cusum: workspace too small or unaligned"); return CT_ERR_ARG;
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(work_counter, 0, 8, st);
+    cudaMemsetAsync(workspace, 0, 24, st);
     if (n_events == 0) return CT_OK;
     // library-owned per-device reciprocal table (built once with the oracle's operations)
     static double* tabs[64] = {nullptr};
@@ -349,31 +545,49 @@ static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_star
     a.rctab = tabs[dev];
     a.y = y; a.ntot = n_total; a.w0 = (const long long*)win_start; a.w1 = (const long long*)win_end; a.type = type;
     a.nev = n_events; a.nev_dev = (const long long*)n_events_dev; a.delta = delta; a.h = h; a.max_levels = max_levels; a.n_levels = n_levels; a.edges = edges;
-    a.mean = level_mean; a.sd = level_std; a.overflow = overflow; a.counter = (unsigned long long*)work_counter;
+    a.mean = level_mean; a.sd = level_std; a.overflow = overflow; a.counter = (unsigned long long*)workspace;
+    a.pending = reinterpret_cast<int*>((unsigned long long*)workspace + 3);
+    // rows of events nobody processes (rejected types) keep edges == -1
+    cudaMemsetAsync(edges, 0xff, (size_t)n_events * (size_t)(max_levels + 1) * sizeof(int32_t), st);
+    const int sms = ct_sm_count();
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_cusum_kernel, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_cusum_seq_kernel, 256, 0);
     if (occ < 1) occ = 1;
-    long long grid = (long long)ct_sm_count() * occ;
-    long long want = (n_events + 3) / 4;
+    long long grid = (long long)sms * occ;
+    long long want = (n_events + 255) / 256;
     if (grid > want) grid = want;
     CT_COUNT_LAUNCH();
-    ct_cusum_kernel<<<(unsigned)grid, 128, 0, st>>>(a);
-    return ct_check_launch("ct_cusum_kernel");
+    ct_cusum_seq_kernel<<<(unsigned)grid, 256, 0, st>>>(a);
+    int rc = ct_check_launch("ct_cusum_seq_kernel"); if (rc) return rc;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_cusum_warp_kernel, 128, 0);
+    if (occ < 1) occ = 1;
+    grid = (long long)sms * occ;
+    want = (n_events + 3) / 4;
+    if (grid > want) grid = want;
+    CT_COUNT_LAUNCH();
+    ct_cusum_warp_kernel<<<(unsigned)grid, 128, 0, st>>>(a);
+    rc = ct_check_launch("ct_cusum_warp_kernel"); if (rc) return rc;
+    grid = (n_events + 255) / 256;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    CT_COUNT_LAUNCH();
+    ct_cusum_finalize_kernel<<<(unsigned)grid, 256, 0, st>>>(a);
+    return ct_check_launch("ct_cusum_finalize_kernel");
 }
 
 extern "C" int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                               const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
                               int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
-                              uint8_t* overflow, uint64_t* work_counter, void* stream) {
+                              uint8_t* overflow, void* workspace, int64_t workspace_bytes, void* stream) {
     return cusum_launch(y, n_total, win_start, win_end, type, n_events, nullptr, delta, h, max_levels, n_levels, edges,
-                        level_mean, level_std, overflow, work_counter, stream);
+                        level_mean, level_std, overflow, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ct_cusum_batch_dev(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                                   const int32_t* type, const int64_t* n_events_dev, int64_t capacity, float delta,
                                   float h, int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean,
-                                  double* level_std, uint8_t* overflow, uint64_t* work_counter, void* stream) {
+                                  double* level_std, uint8_t* overflow, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
     if (!n_events_dev) { ct_set_error("cusum: null event count pointer"); return CT_ERR_ARG; }
     return cusum_launch(y, n_total, win_start, win_end, type, capacity, n_events_dev, delta, h, max_levels, n_levels,
-                        edges, level_mean, level_std, overflow, work_counter, stream);
+                        edges, level_mean, level_std, overflow, workspace, workspace_bytes, stream);
 }

@@ -48,11 +48,13 @@ def cusum_levels(y: torch.Tensor, win_start: torch.Tensor, win_end: torch.Tensor
     mu = torch.zeros((E, max_levels), dtype=torch.float64, device=dev)
     sd = torch.zeros((E, max_levels), dtype=torch.float64, device=dev)
     ov = torch.zeros(E, dtype=torch.uint8, device=dev)
-    ctr = torch.zeros(1, dtype=torch.int64, device=dev)
-    rc = _lib.lib().ct_cusum_batch(y.data_ptr(), y.numel(), win_start.data_ptr(), win_end.data_ptr(),
+    L = _lib.lib()
+    wsb = int(L.ct_cusum_workspace_bytes(E))
+    ws = torch.empty((wsb + 7) // 8, dtype=torch.int64, device=dev)
+    rc = L.ct_cusum_batch(y.data_ptr(), y.numel(), win_start.data_ptr(), win_end.data_ptr(),
                                    types.data_ptr() if types is not None else None, E, float(delta), float(h),
                                    int(max_levels), nl.data_ptr(), ed.data_ptr(), mu.data_ptr(), sd.data_ptr(),
-                                   ov.data_ptr(), ctr.data_ptr(), _stream_ptr(y))
+                                   ov.data_ptr(), ws.data_ptr(), wsb, _stream_ptr(y))
     _lib.check(rc, "ct_cusum_batch")
     return LevelTable(nl, ed, mu, sd, ov, int(max_levels))
 

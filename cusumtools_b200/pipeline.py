@@ -148,13 +148,15 @@ class TraceAnalyzer:
         self.w0 = torch.empty(cap, dtype=torch.int64, device=dev)
         self.w1 = torch.empty(cap, dtype=torch.int64, device=dev)
         self.typ = torch.empty(cap, dtype=torch.int32, device=dev)
-        self.scalars = torch.zeros(4, dtype=torch.int64, device=dev)     # n_starts, n_ends, n_kept, work counter
+        self.scalars = torch.zeros(4, dtype=torch.int64, device=dev)     # n_starts, n_ends, n_kept
         if self.delta is not None:
             self.nl = torch.empty(cap, dtype=torch.int32, device=dev)
             self.ed = torch.empty((cap, ML + 1), dtype=torch.int32, device=dev)
             self.mu = torch.empty((cap, ML), dtype=torch.float64, device=dev)
             self.sd = torch.empty((cap, ML), dtype=torch.float64, device=dev)
             self.ov = torch.empty(cap, dtype=torch.uint8, device=dev)
+            self.cws_bytes = int(_lib.lib().ct_cusum_workspace_bytes(cap))
+            self.cws = torch.empty((self.cws_bytes + 7) // 8, dtype=torch.int64, device=dev)
 
     def run(self, raw_ext: torch.Tensor) -> AnalysisResult:
         if raw_ext.numel() != self.n_ext:
@@ -185,7 +187,8 @@ class TraceAnalyzer:
                 rc = L.ct_cusum_batch_dev(yd.data_ptr(), self.n_det, self.w0.data_ptr(), self.w1.data_ptr(),
                                           self.typ.data_ptr(), sc[2:].data_ptr(), self.cap, float(self.delta),
                                           float(self.h), self.max_levels, self.nl.data_ptr(), self.ed.data_ptr(),
-                                          self.mu.data_ptr(), self.sd.data_ptr(), self.ov.data_ptr(), sc[3:].data_ptr(), st)
+                                          self.mu.data_ptr(), self.sd.data_ptr(), self.ov.data_ptr(), self.cws.data_ptr(),
+                                          self.cws_bytes, st)
                 _lib.check(rc, "ct_cusum_batch_dev")
             host = torch.cat((sc[:3], bl.dev["status"].to(torch.int64))).cpu().numpy()   # the step's one sync
             ns, ne, nk = int(host[0]), int(host[1]), int(host[2])

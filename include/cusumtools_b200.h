@@ -123,17 +123,20 @@ int ct_event_windows(const int64_t* starts, const int64_t* ends, const uint64_t*
  * skipped (type may be NULL).  Outputs per event: n_levels, edges[max_levels+1] (sample
  * offsets inside the window, edges[0] = 0, edges[n_levels] = length, unused = -1),
  * level mean / population std in pA (float64), overflow flag (more jumps than
- * max_levels-1).  work_counter: 8 bytes of device scratch.                             */
+ * max_levels-1).  workspace: ct_cusum_workspace_bytes(n_events) bytes of device scratch
+ * (8-byte aligned).  Windows of up to 16384 samples are segmented one event per lane, longer
+ * ones (and batches too small to fill the GPU that way) one event per warp.                */
+int64_t ct_cusum_workspace_bytes(int64_t n_events);
 int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                    const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
                    int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
-                   uint8_t* overflow, uint64_t* work_counter, void* stream);
+                   uint8_t* overflow, void* workspace, int64_t workspace_bytes, void* stream);
 /* Same with the event count read from device memory (n_events_dev[0], clamped to capacity):
  * the output arrays must hold `capacity` rows; rows at or beyond the count are not written. */
 int ct_cusum_batch_dev(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                        const int32_t* type, const int64_t* n_events_dev, int64_t capacity, float delta, float h,
                        int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
-                       uint8_t* overflow, uint64_t* work_counter, void* stream);
+                       uint8_t* overflow, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- stage 4: Welch PSD ------------------------------------------------------------
  * Replaces scipy.signal.welch(x, fs, nperseg=L) as called at plot-trace.py:442,
