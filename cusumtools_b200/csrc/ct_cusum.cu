@@ -506,6 +506,27 @@ __global__ void ct_cusum_finalize_kernel(CusumArgs a) {
     }
 }
 
+// ---- per-event extrema of the window samples (max_deviation_pA of events.csv) ---------
+__global__ void __launch_bounds__(256) ct_event_extrema_kernel(const float* __restrict__ y, long long ntot,
+                                                                const long long* __restrict__ w0, const long long* __restrict__ w1,
+                                                                long long nev, const long long* __restrict__ nev_dev,
+                                                                float* __restrict__ xmin, float* __restrict__ xmax) {
+    if (nev_dev) { const long long d = *nev_dev; nev = d < nev ? d : nev; }
+    const int lane = ct_lane();
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long ev = gw; ev < nev; ev += nw) {
+        long long a = w0[ev], b = w1[ev];
+        if (a < 0) a = 0;
+        if (b > ntot) b = ntot;
+        float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+        for (long long p = a + lane; p < b; p += 32) { const float v = y[p]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(CT_FULL, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(CT_FULL, hi, o)); }
+        if (lane == 0) { xmin[ev] = lo; xmax[ev] = hi; }
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t ct_cusum_workspace_bytes(int64_t n_events) { return 24 + 4 * (n_events > 0 ? n_events : 0) + 8; }
@@ -590,4 +611,17 @@ extern "C" int ct_cusum_batch_dev(const float* y, int64_t n_total, const int64_t
     if (!n_events_dev) { ct_set_error("cusum: null event count pointer"); return CT_ERR_ARG; }
     return cusum_launch(y, n_total, win_start, win_end, type, capacity, n_events_dev, delta, h, max_levels, n_levels,
                         edges, level_mean, level_std, overflow, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ct_event_extrema_f32(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                                    int64_t n_events, const int64_t* n_events_dev, float* xmin, float* xmax, void* stream) {
+    if (!y || !win_start || !win_end || !xmin || !xmax || n_events < 0) { ct_set_error("event_extrema: bad argument"); return CT_ERR_ARG; }
+    if (n_events == 0) return CT_OK;
+    long long grid = (n_events + 7) / 8;
+    const long long cap = (long long)ct_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    CT_COUNT_LAUNCH();
+    ct_event_extrema_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        y, n_total, (const long long*)win_start, (const long long*)win_end, n_events, (const long long*)n_events_dev, xmin, xmax);
+    return ct_check_launch("ct_event_extrema_kernel");
 }

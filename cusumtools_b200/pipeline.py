@@ -41,42 +41,75 @@ def _all_reduce_(t: torch.Tensor, group) -> torch.Tensor:
     return t
 
 
-def global_code_median(raw_owned: torch.Tensor, mask: int, group=None) -> tuple[int, int]:
-    """Exact median (two middle order statistics) of the masked codes of the WHOLE trace
-    when each rank passes its owned samples; identical to filters.code_median for one rank."""
-    if group is None:
-        return filters.code_median(raw_owned, mask)
-    import torch.distributed as dist
-    L = _lib.lib()
-    dev = raw_owned.device
-    n_local = raw_owned.numel()
-    nt = torch.tensor([n_local], dtype=torch.int64, device=dev)
-    _all_reduce_(nt, group)
-    n = int(nt.item())
+def median_search(n_local: int, mask: int, hist_fn, count_fn, group=None, device=None) -> tuple[int, int]:
+    """Host side of the exact global median: the two middle order statistics of the masked
+    codes of ALL ranks.  `hist_fn(stride)` returns this rank's strided-sample histogram
+    (int tensor[65536]) and `count_fn(lo, step)` its 9 window counters (#codes < lo, then
+    #codes == lo + i*step); both are summed over `group` here, so every rank takes the same
+    decisions and returns the same pair.  (The device kernels are passed in, which is what
+    lets the world-size-2 gloo test drive this logic on CPU.)"""
+    nt = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    n = int(_all_reduce_(nt, group).item())
+    if n == 0:
+        raise ValueError("median of an empty trace")
     shift = 0
     while shift < 16 and not (mask >> shift) & 1:
         shift += 1
     step = 1 << shift
     k1, k2 = (n - 1) // 2, n // 2
-    st = filters._stream_ptr(raw_owned)
     stride = max(1, n // (1 << 22))
-    h = torch.zeros(65536, dtype=torch.int32, device=dev)
-    _lib.check(L.ct_hist_sampled_u16(raw_owned.data_ptr(), n_local, stride, mask, h.data_ptr(), st), "ct_hist_sampled_u16")
-    h = _all_reduce_(h.to(torch.int64), group)
+    h = _all_reduce_(hist_fn(stride).to(torch.int64), group)
     cdf = np.cumsum(h.cpu().numpy())
     if stride == 1:
         return int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
     est = int(np.searchsorted(cdf, (cdf[-1] + 1) // 2))
     lo = max(0, (est >> shift) * step - 3 * step)
     for _ in range(16):
-        cnt = torch.zeros(9, dtype=torch.int64, device=dev)
-        _lib.check(L.ct_count_window_u16(raw_owned.data_ptr(), n_local, mask, lo, step, cnt.data_ptr(), st), "ct_count_window_u16")
-        c = _all_reduce_(cnt, group).cpu().numpy().astype(np.int64)
+        c = _all_reduce_(count_fn(lo, step).to(torch.int64), group).cpu().numpy().astype(np.int64)
         below, cw = int(c[0]), int(c[0]) + np.cumsum(c[1:])
         if below <= k1 and k2 < cw[-1]:
             return lo + int(np.searchsorted(cw, k1 + 1)) * step, lo + int(np.searchsorted(cw, k2 + 1)) * step
         lo = max(0, lo - 6 * step) if k1 < below else lo + 6 * step
-    raise RuntimeError("median window search did not converge")
+    cdf = np.cumsum(_all_reduce_(hist_fn(1).to(torch.int64), group).cpu().numpy())   # pathological distribution
+    return int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
+
+
+def global_code_median(raw_owned: torch.Tensor, mask: int, group=None) -> tuple[int, int]:
+    """Exact median (two middle order statistics) of the masked codes of the WHOLE trace
+    when each rank passes its owned samples; identical to filters.code_median for one rank."""
+    if group is None:
+        return filters.code_median(raw_owned, mask)
+    L = _lib.lib()
+    dev = raw_owned.device
+    n_local = raw_owned.numel()
+    st = filters._stream_ptr(raw_owned)
+
+    def hist_fn(stride):
+        h = torch.zeros(65536, dtype=torch.int32, device=dev)
+        if n_local:
+            _lib.check(L.ct_hist_sampled_u16(raw_owned.data_ptr(), n_local, stride, mask, h.data_ptr(), st), "ct_hist_sampled_u16")
+        return h
+
+    def count_fn(lo, step):
+        cnt = torch.zeros(9, dtype=torch.int64, device=dev)
+        if n_local:
+            _lib.check(L.ct_count_window_u16(raw_owned.data_ptr(), n_local, mask, lo, step, cnt.data_ptr(), st), "ct_count_window_u16")
+        return cnt
+
+    return median_search(n_local, mask, hist_fn, count_fn, group, dev)
+
+
+def event_id_offsets(n_local_events: int, group=None, device=None) -> tuple[int, int]:
+    """(global id of this rank's first event, total events): ranks own consecutive time
+    shards, so ids follow rank order."""
+    if group is None:
+        return 0, int(n_local_events)
+    import torch.distributed as dist
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    counts = torch.zeros(ws, dtype=torch.int64, device=device)
+    counts[rk] = int(n_local_events)
+    c = _all_reduce_(counts, group).cpu().numpy()
+    return int(c[:rk].sum()), int(c.sum())
 
 
 def required_halo(cutoff: float, order: int, samplerate: float, max_event: int, padding: int = 1000,
@@ -206,15 +239,7 @@ class TraceAnalyzer:
         lv = None
         if self.delta is not None:
             lv = cusum.LevelTable(self.nl[:nk], self.ed[:nk], self.mu[:nk], self.sd[:nk], self.ov[:nk], self.max_levels)
-        first_id, total = 0, nk
-        if self.group is not None:
-            import torch.distributed as dist
-            ws, rk = dist.get_world_size(self.group), dist.get_rank(self.group)
-            counts = torch.zeros(ws, dtype=torch.int64, device=self.device)
-            counts[rk] = nk
-            _all_reduce_(counts, self.group)
-            c = counts.cpu().numpy()
-            first_id, total = int(c[:rk].sum()), int(c.sum())
+        first_id, total = event_id_offsets(nk, self.group, self.device)
         return AnalysisResult(filtered=y[lo:lo + n_own], detect_trace=yd, baseline=bl, events=ev,
                               win_start=self.w0[:nk], win_end=self.w1[:nk], types=self.typ[:nk], levels=lv,
                               pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id, total_events=total)

@@ -110,3 +110,60 @@ def spectrum_sample(raw: torch.Tensor, samplerate: float, psdlength, cutoff: flo
     Pxx *= cutoff / current ** 2
     Pxx *= f
     return f, Pxx, current
+
+
+# ---------------------------------------------------------------- exports
+def export_psd(path: str, f: np.ndarray, Pxx: np.ndarray, rms: np.ndarray) -> None:
+    """`App.export_psd` (plot-trace.py:204-207): rows `f,Pxx,rms`, numpy's default '%.18e'."""
+    np.savetxt(path, np.c_[f, Pxx, rms], delimiter=",")
+
+
+def export_psd_tsv(path: str, f: np.ndarray, Pxx: np.ndarray, current: float, bandwidth: float) -> None:
+    """The 4-column tab-separated `.psd` file `legacy/psdfit.py:27` reads
+    (`names=['f','S','integral','norm']`, no header): frequency, PSD, cumulative integral
+    of the PSD (the square of `integrate_noise`), and the PSD normalised as
+    plot-trace.py:445-447 does (`S * bandwidth / I^2`)."""
+    df = f[1] - f[0]
+    integral = np.cumsum(Pxx * df)
+    norm = Pxx / float(current) ** 2 * float(bandwidth)
+    np.savetxt(path, np.c_[f, Pxx, integral, norm], delimiter="\t")
+
+
+# ------------------------------------------------------------------ multi-GPU (SURVEY.md 8e)
+def segment_share(n: int, nperseg: int, world: int, rank: int) -> tuple[int, int, int, int]:
+    """Contiguous block of Welch segments owned by `rank` and the samples it must hold:
+    (first_segment, last_segment_exclusive, first_sample, last_sample_exclusive).  Segment s
+    covers samples [s*hop, s*hop + L), hop = L/2, s < (n - L/2) // hop (scipy's count)."""
+    L = int(nperseg)
+    hop = L // 2
+    nseg = max(0, (int(n) - (L - hop)) // hop)
+    per = -(-nseg // int(world))
+    s0, s1 = min(nseg, rank * per), min(nseg, (rank + 1) * per)
+    return s0, s1, s0 * hop, (s1 - 1) * hop + L if s1 > s0 else s0 * hop
+
+
+def reduce_sums(acc: torch.Tensor, nseg: int, group=None):
+    """Sum the per-rank periodogram sums and segment counts over `group` (the one collective
+    of the PSD stage: L/2+1 float64 values + one integer); returns (acc numpy, nseg)."""
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        t = torch.tensor([int(nseg)], dtype=torch.int64, device=acc.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        nseg = int(t.item())
+    return acc.cpu().numpy(), int(nseg)
+
+
+def welch_sharded(x_local: torch.Tensor, samplerate: float, nperseg, *, use_abs: bool = False, shift: float | None = None,
+                  group=None):
+    """`welch` over a trace whose segments are split over the ranks of `group`: `x_local`
+    holds exactly the samples `segment_share` assigns to this rank.  Every rank must pass
+    the same `shift` (any constant near the global mean; None = 0 for sharded calls would
+    lose float32 headroom, so the caller passes the pad value / global baseline)."""
+    L = int(nperseg)
+    if x_local.numel() >= L:
+        acc, nseg = welch_sums(x_local, L, use_abs=use_abs, shift=shift)
+    else:
+        acc, nseg = torch.zeros(L // 2 + 1, dtype=torch.float64, device=x_local.device), 0
+    a, n = reduce_sums(acc, nseg, group)
+    return scale_sums(a, n, samplerate, L)

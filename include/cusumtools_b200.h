@@ -138,6 +138,11 @@ int ct_cusum_batch_dev(const float* y, int64_t n_total, const int64_t* win_start
                        int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
                        uint8_t* overflow, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Minimum and maximum sample of every event window (max_deviation_pA of events.csv,
+ * mosaicConverter.py:105 / readevents.py:1499); n_events_dev may be NULL.                  */
+int ct_event_extrema_f32(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                         int64_t n_events, const int64_t* n_events_dev, float* xmin, float* xmax, void* stream);
+
 /* ---- stage 4: Welch PSD ------------------------------------------------------------
  * Replaces scipy.signal.welch(x, fs, nperseg=L) as called at plot-trace.py:442,
  * noise-fit.py:92 (use_abs != 0: welch(|x|)), legacy/minimal_psd.py:255: periodic Hann,

@@ -84,3 +84,31 @@ def test_no_valid_baseline_block_raises():
                                 baseline_min=100.0, baseline_max=200.0)
     with pytest.raises(ValueError):
         an.run(torch.from_numpy(codes).cuda())
+
+
+def test_event_table_and_analysis_dir_from_the_gpu_path(tmp_path):
+    import pandas as pd
+    from cusumtools_b200 import writer
+    codes, true_starts = synth.c1_trace(n=400_000, n_events=95, seed=13)
+    an = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, baseline_block=65536, cusum_delta=400.0, cusum_h=10.0, **KW)
+    r = an.run(torch.from_numpy(codes).cuda())
+    y = r.detect_trace.cpu().numpy()
+    lo, hi = writer.event_extrema(r.detect_trace, r.win_start, r.win_end)
+    w0, w1 = r.win_start.cpu().numpy(), r.win_end.cpu().numpy()
+    assert np.array_equal(lo.cpu().numpy(), [y[max(a, 0):b].min() for a, b in zip(w0, w1)])
+    assert np.array_equal(hi.cpu().numpy(), [y[max(a, 0):b].max() for a, b in zip(w0, w1)])
+    tab = writer.event_table_from_result(an, r, samplerate=synth.FS)
+    assert len(true_starts) - 1 <= len(tab) <= len(true_starts)
+    assert abs(np.median(tab.events["max_blockage_pA"]) - 1600) < 15 and np.median(tab.events["n_levels"]) == 3
+    assert np.all(np.abs(tab.events["start_time_s"] - (true_starts[:len(tab)] + 0.0) / synth.FS) < 60 / synth.FS)
+    ids = tab.events["id"][:3]
+    out = str(tmp_path / "an")
+    writer.write_analysis_dir(out, tab, baseline_mean=r.baseline.mean, baseline_std=r.baseline.std, baseline_block=an.block,
+                              samplerate=synth.FS, threshold=5.0, hysteresis=1.0, cutoff=1e5, poles=8,
+                              event_samples=writer.gather_event_samples(an, r, ids, tab))
+    db = pd.read_csv(out + "/events.csv")
+    assert len(db) == len(tab) and list(db.columns) == writer.EVENT_COLUMNS
+    ef = pd.read_csv(out + "/events/event_%08d.csv" % ids[0])
+    i = int(ids[0])
+    assert np.allclose(ef["current_pA"].values, y[w0[i]:w1[i]])
+    assert set(np.round(ef["cusum_fit"].values, 6)) == set(np.round(r.levels.mean.cpu().numpy()[i, :r.levels.n_levels[i].item()], 6))
