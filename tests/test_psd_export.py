@@ -18,8 +18,8 @@ def test_export_formats(tmp_path):
     q = tmp_path / "trace.psd"
     psd.export_psd_tsv(str(q), f, P, current=5000.0, bandwidth=100000.0)
     tab = pd.read_csv(q, sep="\t", names=["f", "S", "integral", "norm"])       # legacy/psdfit.py:27
-    assert np.array_equal(tab["f"].values, f) and np.array_equal(tab["S"].values, P)
-    assert np.allclose(np.sqrt(tab["integral"].values), rms, rtol=1e-15)
-    assert np.allclose(tab["norm"].values, P / 5000.0 ** 2 * 1e5, rtol=1e-15)  # plot-trace.py:445-447
+    assert np.allclose(tab["f"].values, f, rtol=1e-15) and np.allclose(tab["S"].values, P, rtol=1e-15)
+    assert np.allclose(np.sqrt(tab["integral"].values), rms, rtol=1e-14)
+    assert np.allclose(tab["norm"].values, P / 5000.0 ** 2 * 1e5, rtol=1e-14)  # plot-trace.py:445-447
     fx = tab["f"].values[1:100]
     assert np.isfinite(np.log10(tab["norm"].values[1:100])).all() and fx[1] - fx[0] > 0   # what psdfit.py:28-31 uses
