@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcusumtools_b200.so")
+LIB_PATH = os.environ.get("CT_LIB_PATH") or os.path.join(_HERE, "libcusumtools_b200.so")   # override: A/B builds
 
 CT_MAX_SECTIONS = 5
 CT_SCAN_STEPS = 5
@@ -43,10 +43,12 @@ SIGNATURES = {
     "ct_device_info": (C.c_int, [_vp, _vp, _vp, _vp]),
     "ct_filter_tile": (C.c_int, []),
     "ct_filter_chunk": (C.c_int, []),
+    "ct_filter_seq_tile": (C.c_int, []),
+    "ct_filtfilt_workspace_bytes": (_i64, [_i64, _i64, C.c_int]),
     "ct_filtfilt_u16": (C.c_int, [_vp, _i64, _i64, _f32, _u16, _f32, _f32, C.POINTER(CtFilterCoef),
-                                  C.c_int, C.c_int, C.c_int, _vp, _vp]),
+                                  C.c_int, C.c_int, C.c_int, _vp, _vp, _i64, _vp]),
     "ct_filtfilt_f32": (C.c_int, [_vp, _i64, _i64, _f32, C.POINTER(CtFilterCoef), C.c_int, C.c_int,
-                                  C.c_int, _vp, _vp]),
+                                  C.c_int, _vp, _vp, _i64, _vp]),
     "ct_hist_sampled_u16": (C.c_int, [_vp, _i64, _i64, _u16, _vp, _vp]),
     "ct_count_window_u16": (C.c_int, [_vp, _i64, _u16, _u32, _u32, _vp, _vp]),
     "ct_block_stats_f32": (C.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, C.c_int, _vp, _vp, _vp, _vp]),

@@ -1,0 +1,487 @@
+// Zero-phase Bessel as two LANE-SEQUENTIAL passes (forward, then backward) for sm_100a.
+//
+// Why: the warp-scan formulation in ct_filter.cu resolves the lane-to-lane carries with a
+// zero-state run + Kogge-Stone scan + exact re-run, ~75 FP32 lane-operations per sample, and
+// is bound by the FMA pipe at 0.26 of the HBM roofline.  Here every lane owns whole RUNS of
+// R consecutive samples and simply executes the recurrence (the reference's own dataflow,
+// scipy _linear_filter, in cascade form): 4 FMA per section and sample, nothing else.  The
+// price is an IIR warm-up of Hw samples per run (|h| tail < eps, Hw/R ~ 6 %) and that the
+// forward output has to live somewhere until the backward pass reads it: an HBM scratch
+// (4 B/sample written + 4 B/sample read).
+//
+// Mapping: a warp owns 64 adjacent runs; lane l executes run l in the .x halves and run
+// 32+l in the .y halves of float2 registers (FFMA2: one issue slot for two recurrences).
+//
+// Data movement (the part that decides the speed: a lane-sequential kernel needs a
+// transposition between "lane = run" and "lane = consecutive address"):
+//   * the INPUT of the forward pass (natural layout) is fetched as whole 64/128-byte pieces
+//     with cp.async, one tile ahead, into a per-warp shared-memory tile whose row stride is
+//     bank-conflict free; lanes then walk their own row;
+//   * the SCRATCH between the passes is ours, so it is kept in a lane-interleaved layout:
+//     block ((group, tile, 8-sample slot, half)) = 32 lanes x 8 floats = 1 KB.  The forward
+//     pass writes it and the backward pass reads it with 256-bit accesses straight from /
+//     into registers, fully coalesced, with no shared memory at all;
+//   * the FINAL output (natural layout) is transposed back through shared memory and leaves
+//     as coalesced 128-byte pieces.
+//
+// Section arithmetic:  v[n] = x[n] + na1 v[n-1] + na2 v[n-2]        (all-pole part)
+//                      y[n] = x[n] + (na1+n1) v[n-1] + (na2+n2) v[n-2]   (= v + n1 v1 + n2 v2)
+// so the section output does not wait for v[n]: the cascade's dependent chain is 2 FMA per
+// section, and v[n] is off the critical path.
+#include "ct_common.cuh"
+#include "cusumtools_b200.h"
+
+namespace {
+
+#ifndef CT_SEQ_K
+#define CT_SEQ_K 64
+#endif
+constexpr int kK = CT_SEQ_K;        // samples per run per tile (one contiguous piece of global memory)
+constexpr int kG = kK / 8;          // 8-sample slots per tile
+constexpr int kRuns = 64;           // runs per warp (32 lanes x 2 halves)
+constexpr int kRowF = kK + 4;       // float row stride: conflict-free LDS.128 / STS.128
+constexpr int kRowH = kK + 8;       // uint16 row stride in halfwords ((kK+8)/2 words = 4 mod 16: conflict-free LDS.128)
+constexpr int kSeqWarps = 2;
+
+enum { kFwdScratch = 0, kFwdFinal = 1 };
+
+typedef float2 f2;
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 splat(float v) { return make_float2(v, v); }
+
+struct SeqArgs {
+    const void* in;        // FWD: codes (uint16) or samples (float), natural layout; BWD: interleaved scratch
+    float* out;            // kFwdScratch: interleaved scratch; otherwise the final output, natural layout
+    long long n_in;        // valid input positions [0, n_in): FWD n, BWD n + pad
+    long long n_out;       // final output positions [0, n_out)
+    long long ngroups;     // groups of 64 runs this launch processes
+    long long scratch_runs;// runs the scratch holds (BWD: reads beyond are the held value)
+    int R, Hw;             // run length, warm-up (multiples of kK, Hw <= R)
+    float sub; unsigned mask; float scale, offset;   // input x' = (code & mask) - sub ; out = offset + scale*y
+};
+
+struct u8x { unsigned w[8]; };
+static __device__ __forceinline__ u8x ldg256(const void* p) {
+    u8x r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
+                   "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    return r;
+}
+static __device__ __forceinline__ void stg256(float* p, const float (&f)[8]) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+}
+static __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+static __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> static __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <typename InT> struct Tile;
+template <> struct Tile<float> { static constexpr int kInBytes = kRuns * kRowF * 4; };
+template <> struct Tile<uint16_t> { static constexpr int kInBytes = kRuns * kRowH * 2; };
+constexpr int kOutBytes = kRuns * kRowF * 4;
+
+// float offset of the 8-sample slot (tile `to`, slot jj) of run `run` in the interleaved scratch
+static __device__ __forceinline__ long long scratch_off(long long run, int to, int jj, int TO) {
+    const long long g = run >> 6;
+    const int h = (int)(run >> 5) & 1, l = (int)run & 31;
+    return ((((g * TO + to) * kG + jj) * 2 + h) << 8) + l * 8;
+}
+
+// Forward-pass input tile: rows = the K-sample pieces [lo_r, lo_r + K) of the warp's 64 runs.
+// Fast path (whole tile inside the valid domain, 16-byte aligned): cp.async of 16-byte units;
+// otherwise guarded scalar fills (float: the pad value outside; uint16: codes, zeroed later).
+template <typename InT>
+__device__ __forceinline__ void fill_tile(const SeqArgs& a, char* buf, long long run0, long long off, int lane, bool in_aligned) {
+    const InT* in = reinterpret_cast<const InT*>(a.in);
+    const long long lo_first = run0 * a.R + off;
+    const long long lo_last = (run0 + kRuns - 1) * (long long)a.R + off;
+    const bool fast = in_aligned && lo_first >= 0 && lo_last + kK <= a.n_in;
+    if (sizeof(InT) == 4) {
+        float* t = reinterpret_cast<float*>(buf);
+        if (fast) {
+            constexpr int LPR = kK / 4, RPI = 32 / LPR;     // lanes per row (16 B each), rows per instruction
+#pragma unroll
+            for (int u = 0; u < kRuns / RPI; ++u) {
+                const int row = u * RPI + lane / LPR, c = (lane % LPR) * 4;
+                cp_async16(t + row * kRowF + c, in + (run0 + row) * a.R + off + c);
+            }
+        } else {
+            for (int i = lane; i < kRuns * kK; i += 32) {
+                const int row = i / kK, c = i % kK;
+                const long long p = (run0 + row) * a.R + off + c;
+                t[row * kRowF + c] = (p >= 0 && p < a.n_in) ? (float)in[p] : a.sub;
+            }
+        }
+    } else {
+        uint16_t* t = reinterpret_cast<uint16_t*>(buf);
+        if (fast) {
+            constexpr int LPR = kK / 8, RPI = 32 / LPR;
+#pragma unroll
+            for (int u = 0; u < kRuns / RPI; ++u) {
+                const int row = u * RPI + lane / LPR, c = (lane % LPR) * 8;
+                cp_async16(t + row * kRowH + c, in + (run0 + row) * a.R + off + c);
+            }
+        } else {
+            for (int i = lane; i < kRuns * kK; i += 32) {
+                const int row = i / kK, c = i % kK;
+                const long long p = (run0 + row) * a.R + off + c;
+                t[row * kRowH + c] = (p >= 0 && p < a.n_in) ? (uint16_t)in[p] : (uint16_t)0;
+            }
+        }
+    }
+}
+
+// one cascade step for the sample pair u (both halves); returns the cascade output
+template <int NSEC>
+__device__ __forceinline__ f2 cascade_step(f2 u, f2 (&v1)[NSEC], f2 (&v2)[NSEC], const f2 (&na1)[NSEC], const f2 (&na2)[NSEC],
+                                           const f2 (&c1)[NSEC], const f2 (&c2)[NSEC], const f2 gl) {
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        const f2 vn = fma2(na1[s], v1[s], fma2(na2[s], v2[s], u));
+        const f2 yo = fma2(c1[s], v1[s], fma2(c2[s], v2[s], s == NSEC - 1 ? __fmul2_rn(gl, u) : u));
+        v2[s] = v1[s]; v1[s] = vn;
+        u = yo;
+    }
+    return u;
+}
+
+// cooperative, coalesced store of the 64 output pieces (each 128 bytes) of one tile, natural layout
+__device__ __forceinline__ void store_tile(const SeqArgs& a, const float* outb, long long run0, long long off, int lane, bool out_aligned) {
+    const long long plo = run0 * a.R + off, phi = (run0 + kRuns - 1) * (long long)a.R + off + kK;
+    if (out_aligned && plo >= 0 && phi <= a.n_out) {
+        constexpr int LPR = kK / 4, RPI = 32 / LPR;
+#pragma unroll
+        for (int u = 0; u < kRuns / RPI; ++u) {
+            const int row = u * RPI + lane / LPR, c = (lane % LPR) * 4;
+            float4 v = *reinterpret_cast<const float4*>(outb + row * kRowF + c);
+            v.x = fmaf(v.x, a.scale, a.offset); v.y = fmaf(v.y, a.scale, a.offset);
+            v.z = fmaf(v.z, a.scale, a.offset); v.w = fmaf(v.w, a.scale, a.offset);
+            ct_stg_stream(a.out + (run0 + row) * a.R + off + c, v);
+        }
+    } else {
+        for (int i = lane; i < kRuns * kK; i += 32) {
+            const int row = i / kK, c = i % kK;
+            const long long p = (run0 + row) * a.R + off + c;
+            if (p >= 0 && p < a.n_out) a.out[p] = fmaf(outb[row * kRowF + c], a.scale, a.offset);
+        }
+    }
+}
+
+// =============================== forward pass ========================================
+template <int NSEC, typename InT, int MODE>
+__global__ void __launch_bounds__(kSeqWarps * 32)
+ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
+    extern __shared__ __align__(16) char smem[];
+    constexpr int kIn = Tile<InT>::kInBytes;
+    constexpr int kPerWarp = 2 * kIn + (MODE == kFwdFinal ? kOutBytes : 0);
+    const int lane = ct_lane();
+    const int wib = threadIdx.x >> 5;
+    char* wbase = smem + (size_t)wib * kPerWarp;
+    float* outb = reinterpret_cast<float*>(wbase + 2 * kIn);
+    const long long gw = (long long)blockIdx.x * kSeqWarps + wib;
+    const long long nw = (long long)gridDim.x * kSeqWarps;
+    const bool in_aligned = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    const int ntiles = (a.Hw + a.R) / kK, wt = a.Hw / kK, TO = a.R / kK;
+
+    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        na1[s] = splat(k.na1[s]); na2[s] = splat(k.na2[s]);
+        const float g = (s == NSEC - 1) ? k.gain : 1.f;   // the overall gain rides on the last section's output
+        c1[s] = splat((k.na1[s] + k.n1[s]) * g); c2[s] = splat((k.na2[s] + k.n2[s]) * g);
+    }
+    const f2 gl = splat(k.gain);
+    const unsigned m2 = a.mask | (a.mask << 16);
+
+    for (long long g = gw; g < a.ngroups; g += nw) {
+        const long long run0 = g * kRuns;
+        f2 v1[NSEC], v2[NSEC];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(0.f, 0.f); v2[s] = v1[s]; }
+        __syncwarp();
+        fill_tile<InT>(a, wbase, run0, -(long long)a.Hw, lane, in_aligned);
+        cp_commit();
+        for (int t = 0; t < ntiles; ++t) {
+            const long long off = (long long)t * kK - a.Hw;          // tile t covers r*R + off + [0, K)
+            if (t + 1 < ntiles) fill_tile<InT>(a, wbase + (((t + 1) & 1) ? kIn : 0), run0, off + kK, lane, in_aligned);
+            cp_commit();
+            cp_wait<1>();
+            __syncwarp();
+            const bool store = t >= wt;
+            const long long lo0 = (run0 + lane) * a.R + off, lo1 = lo0 + 32LL * a.R;
+            const bool edge = sizeof(InT) == 2 && !(lo0 >= 0 && lo1 + kK <= a.n_in);
+            const char* ib = wbase + ((t & 1) ? kIn : 0);
+            uint4 ra[2], rb[2];
+            auto load_group = [&](int jj) {
+                if (sizeof(InT) == 4) {
+                    const float* t0 = reinterpret_cast<const float*>(ib) + lane * kRowF + jj * 8;
+                    const float* t1 = t0 + 32 * kRowF;
+                    ra[0] = *reinterpret_cast<const uint4*>(t0); ra[1] = *reinterpret_cast<const uint4*>(t0 + 4);
+                    rb[0] = *reinterpret_cast<const uint4*>(t1); rb[1] = *reinterpret_cast<const uint4*>(t1 + 4);
+                } else {
+                    const uint16_t* t0 = reinterpret_cast<const uint16_t*>(ib) + lane * kRowH + jj * 8;
+                    ra[0] = *reinterpret_cast<const uint4*>(t0);
+                    rb[0] = *reinterpret_cast<const uint4*>(t0 + 32 * kRowH);
+                }
+            };
+            load_group(0);
+#pragma unroll
+            for (int jj = 0; jj < kG; ++jj) {
+                f2 x[8];
+                if (sizeof(InT) == 4) {
+                    const unsigned wa[8] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w};
+                    const unsigned wb[8] = {rb[0].x, rb[0].y, rb[0].z, rb[0].w, rb[1].x, rb[1].y, rb[1].z, rb[1].w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = make_float2(__uint_as_float(wa[e]) - a.sub, __uint_as_float(wb[e]) - a.sub);
+                } else {
+                    const unsigned wa[4] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w}, wb[4] = {rb[0].x, rb[0].y, rb[0].z, rb[0].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const unsigned ma = wa[q] & m2, mb = wb[q] & m2;
+                        x[2 * q] = make_float2((float)(int)(ma & 0xffffu) - a.sub, (float)(int)(mb & 0xffffu) - a.sub);
+                        x[2 * q + 1] = make_float2((float)(int)(ma >> 16) - a.sub, (float)(int)(mb >> 16) - a.sub);
+                    }
+                    if (edge) {                            // x' is 0 in the pad and beyond it
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const long long p0 = lo0 + jj * 8 + e, p1 = lo1 + jj * 8 + e;
+                            if (!(p0 >= 0 && p0 < a.n_in)) x[e].x = 0.f;
+                            if (!(p1 >= 0 && p1 < a.n_in)) x[e].y = 0.f;
+                        }
+                    }
+                }
+                if (jj + 1 < kG) load_group(jj + 1);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl);
+                if (store) {
+                    if (MODE == kFwdScratch) {
+                        float oa[8], ob[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { oa[e] = x[e].x; ob[e] = x[e].y; }
+                        float* dst = a.out + scratch_off(run0 + lane, t - wt, jj, TO);
+                        stg256(dst, oa);
+                        stg256(dst + 256, ob);
+                    } else {
+                        float* o0 = outb + lane * kRowF + jj * 8;
+                        float* o1 = o0 + 32 * kRowF;
+                        *reinterpret_cast<float4*>(o0) = make_float4(x[0].x, x[1].x, x[2].x, x[3].x);
+                        *reinterpret_cast<float4*>(o0 + 4) = make_float4(x[4].x, x[5].x, x[6].x, x[7].x);
+                        *reinterpret_cast<float4*>(o1) = make_float4(x[0].y, x[1].y, x[2].y, x[3].y);
+                        *reinterpret_cast<float4*>(o1 + 4) = make_float4(x[4].y, x[5].y, x[6].y, x[7].y);
+                    }
+                }
+            }
+            __syncwarp();
+            if (MODE == kFwdFinal && store) {
+                store_tile(a, outb, run0, off, lane, out_aligned);
+                __syncwarp();
+            }
+        }
+        cp_wait<0>();
+    }
+}
+
+// =============================== backward pass =======================================
+// Reads the interleaved scratch; run r processes positions r*R + R + Hw - 1 down to r*R, the first
+// Hw of them (the first Hw/K tiles of run r+1) only to warm the recursion up.
+template <int NSEC>
+__global__ void __launch_bounds__(kSeqWarps * 32, 8)
+ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
+    extern __shared__ __align__(16) char smem[];
+    const int lane = ct_lane();
+    const int wib = threadIdx.x >> 5;
+    float* outb = reinterpret_cast<float*>(smem + (size_t)wib * kOutBytes);
+    const float* y1 = reinterpret_cast<const float*>(a.in);
+    const long long gw = (long long)blockIdx.x * kSeqWarps + wib;
+    const long long nw = (long long)gridDim.x * kSeqWarps;
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    const int ntiles = (a.Hw + a.R) / kK, wt = a.Hw / kK, TO = a.R / kK;
+
+    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        na1[s] = splat(k.na1[s]); na2[s] = splat(k.na2[s]);
+        const float g = (s == NSEC - 1) ? k.gain : 1.f;
+        c1[s] = splat((k.na1[s] + k.n1[s]) * g); c2[s] = splat((k.na2[s] + k.n2[s]) * g);
+    }
+    const f2 gl = splat(k.gain);
+    // the forward output is held constant beyond n_in (scipy: zi * y[-1], _signaltools.py:4910-4913)
+    const long long last = a.n_in - 1;
+    const float hold = y1[scratch_off(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 3), TO) + (last & 7)];
+
+    for (long long g = gw; g < a.ngroups; g += nw) {
+        const long long run0 = g * kRuns;
+        const long long r0 = run0 + lane, r1 = r0 + 32;
+        f2 v1[NSEC], v2[NSEC];
+        {   // runs whose first processed position lies beyond the data start from the steady state of `hold`
+            const float h0 = r0 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
+            const float h1 = r1 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(h0 * k.ss[s], h1 * k.ss[s]); v2[s] = v1[s]; }
+        }
+        // slot q (0 .. ntiles*kG-1) in processing order: tile t = q / kG, jj = kG-1 - q % kG (descending positions)
+        auto fetch = [&](int q, u8x& xa, u8x& xb) {
+            const int t = q / kG, jj = kG - 1 - (q % kG);
+            const bool warm = t < wt;
+            const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
+            const long long s0 = warm ? r0 + 1 : r0, s1 = warm ? r1 + 1 : r1;
+            const long long p0 = s0 * a.R + (long long)to * kK + jj * 8, p1 = s1 * a.R + (long long)to * kK + jj * 8;
+            if (s0 < a.scratch_runs && p0 + 8 <= a.n_in) xa = ldg256(y1 + scratch_off(s0, to, jj, TO));
+            else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    xa.w[e] = __float_as_uint((s0 < a.scratch_runs && p0 + e < a.n_in) ? y1[scratch_off(s0, to, jj, TO) + e] : hold);
+            }
+            if (s1 < a.scratch_runs && p1 + 8 <= a.n_in) xb = ldg256(y1 + scratch_off(s1, to, jj, TO));
+            else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    xb.w[e] = __float_as_uint((s1 < a.scratch_runs && p1 + e < a.n_in) ? y1[scratch_off(s1, to, jj, TO) + e] : hold);
+            }
+        };
+        // register pipeline two slots deep (slot q+1 in flight while slot q+2 is issued into the
+        // buffer slot q just released); buffer index = j & 1 is static because kG is even
+        u8x pa[2], pb[2];
+        fetch(0, pa[0], pb[0]);
+        fetch(1, pa[1], pb[1]);
+        const int nslots = ntiles * kG;
+        for (int t = 0; t < ntiles; ++t) {
+            const bool store = t >= wt;
+#pragma unroll
+            for (int j = 0; j < kG; ++j) {
+                const int jj = kG - 1 - j;
+                f2 x[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = make_float2(__uint_as_float(pa[j & 1].w[e]), __uint_as_float(pb[j & 1].w[e]));
+                const int qn = t * kG + j + 2;
+                if (qn < nslots) fetch(qn, pa[j & 1], pb[j & 1]);
+#pragma unroll
+                for (int ee = 0; ee < 8; ++ee) { const int e = 7 - ee; x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl); }
+                if (store) {
+                    float* o0 = outb + lane * kRowF + jj * 8;
+                    float* o1 = o0 + 32 * kRowF;
+                    *reinterpret_cast<float4*>(o0) = make_float4(x[0].x, x[1].x, x[2].x, x[3].x);
+                    *reinterpret_cast<float4*>(o0 + 4) = make_float4(x[4].x, x[5].x, x[6].x, x[7].x);
+                    *reinterpret_cast<float4*>(o1) = make_float4(x[0].y, x[1].y, x[2].y, x[3].y);
+                    *reinterpret_cast<float4*>(o1 + 4) = make_float4(x[4].y, x[5].y, x[6].y, x[7].y);
+                }
+            }
+            if (store) {
+                __syncwarp();
+                store_tile(a, outb, run0, (long long)(TO - 1 - (t - wt)) * kK, lane, out_aligned);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template <int NSEC, typename InT, int MODE>
+int launch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    auto kern = ct_filter_fwd_kernel<NSEC, InT, MODE>;
+    const int smem = kSeqWarps * (2 * Tile<InT>::kInBytes + (MODE == kFwdFinal ? kOutBytes : 0));
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSeqWarps * 32, smem);
+    if (occ < 1) occ = 1;
+    long long grid = (long long)ct_sm_count() * occ;
+    const long long want = (a.ngroups + kSeqWarps - 1) / kSeqWarps;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CT_COUNT_LAUNCH();
+    kern<<<(unsigned)grid, kSeqWarps * 32, smem, st>>>(a, k);
+    return ct_check_launch("ct_filter_fwd_kernel");
+}
+template <int NSEC>
+int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    auto kern = ct_filter_bwd_kernel<NSEC>;
+    const int smem = kSeqWarps * kOutBytes;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSeqWarps * 32, smem);
+    if (occ < 1) occ = 1;
+    long long grid = (long long)ct_sm_count() * occ;
+    const long long want = (a.ngroups + kSeqWarps - 1) / kSeqWarps;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CT_COUNT_LAUNCH();
+    kern<<<(unsigned)grid, kSeqWarps * 32, smem, st>>>(a, k);
+    return ct_check_launch("ct_filter_bwd_kernel");
+}
+
+template <typename InT, int MODE>
+int dispatch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    switch (k.nsec) {
+        case 1: return launch_fwd<1, InT, MODE>(a, k, st);
+        case 2: return launch_fwd<2, InT, MODE>(a, k, st);
+        case 3: return launch_fwd<3, InT, MODE>(a, k, st);
+        case 4: return launch_fwd<4, InT, MODE>(a, k, st);
+        case 5: return launch_fwd<5, InT, MODE>(a, k, st);
+    }
+    ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
+    return CT_ERR_ARG;
+}
+int dispatch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    switch (k.nsec) {
+        case 1: return launch_bwd<1>(a, k, st);
+        case 2: return launch_bwd<2>(a, k, st);
+        case 3: return launch_bwd<3>(a, k, st);
+        case 4: return launch_bwd<4>(a, k, st);
+        case 5: return launch_bwd<5>(a, k, st);
+    }
+    ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
+    return CT_ERR_ARG;
+}
+
+// Run length for a trace of n samples: long runs amortise the warm-up, but there must be enough
+// runs to fill the GPU (64 runs per warp, several warps per SM sub-partition).  Hw <= R always.
+int pick_run(long long n, int Hw) {
+    const long long target_runs = (long long)ct_sm_count() * 12 * kRuns;
+    long long R = 4096;
+    while (R > 256 && (n + R - 1) / R < target_runs) R >>= 1;
+    while (R < Hw) R <<= 1;
+    return (int)R;
+}
+
+}  // namespace
+
+extern "C" int64_t ct_filtfilt_workspace_bytes(int64_t n, int64_t pad, int H) {
+    const int Hw = (H + kK - 1) / kK * kK;
+    const int R = pick_run(n + pad, Hw);
+    const long long ngroups = (n + pad + (long long)R * kRuns - 1) / ((long long)R * kRuns);
+    return (int64_t)(ngroups * kRuns * (long long)R * 4 + 256);
+}
+
+// in_kind: 0 = uint16 codes, 1 = float32 samples
+int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float scale,
+                    float offset, const CtFilterCoef* coef, int H, int forward_only, float* out, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t st) {
+    const int Hw = (H + kK - 1) / kK * kK;
+    SeqArgs a;
+    a.in = in; a.n_in = n; a.sub = sub; a.mask = mask; a.scale = scale; a.offset = offset; a.Hw = Hw; a.scratch_runs = 0;
+    if (forward_only) {
+        a.R = pick_run(n, Hw);
+        a.ngroups = (n + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
+        a.out = out; a.n_out = n;
+        return in_kind ? dispatch_fwd<float, kFwdFinal>(a, *coef, st) : dispatch_fwd<uint16_t, kFwdFinal>(a, *coef, st);
+    }
+    if (!workspace || workspace_bytes < ct_filtfilt_workspace_bytes(n, pad, H) || (reinterpret_cast<uintptr_t>(workspace) & 31)) {
+        ct_set_error("filter: workspace missing, too small or not 32-byte aligned"); return CT_ERR_ARG;
+    }
+    float* y1 = reinterpret_cast<float*>(workspace);
+    const long long n1 = n + pad;
+    a.R = pick_run(n1, Hw);
+    a.ngroups = (n1 + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
+    a.out = y1; a.n_out = 0;
+    int rc = in_kind ? dispatch_fwd<float, kFwdScratch>(a, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch>(a, *coef, st);
+    if (rc) return rc;
+    SeqArgs b = a;                                        // backward pass over the forward output
+    b.in = y1; b.n_in = n1; b.out = out; b.n_out = n; b.sub = 0.f;
+    b.scratch_runs = a.ngroups * kRuns;
+    b.ngroups = (n + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
+    return dispatch_bwd(b, *coef, st);
+}

@@ -86,11 +86,25 @@ def halo_samples(design: BesselDesign, eps: float = DEFAULT_HALO_EPS) -> int:
 
 
 def _plan(design: BesselDesign, halo_eps: float, subsegment: int | None):
+    """(S, H) for the kernel: subsegment None selects the lane-sequential passes (S = 0, H =
+    raw warm-up length), a number the warp-scan kernel with that sub-segment length."""
+    if not subsegment:
+        return 0, max(1, design.impulse_tail(halo_eps))
     T = _lib.lib().ct_filter_tile()
     H = halo_samples(design, halo_eps)
-    S = subsegment or DEFAULT_SUBSEGMENT
-    S = max(T, (S + T - 1) // T * T)
+    S = max(T, (int(subsegment) + T - 1) // T * T)
     return S, H
+
+
+def _workspace(n: int, padding: int, S: int, H: int, forward_only: bool, device, workspace):
+    """Device scratch for the forward output of the lane-sequential path (caller may pass a
+    reusable uint8 tensor)."""
+    if S or forward_only:
+        return None, 0
+    need = int(_lib.lib().ct_filtfilt_workspace_bytes(n, padding, H))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=device)
+    return workspace, need
 
 
 def _stream_ptr(t: torch.Tensor) -> C.c_void_p:
@@ -187,9 +201,9 @@ def code_median(raw: torch.Tensor, mask: int = 0xFFFF) -> tuple[int, int]:
 def filtfilt_codes(raw: torch.Tensor, *, alpha: float, pad_value: float, median_code: float, mask: int,
                    design: BesselDesign, padding: int = 1000, forward_only: bool = False,
                    halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
-                   out: torch.Tensor | None = None) -> torch.Tensor:
+                   out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """out = pad_value + alpha * filtfilt((raw & mask) - median_code) with the reference's
-    boundary handling; one fused kernel, 2 B read + 4 B written per sample."""
+    boundary handling (dequantisation fused into the load and the store)."""
     if raw.dtype not in (torch.uint16, torch.int16):
         raise TypeError("raw must hold the 16-bit ADC codes (torch.uint16 or the int16 view)")
     _require_cuda(raw, "raw", raw.dtype)
@@ -201,9 +215,11 @@ def filtfilt_codes(raw: torch.Tensor, *, alpha: float, pad_value: float, median_
         raise ValueError("out has the wrong length")
     coef = make_coef(design)
     S, H = _plan(design, halo_eps, subsegment)
+    ws, wsb = _workspace(n, int(padding), S, H, forward_only, raw.device, workspace)
     rc = _lib.lib().ct_filtfilt_u16(raw.data_ptr(), n, int(padding), float(median_code), int(mask),
                                     float(alpha), float(pad_value), C.byref(coef), S, H,
-                                    int(bool(forward_only)), out.data_ptr(), _stream_ptr(raw))
+                                    int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                    wsb, _stream_ptr(raw))
     _lib.check(rc, "ct_filtfilt_u16")
     return out
 
@@ -212,7 +228,7 @@ def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8,
                      samplerate: float | None = None, padding: int = 1000, forward_only: bool = False,
                      halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
                      median_codes: tuple[int, int] | None = None,
-                     out: torch.Tensor | None = None) -> torch.Tensor:
+                     out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """`App.scale_raw_data` + `App.filter_data` (plot-trace.py:272-287, 313-320) fused:
     raw Chimera codes on the GPU -> filtered pA (float32) on the GPU.
 
@@ -228,7 +244,7 @@ def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8,
     pad_value = float(np.median(vals))
     return filtfilt_codes(raw, alpha=alpha, pad_value=pad_value, median_code=0.5 * (c1 + c2), mask=mask,
                           design=design, padding=padding, forward_only=forward_only, halo_eps=halo_eps,
-                          subsegment=subsegment, out=out)
+                          subsegment=subsegment, out=out, workspace=workspace)
 
 
 def float_median(x: torch.Tensor, *, use_abs: bool = False) -> float:
@@ -262,7 +278,7 @@ def float_median(x: torch.Tensor, *, use_abs: bool = False) -> float:
 def bessel_filtfilt(x: torch.Tensor, samplerate: float, cutoff: float, order: int = 8, *,
                     pad_value: float | None = None, padding: int = 1000, forward_only: bool = False,
                     halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
-                    out: torch.Tensor | None = None) -> torch.Tensor:
+                    out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """Zero-phase Bessel of an already-dequantised float32 trace (e.g. `.bin` data,
     print_trace.py:33): out = pad_value + filtfilt(x - pad_value) with `padding` samples
     of constant pad, i.e. filtfilt(b, a, np.pad(x, padding, constant=pad_value),
@@ -278,8 +294,10 @@ def bessel_filtfilt(x: torch.Tensor, samplerate: float, cutoff: float, order: in
     design = bessel_lowpass(int(order), 2.0 * float(cutoff) / float(samplerate))
     coef = make_coef(design)
     S, H = _plan(design, halo_eps, subsegment)
+    ws, wsb = _workspace(n, int(padding), S, H, forward_only, x.device, workspace)
     rc = _lib.lib().ct_filtfilt_f32(x.data_ptr(), n, int(padding), float(pad_value), C.byref(coef), S, H,
-                                    int(bool(forward_only)), out.data_ptr(), _stream_ptr(x))
+                                    int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                    wsb, _stream_ptr(x))
     _lib.check(rc, "ct_filtfilt_f32")
     return out
 

@@ -56,19 +56,26 @@ int ct_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int6
  *   out[i] = pad_value + alpha * filtfilt(code - median_code)[i],  i in [0, n)
  * with the reference's boundary semantics (constant pad of `pad` samples each side,
  * steady-state initial conditions).  raw codes are masked with `mask` first
- * (plot-trace.py:281-282).  S (sub-segment) and H (IIR warm-up halo) are multiples of
- * ct_filter_tile(); forward_only != 0 gives the causal pass only (scipy.signal.lfilter
- * with zi = lfilter_zi*pad_value), the primitive filtfilt is built from.               */
+ * (plot-trace.py:281-282).  forward_only != 0 gives the causal pass only (scipy.signal.lfilter
+ * with zi = lfilter_zi*pad_value), the primitive filtfilt is built from.
+ *   S == 0 (default path): two lane-sequential passes; H = IIR warm-up per run (any value,
+ *     rounded up to ct_filter_seq_tile()); workspace = ct_filtfilt_workspace_bytes(n, pad, H)
+ *     bytes of device scratch (16-byte aligned) for the forward output, unused if forward_only.
+ *   S > 0: the single-kernel warp-scan formulation; S (sub-segment) and H are multiples of
+ *     ct_filter_tile(), no workspace needed.                                            */
 int ct_filter_tile(void);
+int ct_filter_seq_tile(void);
 int ct_filter_chunk(void);
+int64_t ct_filtfilt_workspace_bytes(int64_t n, int64_t pad, int H);
 int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_code, uint16_t mask,
                     float alpha, float pad_value, const CtFilterCoef* coef, int S, int H,
-                    int forward_only, float* out, void* stream);
+                    int forward_only, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 /* Same for already-dequantised float32 input (.bin traces, print_trace.py:33,
  * noise-fit.py:90; multi-gain file series, plot-trace.py:252-269):
  *   out = pad_value + filtfilt(x - pad_value).                                         */
 int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, const CtFilterCoef* coef,
-                    int S, int H, int forward_only, float* out, void* stream);
+                    int S, int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 
 /* Exact global median of the masked codes, the value np.pad(mode='median') needs
  * (plot-trace.py:319): a strided-sample histogram to locate it and an exact count of

@@ -146,3 +146,12 @@ def test_large_trace_properties():
     want = to.filter_data(x, synth.FS, 1e5, 8)[5000:-5000]
     got = y[lo:hi].cpu().numpy()
     assert np.abs(got - want).max() < ABS_TOL
+
+
+def test_lane_sequential_and_warp_scan_paths_agree():
+    """The default path (two lane-sequential passes) and the single-kernel warp-scan path
+    compute the same cascade with different association: they agree to float32 noise."""
+    codes, _ = synth.c1_trace(n=700000, n_events=170, seed=21)
+    a = gpu_filter(codes, 1e5, 8)
+    b = gpu_filter(codes, 1e5, 8, subsegment=4096)
+    assert np.abs(a - b).max() < 0.02
