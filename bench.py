@@ -184,7 +184,7 @@ def run_ours(args):
     raw = synth.device_trace(n_own + lo_h + hi_h, dev, seed=1234 + rank, start_index=rank * n_own - lo_h)
     have_cusum = True
     stage_ev = []
-    stage_names = ("median", "filter", "baseline", "detect", "windows+cusum")
+    stage_names = ("median", "filter", "baseline", "detect", "cusum")
     an = pipeline.TraceAnalyzer(raw.numel(), S, CUTOFF, ORDER, lo_halo=lo_h, hi_halo=hi_h, threshold=THRESHOLD,
                                 hysteresis=HYSTERESIS, baseline_block=BASELINE_BLOCK, baseline_min=BASELINE_MIN,
                                 baseline_max=BASELINE_MAX, event_padding=EVENT_PAD, minpoints=MINPOINTS,
@@ -196,33 +196,20 @@ def run_ours(args):
         return {"starts": r.events.starts, "ends": r.events.ends, "levels": r.levels}
 
     def staged_step():
-        """The same kernels launched stage by stage with CUDA events between them (only
-        for the per-stage breakdown; not part of the timed region)."""
-        marks = []
+        """The same run with a CUDA event after each stage's launches (only for the per-stage
+        breakdown; not part of the timed region)."""
+        marks = {}
 
-        def mark():
+        def hook(name):
             e = torch.cuda.Event(enable_timing=True)
             e.record()
-            marks.append(e)
+            marks[name] = e
 
-        mask = filters.chimera_bitmask(S)
-        owned = raw[lo_h:lo_h + n_own]
         torch.cuda.synchronize()
-        mark()
-        med = pipeline.global_code_median(owned, mask, group)
-        mark()
-        y = filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y)
-        mark()
-        yd = y[lo_h:]
-        bl = detect.baseline_blocks(yd, BASELINE_BLOCK, BASELINE_MIN, BASELINE_MAX, threshold=THRESHOLD, hysteresis=HYSTERESIS)
-        mark()
-        ev = detect.detect_events(yd, bl)
-        mark()
-        w0, w1, typ = detect.event_windows(ev.starts, ev.ends, yd.numel(), EVENT_PAD, MINPOINTS, MAXPOINTS)
-        cusum.cusum_levels(yd, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H, types=typ)
-        mark()
+        hook("start")
+        an.run(raw, stage_hook=hook)
         torch.cuda.synchronize()
-        stage_ev.append(marks)
+        stage_ev.append([marks[k] for k in ("start",) + stage_names])
 
     def fence():
         torch.cuda.synchronize()
@@ -298,7 +285,7 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("ct_filtfilt_kernel_bytes_per_sample")
+            traffic = json.load(f).get("filter_dram_bytes_per_sample")
             traffic = None if traffic is None else traffic * raw.numel()
     except Exception:
         pass
@@ -314,7 +301,8 @@ def run_ours(args):
         "events_per_s": int(ev_all.item()) / (ms_per_step / 1e3),
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms": stage_ms,
-        "roofline": {"kernel": "ct_filtfilt_kernel (fused dequantise + median pad + filtfilt)", "bound": "hbm",
+        "roofline": {"kernel": "ct_filter_fwd_kernel + ct_filter_bwd_kernel (dequantise + median pad + zero-phase Bessel; "
+                               "the backward pass also tallies the baseline block sums)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "kernel_ms": filt_ms,
                      "algorithmic_bytes_per_sample": FILTER_BYTES_PER_SAMPLE,

@@ -34,6 +34,12 @@ class CtFilterCoef(C.Structure):
 
 _vp, _i64, _i32, _f32, _u16, _u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint16, C.c_uint32
 
+
+class CtFilterStats(C.Structure):
+    _fields_ = [("origin", C.c_int64), ("block", C.c_int64), ("bmin", C.c_float), ("bmax", C.c_float),
+                ("c0", C.c_float), ("shift", C.c_int32), ("cnt", C.c_void_p), ("s1", C.c_void_p), ("s2", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/cusumtools_b200.h declares
 SIGNATURES = {
     "ct_version": (C.c_int, []),
@@ -45,10 +51,11 @@ SIGNATURES = {
     "ct_filter_chunk": (C.c_int, []),
     "ct_filter_seq_tile": (C.c_int, []),
     "ct_filtfilt_workspace_bytes": (_i64, [_i64, _i64, C.c_int]),
+    "ct_filtfilt_stats_granule": (_i64, [_i64, _i64, C.c_int]),
     "ct_filtfilt_u16": (C.c_int, [_vp, _i64, _i64, _f32, _u16, _f32, _f32, C.POINTER(CtFilterCoef),
-                                  C.c_int, C.c_int, C.c_int, _vp, _vp, _i64, _vp]),
+                                  C.c_int, C.c_int, C.c_int, _vp, _vp, _i64, C.POINTER(CtFilterStats), _vp]),
     "ct_filtfilt_f32": (C.c_int, [_vp, _i64, _i64, _f32, C.POINTER(CtFilterCoef), C.c_int, C.c_int,
-                                  C.c_int, _vp, _vp, _i64, _vp]),
+                                  C.c_int, _vp, _vp, _i64, C.POINTER(CtFilterStats), _vp]),
     "ct_hist_sampled_u16": (C.c_int, [_vp, _i64, _i64, _u16, _vp, _vp]),
     "ct_count_window_u16": (C.c_int, [_vp, _i64, _u16, _u32, _u32, _vp, _vp]),
     "ct_block_stats_f32": (C.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, C.c_int, _vp, _vp, _vp, _vp]),

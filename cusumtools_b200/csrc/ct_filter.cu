@@ -704,7 +704,7 @@ int check_common(const void* in, const float* out, long long n, long long pad, i
 // lane-sequential two-pass implementation (ct_filter_seq.cu)
 int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float scale,
                     float offset, const CtFilterCoef* coef, int H, int forward_only, float* out, void* workspace,
-                    int64_t workspace_bytes, cudaStream_t st);
+                    int64_t workspace_bytes, const CtFilterStats* stats, cudaStream_t st);
 
 extern "C" {
 
@@ -714,12 +714,14 @@ int ct_filter_chunk(void) { return kC; }
 
 int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_code, uint16_t mask,
                     float alpha, float pad_value, const CtFilterCoef* coef, int S, int H,
-                    int forward_only, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+                    int forward_only, float* out, void* workspace, int64_t workspace_bytes, const CtFilterStats* stats,
+                    void* stream) {
+    if (S != 0 && stats) { ct_set_error("filter: fused block statistics need the S == 0 path"); return CT_ERR_UNSUPPORTED; }
     if (S == 0) {                       // lane-sequential passes (the default path)
         if (!raw || !out || !coef || n < 0 || pad < 0 || H < 0) { ct_set_error("filter: bad argument"); return CT_ERR_ARG; }
         if (n == 0) return CT_OK;
         return ct_filtfilt_seq(raw, 0, n, pad, median_code, mask, alpha, pad_value, coef, H, forward_only, out, workspace,
-                               workspace_bytes, (cudaStream_t)stream);
+                               workspace_bytes, stats, (cudaStream_t)stream);
     }
     int rc = check_common(raw, out, n, pad, S, H, coef);
     if (rc) return rc;
@@ -736,12 +738,14 @@ int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_co
 }
 
 int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, const CtFilterCoef* coef,
-                    int S, int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+                    int S, int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
+                    const CtFilterStats* stats, void* stream) {
+    if (S != 0 && stats) { ct_set_error("filter: fused block statistics need the S == 0 path"); return CT_ERR_UNSUPPORTED; }
     if (S == 0) {
         if (!x || !out || !coef || n < 0 || pad < 0 || H < 0) { ct_set_error("filter: bad argument"); return CT_ERR_ARG; }
         if (n == 0) return CT_OK;
         return ct_filtfilt_seq(x, 1, n, pad, pad_value, 0xffff, 1.f, pad_value, coef, H, forward_only, out, workspace,
-                               workspace_bytes, (cudaStream_t)stream);
+                               workspace_bytes, stats, (cudaStream_t)stream);
     }
     int rc = check_common(x, out, n, pad, S, H, coef);
     if (rc) return rc;

@@ -58,7 +58,20 @@ struct SeqArgs {
     long long scratch_runs;// runs the scratch holds (BWD: reads beyond are the held value)
     int R, Hw;             // run length, warm-up (multiples of kK, Hw <= R)
     float sub; unsigned mask; float scale, offset;   // input x' = (code & mask) - sub ; out = offset + scale*y
+    long long base;        // position of run 0 (<= 0): shifts the run grid so that groups align with baseline blocks
+    // optional fused baseline block statistics of the final output (ct_block_stats_f32 semantics)
+    long long st_origin, st_block; float st_min, st_max, st_c0, st_scale;
+    long long* st_cnt; long long* st_s1; long long* st_s2;
 };
+
+// |q| < 2^31 by construction of the shift (detect.stats_shift: (half_width 2^shift + 1)^2 block < 2^62), so the
+// quantised value fits an int32 (full-rate F2I) and q*q + s2 is one IMAD.WIDE
+struct StatAcc { int c; long long s1, s2; };
+static __device__ __forceinline__ void tally(const SeqArgs& a, StatAcc& acc, float v) {
+    const bool in = v >= a.st_min && v <= a.st_max;
+    const int q = in ? __float2int_rn(__fmul_rn(__fsub_rn(v, a.st_c0), a.st_scale)) : 0;
+    acc.c += in ? 1 : 0; acc.s1 += q; acc.s2 += (long long)q * q;
+}
 
 struct u8x { unsigned w[8]; };
 static __device__ __forceinline__ u8x ldg256(const void* p) {
@@ -97,39 +110,31 @@ static __device__ __forceinline__ long long scratch_off(long long run, int to, i
 template <typename InT>
 __device__ __forceinline__ void fill_tile(const SeqArgs& a, char* buf, long long run0, long long off, int lane, bool in_aligned) {
     const InT* in = reinterpret_cast<const InT*>(a.in);
-    const long long lo_first = run0 * a.R + off;
-    const long long lo_last = (run0 + kRuns - 1) * (long long)a.R + off;
-    const bool fast = in_aligned && lo_first >= 0 && lo_last + kK <= a.n_in;
-    if (sizeof(InT) == 4) {
-        float* t = reinterpret_cast<float*>(buf);
-        if (fast) {
-            constexpr int LPR = kK / 4, RPI = 32 / LPR;     // lanes per row (16 B each), rows per instruction
+    constexpr int EPU = 16 / sizeof(InT);                 // elements per 16-byte unit
+    constexpr int LPR = kK / EPU, RPI = 32 / LPR;         // lanes per row, rows per instruction
+    constexpr int kRow = sizeof(InT) == 4 ? kRowF : kRowH;
+    InT* t = reinterpret_cast<InT*>(buf);
+    const long long first = a.base + run0 * a.R + off;
+    if (in_aligned && first >= 0 && first + (kRuns - 1) * (long long)a.R + kK <= a.n_in) {   // whole tile inside (warp-uniform)
+        const InT* src = in + first + (long long)(lane / LPR) * a.R + (lane % LPR) * EPU;
+        InT* dst = t + (lane / LPR) * kRow + (lane % LPR) * EPU;
+        const long long sstep = (long long)RPI * a.R;
 #pragma unroll
-            for (int u = 0; u < kRuns / RPI; ++u) {
-                const int row = u * RPI + lane / LPR, c = (lane % LPR) * 4;
-                cp_async16(t + row * kRowF + c, in + (run0 + row) * a.R + off + c);
-            }
-        } else {
-            for (int i = lane; i < kRuns * kK; i += 32) {
-                const int row = i / kK, c = i % kK;
-                const long long p = (run0 + row) * a.R + off + c;
-                t[row * kRowF + c] = (p >= 0 && p < a.n_in) ? (float)in[p] : a.sub;
-            }
-        }
-    } else {
-        uint16_t* t = reinterpret_cast<uint16_t*>(buf);
-        if (fast) {
-            constexpr int LPR = kK / 8, RPI = 32 / LPR;
+        for (int u = 0; u < kRuns / RPI; ++u) cp_async16(dst + u * RPI * kRow, src + u * sstep);
+        return;
+    }
+#pragma unroll 1
+    for (int u = 0; u < kRuns / RPI; ++u) {                // trace edges: per 16-byte unit
+        const int row = u * RPI + lane / LPR, c = (lane % LPR) * EPU;
+        const long long p = a.base + (run0 + row) * a.R + off + c;
+        InT* dst = t + row * kRow + c;
+        if (in_aligned && p >= 0 && p + EPU <= a.n_in) cp_async16(dst, in + p);
+        else {                                             // float gets the pad value, codes are zeroed later
 #pragma unroll
-            for (int u = 0; u < kRuns / RPI; ++u) {
-                const int row = u * RPI + lane / LPR, c = (lane % LPR) * 8;
-                cp_async16(t + row * kRowH + c, in + (run0 + row) * a.R + off + c);
-            }
-        } else {
-            for (int i = lane; i < kRuns * kK; i += 32) {
-                const int row = i / kK, c = i % kK;
-                const long long p = (run0 + row) * a.R + off + c;
-                t[row * kRowH + c] = (p >= 0 && p < a.n_in) ? (uint16_t)in[p] : (uint16_t)0;
+            for (int e = 0; e < EPU; ++e) {
+                const long long q = p + e;
+                if (sizeof(InT) == 4) dst[e] = (q >= 0 && q < a.n_in) ? in[q] : (InT)a.sub;
+                else dst[e] = (q >= 0 && q < a.n_in) ? in[q] : (InT)0;
             }
         }
     }
@@ -149,25 +154,37 @@ __device__ __forceinline__ f2 cascade_step(f2 u, f2 (&v1)[NSEC], f2 (&v2)[NSEC],
     return u;
 }
 
-// cooperative, coalesced store of the 64 output pieces (each 128 bytes) of one tile, natural layout
-__device__ __forceinline__ void store_tile(const SeqArgs& a, const float* outb, long long run0, long long off, int lane, bool out_aligned) {
-    const long long plo = run0 * a.R + off, phi = (run0 + kRuns - 1) * (long long)a.R + off + kK;
-    if (out_aligned && plo >= 0 && phi <= a.n_out) {
-        constexpr int LPR = kK / 4, RPI = 32 / LPR;
+// cooperative, coalesced store of the 64 output pieces of one tile, natural layout; STATS: the stored
+// values are tallied into the lane's baseline-block accumulators on their way out
+template <bool STATS>
+__device__ __forceinline__ void store_tile(const SeqArgs& a, const float* outb, long long run0, long long off, int lane,
+                                           bool out_aligned, StatAcc& acc) {
+    constexpr int LPR = kK / 4, RPI = 32 / LPR;
+    const long long first = a.base + run0 * a.R + off;
+    if (out_aligned && first >= 0 && first + (kRuns - 1) * (long long)a.R + kK <= a.n_out) {  // whole tile inside (warp-uniform)
+        float* dst = a.out + first + (long long)(lane / LPR) * a.R + (lane % LPR) * 4;
+        const float* src = outb + (lane / LPR) * kRowF + (lane % LPR) * 4;
+        const long long dstep = (long long)RPI * a.R;
 #pragma unroll
         for (int u = 0; u < kRuns / RPI; ++u) {
-            const int row = u * RPI + lane / LPR, c = (lane % LPR) * 4;
-            float4 v = *reinterpret_cast<const float4*>(outb + row * kRowF + c);
+            float4 v = *reinterpret_cast<const float4*>(src + u * RPI * kRowF);
             v.x = fmaf(v.x, a.scale, a.offset); v.y = fmaf(v.y, a.scale, a.offset);
             v.z = fmaf(v.z, a.scale, a.offset); v.w = fmaf(v.w, a.scale, a.offset);
-            ct_stg_stream(a.out + (run0 + row) * a.R + off + c, v);
+            ct_stg_stream(dst + u * dstep, v);
+            if (STATS) { tally(a, acc, v.x); tally(a, acc, v.y); tally(a, acc, v.z); tally(a, acc, v.w); }
         }
-    } else {
-        for (int i = lane; i < kRuns * kK; i += 32) {
-            const int row = i / kK, c = i % kK;
-            const long long p = (run0 + row) * a.R + off + c;
-            if (p >= 0 && p < a.n_out) a.out[p] = fmaf(outb[row * kRowF + c], a.scale, a.offset);
-        }
+        return;
+    }
+#pragma unroll 1
+    for (int u = 0; u < kRuns / RPI; ++u) {                // trace edges: per element
+        const int row = u * RPI + lane / LPR, c = (lane % LPR) * 4;
+        const long long p = a.base + (run0 + row) * a.R + off + c;
+        const float4 v = *reinterpret_cast<const float4*>(outb + row * kRowF + c);
+        const float w[4] = {fmaf(v.x, a.scale, a.offset), fmaf(v.y, a.scale, a.offset), fmaf(v.z, a.scale, a.offset),
+                            fmaf(v.w, a.scale, a.offset)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (p + e >= 0 && p + e < a.n_out) { a.out[p + e] = w[e]; if (STATS) tally(a, acc, w[e]); }
     }
 }
 
@@ -213,7 +230,7 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
             cp_wait<1>();
             __syncwarp();
             const bool store = t >= wt;
-            const long long lo0 = (run0 + lane) * a.R + off, lo1 = lo0 + 32LL * a.R;
+            const long long lo0 = a.base + (run0 + lane) * a.R + off, lo1 = lo0 + 32LL * a.R;
             const bool edge = sizeof(InT) == 2 && !(lo0 >= 0 && lo1 + kK <= a.n_in);
             const char* ib = wbase + ((t & 1) ? kIn : 0);
             uint4 ra[2], rb[2];
@@ -278,7 +295,8 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
             }
             __syncwarp();
             if (MODE == kFwdFinal && store) {
-                store_tile(a, outb, run0, off, lane, out_aligned);
+                StatAcc none;
+                store_tile<false>(a, outb, run0, off, lane, out_aligned, none);
                 __syncwarp();
             }
         }
@@ -289,7 +307,7 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
 // =============================== backward pass =======================================
 // Reads the interleaved scratch; run r processes positions r*R + R + Hw - 1 down to r*R, the first
 // Hw of them (the first Hw/K tiles of run r+1) only to warm the recursion up.
-template <int NSEC>
+template <int NSEC, bool STATS>
 __global__ void __launch_bounds__(kSeqWarps * 32, 8)
 ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
     extern __shared__ __align__(16) char smem[];
@@ -311,7 +329,7 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
     }
     const f2 gl = splat(k.gain);
     // the forward output is held constant beyond n_in (scipy: zi * y[-1], _signaltools.py:4910-4913)
-    const long long last = a.n_in - 1;
+    const long long last = a.n_in - 1 - a.base;           // relative to the run grid
     const float hold = y1[scratch_off(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 3), TO) + (last & 7)];
 
     for (long long g = gw; g < a.ngroups; g += nw) {
@@ -319,8 +337,8 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
         const long long r0 = run0 + lane, r1 = r0 + 32;
         f2 v1[NSEC], v2[NSEC];
         {   // runs whose first processed position lies beyond the data start from the steady state of `hold`
-            const float h0 = r0 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
-            const float h1 = r1 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
+            const float h0 = a.base + r0 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
+            const float h1 = a.base + r1 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
 #pragma unroll
             for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(h0 * k.ss[s], h1 * k.ss[s]); v2[s] = v1[s]; }
         }
@@ -330,7 +348,7 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
             const bool warm = t < wt;
             const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
             const long long s0 = warm ? r0 + 1 : r0, s1 = warm ? r1 + 1 : r1;
-            const long long p0 = s0 * a.R + (long long)to * kK + jj * 8, p1 = s1 * a.R + (long long)to * kK + jj * 8;
+            const long long p0 = a.base + s0 * a.R + (long long)to * kK + jj * 8, p1 = a.base + s1 * a.R + (long long)to * kK + jj * 8;
             if (s0 < a.scratch_runs && p0 + 8 <= a.n_in) xa = ldg256(y1 + scratch_off(s0, to, jj, TO));
             else {
 #pragma unroll
@@ -346,6 +364,7 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
         };
         // register pipeline two slots deep (slot q+1 in flight while slot q+2 is issued into the
         // buffer slot q just released); buffer index = j & 1 is static because kG is even
+        StatAcc acc; acc.c = 0; acc.s1 = 0; acc.s2 = 0;
         u8x pa[2], pb[2];
         fetch(0, pa[0], pb[0]);
         fetch(1, pa[1], pb[1]);
@@ -373,8 +392,22 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
             }
             if (store) {
                 __syncwarp();
-                store_tile(a, outb, run0, (long long)(TO - 1 - (t - wt)) * kK, lane, out_aligned);
+                store_tile<STATS>(a, outb, run0, (long long)(TO - 1 - (t - wt)) * kK, lane, out_aligned, acc);
                 __syncwarp();
+            }
+        }
+        if (STATS) {                                       // the group lies inside one baseline block (grid aligned by `base`)
+            long long c = acc.c, s1 = acc.s1, s2 = acc.s2;   // (a group has < 2^31 samples per lane)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c += __shfl_xor_sync(CT_FULL, c, o); s1 += __shfl_xor_sync(CT_FULL, s1, o); s2 += __shfl_xor_sync(CT_FULL, s2, o);
+            }
+            const long long rel = a.base + run0 * a.R - a.st_origin;
+            if (lane == 0 && c && rel >= 0) {
+                const long long kb = rel / a.st_block;
+                atomicAdd(reinterpret_cast<unsigned long long*>(a.st_cnt + kb), (unsigned long long)c);
+                atomicAdd(reinterpret_cast<unsigned long long*>(a.st_s1 + kb), (unsigned long long)s1);
+                atomicAdd(reinterpret_cast<unsigned long long*>(a.st_s2 + kb), (unsigned long long)s2);
             }
         }
     }
@@ -396,9 +429,9 @@ int launch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
     kern<<<(unsigned)grid, kSeqWarps * 32, smem, st>>>(a, k);
     return ct_check_launch("ct_filter_fwd_kernel");
 }
-template <int NSEC>
+template <int NSEC, bool STATS>
 int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    auto kern = ct_filter_bwd_kernel<NSEC>;
+    auto kern = ct_filter_bwd_kernel<NSEC, STATS>;
     const int smem = kSeqWarps * kOutBytes;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int occ = 0;
@@ -426,12 +459,13 @@ int dispatch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
     return CT_ERR_ARG;
 }
 int dispatch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    const bool stats = a.st_cnt != nullptr;
     switch (k.nsec) {
-        case 1: return launch_bwd<1>(a, k, st);
-        case 2: return launch_bwd<2>(a, k, st);
-        case 3: return launch_bwd<3>(a, k, st);
-        case 4: return launch_bwd<4>(a, k, st);
-        case 5: return launch_bwd<5>(a, k, st);
+        case 1: return stats ? launch_bwd<1, true>(a, k, st) : launch_bwd<1, false>(a, k, st);
+        case 2: return stats ? launch_bwd<2, true>(a, k, st) : launch_bwd<2, false>(a, k, st);
+        case 3: return stats ? launch_bwd<3, true>(a, k, st) : launch_bwd<3, false>(a, k, st);
+        case 4: return stats ? launch_bwd<4, true>(a, k, st) : launch_bwd<4, false>(a, k, st);
+        case 5: return stats ? launch_bwd<5, true>(a, k, st) : launch_bwd<5, false>(a, k, st);
     }
     ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
     return CT_ERR_ARG;
@@ -452,18 +486,28 @@ int pick_run(long long n, int Hw) {
 extern "C" int64_t ct_filtfilt_workspace_bytes(int64_t n, int64_t pad, int H) {
     const int Hw = (H + kK - 1) / kK * kK;
     const int R = pick_run(n + pad, Hw);
-    const long long ngroups = (n + pad + (long long)R * kRuns - 1) / ((long long)R * kRuns);
+    // one extra group: the run grid may be shifted left by up to a group to align with baseline blocks
+    const long long ngroups = (n + pad + (long long)R * kRuns - 1) / ((long long)R * kRuns) + 1;
     return (int64_t)(ngroups * kRuns * (long long)R * 4 + 256);
 }
 
-// in_kind: 0 = uint16 codes, 1 = float32 samples
+extern "C" int64_t ct_filtfilt_stats_granule(int64_t n, int64_t pad, int H) {
+    const int Hw = (H + kK - 1) / kK * kK;
+    return (int64_t)pick_run(n + pad, Hw) * kRuns;
+}
+
+// in_kind: 0 = uint16 codes, 1 = float32 samples.  stats (may be NULL): fused baseline block statistics
+// of the final output; the block grid starts at sample stats->origin of the output.
 int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float scale,
                     float offset, const CtFilterCoef* coef, int H, int forward_only, float* out, void* workspace,
-                    int64_t workspace_bytes, cudaStream_t st) {
+                    int64_t workspace_bytes, const CtFilterStats* stats, cudaStream_t st) {
     const int Hw = (H + kK - 1) / kK * kK;
     SeqArgs a;
     a.in = in; a.n_in = n; a.sub = sub; a.mask = mask; a.scale = scale; a.offset = offset; a.Hw = Hw; a.scratch_runs = 0;
+    a.base = 0; a.st_cnt = nullptr; a.st_s1 = nullptr; a.st_s2 = nullptr;
+    a.st_origin = 0; a.st_block = 1; a.st_min = a.st_max = a.st_c0 = a.st_scale = 0.f;
     if (forward_only) {
+        if (stats) { ct_set_error("filter: block statistics are fused into the zero-phase path only"); return CT_ERR_UNSUPPORTED; }
         a.R = pick_run(n, Hw);
         a.ngroups = (n + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
         a.out = out; a.n_out = n;
@@ -475,13 +519,30 @@ int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float s
     float* y1 = reinterpret_cast<float*>(workspace);
     const long long n1 = n + pad;
     a.R = pick_run(n1, Hw);
-    a.ngroups = (n1 + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
+    const long long G = (long long)a.R * kRuns;           // samples per warp group
+    if (stats) {
+        if (stats->block <= 0 || stats->block % G || stats->origin < 0 || !stats->cnt || !stats->s1 || !stats->s2) {
+            ct_set_error("filter: fused block statistics need block %% %lld == 0 (block = %lld)", G, (long long)stats->block);
+            return CT_ERR_ARG;
+        }
+        a.base = -((G - stats->origin % G) % G);          // groups then start at origin + k*G: never straddle a block
+        const long long nb = (n - stats->origin + stats->block - 1) / stats->block;
+        if (nb > 0) {
+            cudaMemsetAsync(stats->cnt, 0, nb * 8, st); cudaMemsetAsync(stats->s1, 0, nb * 8, st); cudaMemsetAsync(stats->s2, 0, nb * 8, st);
+        }
+    }
+    a.ngroups = (n1 - a.base + G - 1) / G;
     a.out = y1; a.n_out = 0;
     int rc = in_kind ? dispatch_fwd<float, kFwdScratch>(a, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch>(a, *coef, st);
     if (rc) return rc;
     SeqArgs b = a;                                        // backward pass over the forward output
     b.in = y1; b.n_in = n1; b.out = out; b.n_out = n; b.sub = 0.f;
     b.scratch_runs = a.ngroups * kRuns;
-    b.ngroups = (n + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
+    b.ngroups = (n - a.base + G - 1) / G;
+    if (stats) {
+        b.st_origin = stats->origin; b.st_block = stats->block; b.st_min = stats->bmin; b.st_max = stats->bmax;
+        b.st_c0 = stats->c0; b.st_scale = ldexpf(1.f, stats->shift);
+        b.st_cnt = (long long*)stats->cnt; b.st_s1 = (long long*)stats->s1; b.st_s2 = (long long*)stats->s2;
+    }
     return dispatch_bwd(b, *coef, st);
 }

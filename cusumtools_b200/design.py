@@ -93,6 +93,13 @@ class BesselDesign:
         """Smallest n with sum_{m>=n} |h[m]| < eps (h = causal impulse response).
         This is the IIR warm-up halo length H: starting the recursion n samples
         early from a wrong state leaves an error below eps * max|x - median|."""
+        cache = self.__dict__.setdefault("_tail_cache", {})
+        key = (float(eps), int(nmax))
+        if key not in cache:
+            cache[key] = self._impulse_tail(eps, nmax)
+        return cache[key]
+
+    def _impulse_tail(self, eps: float, nmax: int) -> int:
         n = 4096
         while True:
             h = self._impulse(n)

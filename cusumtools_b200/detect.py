@@ -122,6 +122,33 @@ class Baseline:
                 torch.from_numpy(np.ascontiguousarray(self._t_end, np.float32)).to(device))
 
 
+def new_baseline(n: int, block: int, baseline_min: float, baseline_max: float, device, min_count: int = 16) -> Baseline:
+    """An empty device-resident baseline table for a trace of `n` samples; the block sums are
+    filled either by `baseline_blocks` (own kernel) or by the filter (`stats_args`)."""
+    block = int(block)
+    nb = (int(n) + block - 1) // block
+    c0 = np.float32(0.5 * (np.float32(baseline_min) + np.float32(baseline_max)))
+    hw = max(float(c0) - float(np.float32(baseline_min)), float(np.float32(baseline_max)) - float(c0))
+    shift = stats_shift(hw, block)
+    m = max(nb, 1)
+    acc = torch.empty((3, m), dtype=torch.int64, device=device)
+    f64 = torch.empty((2, m), dtype=torch.float64, device=device)
+    lines = torch.empty((2, m), dtype=torch.float32, device=device)
+    d = {"cnt": acc[0, :nb], "s1": acc[1, :nb], "s2": acc[2, :nb], "mean": f64[0, :nb], "std": f64[1, :nb],
+         "sign": torch.empty(m, dtype=torch.int32, device=device)[:nb], "t_start": lines[0, :nb], "t_end": lines[1, :nb],
+         "status": torch.zeros(1, dtype=torch.int32, device=device), "c0": float(c0), "shift": shift,
+         "min_count": int(min_count), "have_thresholds": False, "bmin": float(baseline_min), "bmax": float(baseline_max)}
+    return Baseline(block, dev=d)
+
+
+def stats_args(bl: Baseline, origin: int = 0) -> "_lib.CtFilterStats":
+    """The filter-side description of `bl`'s block sums (ct_filtfilt_u16 `stats`): blocks are
+    counted from output sample `origin`."""
+    d = bl.dev
+    return _lib.CtFilterStats(int(origin), bl.block, d["bmin"], d["bmax"], d["c0"], d["shift"],
+                              d["cnt"].data_ptr(), d["s1"].data_ptr(), d["s2"].data_ptr())
+
+
 def baseline_blocks(y: torch.Tensor, block: int, baseline_min: float, baseline_max: float,
                     min_count: int = 16, *, threshold: float | None = None, hysteresis: float | None = None) -> Baseline:
     """Mean / population std of the samples inside [baseline_min, baseline_max] for every
@@ -130,30 +157,21 @@ def baseline_blocks(y: torch.Tensor, block: int, baseline_min: float, baseline_m
     trip; the arithmetic is oracle/events_oracle.py::baseline_from_stats, operation for
     operation."""
     _require_cuda(y, "y", torch.float32)
-    L = _lib.lib()
     n = y.numel()
-    block = int(block)
-    nb = (n + block - 1) // block
-    c0 = np.float32(0.5 * (np.float32(baseline_min) + np.float32(baseline_max)))
-    hw = max(float(c0) - float(np.float32(baseline_min)), float(np.float32(baseline_max)) - float(c0))
-    shift = stats_shift(hw, block)
-    dev = y.device
-    m = max(nb, 1)
-    acc = torch.empty((3, m), dtype=torch.int64, device=dev)
-    f64 = torch.empty((2, m), dtype=torch.float64, device=dev)
-    lines = torch.empty((2, m), dtype=torch.float32, device=dev)
-    d = {"cnt": acc[0, :nb], "s1": acc[1, :nb], "s2": acc[2, :nb], "mean": f64[0, :nb], "std": f64[1, :nb],
-         "sign": torch.empty(m, dtype=torch.int32, device=dev)[:nb], "t_start": lines[0, :nb], "t_end": lines[1, :nb],
-         "status": torch.zeros(1, dtype=torch.int32, device=dev), "c0": float(c0), "shift": shift,
-         "min_count": int(min_count), "have_thresholds": False}
-    rc = L.ct_block_stats_f32(y.data_ptr(), n, block, float(baseline_min), float(baseline_max), float(c0), shift,
-                              acc[0].data_ptr(), acc[1].data_ptr(), acc[2].data_ptr(), _stream_ptr(y))
+    bl = new_baseline(n, block, baseline_min, baseline_max, y.device, min_count)
+    d = bl.dev
+    rc = _lib.lib().ct_block_stats_f32(y.data_ptr(), n, bl.block, d["bmin"], d["bmax"], d["c0"], d["shift"],
+                                       d["cnt"].data_ptr(), d["s1"].data_ptr(), d["s2"].data_ptr(), _stream_ptr(y))
     _lib.check(rc, "ct_block_stats_f32")
-    bl = Baseline(block, dev=d)
+    return finish_baseline(bl, threshold, hysteresis)
+
+
+def finish_baseline(bl: Baseline, threshold: float | None = None, hysteresis: float | None = None) -> Baseline:
+    """Block sums -> table (+ detector lines when `threshold` is given), on the device."""
     thr = float("nan") if threshold is None else float(threshold)
     hys = 0.0 if hysteresis is None else float(hysteresis)
     bl.with_thresholds(thr, hys)
-    d["have_thresholds"] = threshold is not None
+    bl.dev["have_thresholds"] = threshold is not None
     return bl
 
 

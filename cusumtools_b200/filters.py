@@ -201,9 +201,11 @@ def code_median(raw: torch.Tensor, mask: int = 0xFFFF) -> tuple[int, int]:
 def filtfilt_codes(raw: torch.Tensor, *, alpha: float, pad_value: float, median_code: float, mask: int,
                    design: BesselDesign, padding: int = 1000, forward_only: bool = False,
                    halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
-                   out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
+                   out: torch.Tensor | None = None, workspace: torch.Tensor | None = None, stats=None) -> torch.Tensor:
     """out = pad_value + alpha * filtfilt((raw & mask) - median_code) with the reference's
-    boundary handling (dequantisation fused into the load and the store)."""
+    boundary handling (dequantisation fused into the load and the store).  `stats`: a
+    `_lib.CtFilterStats` to have the baseline block sums of the output tallied on the way
+    out (detect.Baseline.stats_args; needs block % stats_granule == 0)."""
     if raw.dtype not in (torch.uint16, torch.int16):
         raise TypeError("raw must hold the 16-bit ADC codes (torch.uint16 or the int16 view)")
     _require_cuda(raw, "raw", raw.dtype)
@@ -219,7 +221,7 @@ def filtfilt_codes(raw: torch.Tensor, *, alpha: float, pad_value: float, median_
     rc = _lib.lib().ct_filtfilt_u16(raw.data_ptr(), n, int(padding), float(median_code), int(mask),
                                     float(alpha), float(pad_value), C.byref(coef), S, H,
                                     int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
-                                    wsb, _stream_ptr(raw))
+                                    wsb, C.byref(stats) if stats is not None else None, _stream_ptr(raw))
     _lib.check(rc, "ct_filtfilt_u16")
     return out
 
@@ -228,7 +230,7 @@ def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8,
                      samplerate: float | None = None, padding: int = 1000, forward_only: bool = False,
                      halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
                      median_codes: tuple[int, int] | None = None,
-                     out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
+                     out: torch.Tensor | None = None, workspace: torch.Tensor | None = None, stats=None) -> torch.Tensor:
     """`App.scale_raw_data` + `App.filter_data` (plot-trace.py:272-287, 313-320) fused:
     raw Chimera codes on the GPU -> filtered pA (float32) on the GPU.
 
@@ -244,7 +246,13 @@ def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8,
     pad_value = float(np.median(vals))
     return filtfilt_codes(raw, alpha=alpha, pad_value=pad_value, median_code=0.5 * (c1 + c2), mask=mask,
                           design=design, padding=padding, forward_only=forward_only, halo_eps=halo_eps,
-                          subsegment=subsegment, out=out, workspace=workspace)
+                          subsegment=subsegment, out=out, workspace=workspace, stats=stats)
+
+
+def stats_granule(n: int, padding: int, design: BesselDesign, halo_eps: float = DEFAULT_HALO_EPS) -> int:
+    """Baseline blocks must be a multiple of this many samples for the statistics to be fused
+    into the filter (one warp group of the lane-sequential passes)."""
+    return int(_lib.lib().ct_filtfilt_stats_granule(int(n), int(padding), max(1, design.impulse_tail(halo_eps))))
 
 
 def float_median(x: torch.Tensor, *, use_abs: bool = False) -> float:
@@ -297,7 +305,7 @@ def bessel_filtfilt(x: torch.Tensor, samplerate: float, cutoff: float, order: in
     ws, wsb = _workspace(n, int(padding), S, H, forward_only, x.device, workspace)
     rc = _lib.lib().ct_filtfilt_f32(x.data_ptr(), n, int(padding), float(pad_value), C.byref(coef), S, H,
                                     int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
-                                    wsb, _stream_ptr(x))
+                                    wsb, None, _stream_ptr(x))
     _lib.check(rc, "ct_filtfilt_f32")
     return out
 

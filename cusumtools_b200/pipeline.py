@@ -169,6 +169,10 @@ class TraceAnalyzer:
         if self.block % L.ct_detect_run():
             raise ValueError(f"baseline block must be a multiple of {L.ct_detect_run()} samples")
         self.y = torch.empty(self.n_ext, dtype=torch.float32, device=self.device)
+        self.design = bessel_lowpass(self.order, 2.0 * self.cutoff / float(np.floor(np.squeeze(settings["ADCSAMPLERATE"]))))
+        # baseline block sums ride on the filter's epilogue when the block is a whole number of its warp groups
+        self.fuse_stats = self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0
+        self.filter_ws = None
         self.ws_bytes = int(L.ct_detect_workspace_bytes(self.n_det))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self._alloc_events(int(event_capacity) if event_capacity else max(1024, self.n_det // 2048))
@@ -191,21 +195,35 @@ class TraceAnalyzer:
             self.cws_bytes = int(_lib.lib().ct_cusum_workspace_bytes(cap))
             self.cws = torch.empty((self.cws_bytes + 7) // 8, dtype=torch.int64, device=dev)
 
-    def run(self, raw_ext: torch.Tensor) -> AnalysisResult:
+    def run(self, raw_ext: torch.Tensor, stage_hook=None) -> AnalysisResult:
+        """One pass of stages 1-3.  `stage_hook(name)` (optional) is called after the launches of each
+        stage have been enqueued: 'median', 'filter', 'baseline', 'detect', 'cusum' (profiling only)."""
+        hook = stage_hook or (lambda name: None)
         if raw_ext.numel() != self.n_ext:
             raise ValueError(f"analyzer was planned for {self.n_ext} samples, got {raw_ext.numel()}")
         L = _lib.lib()
         lo, n_own = self.lo_halo, self.n_own
         owned = raw_ext[lo:lo + n_own]
         c1, c2 = global_code_median(owned, self.mask, self.group)
+        hook("median")
+        if self.filter_ws is None:
+            need = int(L.ct_filtfilt_workspace_bytes(self.n_ext, self.padding, max(1, self.design.impulse_tail(filters.DEFAULT_HALO_EPS))))
+            self.filter_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        bl = detect.new_baseline(self.n_det, self.block, self.bmin, self.bmax, self.device) if self.fuse_stats else None
         y = filters.dequant_filtfilt(raw_ext, self.settings, self.cutoff, self.order, padding=self.padding,
-                                     median_codes=(c1, c2), out=self.y)
+                                     median_codes=(c1, c2), out=self.y, workspace=self.filter_ws,
+                                     stats=detect.stats_args(bl, origin=lo) if bl is not None else None)
         pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), self.settings)))
         yd = y[lo:]
         st = filters._stream_ptr(y)
-        bl = detect.baseline_blocks(yd, self.block, self.bmin, self.bmax, threshold=self.threshold,
-                                    hysteresis=self.hysteresis)
+        hook("filter")
+        if bl is not None:
+            detect.finish_baseline(bl, self.threshold, self.hysteresis)
+        else:
+            bl = detect.baseline_blocks(yd, self.block, self.bmin, self.bmax, threshold=self.threshold,
+                                        hysteresis=self.hysteresis)
         sign, ts, te = bl.device_lines(self.device)
+        hook("baseline")
         while True:
             sc = self.scalars
             rc = L.ct_detect_f32(yd.data_ptr(), self.n_det, self.block, sign.data_ptr(), ts.data_ptr(), te.data_ptr(), 0,
@@ -216,6 +234,7 @@ class TraceAnalyzer:
                                     n_own, self.event_padding, self.minpoints, self.maxpoints, self.w0.data_ptr(),
                                     self.w1.data_ptr(), self.typ.data_ptr(), sc[2:].data_ptr(), st)
             _lib.check(rc, "ct_event_windows")
+            hook("detect")
             if self.delta is not None:
                 rc = L.ct_cusum_batch_dev(yd.data_ptr(), self.n_det, self.w0.data_ptr(), self.w1.data_ptr(),
                                           self.typ.data_ptr(), sc[2:].data_ptr(), self.cap, float(self.delta),
@@ -223,6 +242,7 @@ class TraceAnalyzer:
                                           self.mu.data_ptr(), self.sd.data_ptr(), self.ov.data_ptr(), self.cws.data_ptr(),
                                           self.cws_bytes, st)
                 _lib.check(rc, "ct_cusum_batch_dev")
+            hook("cusum")
             host = torch.cat((sc[:3], bl.dev["status"].to(torch.int64))).cpu().numpy()   # the step's one sync
             ns, ne, nk = int(host[0]), int(host[1]), int(host[2])
             if max(ns, ne) <= self.cap:

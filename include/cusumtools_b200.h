@@ -63,19 +63,33 @@ int ct_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int6
  *     bytes of device scratch (16-byte aligned) for the forward output, unused if forward_only.
  *   S > 0: the single-kernel warp-scan formulation; S (sub-segment) and H are multiples of
  *     ct_filter_tile(), no workspace needed.                                            */
+/* Optional fusion of ct_block_stats_f32 into the zero-phase filter (S == 0 path): the final
+ * samples are tallied on their way out, which saves the separate 4 B/sample pass.  The block
+ * grid starts at output sample `origin` (samples before it are not tallied; time shards put
+ * their left halo there); `block` must be a multiple of ct_filtfilt_stats_granule(n, pad, H).
+ * cnt/s1/s2: int64[ceil((n - origin)/block)] device arrays, zeroed by the call.          */
+typedef struct CtFilterStats {
+    int64_t origin, block;
+    float bmin, bmax, c0;
+    int32_t shift;
+    int64_t* cnt; int64_t* s1; int64_t* s2;
+} CtFilterStats;
+
 int ct_filter_tile(void);
 int ct_filter_seq_tile(void);
+int64_t ct_filtfilt_stats_granule(int64_t n, int64_t pad, int H);
 int ct_filter_chunk(void);
 int64_t ct_filtfilt_workspace_bytes(int64_t n, int64_t pad, int H);
 int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_code, uint16_t mask,
                     float alpha, float pad_value, const CtFilterCoef* coef, int S, int H,
-                    int forward_only, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+                    int forward_only, float* out, void* workspace, int64_t workspace_bytes,
+                    const CtFilterStats* stats, void* stream);
 /* Same for already-dequantised float32 input (.bin traces, print_trace.py:33,
  * noise-fit.py:90; multi-gain file series, plot-trace.py:252-269):
  *   out = pad_value + filtfilt(x - pad_value).                                         */
 int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, const CtFilterCoef* coef,
                     int S, int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
-                    void* stream);
+                    const CtFilterStats* stats, void* stream);
 
 /* Exact global median of the masked codes, the value np.pad(mode='median') needs
  * (plot-trace.py:319): a strided-sample histogram to locate it and an exact count of

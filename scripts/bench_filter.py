@@ -19,7 +19,7 @@ wsb = L.ct_filtfilt_workspace_bytes(n, 1000, Hraw)
 ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
 for S in subs:
     def run():
-        rc = L.ct_filtfilt_u16(raw.data_ptr(), n, 1000, 40900.0, 0xFFFC, 2.3385, 5000.0, C.byref(coef), S, H if S else Hraw, 0, out.data_ptr(), ws.data_ptr(), wsb, st)
+        rc = L.ct_filtfilt_u16(raw.data_ptr(), n, 1000, 40900.0, 0xFFFC, 2.3385, 5000.0, C.byref(coef), S, H if S else Hraw, 0, out.data_ptr(), ws.data_ptr(), wsb, None, st)
         assert rc == 0, L.ct_last_error()
     run(); run(); torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

@@ -47,9 +47,9 @@ def test_argument_errors_are_reported_without_gpu():
     L = _lib.lib()
     coef = _lib.CtFilterCoef()
     coef.nsec, coef.tile_c = 4, L.ct_filter_chunk()
-    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 4096, 512, 0, None, None, 0, None)
+    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 4096, 512, 0, None, None, 0, None, None)
     assert rc == -1 and b"null" in L.ct_last_error()
-    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 0, 238, 0, None, None, 0, None)
+    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 0, 238, 0, None, None, 0, None, None)
     assert rc == -1 and b"bad argument" in L.ct_last_error()
     assert L.ct_filtfilt_workspace_bytes(10_000_000, 1000, 238) >= 4 * 10_001_000
     with pytest.raises(ValueError):
