@@ -564,9 +564,16 @@ __global__ void ct_hist_sampled_kernel(const uint16_t* __restrict__ raw, long lo
 }
 
 constexpr int kWin = 8;
-// out[0] = #codes < lo ; out[1+i] = #codes == lo + i*step (step = power of two).  Eight
-// 16-bit in-register counters packed in two 64-bit words keep the tally at ~8 integer ops
-// per sample, so the pass runs at HBM speed (2 B/sample).
+// out[0] = #codes < lo ; out[1+i] = #codes == lo + i*step (step = power of two, lo a multiple of it).
+// Eight 8-bit in-register counters in two 32-bit words: with d = code - lo (negative below the
+// window) the increment is 1 << (8 * d/step) through PTX shl.b32, which CLAMPS shift amounts >= 32 to
+// "all bits out" (result 0), so codes below or above the window add nothing without any compare; the
+// sign bit of d is the "below" count.  ~10 integer operations per code.
+static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
+    return r;
+}
 __global__ void __launch_bounds__(256)
 ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned mask, unsigned lo,
                        unsigned step, unsigned long long* __restrict__ out /*[1+kWin]*/) {
@@ -574,52 +581,53 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
     unsigned long long tot[1 + kWin];
 #pragma unroll
     for (int i = 0; i <= kWin; ++i) tot[i] = 0;
-    unsigned below = 0;
-    unsigned long long p0 = 0, p1 = 0;
-    auto tally = [&](unsigned code) {
-        code &= mask;
-        below += code < lo;
-        const unsigned idx = (code - lo) >> sh;            // wraps to a huge value below lo
-        const unsigned long long one = 1ULL << ((idx & 3) * 16);
-        p0 += idx < 4 ? one : 0ULL;
-        p1 += (idx - 4) < 4 ? one : 0ULL;
+    unsigned below = 0, c0 = 0, c1 = 0;
+    auto tally = [&](unsigned code) {                      // code already masked
+        const unsigned d = code - lo;
+        below += d >> 31;                                  // codes and lo are < 2^16: negative iff code < lo
+        const unsigned amt = sh >= 3 ? d >> (sh - 3) : d << (3 - sh);   // 8 * (d / step): d is a multiple of step
+        c0 += shl_clamp(1u, amt);
+        c1 += shl_clamp(1u, amt - 32u);
     };
     auto flush = [&]() {
         tot[0] += below; below = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { tot[1 + i] += (p0 >> (16 * i)) & 0xffff; tot[5 + i] += (p1 >> (16 * i)) & 0xffff; }
-        p0 = 0; p1 = 0;
+        for (int i = 0; i < 4; ++i) { tot[1 + i] += (c0 >> (8 * i)) & 0xffu; tot[5 + i] += (c1 >> (8 * i)) & 0xffu; }
+        c0 = 0; c1 = 0;
     };
+    const unsigned m2 = mask | (mask << 16);
     const long long nvec = n / 8;
     const uint4* v = reinterpret_cast<const uint4*>(raw);
     const bool aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
     if (aligned) {
-        int since = 0;
         long long i = tid;
+        int rounds = 0;
         for (; i + 3 * nth < nvec; i += 4 * nth) {          // four independent 16-byte loads in flight
             uint4 q[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) q[u] = ct_ldg_stream(v + i + u * nth);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                unsigned ww[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+                const unsigned ww[4] = {q[u].x & m2, q[u].y & m2, q[u].z & m2, q[u].w & m2};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { tally(ww[j] & 0xffffu); tally(ww[j] >> 16); }
             }
-            if (++since == 1024) { flush(); since = 0; }
+            if (++rounds == 7) { flush(); rounds = 0; }     // 32 tallies per round: an 8-bit counter holds 7 rounds
         }
+        flush();
         for (; i < nvec; i += nth) {
-            uint4 q = ct_ldg_stream(v + i);
-            unsigned ww[4] = {q.x, q.y, q.z, q.w};
+            const uint4 q = ct_ldg_stream(v + i);
+            const unsigned ww[4] = {q.x & m2, q.y & m2, q.z & m2, q.w & m2};
 #pragma unroll
             for (int j = 0; j < 4; ++j) { tally(ww[j] & 0xffffu); tally(ww[j] >> 16); }
+            flush();
         }
-        for (long long i = nvec * 8 + tid; i < n; i += nth) tally(raw[i]);
+        for (long long k = nvec * 8 + tid; k < n; k += nth) { tally(raw[k] & mask); flush(); }
     } else {
         int since = 0;
-        for (long long i = tid; i < n; i += nth) { tally(raw[i]); if (++since == 32768) { flush(); since = 0; } }
+        for (long long k = tid; k < n; k += nth) { tally(raw[k] & mask); if (++since == 128) { flush(); since = 0; } }
     }
     flush();
 #pragma unroll
