@@ -714,7 +714,32 @@ int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float s
                     float offset, const CtFilterCoef* coef, int H, int forward_only, float* out, void* workspace,
                     int64_t workspace_bytes, const CtFilterStats* stats, cudaStream_t st);
 
+int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float pad_x,
+                          const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t cw_lo, uint32_t cw_step,
+                          int64_t cw_begin, int64_t cw_end, uint64_t* counts9, int64_t from_pos, int64_t to_pos,
+                          void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H,
+                           int64_t origin, float* out, const void* workspace, int64_t workspace_bytes,
+                           const CtFilterStats* stats, cudaStream_t st);
+
 extern "C" {
+
+int ct_filter_forward_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub_code, uint16_t mask, float pad_x,
+                          const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t window_lo,
+                          uint32_t window_step, int64_t count_begin, int64_t count_end, uint64_t* counts9, int64_t from_pos,
+                          int64_t to_pos, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!raw || !coef || n <= 0 || pad < 0 || H < 0 || origin < 0) { ct_set_error("filter_forward: bad argument"); return CT_ERR_ARG; }
+    return ct_filter_forward_seq(raw, 0, n, pad, sub_code, mask, pad_x, coef, H, origin, part, window_lo, window_step,
+                                 count_begin, count_end, counts9, from_pos, to_pos, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+}
+
+int ct_filter_backward(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H, int64_t origin,
+                       float* out, const void* workspace, int64_t workspace_bytes, const CtFilterStats* stats, void* stream) {
+    if (!out || !coef || n <= 0 || pad < 0 || H < 0 || origin < 0) { ct_set_error("filter_backward: bad argument"); return CT_ERR_ARG; }
+    return ct_filter_backward_seq(n, pad, scale, offset, coef, H, origin, out, workspace, workspace_bytes, stats,
+                                  (cudaStream_t)stream);
+}
 
 int ct_filter_tile(void) { return kT; }
 int ct_filter_seq_tile(void) { return 32; }

@@ -59,6 +59,11 @@ struct SeqArgs {
     int R, Hw;             // run length, warm-up (multiples of kK, Hw <= R)
     float sub; unsigned mask; float scale, offset;   // input x' = (code & mask) - sub ; out = offset + scale*y
     long long base;        // position of run 0 (<= 0): shifts the run grid so that groups align with baseline blocks
+    long long g_first;     // first group to process (partial re-runs of the trace ends)
+    float pad_x;           // FWD: value of x' in the pad and beyond (0 when `sub` is the exact median)
+    // optional fused window count for the exact median (ct_count_window_u16 semantics), FWD uint16 only
+    unsigned cw_lo; int cw_sh; unsigned long long* cw_out;
+    long long cw_p0, cw_p1; // only codes at positions [cw_p0, cw_p1) are tallied (a shard's owned samples)
     // optional fused baseline block statistics of the final output (ct_block_stats_f32 semantics)
     long long st_origin, st_block; float st_min, st_max, st_c0, st_scale;
     long long* st_cnt; long long* st_s1; long long* st_s2;
@@ -66,6 +71,26 @@ struct SeqArgs {
 
 // |q| < 2^31 by construction of the shift (detect.stats_shift: (half_width 2^shift + 1)^2 block < 2^62), so the
 // quantised value fits an int32 (full-rate F2I) and q*q + s2 is one IMAD.WIDE
+// window count for the exact median: see ct_count_window_kernel (ct_filter.cu)
+static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
+    return r;
+}
+static __device__ __forceinline__ void cw_tally(unsigned code, const SeqArgs& a, unsigned& below, unsigned& c0, unsigned& c1) {
+    const unsigned d = code - a.cw_lo;
+    below += d >> 31;
+    const unsigned amt = a.cw_sh >= 3 ? d >> (a.cw_sh - 3) : d << (3 - a.cw_sh);
+    c0 += shl_clamp(1u, amt);
+    c1 += shl_clamp(1u, amt - 32u);
+}
+static __device__ __forceinline__ void cw_flush(unsigned (&tot)[9], unsigned& below, unsigned& c0, unsigned& c1) {
+    tot[0] += below; below = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { tot[1 + i] += (c0 >> (8 * i)) & 0xffu; tot[5 + i] += (c1 >> (8 * i)) & 0xffu; }
+    c0 = 0; c1 = 0;
+}
+
 struct StatAcc { int c; long long s1, s2; };
 static __device__ __forceinline__ void tally(const SeqArgs& a, StatAcc& acc, float v) {
     const bool in = v >= a.st_min && v <= a.st_max;
@@ -133,7 +158,7 @@ __device__ __forceinline__ void fill_tile(const SeqArgs& a, char* buf, long long
 #pragma unroll
             for (int e = 0; e < EPU; ++e) {
                 const long long q = p + e;
-                if (sizeof(InT) == 4) dst[e] = (q >= 0 && q < a.n_in) ? in[q] : (InT)a.sub;
+                if (sizeof(InT) == 4) dst[e] = (q >= 0 && q < a.n_in) ? in[q] : (InT)(a.sub + a.pad_x);
                 else dst[e] = (q >= 0 && q < a.n_in) ? in[q] : (InT)0;
             }
         }
@@ -189,7 +214,7 @@ __device__ __forceinline__ void store_tile(const SeqArgs& a, const float* outb, 
 }
 
 // =============================== forward pass ========================================
-template <int NSEC, typename InT, int MODE>
+template <int NSEC, typename InT, int MODE, bool COUNT>
 __global__ void __launch_bounds__(kSeqWarps * 32)
 ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
     extern __shared__ __align__(16) char smem[];
@@ -215,11 +240,17 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
     const f2 gl = splat(k.gain);
     const unsigned m2 = a.mask | (a.mask << 16);
 
-    for (long long g = gw; g < a.ngroups; g += nw) {
+    for (long long g = a.g_first + gw; g < a.ngroups; g += nw) {
         const long long run0 = g * kRuns;
+        unsigned cw_tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, cw_below = 0, cw_c0 = 0, cw_c1 = 0;
+        int cw_since = 0;
         f2 v1[NSEC], v2[NSEC];
+        {   // runs that begin in the left pad start from the steady state of the pad value (scipy: zi * x[0])
+            const float p0 = a.base + (run0 + lane) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
+            const float p1 = a.base + (run0 + lane + 32) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
 #pragma unroll
-        for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(0.f, 0.f); v2[s] = v1[s]; }
+            for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(p0 * k.ss[s], p1 * k.ss[s]); v2[s] = v1[s]; }
+        }
         __syncwarp();
         fill_tile<InT>(a, wbase, run0, -(long long)a.Hw, lane, in_aligned);
         cp_commit();
@@ -263,12 +294,37 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
                         x[2 * q] = make_float2((float)(int)(ma & 0xffffu) - a.sub, (float)(int)(mb & 0xffffu) - a.sub);
                         x[2 * q + 1] = make_float2((float)(int)(ma >> 16) - a.sub, (float)(int)(mb >> 16) - a.sub);
                     }
-                    if (edge) {                            // x' is 0 in the pad and beyond it
+                    if (edge) {                            // x' = pad_x in the pad and beyond it
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const long long p0 = lo0 + jj * 8 + e, p1 = lo1 + jj * 8 + e;
-                            if (!(p0 >= 0 && p0 < a.n_in)) x[e].x = 0.f;
-                            if (!(p1 >= 0 && p1 < a.n_in)) x[e].y = 0.f;
+                            if (!(p0 >= 0 && p0 < a.n_in)) x[e].x = a.pad_x;
+                            if (!(p1 >= 0 && p1 < a.n_in)) x[e].y = a.pad_x;
+                        }
+                    }
+                    if (COUNT && store) {                  // every code of [cw_p0, cw_p1) is tallied exactly once
+                        const bool part0 = !(lo0 >= a.cw_p0 && lo0 + kK <= a.cw_p1), part1 = !(lo1 >= a.cw_p0 && lo1 + kK <= a.cw_p1);
+                        if (!(part0 | part1)) {            // both pieces inside the counted range: no per-code tests
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const unsigned ma = wa[q] & m2, mb = wb[q] & m2;
+                                cw_tally(ma & 0xffffu, a, cw_below, cw_c0, cw_c1); cw_tally(ma >> 16, a, cw_below, cw_c0, cw_c1);
+                                cw_tally(mb & 0xffffu, a, cw_below, cw_c0, cw_c1); cw_tally(mb >> 16, a, cw_below, cw_c0, cw_c1);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int q = 0; q < 4; ++q) {
+                                const unsigned ma = wa[q] & m2, mb = wb[q] & m2;
+                                const long long pa0 = lo0 + jj * 8 + 2 * q, pb0 = lo1 + jj * 8 + 2 * q;
+                                if (pa0 >= a.cw_p0 && pa0 < a.cw_p1) cw_tally(ma & 0xffffu, a, cw_below, cw_c0, cw_c1);
+                                if (pa0 + 1 >= a.cw_p0 && pa0 + 1 < a.cw_p1) cw_tally(ma >> 16, a, cw_below, cw_c0, cw_c1);
+                                if (pb0 >= a.cw_p0 && pb0 < a.cw_p1) cw_tally(mb & 0xffffu, a, cw_below, cw_c0, cw_c1);
+                                if (pb0 + 1 >= a.cw_p0 && pb0 + 1 < a.cw_p1) cw_tally(mb >> 16, a, cw_below, cw_c0, cw_c1);
+                            }
+                        }
+                        if (++cw_since == 15) {            // 16 tallies per slot: an 8-bit counter holds 15 slots
+                            cw_flush(cw_tot, cw_below, cw_c0, cw_c1);
+                            cw_since = 0;
                         }
                     }
                 }
@@ -301,6 +357,16 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
             }
         }
         cp_wait<0>();
+        if (COUNT) {                                       // (a lane tallies < 2^32 codes per group)
+            cw_flush(cw_tot, cw_below, cw_c0, cw_c1);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                unsigned v = cw_tot[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CT_FULL, v, o);
+                if (lane == 0 && v) atomicAdd(a.cw_out + i, (unsigned long long)v);
+            }
+        }
     }
 }
 
@@ -332,7 +398,7 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
     const long long last = a.n_in - 1 - a.base;           // relative to the run grid
     const float hold = y1[scratch_off(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 3), TO) + (last & 7)];
 
-    for (long long g = gw; g < a.ngroups; g += nw) {
+    for (long long g = a.g_first + gw; g < a.ngroups; g += nw) {
         const long long run0 = g * kRuns;
         const long long r0 = run0 + lane, r1 = r0 + 32;
         f2 v1[NSEC], v2[NSEC];
@@ -413,16 +479,16 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
     }
 }
 
-template <int NSEC, typename InT, int MODE>
+template <int NSEC, typename InT, int MODE, bool COUNT>
 int launch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    auto kern = ct_filter_fwd_kernel<NSEC, InT, MODE>;
+    auto kern = ct_filter_fwd_kernel<NSEC, InT, MODE, COUNT>;
     const int smem = kSeqWarps * (2 * Tile<InT>::kInBytes + (MODE == kFwdFinal ? kOutBytes : 0));
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSeqWarps * 32, smem);
     if (occ < 1) occ = 1;
     long long grid = (long long)ct_sm_count() * occ;
-    const long long want = (a.ngroups + kSeqWarps - 1) / kSeqWarps;
+    const long long want = (a.ngroups - a.g_first + kSeqWarps - 1) / kSeqWarps;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     CT_COUNT_LAUNCH();
@@ -438,7 +504,7 @@ int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSeqWarps * 32, smem);
     if (occ < 1) occ = 1;
     long long grid = (long long)ct_sm_count() * occ;
-    const long long want = (a.ngroups + kSeqWarps - 1) / kSeqWarps;
+    const long long want = (a.ngroups - a.g_first + kSeqWarps - 1) / kSeqWarps;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     CT_COUNT_LAUNCH();
@@ -448,12 +514,21 @@ int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
 
 template <typename InT, int MODE>
 int dispatch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
+    if (sizeof(InT) == 2 && MODE == kFwdScratch && a.cw_out) {
+        switch (k.nsec) {
+            case 1: return launch_fwd<1, uint16_t, kFwdScratch, true>(a, k, st);
+            case 2: return launch_fwd<2, uint16_t, kFwdScratch, true>(a, k, st);
+            case 3: return launch_fwd<3, uint16_t, kFwdScratch, true>(a, k, st);
+            case 4: return launch_fwd<4, uint16_t, kFwdScratch, true>(a, k, st);
+            case 5: return launch_fwd<5, uint16_t, kFwdScratch, true>(a, k, st);
+        }
+    }
     switch (k.nsec) {
-        case 1: return launch_fwd<1, InT, MODE>(a, k, st);
-        case 2: return launch_fwd<2, InT, MODE>(a, k, st);
-        case 3: return launch_fwd<3, InT, MODE>(a, k, st);
-        case 4: return launch_fwd<4, InT, MODE>(a, k, st);
-        case 5: return launch_fwd<5, InT, MODE>(a, k, st);
+        case 1: return launch_fwd<1, InT, MODE, false>(a, k, st);
+        case 2: return launch_fwd<2, InT, MODE, false>(a, k, st);
+        case 3: return launch_fwd<3, InT, MODE, false>(a, k, st);
+        case 4: return launch_fwd<4, InT, MODE, false>(a, k, st);
+        case 5: return launch_fwd<5, InT, MODE, false>(a, k, st);
     }
     ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
     return CT_ERR_ARG;
@@ -496,53 +571,115 @@ extern "C" int64_t ct_filtfilt_stats_granule(int64_t n, int64_t pad, int H) {
     return (int64_t)pick_run(n + pad, Hw) * kRuns;
 }
 
-// in_kind: 0 = uint16 codes, 1 = float32 samples.  stats (may be NULL): fused baseline block statistics
-// of the final output; the block grid starts at sample stats->origin of the output.
-int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float scale,
-                    float offset, const CtFilterCoef* coef, int H, int forward_only, float* out, void* workspace,
-                    int64_t workspace_bytes, const CtFilterStats* stats, cudaStream_t st) {
-    const int Hw = (H + kK - 1) / kK * kK;
-    SeqArgs a;
-    a.in = in; a.n_in = n; a.sub = sub; a.mask = mask; a.scale = scale; a.offset = offset; a.Hw = Hw; a.scratch_runs = 0;
-    a.base = 0; a.st_cnt = nullptr; a.st_s1 = nullptr; a.st_s2 = nullptr;
-    a.st_origin = 0; a.st_block = 1; a.st_min = a.st_max = a.st_c0 = a.st_scale = 0.f;
-    if (forward_only) {
-        if (stats) { ct_set_error("filter: block statistics are fused into the zero-phase path only"); return CT_ERR_UNSUPPORTED; }
-        a.R = pick_run(n, Hw);
-        a.ngroups = (n + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
-        a.out = out; a.n_out = n;
-        return in_kind ? dispatch_fwd<float, kFwdFinal>(a, *coef, st) : dispatch_fwd<uint16_t, kFwdFinal>(a, *coef, st);
-    }
+namespace {
+
+struct Plan { int Hw, R; long long G, base, n1, ng_fwd, ng_bwd, g_right; };
+// Run grid of a trace of n samples (+ pad): groups of G = 64 R samples starting at `base` <= 0 with
+// base = origin (mod G), so that groups never straddle a baseline block counted from `origin`.
+Plan make_plan(long long n, long long pad, int H, long long origin) {
+    Plan p;
+    p.Hw = (H + kK - 1) / kK * kK;
+    p.n1 = n + pad;
+    p.R = pick_run(p.n1, p.Hw);
+    p.G = (long long)p.R * kRuns;
+    p.base = -((p.G - origin % p.G) % p.G);
+    p.ng_fwd = (p.n1 - p.base + p.G - 1) / p.G;
+    p.ng_bwd = (n - p.base + p.G - 1) / p.G;
+    p.g_right = (n - p.base) / p.G;                       // first group that sees positions >= n (the right pad)
+    return p;
+}
+void init_args(SeqArgs& a) {
+    a.scratch_runs = 0; a.base = 0; a.g_first = 0; a.pad_x = 0.f; a.cw_lo = 0; a.cw_sh = 0; a.cw_out = nullptr;
+    a.cw_p0 = 0; a.cw_p1 = 0;
+    a.st_cnt = nullptr; a.st_s1 = nullptr; a.st_s2 = nullptr; a.st_origin = 0; a.st_block = 1;
+    a.st_min = a.st_max = a.st_c0 = a.st_scale = 0.f; a.n_out = 0; a.sub = 0.f; a.mask = 0xffffu; a.scale = 1.f; a.offset = 0.f;
+}
+int check_ws(const void* workspace, int64_t workspace_bytes, int64_t n, int64_t pad, int H) {
     if (!workspace || workspace_bytes < ct_filtfilt_workspace_bytes(n, pad, H) || (reinterpret_cast<uintptr_t>(workspace) & 31)) {
         ct_set_error("filter: workspace missing, too small or not 32-byte aligned"); return CT_ERR_ARG;
     }
-    float* y1 = reinterpret_cast<float*>(workspace);
-    const long long n1 = n + pad;
-    a.R = pick_run(n1, Hw);
-    const long long G = (long long)a.R * kRuns;           // samples per warp group
+    return CT_OK;
+}
+
+}  // namespace
+
+// Forward pass into the scratch.  in_kind: 0 = uint16 codes, 1 = float32 samples.  part: 0 = whole
+// trace, 1 = only the groups whose result depends on pad_x (the two ends of the trace).
+// counts9 != NULL (uint16 only, part 0): also tally the window count for the exact median.
+int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float pad_x,
+                          const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t cw_lo, uint32_t cw_step,
+                          int64_t cw_begin, int64_t cw_end, uint64_t* counts9, int64_t from_pos, int64_t to_pos,
+                          void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+    int rc = check_ws(workspace, workspace_bytes, n, pad, H); if (rc) return rc;
+    const Plan p = make_plan(n, pad, H, origin);
+    SeqArgs a; init_args(a);
+    a.in = in; a.n_in = n; a.sub = sub; a.mask = mask; a.pad_x = pad_x; a.Hw = p.Hw; a.R = p.R; a.base = p.base;
+    a.out = reinterpret_cast<float*>(workspace);
+    if (counts9 && part != 1 && in_kind == 0) {
+        if (!cw_step || (cw_step & (cw_step - 1))) { ct_set_error("filter: window step must be a power of two"); return CT_ERR_ARG; }
+        a.cw_lo = cw_lo; a.cw_sh = __builtin_ctz(cw_step); a.cw_out = (unsigned long long*)counts9;
+        a.cw_p0 = cw_begin < 0 ? 0 : cw_begin; a.cw_p1 = cw_end > n ? n : cw_end;
+    }
+    auto go = [&](const SeqArgs& x) { return in_kind ? dispatch_fwd<float, kFwdScratch>(x, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch>(x, *coef, st); };
+    if (part == 0) { a.g_first = 0; a.ngroups = p.ng_fwd; return go(a); }
+    if (part == 2) {
+        // streaming: the groups whose input [.., group end) lies below to_pos (all remaining ones once to_pos >= n)
+        // and that were not covered by the previous call (which ended at from_pos)
+        auto done = [&](long long pos) { return pos >= n ? p.ng_fwd : (pos <= p.base ? 0 : (pos - p.base) / p.G); };
+        a.g_first = done(from_pos); a.ngroups = done(to_pos);
+        return a.g_first < a.ngroups ? go(a) : CT_OK;
+    }
+    a.g_first = 0; a.ngroups = p.ng_fwd < 1 ? p.ng_fwd : 1;            // left end: group 0
+    rc = go(a); if (rc) return rc;
+    if (p.g_right >= 1 || p.ng_fwd > 1) {                                 // right end: groups that reach the right pad
+        a.g_first = p.g_right > 1 ? p.g_right : 1; a.ngroups = p.ng_fwd;
+        if (a.g_first < a.ngroups) rc = go(a);
+    }
+    return rc;
+}
+
+// Backward pass scratch -> out = offset + scale * y (+ optional fused baseline block sums).
+int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H,
+                           int64_t origin, float* out, const void* workspace, int64_t workspace_bytes,
+                           const CtFilterStats* stats, cudaStream_t st) {
+    int rc = check_ws(workspace, workspace_bytes, n, pad, H); if (rc) return rc;
+    const Plan p = make_plan(n, pad, H, origin);
+    SeqArgs b; init_args(b);
+    b.in = workspace; b.n_in = p.n1; b.out = out; b.n_out = n; b.scale = scale; b.offset = offset;
+    b.Hw = p.Hw; b.R = p.R; b.base = p.base; b.scratch_runs = p.ng_fwd * kRuns; b.ngroups = p.ng_bwd;
     if (stats) {
-        if (stats->block <= 0 || stats->block % G || stats->origin < 0 || !stats->cnt || !stats->s1 || !stats->s2) {
-            ct_set_error("filter: fused block statistics need block %% %lld == 0 (block = %lld)", G, (long long)stats->block);
+        if (stats->block <= 0 || stats->block % p.G || stats->origin != origin || !stats->cnt || !stats->s1 || !stats->s2) {
+            ct_set_error("filter: fused block statistics need block %% %lld == 0 and the grid origin (block = %lld)", p.G,
+                         (long long)stats->block);
             return CT_ERR_ARG;
         }
-        a.base = -((G - stats->origin % G) % G);          // groups then start at origin + k*G: never straddle a block
         const long long nb = (n - stats->origin + stats->block - 1) / stats->block;
         if (nb > 0) {
             cudaMemsetAsync(stats->cnt, 0, nb * 8, st); cudaMemsetAsync(stats->s1, 0, nb * 8, st); cudaMemsetAsync(stats->s2, 0, nb * 8, st);
         }
-    }
-    a.ngroups = (n1 - a.base + G - 1) / G;
-    a.out = y1; a.n_out = 0;
-    int rc = in_kind ? dispatch_fwd<float, kFwdScratch>(a, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch>(a, *coef, st);
-    if (rc) return rc;
-    SeqArgs b = a;                                        // backward pass over the forward output
-    b.in = y1; b.n_in = n1; b.out = out; b.n_out = n; b.sub = 0.f;
-    b.scratch_runs = a.ngroups * kRuns;
-    b.ngroups = (n - a.base + G - 1) / G;
-    if (stats) {
         b.st_origin = stats->origin; b.st_block = stats->block; b.st_min = stats->bmin; b.st_max = stats->bmax;
         b.st_c0 = stats->c0; b.st_scale = ldexpf(1.f, stats->shift);
         b.st_cnt = (long long*)stats->cnt; b.st_s1 = (long long*)stats->s1; b.st_s2 = (long long*)stats->s2;
     }
     return dispatch_bwd(b, *coef, st);
+}
+
+// One call: forward (+ backward).  stats (may be NULL): fused baseline block sums of the output.
+int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float scale,
+                    float offset, const CtFilterCoef* coef, int H, int forward_only, float* out, void* workspace,
+                    int64_t workspace_bytes, const CtFilterStats* stats, cudaStream_t st) {
+    if (forward_only) {
+        if (stats) { ct_set_error("filter: block statistics are fused into the zero-phase path only"); return CT_ERR_UNSUPPORTED; }
+        SeqArgs a; init_args(a);
+        a.in = in; a.n_in = n; a.sub = sub; a.mask = mask; a.scale = scale; a.offset = offset;
+        a.Hw = (H + kK - 1) / kK * kK; a.R = pick_run(n, a.Hw);
+        a.ngroups = (n + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
+        a.out = out; a.n_out = n;
+        return in_kind ? dispatch_fwd<float, kFwdFinal>(a, *coef, st) : dispatch_fwd<uint16_t, kFwdFinal>(a, *coef, st);
+    }
+    const int64_t origin = stats ? stats->origin : 0;
+    int rc = ct_filter_forward_seq(in, in_kind, n, pad, sub, mask, 0.f, coef, H, origin, 0, 0, 1, 0, 0, nullptr, 0, 0, workspace,
+                                   workspace_bytes, st);
+    if (rc) return rc;
+    return ct_filter_backward_seq(n, pad, scale, offset, coef, H, origin, out, workspace, workspace_bytes, stats, st);
 }

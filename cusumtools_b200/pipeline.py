@@ -41,13 +41,23 @@ def _all_reduce_(t: torch.Tensor, group) -> torch.Tensor:
     return t
 
 
-def median_search(n_local: int, mask: int, hist_fn, count_fn, group=None, device=None) -> tuple[int, int]:
-    """Host side of the exact global median: the two middle order statistics of the masked
-    codes of ALL ranks.  `hist_fn(stride)` returns this rank's strided-sample histogram
-    (int tensor[65536]) and `count_fn(lo, step)` its 9 window counters (#codes < lo, then
-    #codes == lo + i*step); both are summed over `group` here, so every rank takes the same
-    decisions and returns the same pair.  (The device kernels are passed in, which is what
-    lets the world-size-2 gloo test drive this logic on CPU.)"""
+@dataclass
+class MedianPlan:
+    """State of the exact-median search between its two phases (estimate, verify)."""
+    n: int                      # samples of all ranks
+    k1: int                     # ranks of the two middle order statistics
+    k2: int
+    step: int                   # spacing of the masked codes
+    shift: int
+    est: int                    # estimated median code (a multiple of step)
+    lo: int                     # first code of the 8-code verification window
+    exact: tuple[int, int] | None = None     # already exact (small traces: full histogram)
+
+
+def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n_sampled: int | None = None) -> MedianPlan:
+    """Phase 1: a strided-sample histogram (summed over `group`) locates the median code.  `n_sampled`:
+    the histogram covers only that many of the rank's samples (streaming: the first chunk), so it
+    is an estimate even for small traces."""
     nt = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
     n = int(_all_reduce_(nt, group).item())
     if n == 0:
@@ -57,28 +67,54 @@ def median_search(n_local: int, mask: int, hist_fn, count_fn, group=None, device
         shift += 1
     step = 1 << shift
     k1, k2 = (n - 1) // 2, n // 2
-    stride = max(1, n // (1 << 22))
+    stride = max(1, (n if n_sampled is None else int(n_sampled)) // (1 << 22))
     h = _all_reduce_(hist_fn(stride).to(torch.int64), group)
     cdf = np.cumsum(h.cpu().numpy())
-    if stride == 1:
-        return int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
-    est = int(np.searchsorted(cdf, (cdf[-1] + 1) // 2))
-    lo = max(0, (est >> shift) * step - 3 * step)
+    if stride == 1 and n_sampled is None:
+        c1, c2 = int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
+        return MedianPlan(n, k1, k2, step, shift, c1, max(0, c1 - 3 * step), exact=(c1, c2))
+    est = (int(np.searchsorted(cdf, (cdf[-1] + 1) // 2)) >> shift) * step
+    return MedianPlan(n, k1, k2, step, shift, est, max(0, est - 3 * step))
+
+
+def median_verify(plan: MedianPlan, counts9, group=None):
+    """Phase 2: the exact counts of the codes below / inside the window (summed over `group`) either pin
+    the two middle order statistics or say which way the window has to move (returns None, new lo)."""
+    c = _all_reduce_(counts9.to(torch.int64), group).cpu().numpy().astype(np.int64)
+    below, cw = int(c[0]), int(c[0]) + np.cumsum(c[1:])
+    if below <= plan.k1 and plan.k2 < cw[-1]:
+        return (plan.lo + int(np.searchsorted(cw, plan.k1 + 1)) * plan.step,
+                plan.lo + int(np.searchsorted(cw, plan.k2 + 1)) * plan.step), plan.lo
+    return None, (max(0, plan.lo - 6 * plan.step) if plan.k1 < below else plan.lo + 6 * plan.step)
+
+
+def median_search(n_local: int, mask: int, hist_fn, count_fn, group=None, device=None, plan: MedianPlan | None = None,
+                  first_counts=None) -> tuple[int, int]:
+    """Host side of the exact global median: the two middle order statistics of the masked
+    codes of ALL ranks.  `hist_fn(stride)` returns this rank's strided-sample histogram
+    (int tensor[65536]) and `count_fn(lo, step)` its 9 window counters (#codes < lo, then
+    #codes == lo + i*step); both are summed over `group` here, so every rank takes the same
+    decisions and returns the same pair.  (The device kernels are passed in, which is what
+    lets the world-size-2 gloo test drive this logic on CPU.)  `plan` / `first_counts`: an
+    estimate already made and the window counts a fused kernel already produced for it."""
+    if plan is None:
+        plan = median_estimate(n_local, mask, hist_fn, group, device)
+    if plan.exact is not None:
+        return plan.exact
+    counts = first_counts
     for _ in range(16):
-        c = _all_reduce_(count_fn(lo, step).to(torch.int64), group).cpu().numpy().astype(np.int64)
-        below, cw = int(c[0]), int(c[0]) + np.cumsum(c[1:])
-        if below <= k1 and k2 < cw[-1]:
-            return lo + int(np.searchsorted(cw, k1 + 1)) * step, lo + int(np.searchsorted(cw, k2 + 1)) * step
-        lo = max(0, lo - 6 * step) if k1 < below else lo + 6 * step
+        if counts is None:
+            counts = count_fn(plan.lo, plan.step)
+        pair, plan.lo = median_verify(plan, counts, group)
+        if pair is not None:
+            return pair
+        counts = None
     cdf = np.cumsum(_all_reduce_(hist_fn(1).to(torch.int64), group).cpu().numpy())   # pathological distribution
-    return int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
+    return int(np.searchsorted(cdf, plan.k1 + 1)), int(np.searchsorted(cdf, plan.k2 + 1))
 
 
-def global_code_median(raw_owned: torch.Tensor, mask: int, group=None) -> tuple[int, int]:
-    """Exact median (two middle order statistics) of the masked codes of the WHOLE trace
-    when each rank passes its owned samples; identical to filters.code_median for one rank."""
-    if group is None:
-        return filters.code_median(raw_owned, mask)
+def _median_kernels(raw_owned: torch.Tensor, mask: int):
+    """(hist_fn, count_fn) over this rank's owned codes."""
     L = _lib.lib()
     dev = raw_owned.device
     n_local = raw_owned.numel()
@@ -96,7 +132,16 @@ def global_code_median(raw_owned: torch.Tensor, mask: int, group=None) -> tuple[
             _lib.check(L.ct_count_window_u16(raw_owned.data_ptr(), n_local, mask, lo, step, cnt.data_ptr(), st), "ct_count_window_u16")
         return cnt
 
-    return median_search(n_local, mask, hist_fn, count_fn, group, dev)
+    return hist_fn, count_fn
+
+
+def global_code_median(raw_owned: torch.Tensor, mask: int, group=None) -> tuple[int, int]:
+    """Exact median (two middle order statistics) of the masked codes of the WHOLE trace
+    when each rank passes its owned samples; identical to filters.code_median for one rank."""
+    if group is None:
+        return filters.code_median(raw_owned, mask)
+    hist_fn, count_fn = _median_kernels(raw_owned, mask)
+    return median_search(raw_owned.numel(), mask, hist_fn, count_fn, group, raw_owned.device)
 
 
 def event_id_offsets(n_local_events: int, group=None, device=None) -> tuple[int, int]:
@@ -153,7 +198,7 @@ class TraceAnalyzer:
                  baseline_min: float, baseline_max: float, padding: int = 1000, event_padding: int = 100,
                  minpoints: int = 8, maxpoints: int = 100_000, cusum_delta: float | None = None,
                  cusum_h: float | None = None, max_levels: int = cusum.DEFAULT_MAX_LEVELS,
-                 event_capacity: int | None = None, group=None, device="cuda"):
+                 event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = False):
         self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
         self.n_own = self.n_ext - self.lo_halo - self.hi_halo
         self.n_det = self.n_ext - self.lo_halo
@@ -171,8 +216,9 @@ class TraceAnalyzer:
         self.y = torch.empty(self.n_ext, dtype=torch.float32, device=self.device)
         self.design = bessel_lowpass(self.order, 2.0 * self.cutoff / float(np.floor(np.squeeze(settings["ADCSAMPLERATE"]))))
         # baseline block sums ride on the filter's epilogue when the block is a whole number of its warp groups
-        self.fuse_stats = self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0
+        self.fuse_stats = bool(fuse_stats) and self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0
         self.filter_ws = None
+        self.H = max(1, self.design.impulse_tail(filters.DEFAULT_HALO_EPS))
         self.ws_bytes = int(L.ct_detect_workspace_bytes(self.n_det))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self._alloc_events(int(event_capacity) if event_capacity else max(1024, self.n_det // 2048))
@@ -195,7 +241,32 @@ class TraceAnalyzer:
             self.cws_bytes = int(_lib.lib().ct_cusum_workspace_bytes(cap))
             self.cws = torch.empty((self.cws_bytes + 7) // 8, dtype=torch.int64, device=dev)
 
-    def run(self, raw_ext: torch.Tensor, stage_hook=None) -> AnalysisResult:
+    def run_from_host(self, host_codes: torch.Tensor, chunks: int = 16, stage_hook=None) -> AnalysisResult:
+        """`run` with the codes still in (pinned) host memory: the host->device copy is cut into
+        `chunks` pieces on a copy stream and the forward filter pass (with the median count on its
+        side) follows the copy chunk by chunk, so only the work after the forward pass is left when the
+        last byte arrives.  Possible because the forward pass needs the median only approximately:
+        the estimate comes from the first chunk, the exact value from the fused count."""
+        if host_codes.numel() != self.n_ext or host_codes.dtype not in (torch.uint16, torch.int16) or host_codes.is_cuda:
+            raise ValueError("host_codes must be a CPU uint16/int16 tensor of the planned length")
+        if getattr(self, "raw_dev", None) is None:
+            self.raw_dev = torch.empty(self.n_ext, dtype=host_codes.dtype, device=self.device)
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        gran = 1 << 20
+        per = max(gran, -(-self.n_ext // int(chunks) // gran) * gran)
+        bounds = list(range(0, self.n_ext, per)) + [self.n_ext]
+        events = []
+        cur = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(cur)                      # the previous step may still read raw_dev
+        with torch.cuda.stream(self.copy_stream):
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                self.raw_dev[a:b].copy_(host_codes[a:b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self.copy_stream)
+                events.append(e)
+        return self.run(self.raw_dev, stage_hook=stage_hook, _arrivals=(bounds, events))
+
+    def run(self, raw_ext: torch.Tensor, stage_hook=None, _arrivals=None) -> AnalysisResult:
         """One pass of stages 1-3.  `stage_hook(name)` (optional) is called after the launches of each
         stage have been enqueued: 'median', 'filter', 'baseline', 'detect', 'cusum' (profiling only)."""
         hook = stage_hook or (lambda name: None)
@@ -204,15 +275,54 @@ class TraceAnalyzer:
         L = _lib.lib()
         lo, n_own = self.lo_halo, self.n_own
         owned = raw_ext[lo:lo + n_own]
-        c1, c2 = global_code_median(owned, self.mask, self.group)
+        st = filters._stream_ptr(raw_ext)
+        cur = torch.cuda.current_stream(self.device)
+        # ---- median, phase 1: estimate (subtraction constant of the filter, verification window)
+        hist_fn, count_fn = _median_kernels(owned, self.mask)
+        if _arrivals is None:
+            plan = median_estimate(n_own, self.mask, hist_fn, self.group, self.device)
+        else:                                                  # only the first chunk has arrived: estimate from it
+            bounds, events = _arrivals
+            cur.wait_event(events[0])
+            first = raw_ext[lo:max(lo + 1, min(bounds[1], lo + n_own))]
+            plan = median_estimate(n_own, self.mask, _median_kernels(first, self.mask)[0], self.group, self.device,
+                                   n_sampled=first.numel())
         hook("median")
         if self.filter_ws is None:
-            need = int(L.ct_filtfilt_workspace_bytes(self.n_ext, self.padding, max(1, self.design.impulse_tail(filters.DEFAULT_HALO_EPS))))
+            need = int(L.ct_filtfilt_workspace_bytes(self.n_ext, self.padding, self.H))
             self.filter_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        coef = filters.make_coef(self.design)
+        alpha, _ = filters.chimera_affine(self.settings)
+        origin = lo if self.fuse_stats else 0
+        # ---- forward pass with the estimate; it tallies the window counts of the owned codes on the side
+        counts = torch.zeros(9, dtype=torch.int64, device=self.device)
+        fused = plan.exact is None
+        pieces = [(0, 0, 0)] if _arrivals is None else [(2, a, b) for a, b in zip(_arrivals[0][:-1], _arrivals[0][1:])]
+        for i, (part, a, b) in enumerate(pieces):
+            if _arrivals is not None:
+                cur.wait_event(_arrivals[1][i])
+            rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask, 0.0,
+                                         C.byref(coef), self.H, origin, part, plan.lo, plan.step, lo, lo + n_own,
+                                         counts.data_ptr() if fused else None, a, b, self.filter_ws.data_ptr(),
+                                         self.filter_ws.numel(), st)
+            _lib.check(rc, "ct_filter_forward_u16")
+        # ---- median, phase 2: exact order statistics (one small read; retries only if the window missed)
+        c1, c2 = median_search(n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
+                               first_counts=counts if fused else None)
+        pad_x = 0.5 * (c1 + c2) - plan.est
+        if pad_x != 0.0:        # the pad holds median - estimate: redo the groups at the two ends of the trace
+            rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask,
+                                         float(pad_x), C.byref(coef), self.H, origin, 1, 0, 1, 0, 0, None, 0, 0,
+                                         self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
+            _lib.check(rc, "ct_filter_forward_u16")
         bl = detect.new_baseline(self.n_det, self.block, self.bmin, self.bmax, self.device) if self.fuse_stats else None
-        y = filters.dequant_filtfilt(raw_ext, self.settings, self.cutoff, self.order, padding=self.padding,
-                                     median_codes=(c1, c2), out=self.y, workspace=self.filter_ws,
-                                     stats=detect.stats_args(bl, origin=lo) if bl is not None else None)
+        stats = detect.stats_args(bl, origin=lo) if bl is not None else None
+        offset = float(filters.scale_codes_host(np.array([plan.est], dtype=np.uint16), self.settings)[0])
+        y = self.y
+        rc = L.ct_filter_backward(self.n_ext, self.padding, float(alpha), offset, C.byref(coef), self.H, origin,
+                                  y.data_ptr(), self.filter_ws.data_ptr(), self.filter_ws.numel(),
+                                  C.byref(stats) if stats is not None else None, st)
+        _lib.check(rc, "ct_filter_backward")
         pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), self.settings)))
         yd = y[lo:]
         st = filters._stream_ptr(y)

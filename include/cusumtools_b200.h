@@ -91,6 +91,26 @@ int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, con
                     int S, int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
                     const CtFilterStats* stats, void* stream);
 
+/* The two passes of the S == 0 path as separate calls, for callers that know the median only
+ * approximately when the forward pass starts (streaming loads; fusing the exact count into the
+ * pass that reads every code anyway).  With DC gain exactly 1,
+ *     filtfilt(code - m) + m == filtfilt(code - c) + c      for ANY constant c,
+ * provided the pad holds m - c instead of 0.  So the forward pass may subtract an estimate c
+ * (`sub_code`) with pad_x = 0; it can tally, on the side, the window counts that pin the exact
+ * median m (counts9: as ct_count_window_u16, zeroed by the caller); if m != c the caller re-runs
+ * only the groups the pad influences (`part` = 1, pad_x = m - c) and then runs the backward
+ * pass with offset = value(c).  `origin` (>= 0) aligns the run grid with baseline blocks counted
+ * from that output sample; both passes must get the same value.  Only codes at positions
+ * [count_begin, count_end) are tallied (a time shard counts its owned samples, not its halos).
+ * part = 2 streams the pass while the codes are still arriving: each call processes the groups
+ * whose input lies below to_pos and that the previous call (which ended at from_pos) did not. */
+int ct_filter_forward_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub_code, uint16_t mask, float pad_x,
+                          const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t window_lo,
+                          uint32_t window_step, int64_t count_begin, int64_t count_end, uint64_t* counts9, int64_t from_pos,
+                          int64_t to_pos, void* workspace, int64_t workspace_bytes, void* stream);
+int ct_filter_backward(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H, int64_t origin,
+                       float* out, const void* workspace, int64_t workspace_bytes, const CtFilterStats* stats, void* stream);
+
 /* Exact global median of the masked codes, the value np.pad(mode='median') needs
  * (plot-trace.py:319): a strided-sample histogram to locate it and an exact count of
  * the codes below / inside a window of 8 codes {lo + i*step} to verify it.

@@ -133,3 +133,49 @@ def test_block_sums_fused_into_the_filter_equal_the_standalone_kernel(origin):
     ref = detect.baseline_blocks(y[origin:], block, 4700.0, 5300.0)
     for k in ("cnt", "s1", "s2"):
         assert torch.equal(bl.dev[k], ref.dev[k]), k
+
+
+@pytest.mark.parametrize("n,lo,hi", [(300_001, 0, 0), (300_000, 0, 0), (5_000_000, 0, 0), (5_000_001, 4096, 8192)])
+def test_analyzer_filter_with_estimated_median_matches_the_oracle_at_the_trace_ends(n, lo, hi):
+    """The analyzer filters with an ESTIMATED median as subtraction constant, counts the exact
+    median on the side and repairs the pad at both ends (pipeline.TraceAnalyzer.run): the result
+    must equal the reference's filter_data over the whole trace, ends included, and the median /
+    pad value must be the exact ones."""
+    from cusumtools_b200 import filters
+    from oracle import trace_oracle as to
+    codes, _ = synth.c1_trace(n=n, n_events=min(1000, (n - 4000) // synth.EVENT_PERIOD), seed=n % 97)
+    raw = torch.from_numpy(codes).cuda()
+    an = pipeline.TraceAnalyzer(n, S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=65536, **KW)
+    r = an.run(raw)
+    own = codes[lo:n - hi]
+    srt = np.sort(own & np.uint16(filters.chimera_bitmask(S)))
+    assert r.median_codes == (int(srt[(own.size - 1) // 2]), int(srt[own.size // 2]))
+    x = to.scale_raw_data(codes, S)
+    # the shard's pad value is the median of its OWNED samples (all ranks together: of the whole trace)
+    assert r.pad_value == float(np.median(to.scale_raw_data(own, S)))
+    want = filters.dequant_filtfilt(raw, S, 1e5, 8, median_codes=r.median_codes).cpu().numpy()   # one-call path, exact median
+    got = torch.cat((an.y[:lo], r.detect_trace)).cpu().numpy()
+    assert np.abs(got - want).max() < 0.02
+    if lo == 0 and hi == 0:
+        ref = to.filter_data(x, synth.FS, 1e5, 8)
+        assert np.abs(got[:3000] - ref[:3000]).max() < 0.05 and np.abs(got[-3000:] - ref[-3000:]).max() < 0.05
+        assert np.abs(got - ref).max() < 0.05
+
+
+def test_streamed_run_from_host_equals_the_resident_run():
+    """run_from_host (chunked copy overlapped with the forward pass, median estimated from the
+    first chunk) gives the same events / levels and, to rounding, the same samples as run()."""
+    codes, _ = synth.c1_trace(n=3_400_000, n_events=800, seed=31)
+    codes[:400_000] += np.uint16(64)          # the first chunk sits 16 codes higher: its median is a poor estimate
+    host = torch.from_numpy(codes).pin_memory()
+    kw = dict(baseline_block=65536, cusum_delta=400.0, cusum_h=10.0, **KW)
+    a = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, **kw)
+    b = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, **kw)
+    ra = a.run(host.cuda())
+    for chunks in (3, 16):
+        rb = b.run_from_host(host, chunks=chunks)
+        assert rb.median_codes == ra.median_codes and rb.pad_value == ra.pad_value
+        assert torch.max(torch.abs(ra.filtered - rb.filtered)).item() < 0.02
+        assert len(rb.events) == len(ra.events)
+        # near-ties may move by one sample
+        assert (ra.events.starts - rb.events.starts).abs().max().item() <= 1
