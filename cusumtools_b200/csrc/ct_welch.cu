@@ -17,7 +17,9 @@
 // the 126 MB L2.  Mean removal is applied in the spectrum: with the input shifted by a
 // constant c near the mean (for float32 headroom), FFT(w (x - mu)) = FFT(w (x - c)) -
 // (mu - c) FFT(w) and FFT(w) of the periodic Hann is L/2 at bin 0 and -L/4 at bins +-1.
-// FFT passes are Stockham autosort radix-8/4/2 with twiddles from sincospif.
+// FFT passes are Stockham autosort radix-8/4/2.  Every trigonometric factor (window, Stockham and
+// four-step twiddles, real-FFT split) comes from ONE table T[j] = e^{-2 pi i j / L}, j < L, built once per
+// call with sincospif (8 MB for L = 2^20, L2 resident); the sub-FFT twiddles are staged in shared memory.
 #include "ct_common.cuh"
 #include "cusumtools_b200.h"
 
@@ -50,19 +52,20 @@ template <> __device__ __forceinline__ void dft<8>(cpx* v) {
 
 // One Stockham radix-R pass over `batch` interleaved FFTs of length N held as
 // [index][batch] (batch fastest): in -> out.  Ns = product of the radices already done.
+// tws[m] = e^{-2 pi i m / N} (shared memory): the pass twiddle e^{-2 pi i k r / (Ns R)} is tws[k r N/(Ns R)].
 template <int R>
-__device__ __forceinline__ void stockham_pass(const cpx* __restrict__ in, cpx* __restrict__ out, int N, int Ns,
-                                              int batch, int tid, int nthreads) {
+__device__ __forceinline__ void stockham_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tws,
+                                              int N, int Ns, int batch, int tid, int nthreads) {
     const int work = (N / R) * batch;
+    const int tstride = N / (Ns * R);
     for (int w = tid; w < work; w += nthreads) {
         const int b = w % batch, j = w / batch;
         const int k = j % Ns;
         cpx v[R];
-        const float ang = 2.0f * (float)k / (float)(Ns * R);      // twiddle e^{-i pi ang r}
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             cpx x = in[(j + r * (N / R)) * batch + b];
-            v[r] = r == 0 ? x : cmul(x, expmi(ang * (float)r));
+            v[r] = (r == 0 || Ns == 1) ? x : cmul(x, tws[k * r * tstride]);
         }
         dft<R>(v);
         const int j0 = (j / Ns) * Ns * R + k;
@@ -72,20 +75,23 @@ __device__ __forceinline__ void stockham_pass(const cpx* __restrict__ in, cpx* _
 }
 
 // full FFT of length N = 2^logn for `batch` interleaved transforms; result pointer returned
-__device__ cpx* fft_smem(cpx* a, cpx* b, int logn, int batch, int tid, int nthreads) {
+__device__ cpx* fft_smem(cpx* a, cpx* b, const cpx* tws, int logn, int batch, int tid, int nthreads) {
     const int N = 1 << logn;
     int Ns = 1, rem = logn;
     while (rem > 0) {
-        if (rem >= 3 && rem != 4) { stockham_pass<8>(a, b, N, Ns, batch, tid, nthreads); Ns *= 8; rem -= 3; }
-        else if (rem >= 2) { stockham_pass<4>(a, b, N, Ns, batch, tid, nthreads); Ns *= 4; rem -= 2; }
-        else { stockham_pass<2>(a, b, N, Ns, batch, tid, nthreads); Ns *= 2; rem -= 1; }
+        if (rem >= 3 && rem != 4) { stockham_pass<8>(a, b, tws, N, Ns, batch, tid, nthreads); Ns *= 8; rem -= 3; }
+        else if (rem >= 2) { stockham_pass<4>(a, b, tws, N, Ns, batch, tid, nthreads); Ns *= 4; rem -= 2; }
+        else { stockham_pass<2>(a, b, tws, N, Ns, batch, tid, nthreads); Ns *= 2; rem -= 1; }
         __syncthreads();
         cpx* t = a; a = b; b = t;
     }
     return a;
 }
 
-constexpr int kCols = 16;      // columns per CTA in kernel A
+#ifndef CT_WELCH_COLS
+#define CT_WELCH_COLS 8
+#endif
+constexpr int kCols = CT_WELCH_COLS;      // columns per CTA in kernel A (smem: 2 x N1 x kCols complex)
 constexpr int kThreads = 256;
 
 struct WelchArgs {
@@ -93,17 +99,26 @@ struct WelchArgs {
     int L, logn1, logn2;       // N = L/2 = 2^logn1 * 2^logn2
     long long seg0; int nseg;  // segments [seg0, seg0+nseg) in this launch
     float c; int use_abs;
+    const cpx* T;              // T[j] = e^{-2 pi i j / L}, j < L
+    int rsplit;                // the segments of a batch are split over this many CTAs per row pair
     cpx* Y;                    // [nseg][N1][N2]
     double* segsum;            // [nseg] sum of (x - c) over the segment
     double* acc;               // [N+1]
     double mu_scale;           // 1/L
 };
 
+__global__ void ct_welch_table(cpx* T, int L) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < L) T[j] = expmi(2.0f * (float)j / (float)L);
+}
+
 __global__ void __launch_bounds__(kThreads) ct_welch_cols(WelchArgs a) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N1 = 1 << a.logn1, N2 = 1 << a.logn2;
     cpx* A = reinterpret_cast<cpx*>(smraw);
     cpx* B = A + (size_t)N1 * kCols;
+    cpx* tws = B + (size_t)N1 * kCols;             // e^{-2 pi i m / N1} = T[m * L / N1]
+    for (int m = threadIdx.x; m < N1; m += kThreads) tws[m] = a.T[(size_t)m * (a.L / N1)];
     const int groups = N2 / kCols;
     const int s = blockIdx.x / groups, g = blockIdx.x % groups;
     const long long base = (a.seg0 + s) * (long long)(a.L / 2);   // hop = L/2
@@ -117,10 +132,8 @@ __global__ void __launch_bounds__(kThreads) ct_welch_cols(WelchArgs a) {
         if (a.use_abs) { v.x = fabsf(v.x); v.y = fabsf(v.y); }
         v.x -= a.c; v.y -= a.c;
         part += (double)v.x + (double)v.y;
-        float s0, c0, s1, c1;
-        sincospif(2.0f * (float)(2 * j) / (float)a.L, &s0, &c0);
-        sincospif(2.0f * (float)(2 * j + 1) / (float)a.L, &s1, &c1);
-        A[w] = make_float2(v.x * (0.5f - 0.5f * c0), v.y * (0.5f - 0.5f * c1));
+        const float4 t01 = *reinterpret_cast<const float4*>(a.T + 2 * j);      // T[2j], T[2j+1]: cos = .x, .z
+        A[w] = make_float2(v.x * (0.5f - 0.5f * t01.x), v.y * (0.5f - 0.5f * t01.z));
     }
     // segment sum for the mean (warp + block reduction, one atomic per CTA)
 #pragma unroll
@@ -132,17 +145,14 @@ __global__ void __launch_bounds__(kThreads) ct_welch_cols(WelchArgs a) {
         double t = 0; for (int i = 0; i < kThreads / 32; ++i) t += wsum[i];
         atomicAdd(a.segsum + s, t);
     }
-    cpx* R = fft_smem(A, B, a.logn1, kCols, tid, kThreads);
+    cpx* R = fft_smem(A, B, tws, a.logn1, kCols, tid, kThreads);
     // twiddle W_N^(n2 k1) and store Y[k1][n2]
     cpx* Y = a.Y + (size_t)s * N1 * N2;
-    const float invN = 1.0f / (float)(N1 * N2);
     for (int w = tid; w < N1 * kCols; w += kThreads) {
         const int col = w % kCols, k1 = w / kCols;
         const int n2 = g * kCols + col;
-        // exponent n2*k1 < N: exact in float up to 2^24; reduce mod N first for large N
-        const long long e = ((long long)n2 * k1) % ((long long)N1 * N2);
-        cpx t = expmi(2.0f * (float)e * invN);
-        Y[(size_t)k1 * N2 + n2] = cmul(R[w], t);
+        // W_N^(n2 k1) = T[2 (n2 k1 mod N)]   (n2 k1 < N1 N2 = N always)
+        Y[(size_t)k1 * N2 + n2] = cmul(R[w], a.T[2 * (size_t)n2 * k1]);
     }
 }
 
@@ -152,7 +162,10 @@ __global__ void __launch_bounds__(kThreads) ct_welch_rows(WelchArgs a) {
     const long long N = (long long)N1 * N2;
     cpx* A = reinterpret_cast<cpx*>(smraw);       // [N2][2] interleaved pair of rows
     cpx* B = A + (size_t)N2 * 2;
-    const int r = blockIdx.x;                      // 0 .. N1/2
+    cpx* tws = B + (size_t)N2 * 2;                 // e^{-2 pi i m / N2} = T[m * L / N2]
+    for (int m = threadIdx.x; m < N2; m += kThreads) tws[m] = a.T[(size_t)m * (a.L / N2)];
+    const int r = blockIdx.x / a.rsplit;           // 0 .. N1/2
+    const int part = blockIdx.x % a.rsplit;
     const int r2 = (r == 0) ? 0 : N1 - r;          // partner row (== r for r = 0 and N1/2)
     const bool self = (r2 == r);
     const int tid = threadIdx.x;
@@ -161,15 +174,14 @@ __global__ void __launch_bounds__(kThreads) ct_welch_rows(WelchArgs a) {
     float accA[kMaxOwn], accB[kMaxOwn];
 #pragma unroll
     for (int i = 0; i < kMaxOwn; ++i) { accA[i] = 0.f; accB[i] = 0.f; }
-    const float invN = 1.0f / (float)N;
-    for (int s = 0; s < a.nseg; ++s) {
+    for (int s = part; s < a.nseg; s += a.rsplit) {
         const cpx* Y = a.Y + (size_t)s * N1 * N2;
         for (int w = tid; w < N2; w += kThreads) {
             A[2 * w] = Y[(size_t)r * N2 + w];
             A[2 * w + 1] = Y[(size_t)r2 * N2 + w];
         }
         __syncthreads();
-        cpx* Z = fft_smem(A, B, a.logn2, 2, tid, kThreads);
+        cpx* Z = fft_smem(A, B, tws, a.logn2, 2, tid, kThreads);
         const float dmu = (float)(a.segsum[s] * a.mu_scale);     // mu - c for this segment
         int own = 0;
         for (int k2 = tid; k2 < N2; k2 += kThreads, ++own) {
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) ct_welch_rows(WelchArgs a) {
             if (r == 0) { m2 = (N2 - k2) % N2; Zm = Z[2 * m2]; }
             else { m2 = N2 - 1 - k2; Zm = Z[2 * m2 + 1]; }
             cpx E = cadd(Zk, cconj(Zm)), O = csub(Zk, cconj(Zm));
-            cpx tw = expmi((float)k * invN);                      // e^{-i pi k / N}
+            const cpx tw = a.T[k];                                // e^{-i pi k / N} = e^{-2 pi i k / L}
             cpx X = cadd(make_float2(0.5f * E.x, 0.5f * E.y), cmul(make_float2(0.5f * O.y, -0.5f * O.x), tw));
             // (-i/2) O tw  ==  (0.5*O.y, -0.5*O.x) * tw
             if (k == 0) X.x -= dmu * 0.5f * (float)a.L;
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) ct_welch_rows(WelchArgs a) {
             accA[own] += X.x * X.x + X.y * X.y;
             // mirror bin N-k (k != 0): swap roles
             cpx E2 = cadd(Zm, cconj(Zk)), O2 = csub(Zm, cconj(Zk));
-            cpx tw2 = expmi((float)(N - k) * invN);
+            const cpx tw2 = make_float2(-tw.x, tw.y);             // e^{-i pi (N-k)/N} = -conj(e^{-i pi k/N})
             cpx X2 = cadd(make_float2(0.5f * E2.x, 0.5f * E2.y), cmul(make_float2(0.5f * O2.y, -0.5f * O2.x), tw2));
             if (k == 0) {                                         // bin N (Nyquist) lives here
                 X2 = make_float2(Zk.x - Zk.y, 0.f);
@@ -216,7 +228,7 @@ extern "C" {
 
 int64_t ct_welch_workspace_bytes(int32_t nperseg, int32_t batch) {
     if (nperseg < 256 || (nperseg & (nperseg - 1))) return -1;
-    return (int64_t)batch * (nperseg / 2) * 8 + (int64_t)batch * 8 + 256;
+    return (int64_t)batch * (nperseg / 2) * 8 + (int64_t)batch * 8 + 256 + (int64_t)nperseg * 8;
 }
 
 int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_t use_abs, int32_t batch,
@@ -243,9 +255,14 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
     a.x = x; a.n = n; a.L = L; a.logn1 = logn1; a.logn2 = logn2; a.c = shift; a.use_abs = use_abs;
     a.Y = (cpx*)workspace;
     a.segsum = (double*)((char*)workspace + (size_t)batch * N * 8);
+    cpx* T = (cpx*)((char*)workspace + (((size_t)batch * N * 8 + (size_t)batch * 8 + 255) / 256) * 256);
+    a.T = T;
     a.acc = acc; a.mu_scale = 1.0 / (double)L;
     const int N1 = 1 << logn1, N2 = 1 << logn2;
-    size_t smA = (size_t)2 * N1 * kCols * sizeof(cpx), smB = (size_t)2 * 2 * N2 * sizeof(cpx);
+    CT_COUNT_LAUNCH();
+    ct_welch_table<<<(L + 255) / 256, 256, 0, st>>>(T, L);
+    { int rc = ct_check_launch("ct_welch_table"); if (rc) return rc; }
+    size_t smA = (size_t)(2 * N1 * kCols + N1) * sizeof(cpx), smB = (size_t)(2 * 2 * N2 + N2) * sizeof(cpx);
     cudaFuncSetAttribute(ct_welch_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
     cudaFuncSetAttribute(ct_welch_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
     for (long long s0 = 0; s0 < nseg; s0 += batch) {
@@ -254,8 +271,11 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
         CT_COUNT_LAUNCH();
         ct_welch_cols<<<(unsigned)(a.nseg * (N2 / kCols)), kThreads, smA, st>>>(a);
         int rc = ct_check_launch("ct_welch_cols"); if (rc) return rc;
+        // enough CTAs to fill the GPU: the segments of the batch are split over rsplit CTAs per row pair
+        a.rsplit = 1;
+        while ((N1 / 2 + 1) * a.rsplit < 4 * ct_sm_count() && a.rsplit * 2 <= a.nseg) a.rsplit *= 2;
         CT_COUNT_LAUNCH();
-        ct_welch_rows<<<(unsigned)(N1 / 2 + 1), kThreads, smB, st>>>(a);
+        ct_welch_rows<<<(unsigned)((N1 / 2 + 1) * a.rsplit), kThreads, smB, st>>>(a);
         rc = ct_check_launch("ct_welch_rows"); if (rc) return rc;
     }
     return CT_OK;
