@@ -178,7 +178,7 @@ def run_ours(args):
     S = synth.CHIMERA_SETTINGS
     n_own = int(args.samples)
     n_own = n_own // BASELINE_BLOCK * BASELINE_BLOCK if world > 1 else n_own
-    halo = pipeline.required_halo(CUTOFF, ORDER, synth.FS, max_event=4096) if world > 1 else 0
+    halo = pipeline.required_halo(CUTOFF, ORDER, synth.FS, max_event=4096, block=BASELINE_BLOCK) if world > 1 else 0
     lo_h = halo if rank > 0 else 0
     hi_h = halo if rank < world - 1 else 0
     raw = synth.device_trace(n_own + lo_h + hi_h, dev, seed=1234 + rank, start_index=rank * n_own - lo_h)
@@ -253,7 +253,19 @@ def run_ours(args):
     if group is not None:
         dist.all_reduce(ev_all, group=group)
     stage_ms = {nm: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in stage_ev])) for i, nm in enumerate(stage_names)}
-    filt_ms = stage_ms["filter"]
+    # the dominant kernel pair alone (forward + backward filter pass, no host round trip in between),
+    # timed with CUDA events on the launching stream: the roofline entry
+    med = an.last_median if hasattr(an, "last_median") else filters.code_median(raw[lo_h:lo_h + n_own], filters.chimera_bitmask(S))
+    for _ in range(2):
+        filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y, workspace=an.filter_ws)
+    fa = torch.cuda.Event(enable_timing=True); fb = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    fa.record()
+    for _ in range(3):
+        filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y, workspace=an.filter_ws)
+    fb.record()
+    torch.cuda.synchronize()
+    filt_ms = fa.elapsed_time(fb) / 3
     ms_per_step = dev_ms / args.steps
     total = n_own * world
     value = total / (ms_per_step / 1e3) / 1e6
@@ -300,12 +312,14 @@ def run_ours(args):
         "events_per_s": int(ev_all.item()) / (ms_per_step / 1e3),
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms": stage_ms,
-        "roofline": {"kernel": "ct_filter_fwd_kernel + ct_filter_bwd_kernel (dequantise + median pad + zero-phase Bessel; "
-                               "the backward pass also tallies the baseline block sums)", "bound": "hbm",
+        "roofline": {"kernel": "ct_filter_fwd_kernel + ct_filter_bwd_kernel (fused dequantise + median pad + zero-phase "
+                               "Bessel as two lane-sequential passes; timed alone, 3 back-to-back calls)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "kernel_ms": filt_ms,
                      "algorithmic_bytes_per_sample": FILTER_BYTES_PER_SAMPLE,
-                     "share_of_step": filt_ms / ms_per_step},
+                     "share_of_step": filt_ms / ms_per_step,
+                     "note": "traffic = ncu dram bytes per launch pair (profiles/): the forward output crosses HBM "
+                             "once (4 B/sample written + 4 B/sample read) on top of the 6 algorithmic bytes"},
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(raw.numel() * 2 * world),
                 "d2h_bytes_per_step": int(d2h[0] * world), "ms_per_step": e_ms},
         "gpu_launches": int(launches),

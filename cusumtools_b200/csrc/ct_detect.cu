@@ -352,31 +352,37 @@ ct_baseline_finalize_kernel(const long long* __restrict__ cnt, const long long* 
 // oracle/events_oracle.py::event_windows on the device, with the event count read from
 // device memory (counts2 of ct_detect_f32) so no host round trip separates detection from
 // CUSUM+.  Events are [starts[i], ends[i]) for i < min(n_starts, n_ends, capacity); only
-// events starting before n_keep are kept (time shards: the owner is the rank containing the
-// start).  n_events_out[0] = number kept.
+// events with pos_lo <= start < pos_hi are kept (time shards: the rank whose owned range
+// holds the start owns the event; detection itself runs from the left halo on so that the
+// state at the first owned sample is right).  The kept events are the index range
+// [i0, i0 + count); outputs are written compacted (index i - i0).  out2 = {count, i0}.
 __global__ void ct_event_windows_kernel(const long long* __restrict__ starts, const long long* __restrict__ ends,
                                         const unsigned long long* __restrict__ counts2, long long capacity,
-                                        long long n_total, long long n_keep, long long padding, long long minpoints,
-                                        long long maxpoints, long long* __restrict__ w0, long long* __restrict__ w1,
-                                        int* __restrict__ type, long long* __restrict__ n_events_out) {
+                                        long long n_total, long long pos_lo, long long pos_hi, long long padding,
+                                        long long minpoints, long long maxpoints, long long* __restrict__ w0,
+                                        long long* __restrict__ w1, int* __restrict__ type, long long* __restrict__ out2) {
     long long ne = (long long)min(counts2[0], counts2[1]);
     if (ne > capacity) ne = capacity;
-    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // starts are sorted: lower bounds of pos_lo and pos_hi by binary search (every thread, L2 resident)
+    auto lower = [&](long long pos) {
+        long long a = 0, b = ne;
+        while (a < b) { const long long m = (a + b) >> 1; if (starts[m] < pos) a = m + 1; else b = m; }
+        return a;
+    };
+    const long long i0 = lower(pos_lo), i1 = lower(pos_hi);
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    if (i0 == 0 && (ne == 0 || starts[0] >= n_keep)) n_events_out[0] = 0;
-    for (long long i = i0; i < ne; i += stride) {
+    if (t0 == 0) { out2[0] = i1 - i0; out2[1] = i0; }
+    for (long long i = i0 + t0; i < i1; i += stride) {
         const long long s = starts[i], e = ends[i];
-        if (s >= n_keep) continue;
-        const bool lastkept = (i + 1 == ne) || starts[i + 1] >= n_keep;
-        if (lastkept) n_events_out[0] = i + 1;
         const long long a = s - padding, b = e + padding, len = e - s;
-        const long long prev_end = i ? ends[i - 1] : 0;
-        const long long next_start = lastkept ? n_total : starts[i + 1];
+        const long long prev_end = i > i0 ? ends[i - 1] : (i0 > 0 ? ends[i0 - 1] : 0);
+        const long long next_start = i + 1 < ne ? starts[i + 1] : n_total;
         int t = 0;
         if (a < prev_end || b > next_start || a < 0 || b > n_total) t = 4;
         if (len > maxpoints) t = 3;
         if (len < minpoints) t = 2;
-        w0[i] = a; w1[i] = b; type[i] = t;
+        w0[i - i0] = a; w1[i - i0] = b; type[i - i0] = t;
     }
 }
 
@@ -464,21 +470,21 @@ int ct_baseline_finalize(const int64_t* cnt, const int64_t* s1, const int64_t* s
 }
 
 int ct_event_windows(const int64_t* starts, const int64_t* ends, const uint64_t* counts2, int64_t capacity,
-                     int64_t n_total, int64_t n_keep, int64_t padding, int64_t minpoints, int64_t maxpoints,
-                     int64_t* win_start, int64_t* win_end, int32_t* type, int64_t* n_events_out, void* stream) {
-    if (!starts || !ends || !counts2 || !win_start || !win_end || !type || !n_events_out || capacity < 0) {
+                     int64_t n_total, int64_t pos_lo, int64_t pos_hi, int64_t padding, int64_t minpoints, int64_t maxpoints,
+                     int64_t* win_start, int64_t* win_end, int32_t* type, int64_t* out2, void* stream) {
+    if (!starts || !ends || !counts2 || !win_start || !win_end || !type || !out2 || capacity < 0) {
         ct_set_error("event_windows: bad argument"); return CT_ERR_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(n_events_out, 0, 8, st);
+    cudaMemsetAsync(out2, 0, 16, st);
     if (capacity == 0) return CT_OK;
     long long grid = (capacity + 255) / 256;
     const long long cap = (long long)ct_sm_count() * 8;
     if (grid > cap) grid = cap;
     CT_COUNT_LAUNCH();
     ct_event_windows_kernel<<<(unsigned)grid, 256, 0, st>>>(
-        (const long long*)starts, (const long long*)ends, (const unsigned long long*)counts2, capacity, n_total, n_keep,
-        padding, minpoints, maxpoints, (long long*)win_start, (long long*)win_end, type, (long long*)n_events_out);
+        (const long long*)starts, (const long long*)ends, (const unsigned long long*)counts2, capacity, n_total, pos_lo, pos_hi,
+        padding, minpoints, maxpoints, (long long*)win_start, (long long*)win_end, type, (long long*)out2);
     return ct_check_launch("ct_event_windows_kernel");
 }
 

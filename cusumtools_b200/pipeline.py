@@ -158,12 +158,14 @@ def event_id_offsets(n_local_events: int, group=None, device=None) -> tuple[int,
 
 
 def required_halo(cutoff: float, order: int, samplerate: float, max_event: int, padding: int = 1000,
-                  eps: float = filters.DEFAULT_HALO_EPS) -> int:
+                  eps: float = filters.DEFAULT_HALO_EPS, block: int = 1) -> int:
     """Samples a rank must read beyond each end of its owned range: IIR warm-up on both
     sides (forward and backward pass) plus one maximal event so that an event straddling
-    a shard boundary is seen whole by the rank that owns its start."""
+    a shard boundary is seen whole by the rank that owns its start, rounded up to a multiple
+    of the baseline `block` (the left halo keeps every rank on the global block grid)."""
     d = bessel_lowpass(int(order), 2.0 * float(cutoff) / float(samplerate))
-    return 2 * filters.halo_samples(d, eps) + int(max_event)
+    h = 2 * max(1, d.impulse_tail(eps)) + int(max_event)
+    return -(-h // int(block)) * int(block)
 
 
 @dataclass
@@ -171,10 +173,11 @@ class AnalysisResult:
     """Everything one pass of the hot path over a (shard of a) trace produces; all tensors
     are device-resident views into the analyzer's buffers (valid until its next run)."""
     filtered: torch.Tensor          # float32, the rank's owned samples
-    detect_trace: torch.Tensor      # float32, owned + right halo: what event indices refer to
+    detect_trace: torch.Tensor      # float32, [left halo | owned | right halo]: what the windows refer to
+    lo_halo: int                    # samples of detect_trace before the first owned one
     baseline: detect.Baseline
     events: detect.EventList        # indices relative to the rank's first owned sample
-    win_start: torch.Tensor         # int64 [E]  CUSUM+ windows [start - padding, end + padding)
+    win_start: torch.Tensor         # int64 [E]  CUSUM+ windows [start - padding, end + padding) in detect_trace
     win_end: torch.Tensor           # int64 [E]
     types: torch.Tensor             # int32 [E]  rate.csv type code (0 accepted, >1 rejected)
     levels: "cusum.LevelTable | None"
@@ -189,9 +192,12 @@ class TraceAnalyzer:
     synchronisation at the end of the step (the median needs two small ones up front).
 
     `raw_ext` = [lo_halo | owned | hi_halo] codes.  The filter runs over the extended range
-    (its constant pad only matters at the true ends of the trace); detection and CUSUM+ run
-    over [owned | hi_halo] so an event that starts in the owned range and ends in the halo
-    is completed, and events starting in the halo are left to the next rank."""
+    (its constant pad only matters at the true ends of the trace), and so do the baseline
+    blocks and the detector: the state at the first owned sample is then the true one (an
+    event in progress at a shard boundary is not seen twice) and an event that starts in the
+    owned range and ends in the right halo is completed.  Events are owned by the rank whose
+    owned range holds their start.  `lo_halo` must be a multiple of the baseline block so
+    that the block grid of every rank is the global one (`required_halo(..., block=)`)."""
 
     def __init__(self, n_ext: int, settings, cutoff: float, order: int = 8, *, lo_halo: int = 0, hi_halo: int = 0,
                  threshold: float = 5.0, hysteresis: float = 1.0, baseline_block: int = detect.DEFAULT_BASELINE_BLOCK,
@@ -201,7 +207,9 @@ class TraceAnalyzer:
                  event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = False):
         self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
         self.n_own = self.n_ext - self.lo_halo - self.hi_halo
-        self.n_det = self.n_ext - self.lo_halo
+        self.n_det = self.n_ext
+        if self.lo_halo % int(baseline_block):
+            raise ValueError("lo_halo must be a multiple of the baseline block (pipeline.required_halo(..., block=))")
         self.settings, self.cutoff, self.order, self.padding = settings, float(cutoff), int(order), int(padding)
         self.threshold, self.hysteresis = float(threshold), float(hysteresis)
         self.block, self.bmin, self.bmax = int(baseline_block), float(baseline_min), float(baseline_max)
@@ -231,7 +239,7 @@ class TraceAnalyzer:
         self.w0 = torch.empty(cap, dtype=torch.int64, device=dev)
         self.w1 = torch.empty(cap, dtype=torch.int64, device=dev)
         self.typ = torch.empty(cap, dtype=torch.int32, device=dev)
-        self.scalars = torch.zeros(4, dtype=torch.int64, device=dev)     # n_starts, n_ends, n_kept
+        self.scalars = torch.zeros(4, dtype=torch.int64, device=dev)     # n_starts, n_ends, n_kept, first kept index
         if self.delta is not None:
             self.nl = torch.empty(cap, dtype=torch.int32, device=dev)
             self.ed = torch.empty((cap, ML + 1), dtype=torch.int32, device=dev)
@@ -293,7 +301,7 @@ class TraceAnalyzer:
             self.filter_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         coef = filters.make_coef(self.design)
         alpha, _ = filters.chimera_affine(self.settings)
-        origin = lo if self.fuse_stats else 0
+        origin = 0
         # ---- forward pass with the estimate; it tallies the window counts of the owned codes on the side
         counts = torch.zeros(9, dtype=torch.int64, device=self.device)
         fused = plan.exact is None
@@ -309,6 +317,7 @@ class TraceAnalyzer:
         # ---- median, phase 2: exact order statistics (one small read; retries only if the window missed)
         c1, c2 = median_search(n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
                                first_counts=counts if fused else None)
+        self.last_median = (c1, c2)
         pad_x = 0.5 * (c1 + c2) - plan.est
         if pad_x != 0.0:        # the pad holds median - estimate: redo the groups at the two ends of the trace
             rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask,
@@ -316,7 +325,7 @@ class TraceAnalyzer:
                                          self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
             _lib.check(rc, "ct_filter_forward_u16")
         bl = detect.new_baseline(self.n_det, self.block, self.bmin, self.bmax, self.device) if self.fuse_stats else None
-        stats = detect.stats_args(bl, origin=lo) if bl is not None else None
+        stats = detect.stats_args(bl, origin=0) if bl is not None else None
         offset = float(filters.scale_codes_host(np.array([plan.est], dtype=np.uint16), self.settings)[0])
         y = self.y
         rc = L.ct_filter_backward(self.n_ext, self.padding, float(alpha), offset, C.byref(coef), self.H, origin,
@@ -324,7 +333,7 @@ class TraceAnalyzer:
                                   C.byref(stats) if stats is not None else None, st)
         _lib.check(rc, "ct_filter_backward")
         pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), self.settings)))
-        yd = y[lo:]
+        yd = y
         st = filters._stream_ptr(y)
         hook("filter")
         if bl is not None:
@@ -341,7 +350,7 @@ class TraceAnalyzer:
                                  self.cap, sc[0:].data_ptr(), st)
             _lib.check(rc, "ct_detect_f32")
             rc = L.ct_event_windows(self.starts.data_ptr(), self.ends.data_ptr(), sc[0:].data_ptr(), self.cap, self.n_det,
-                                    n_own, self.event_padding, self.minpoints, self.maxpoints, self.w0.data_ptr(),
+                                    lo, lo + n_own, self.event_padding, self.minpoints, self.maxpoints, self.w0.data_ptr(),
                                     self.w1.data_ptr(), self.typ.data_ptr(), sc[2:].data_ptr(), st)
             _lib.check(rc, "ct_event_windows")
             hook("detect")
@@ -353,24 +362,25 @@ class TraceAnalyzer:
                                           self.cws_bytes, st)
                 _lib.check(rc, "ct_cusum_batch_dev")
             hook("cusum")
-            host = torch.cat((sc[:3], bl.dev["status"].to(torch.int64))).cpu().numpy()   # the step's one sync
-            ns, ne, nk = int(host[0]), int(host[1]), int(host[2])
+            host = torch.cat((sc[:4], bl.dev["status"].to(torch.int64))).cpu().numpy()   # the step's one sync
+            ns, ne, nk, i0 = int(host[0]), int(host[1]), int(host[2]), int(host[3])
             if max(ns, ne) <= self.cap:
                 break
             self._alloc_events(max(ns, ne))          # more events than planned: grow and redo stages 2-3
-        if int(host[3]) != 0:
+        if int(host[4]) != 0:
             raise ValueError("no baseline block has enough samples inside [baseline_min, baseline_max]")
         bl._checked = True
         open_start = -1
         if ns > ne:                                   # an event still open at the end of the data
-            o = int(self.starts[ne].item())
-            open_start = o if o < n_own else -1
-        ev = detect.EventList(self.starts[:nk], self.ends[:nk], open_start)
+            o = int(self.starts[ne].item()) - lo
+            open_start = o if 0 <= o < n_own else -1
+        # event indices are reported relative to the first owned sample
+        ev = detect.EventList(self.starts[i0:i0 + nk] - lo, self.ends[i0:i0 + nk] - lo, open_start)
         lv = None
         if self.delta is not None:
             lv = cusum.LevelTable(self.nl[:nk], self.ed[:nk], self.mu[:nk], self.sd[:nk], self.ov[:nk], self.max_levels)
         first_id, total = event_id_offsets(nk, self.group, self.device)
-        return AnalysisResult(filtered=y[lo:lo + n_own], detect_trace=yd, baseline=bl, events=ev,
+        return AnalysisResult(filtered=y[lo:lo + n_own], detect_trace=yd, lo_halo=lo, baseline=bl, events=ev,
                               win_start=self.w0[:nk], win_end=self.w1[:nk], types=self.typ[:nk], levels=lv,
                               pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id, total_events=total)
 

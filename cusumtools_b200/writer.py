@@ -79,7 +79,8 @@ def _fmt_list(v) -> str:
 
 def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level_std, overflow, xmin, xmax,
                       samplerate: float, threshold: float, baseline_mean, baseline_std, baseline_block: int,
-                      padding: int, first_id: int = 0, time_offset_s: float = 0.0, index_offset: int = 0) -> EventTable:
+                      padding: int, first_id: int = 0, time_offset_s: float = 0.0, index_offset: int = 0,
+                      block_offset: int = 0) -> EventTable:
     """Per-event columns from the detector / CUSUM+ tables (numpy arrays, one row per detected
     event).  `index_offset` is the global sample index of the shard's first owned sample,
     `first_id` the global id of its first event (multi-GPU: pipeline.AnalysisResult)."""
@@ -97,7 +98,8 @@ def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level
     ids = first_id + np.arange(E, dtype=np.int64)
     t_start = time_offset_s + (index_offset + starts) / fs
     t_end = time_offset_s + (index_offset + ends) / fs
-    blk = np.minimum(starts // int(baseline_block), len(baseline_mean) - 1) if E else np.zeros(0, np.int64)
+    # `block_offset`: samples the baseline table starts before the first owned sample (a shard's left halo)
+    blk = np.minimum((starts + int(block_offset)) // int(baseline_block), len(baseline_mean) - 1) if E else np.zeros(0, np.int64)
     rate = {"id": ids, "type": types, "start_time_s": t_start, "end_time_s": t_end,
             "intra_crossing_times_us": np.array([""] * E, dtype=object),
             "local_stdev": np.asarray(baseline_std, np.float64)[blk] if E else np.zeros(0),
@@ -169,7 +171,8 @@ def event_table_from_result(an, r, *, samplerate: float, time_offset_s: float = 
                              overflow=tabs["overflow"], xmin=lo.cpu().numpy(), xmax=hi.cpu().numpy(),
                              samplerate=samplerate, threshold=an.threshold, baseline_mean=r.baseline.mean,
                              baseline_std=r.baseline.std, baseline_block=an.block, padding=an.event_padding,
-                             first_id=r.first_event_id, time_offset_s=time_offset_s, index_offset=index_offset)
+                             first_id=r.first_event_id, time_offset_s=time_offset_s, index_offset=index_offset,
+                             block_offset=r.lo_halo)
 
 
 def _write_csv(path: str, columns, table: dict) -> None:

@@ -149,12 +149,15 @@ int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign,
  * minpoints, 3 longer than maxpoints, 4 padding leaves the trace or overlaps a neighbour;
  * plot-trace.py:354-357 treats type > 1 as rejected), computed on the device from the
  * detector's own counters so no host round trip separates detection from CUSUM+.
- * Event i is [starts[i], ends[i]) for i < min(counts2[0], counts2[1], capacity); events
- * starting at or beyond n_keep are dropped (time shards: the rank that holds the start owns
- * the event).  win = [start - padding, end + padding); n_events_out[0] = events kept.      */
+ * Event i is [starts[i], ends[i]) for i < min(counts2[0], counts2[1], capacity); the events
+ * with pos_lo <= start < pos_hi are kept (time shards: the rank whose owned range holds the
+ * start owns the event; detection itself starts in the left halo so that the state at the
+ * first owned sample is right).  They are the index range [i0, i0 + count) of starts/ends;
+ * win = [start - padding, end + padding) and type are written compacted (index i - i0);
+ * out2 = {count, i0}.                                                                    */
 int ct_event_windows(const int64_t* starts, const int64_t* ends, const uint64_t* counts2, int64_t capacity,
-                     int64_t n_total, int64_t n_keep, int64_t padding, int64_t minpoints, int64_t maxpoints,
-                     int64_t* win_start, int64_t* win_end, int32_t* type, int64_t* n_events_out, void* stream);
+                     int64_t n_total, int64_t pos_lo, int64_t pos_hi, int64_t padding, int64_t minpoints, int64_t maxpoints,
+                     int64_t* win_start, int64_t* win_end, int32_t* type, int64_t* out2, void* stream);
 
 /* ---- stage 3: batched per-event CUSUM+ level segmentation -----------------------
  * No reference implementation exists (readevents.py:843-846,1297-1306 only consumes the

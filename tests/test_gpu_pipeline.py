@@ -14,16 +14,19 @@ S = synth.CHIMERA_SETTINGS
 KW = dict(threshold=5.0, hysteresis=1.0, baseline_min=4700.0, baseline_max=5300.0)
 
 
-def oracle_chain(y, n_keep, block, pad=100, minp=8, maxp=100000, delta=400.0, h=10.0, max_levels=16):
+def oracle_chain(y, n_keep, block, pad=100, minp=8, maxp=100000, delta=400.0, h=10.0, max_levels=16, lo=0):
+    """The oracle's stages 2-3 over the whole detection trace `y`; events whose start lies in
+    [lo, lo + n_keep) are kept and reported relative to `lo` (windows stay in `y` coordinates)."""
     c0 = np.float32(5000.0)
     sh = eo.stats_shift(300.0, block)
     cnt, s1, s2 = c_twin.block_stats(y, block, 4700.0, 5300.0, c0, sh)
     mean, std = eo.baseline_from_stats(cnt, s1, s2, c0, sh)
     sign, ts, te = eo.thresholds(mean, std, 5.0, 1.0)
     s, e, o = c_twin.detect_events(y, block, sign, ts, te)
-    keep = s < n_keep
-    s, e = s[keep], e[keep]
     w0, w1, typ = eo.event_windows(s, e, len(y), pad, minp, maxp)
+    keep = (s >= lo) & (s < lo + n_keep)
+    s, e, w0, w1, typ = s[keep] - lo, e[keep] - lo, w0[keep], w1[keep], typ[keep]
+    o = o - lo if 0 <= o - lo < n_keep else -1
     ok = typ == 0
     offs = np.concatenate(([0], np.cumsum((w1 - w0)[ok])))
     flat = np.concatenate([y[a:b] for a, b in zip(w0[ok], w1[ok])]) if ok.any() else np.zeros(0, np.float32)
@@ -74,8 +77,8 @@ def test_analyzer_with_halos_keeps_only_owned_events():
                                 cusum_delta=400.0, cusum_h=10.0, **KW)
     r = an.run(raw)
     y = r.detect_trace.cpu().numpy()
-    assert y.size == len(codes) - lo and r.filtered.numel() == len(codes) - lo - hi
-    check(r, oracle_chain(y, len(codes) - lo - hi, 4096))
+    assert y.size == len(codes) and r.filtered.numel() == len(codes) - lo - hi and r.lo_halo == lo
+    check(r, oracle_chain(y, len(codes) - lo - hi, 4096, lo=lo))
 
 
 def test_no_valid_baseline_block_raises():
@@ -135,7 +138,7 @@ def test_block_sums_fused_into_the_filter_equal_the_standalone_kernel(origin):
         assert torch.equal(bl.dev[k], ref.dev[k]), k
 
 
-@pytest.mark.parametrize("n,lo,hi", [(300_001, 0, 0), (300_000, 0, 0), (5_000_000, 0, 0), (5_000_001, 4096, 8192)])
+@pytest.mark.parametrize("n,lo,hi", [(300_001, 0, 0), (300_000, 0, 0), (5_000_000, 0, 0), (5_000_001, 65536, 8192)])
 def test_analyzer_filter_with_estimated_median_matches_the_oracle_at_the_trace_ends(n, lo, hi):
     """The analyzer filters with an ESTIMATED median as subtraction constant, counts the exact
     median on the side and repairs the pad at both ends (pipeline.TraceAnalyzer.run): the result
@@ -154,7 +157,7 @@ def test_analyzer_filter_with_estimated_median_matches_the_oracle_at_the_trace_e
     # the shard's pad value is the median of its OWNED samples (all ranks together: of the whole trace)
     assert r.pad_value == float(np.median(to.scale_raw_data(own, S)))
     want = filters.dequant_filtfilt(raw, S, 1e5, 8, median_codes=r.median_codes).cpu().numpy()   # one-call path, exact median
-    got = torch.cat((an.y[:lo], r.detect_trace)).cpu().numpy()
+    got = r.detect_trace.cpu().numpy()
     assert np.abs(got - want).max() < 0.02
     if lo == 0 and hi == 0:
         ref = to.filter_data(x, synth.FS, 1e5, 8)
