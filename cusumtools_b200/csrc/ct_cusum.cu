@@ -355,17 +355,17 @@ __device__ __forceinline__ SeqOut seq_increments(const double* __restrict__ rcta
     const double m = __dmul_rn(Sqd, rc);
     const double vv = __dmul_rn(__dsub_rn((double)Sqq, __dmul_rn(Sqd, m)), rc);
     const float v = __double2float_rn(vv);
-    SeqOut o; o.sp = 0; o.sn = 0;
-    if (v > 0.f) {
-        const float r = __fdiv_rn(dq, v);
-        const float t = __fsub_rn((float)q, __double2float_rn(m));
-        float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
-        float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
-        fa = fminf(fmaxf(fa, -kSMax), kSMax);
-        fb = fminf(fmaxf(fb, -kSMax), kSMax);
-        o.sp = __float2int_rn(fa);
-        o.sn = __float2int_rn(fb);
-    }
+    // branch-free: evaluate with a harmless divisor when the variance carries no information, then mask
+    const bool ok = v > 0.f;
+    const float r = __fdiv_rn(dq, ok ? v : 1.f);
+    const float t = __fsub_rn((float)q, __double2float_rn(m));
+    float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
+    float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
+    fa = fminf(fmaxf(fa, -kSMax), kSMax);
+    fb = fminf(fmaxf(fb, -kSMax), kSMax);
+    SeqOut o;
+    o.sp = ok ? __float2int_rn(fa) : 0;
+    o.sn = ok ? __float2int_rn(fb) : 0;
     return o;
 }
 
@@ -388,6 +388,20 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
     int k0 = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0, overflow = 0;
     long long Sq = 0, Sqq = 0;           // sums over [k0, k]
     long long Lp = 0, Lpp = 0;           // sums over [e0, k0): the part of the open level before the anchor
+    float nx[kE];                        // the lane's next group of samples (software prefetch)
+#pragma unroll
+    for (int e = 0; e < kE; ++e) nx[e] = 0.f;
+    auto load_group = [&](long long pa, float (&x)[kE]) {
+        if (aligned && pa >= 0 && pa + kE <= a.ntot) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
+            const uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
+            x[0] = __uint_as_float(lo.x); x[1] = __uint_as_float(lo.y); x[2] = __uint_as_float(lo.z); x[3] = __uint_as_float(lo.w);
+            x[4] = __uint_as_float(hi.x); x[5] = __uint_as_float(hi.y); x[6] = __uint_as_float(hi.z); x[7] = __uint_as_float(hi.w);
+        } else {
+#pragma unroll
+            for (int e = 0; e < kE; ++e) { const long long p = pa + e; x[e] = (p >= 0 && p < a.ntot) ? a.y[p] : 0.f; }
+        }
+    };
 
     for (;;) {
         // ---- lanes without an event fetch the next ones (one atomic per warp)
@@ -412,6 +426,7 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
                         k0 = 0; gp = gn = 0; rp = rn = 0; nedge = 1; e0 = 0; overflow = 0;
                         Sq = Sqq = 0; Lp = Lpp = 0;
                         a.edges[ev * (ML + 1)] = 0;
+                        load_group(p0 + gk, nx);
                         active = true;
                     }
                 }
@@ -422,29 +437,23 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
             continue;
         }
         if (active) {
-            // ---- one group of 8 consecutive samples of this lane's event
+            // ---- one group of 8 consecutive samples of this lane's event (the next group is already on its way)
             float xv[kE];
-            const long long pa = p0 + gk;
-            if (aligned && pa >= 0 && pa + kE <= a.ntot) {
-                const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
-                const uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
-                xv[0] = __uint_as_float(lo.x); xv[1] = __uint_as_float(lo.y); xv[2] = __uint_as_float(lo.z); xv[3] = __uint_as_float(lo.w);
-                xv[4] = __uint_as_float(hi.x); xv[5] = __uint_as_float(hi.y); xv[6] = __uint_as_float(hi.z); xv[7] = __uint_as_float(hi.w);
-            } else {
 #pragma unroll
-                for (int e = 0; e < kE; ++e) { const long long p = pa + e; xv[e] = (p >= 0 && p < a.ntot) ? a.y[p] : 0.f; }
-            }
+            for (int e = 0; e < kE; ++e) xv[e] = nx[e];
+            if (gk + kE < n) load_group(p0 + gk + kE, nx);
+            const unsigned nlim = overflow ? 0u : (unsigned)n;
 #pragma unroll
             for (int e = 0; e < kE; ++e) {
                 const int k = gk + e;
-                if (k < 0 || k >= n || overflow) continue;
-                if (k == 0) x0 = xv[e];
+                if ((unsigned)k >= nlim) continue;       // before the window (k < 0 wraps), behind it, or frozen by overflow
+                x0 = k == 0 ? xv[e] : x0;
                 const int q = quantise(xv[e], x0);
                 Sq += q; Sqq += (long long)q * q;
                 const SeqOut s = seq_increments(a.rctab, Sq, Sqq, k - k0 + 1, q, dq, hq);
-                gp += s.sp; if (gp <= 0) { gp = 0; rp = k; }
-                gn += s.sn; if (gn <= 0) { gn = 0; rn = k; }
-                if (gp > H || gn > H) {
+                gp = max(gp + s.sp, 0); rp = gp == 0 ? k : rp;
+                gn = max(gn + s.sn, 0); rn = gn == 0 ? k : rn;
+                if (max(gp, gn) > H) {
                     if (nedge >= ML) { overflow = 1; continue; }
                     const int edge = ((gp >= gn) ? rp : rn) + 1;
                     long long T = 0, TT = 0;             // sums over [edge, k]
