@@ -52,35 +52,40 @@ ct_detect_pass1(const float* __restrict__ y, long long n, long long block,
                 const float* __restrict__ t_end, uint2* __restrict__ masks,
                 RunSummary* __restrict__ summ, long long nruns) {
     const int lane = ct_lane();
-    const long long run = (long long)blockIdx.x * kDetWarps + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const long long run = (long long)blockIdx.x * kDetWarps + wib;
     if (run >= nruns) return;
+    __shared__ uint2 s_ab[kDetWarps][32];        // the 32 ballot pairs of a batch, one row per warp
     const long long base = run * kRun;
     // block is a multiple of kRun, so a run never straddles two baseline blocks
     const long long kb = base / block;
-    const bool pos = sign[kb] > 0;
-    const float ts = t_start[kb], te = t_end[kb];
+    // a negative baseline mirrors the comparisons: work on sgn*v so that "beyond the start line" is always
+    // v' < ts' and "back beyond the end line" always v' > te' (x -> -x is exact, comparisons are unchanged)
+    const float sgn = sign[kb] > 0 ? 1.f : -1.f;
+    const float ts = sgn * t_start[kb], te = sgn * t_end[kb];
     const bool full = base + kRun <= n;
     unsigned cin = 0, first = 0, last = 0, ns = 0, ne = 0;
     for (int b = 0; b < kRun / 1024; ++b) {
         const long long bb = base + b * 1024;
-        unsigned myA = 0, myB = 0;
 #pragma unroll
         for (int w0 = 0; w0 < 32; w0 += 8) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const long long p = bb + (w0 + j) * 32 + lane;
-                v[j] = (full || p < n) ? y[p] : te;          // == te is neither symbol
+                v[j] = (full || p < n) ? sgn * y[p] : te;    // == te is neither symbol
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const bool sa = pos ? v[j] < ts : v[j] > ts;
-                const bool sb = pos ? v[j] > te : v[j] < te;
-                const unsigned A = __ballot_sync(CT_FULL, sa);
-                const unsigned B = __ballot_sync(CT_FULL, sb);
-                if (lane == w0 + j) { myA = A; myB = B; }
+                const unsigned A = __ballot_sync(CT_FULL, v[j] < ts);
+                const unsigned B = __ballot_sync(CT_FULL, v[j] > te);
+                if (lane == 0) s_ab[wib][w0 + j] = make_uint2(A, B);     // one predicated 64-bit store per row
             }
         }
+        __syncwarp();
+        const uint2 ab = s_ab[wib][lane];          // lane w owns the ballots of row w
+        __syncwarp();
+        const unsigned myA = ab.x, myB = ab.y;
         masks[run * kRunWords + b * 32 + lane] = make_uint2(myA, myB);
         const unsigned nz = myA | myB;
         const unsigned lastIn = nz ? ((myA >> (31 - __clz(nz))) & 1u) : 0u;

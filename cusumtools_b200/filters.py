@@ -173,7 +173,7 @@ def code_median(raw: torch.Tensor, mask: int = 0xFFFF) -> tuple[int, int]:
         _lib.check(L.ct_hist_sampled_u16(raw.data_ptr(), n, stride, mask, h.data_ptr(), st), "ct_hist_sampled_u16")
         return h.cpu().numpy().astype(np.int64)
 
-    stride = max(1, n // (1 << 22))
+    stride = max(1, n // (1 << 20))
     hist = sampled_hist(stride)
     if stride == 1:
         cdf = np.cumsum(hist)

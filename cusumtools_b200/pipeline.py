@@ -67,7 +67,7 @@ def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n
         shift += 1
     step = 1 << shift
     k1, k2 = (n - 1) // 2, n // 2
-    stride = max(1, (n if n_sampled is None else int(n_sampled)) // (1 << 22))
+    stride = max(1, (n if n_sampled is None else int(n_sampled)) // (1 << 20))      # ~1 M samples: median s.e. < 0.1 code
     h = _all_reduce_(hist_fn(stride).to(torch.int64), group)
     cdf = np.cumsum(h.cpu().numpy())
     if stride == 1 and n_sampled is None:
