@@ -182,3 +182,37 @@ def test_streamed_run_from_host_equals_the_resident_run():
         assert len(rb.events) == len(ra.events)
         # near-ties may move by one sample
         assert (ra.events.starts - rb.events.starts).abs().max().item() <= 1
+
+
+def test_config_c1_end_to_end_against_the_cpu_path():
+    """BASELINE.json configs[0]: 1 s synthetic Chimera trace (4 166 666 samples), 8-pole 100 kHz Bessel,
+    1000 injected two-level events, threshold detection + CUSUM+.  The GPU path runs on the codes; the CPU
+    path is the reference's call sequence (scale_raw_data -> median pad -> scipy filtfilt, float64) followed
+    by the oracle's detection / CUSUM+ on ITS OWN filtered trace.  End to end the two filtered traces differ
+    by float32 rounding, so indices may move where a sample sits within that tolerance of a line (SURVEY.md
+    H2): every injected event must be found by both, and event boundaries / changepoints must agree
+    to within one sample on (almost) all of them."""
+    from oracle import trace_oracle as to
+    codes, true_starts = synth.c1_trace()
+    n = len(codes)
+    assert n == 4_166_666 and len(true_starts) == 1000
+    an = pipeline.TraceAnalyzer(n, S, 1e5, 8, baseline_block=65536, cusum_delta=400.0, cusum_h=10.0, **KW)
+    r = an.run(torch.from_numpy(codes).cuda())
+    y_ref = to.filter_data(to.scale_raw_data(codes, S), synth.FS, 1e5, 8)
+    assert np.abs(r.filtered.cpu().numpy() - y_ref).max() < 0.05
+    ref = oracle_chain(y_ref.astype(np.float32), n, 65536)
+    gs, ge = r.events.starts.cpu().numpy(), r.events.ends.cpu().numpy()
+    assert len(gs) == len(ref["s"])
+    assert 1000 <= len(gs) <= 1002                      # + at most the pad artefacts at the two ends
+    assert np.abs(gs - ref["s"]).max() <= 1 and np.abs(ge - ref["e"]).max() <= 1
+    assert np.mean(gs == ref["s"]) > 0.995 and np.mean(ge == ref["e"]) > 0.995
+    ok = ref["ok"]
+    gnl = r.levels.n_levels.cpu().numpy()[ok]
+    assert np.mean(gnl == ref["lv"][0]) > 0.99
+    same = gnl == ref["lv"][0]
+    ged = r.levels.edges.cpu().numpy()[ok][same]
+    assert np.mean(np.abs(ged - ref["lv"][1][same]).max(axis=1) <= 1) > 0.99
+    gm = r.levels.mean.cpu().numpy()[ok][same]
+    nl = ref["lv"][0][same]
+    lvl_err = max(np.abs(gm[i, :nl[i]] - ref["lv"][2][same][i, :nl[i]]).max() for i in range(0, len(nl), 10))
+    assert lvl_err < 1.0                                 # pA; a changepoint moved by one sample shifts a level mean slightly
