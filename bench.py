@@ -160,6 +160,36 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def side_kernels(torch, dev, peak):
+    """Kernel-only numbers of the two stages the C2 step does not exercise at their own config shape
+    (reported next to the headline, not part of `value`): CUSUM+ on pre-extracted events (C3 shape, 200 k
+    events) and the Welch PSD (C4 shape, 2^20-point segments over 2^28 samples); 4 B/sample algorithmic."""
+    from cusumtools_b200 import cusum, psd, synth
+    out = {}
+    x, offs, _ = synth.c3_events_device(200_000, dev)
+    w0, w1 = offs[:-1].contiguous(), offs[1:].contiguous()
+    cusum.cusum_levels(x, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H)
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(3):
+        cusum.cusum_levels(x, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 3
+    out["cusum_c3_200k_events"] = {"Msamples_per_s": x.numel() / ms / 1e3, "Mevents_per_s": 200_000 / ms / 1e3,
+                                   "hbm_frac": 4.0 * x.numel() / ms / 1e6 / peak}
+    del x, offs, w0, w1
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    y = torch.randn(1 << 28, generator=g, device=dev) * 24 + 5000
+    psd.welch_sums(y, 1 << 20, shift=5000.0)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(3):
+        psd.welch_sums(y, 1 << 20, shift=5000.0)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 3
+    out["welch_c4_2p20_segments"] = {"Msamples_per_s": y.numel() / ms / 1e3, "hbm_frac": 4.0 * y.numel() / ms / 1e6 / peak}
+    return out
+
+
 # ------------------------------------------------------------------------------- ours
 def run_ours(args):
     import torch
@@ -325,6 +355,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if world == 1:
+        line["other_kernels"] = side_kernels(torch, dev, peak)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
     print(json.dumps(line), flush=True)

@@ -431,6 +431,31 @@ def analyze_trace(raw: torch.Tensor, settings, cutoff: float, order: int = 8, *,
                          baseline_max=baseline_max, padding=padding)
 
 
+def gather_tables(tables: dict, group=None, dst: int = 0) -> dict | None:
+    """Gather per-rank event-table columns (tensors whose first dimension is the rank's event count) to rank
+    `dst` in rank order = time order (the one data-sized collective of the path, O(events)).
+    Returns the concatenated columns on `dst`, None elsewhere; with `group=None` the input itself."""
+    if group is None:
+        return tables
+    import torch.distributed as dist
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    first = next(iter(tables.values()))
+    dev = first.device
+    counts = torch.zeros(ws, dtype=torch.int64, device=dev)
+    counts[rk] = first.shape[0]
+    counts = _all_reduce_(counts, group).cpu().numpy()
+    m = int(counts.max())
+    out = {}
+    for name, t in tables.items():
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        pad[:t.shape[0]] = t
+        bufs = [torch.empty_like(pad) for _ in range(ws)]
+        dist.all_gather(bufs, pad, group=group)          # NCCL has no gatherv: pad to the longest table
+        if rk == dst:
+            out[name] = torch.cat([b[:int(c)] for b, c in zip(bufs, counts)])
+    return out if rk == dst else None
+
+
 def shard_bounds(n: int, world: int, rank: int, align: int) -> tuple[int, int]:
     """Owned range of `rank`: equal shares rounded to `align` (the baseline block), so
     baseline blocks never straddle ranks."""

@@ -117,3 +117,18 @@ def test_segment_share_partitions_scipys_segments():
         sh = [psd.segment_share(n, L, world, r) for r in range(world)]
         assert sum(s1 - s0 for s0, s1, _, _ in sh) == nseg
         assert all(b <= n for _, _, _, b in sh)
+
+
+def _gather_job(rank, world, group):
+    n = 5 + 3 * rank
+    tabs = {"starts": torch.arange(n, dtype=torch.int64) + 1000 * rank, "mean": torch.full((n, 4), float(rank))}
+    got = pipeline.gather_tables(tabs, group, dst=0)
+    return None if got is None else {k: v.numpy() for k, v in got.items()}
+
+
+def test_event_tables_are_gathered_in_rank_order():
+    res = run2(_gather_job, world=3)
+    assert res[1] is None and res[2] is None
+    want = np.concatenate([np.arange(5 + 3 * r) + 1000 * r for r in range(3)])
+    assert np.array_equal(res[0]["starts"], want)
+    assert res[0]["mean"].shape == (want.size, 4) and np.array_equal(res[0]["mean"][:, 0], np.repeat([0.0, 1.0, 2.0], [5, 8, 11]))
