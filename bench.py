@@ -162,11 +162,11 @@ def run_reference(args):
 
 def side_kernels(torch, dev, peak):
     """Kernel-only numbers of the two stages the C2 step does not exercise at their own config shape
-    (reported next to the headline, not part of `value`): CUSUM+ on pre-extracted events (C3 shape, 200 k
+    (reported next to the headline, not part of `value`): CUSUM+ on pre-extracted events (C3: 1 M
     events) and the Welch PSD (C4 shape, 2^20-point segments over 2^28 samples); 4 B/sample algorithmic."""
     from cusumtools_b200 import cusum, psd, synth
     out = {}
-    x, offs, _ = synth.c3_events_device(200_000, dev)
+    x, offs, _ = synth.c3_events_device(1_000_000, dev)
     w0, w1 = offs[:-1].contiguous(), offs[1:].contiguous()
     cusum.cusum_levels(x, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H)
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
@@ -175,7 +175,7 @@ def side_kernels(torch, dev, peak):
         cusum.cusum_levels(x, w0, w1, delta=CUSUM_DELTA, h=CUSUM_H)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 3
-    out["cusum_c3_200k_events"] = {"Msamples_per_s": x.numel() / ms / 1e3, "Mevents_per_s": 200_000 / ms / 1e3,
+    out["cusum_c3_1M_events"] = {"Msamples_per_s": x.numel() / ms / 1e3, "Mevents_per_s": 1_000_000 / ms / 1e3,
                                    "hbm_frac": 4.0 * x.numel() / ms / 1e6 / peak}
     del x, offs, w0, w1
     g = torch.Generator(device=dev); g.manual_seed(3)
