@@ -203,6 +203,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     S = synth.CHIMERA_SETTINGS
