@@ -30,6 +30,7 @@
 // section, and v[n] is off the critical path.
 #include "ct_common.cuh"
 #include "cusumtools_b200.h"
+#include <math.h>
 
 namespace {
 
@@ -43,7 +44,7 @@ constexpr int kRowF = kK + 4;       // float row stride: conflict-free LDS.128 /
 constexpr int kRowH = kK + 8;       // uint16 row stride in halfwords ((kK+8)/2 words = 4 mod 16: conflict-free LDS.128)
 constexpr int kSeqWarps = 2;
 
-enum { kFwdScratch = 0, kFwdFinal = 1 };
+enum { kFwdScratch = 0, kFwdFinal = 1, kFwdScratch2 = 2 };   // Scratch2: the scratch holds every second sample
 
 typedef float2 f2;
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
@@ -127,6 +128,13 @@ static __device__ __forceinline__ long long scratch_off(long long run, int to, i
     const long long g = run >> 6;
     const int h = (int)(run >> 5) & 1, l = (int)run & 31;
     return ((((g * TO + to) * kG + jj) * 2 + h) << 8) + l * 8;
+}
+
+// half-rate scratch: one 1 KB block holds the even-position samples of TWO consecutive slots (16 positions)
+static __device__ __forceinline__ long long scratch_off2(long long run, int to, int jp, int TO) {
+    const long long g = run >> 6;
+    const int h = (int)(run >> 5) & 1, l = (int)run & 31;
+    return ((((g * TO + to) * (kG / 2) + jp) * 2 + h) << 8) + l * 8;
 }
 
 // Forward-pass input tile: rows = the K-sample pieces [lo_r, lo_r + K) of the warp's 64 runs.
@@ -220,6 +228,7 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
     extern __shared__ __align__(16) char smem[];
     constexpr int kIn = Tile<InT>::kInBytes;
     constexpr int kPerWarp = 2 * kIn + (MODE == kFwdFinal ? kOutBytes : 0);
+    static_assert(kG % 2 == 0, "the half-rate scratch pairs slots");
     const int lane = ct_lane();
     const int wib = threadIdx.x >> 5;
     char* wbase = smem + (size_t)wib * kPerWarp;
@@ -278,6 +287,7 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
                 }
             };
             load_group(0);
+            f2 keep[4];
 #pragma unroll
             for (int jj = 0; jj < kG; ++jj) {
                 f2 x[8];
@@ -339,6 +349,18 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
                         float* dst = a.out + scratch_off(run0 + lane, t - wt, jj, TO);
                         stg256(dst, oa);
                         stg256(dst + 256, ob);
+                    } else if (MODE == kFwdScratch2) {      // band-limited output: keep the even positions only
+                        if ((jj & 1) == 0) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) keep[e] = x[2 * e];
+                        } else {
+                            float oa[8], ob[8];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { oa[e] = keep[e].x; ob[e] = keep[e].y; oa[4 + e] = x[2 * e].x; ob[4 + e] = x[2 * e].y; }
+                            float* dst = a.out + scratch_off2(run0 + lane, t - wt, jj >> 1, TO);
+                            stg256(dst, oa);
+                            stg256(dst + 256, ob);
+                        }
                     } else {
                         float* o0 = outb + lane * kRowF + jj * 8;
                         float* o1 = o0 + 32 * kRowF;
@@ -373,7 +395,7 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
 // =============================== backward pass =======================================
 // Reads the interleaved scratch; run r processes positions r*R + R + Hw - 1 down to r*R, the first
 // Hw of them (the first Hw/K tiles of run r+1) only to warm the recursion up.
-template <int NSEC, bool STATS>
+template <int NSEC, bool STATS, bool DEC2>
 __global__ void __launch_bounds__(kSeqWarps * 32, 8)
 ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
     extern __shared__ __align__(16) char smem[];
@@ -395,8 +417,11 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
     }
     const f2 gl = splat(k.gain);
     // the forward output is held constant beyond n_in (scipy: zi * y[-1], _signaltools.py:4910-4913)
-    const long long last = a.n_in - 1 - a.base;           // relative to the run grid
-    const float hold = y1[scratch_off(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 3), TO) + (last & 7)];
+    // (half-rate scratch: the last stored, i.e. even, position; the forward output is flat at the end of the pad)
+    const long long last = ((a.n_in - 1 - a.base) >> (DEC2 ? 1 : 0)) << (DEC2 ? 1 : 0);      // relative to the run grid
+    const float hold = DEC2
+        ? y1[scratch_off2(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 4), TO) + ((last & 15) >> 1)]
+        : y1[scratch_off(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 3), TO) + (last & 7)];
 
     for (long long g = a.g_first + gw; g < a.ngroups; g += nw) {
         const long long run0 = g * kRuns;
@@ -409,6 +434,16 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
             for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(h0 * k.ss[s], h1 * k.ss[s]); v2[s] = v1[s]; }
         }
         // slot q (0 .. ntiles*kG-1) in processing order: tile t = q / kG, jj = kG-1 - q % kG (descending positions)
+        // half-rate scratch: pair qp (0 .. ntiles*kG/2-1) in processing order holds the even positions of two slots
+        auto fetch2 = [&](int qp, u8x& xa, u8x& xb) {
+            const int t = qp / (kG / 2), jp = kG / 2 - 1 - (qp % (kG / 2));
+            const bool warm = t < wt;
+            const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
+            const long long s0 = warm ? r0 + 1 : r0, s1 = warm ? r1 + 1 : r1;
+            // out-of-range blocks are never dereferenced; their values are replaced by `hold` position by position below
+            if (s0 < a.scratch_runs) xa = ldg256(y1 + scratch_off2(s0, to, jp, TO));
+            if (s1 < a.scratch_runs) xb = ldg256(y1 + scratch_off2(s1, to, jp, TO));
+        };
         auto fetch = [&](int q, u8x& xa, u8x& xb) {
             const int t = q / kG, jj = kG - 1 - (q % kG);
             const bool warm = t < wt;
@@ -432,8 +467,12 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
         // buffer slot q just released); buffer index = j & 1 is static because kG is even
         StatAcc acc; acc.c = 0; acc.s1 = 0; acc.s2 = 0;
         u8x pa[2], pb[2];
-        fetch(0, pa[0], pb[0]);
-        fetch(1, pa[1], pb[1]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { pa[i].w[e] = 0u; pb[i].w[e] = 0u; }
+        if (DEC2) { fetch2(0, pa[0], pb[0]); fetch2(1, pa[1], pb[1]); }
+        else { fetch(0, pa[0], pb[0]); fetch(1, pa[1], pb[1]); }
         const int nslots = ntiles * kG;
         for (int t = 0; t < ntiles; ++t) {
             const bool store = t >= wt;
@@ -441,10 +480,32 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
             for (int j = 0; j < kG; ++j) {
                 const int jj = kG - 1 - j;
                 f2 x[8];
+                if (DEC2) {
+                    // slot jj of the pair buffer (j >> 1) & 1: the upper slot of a pair (jj odd) is processed first and
+                    // holds kept samples 4..7; x = 2 * kept at even positions, 0 at odd ones (zero stuffing: the
+                    // images sit above fs/4 where this very filter has no gain), `hold` beyond the forward output
+                    const int bi = (j >> 1) & 1, sub = (jj & 1) * 4;
+                    const bool warm = t < wt;
+                    const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
+                    const long long q0 = a.base + (warm ? r0 + 1 : r0) * a.R + (long long)to * kK + jj * 8, q1 = q0 + 32LL * a.R;
+                    const bool tail = q1 + 8 > a.n_in;         // (q0 < q1: both pieces inside the forward output)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = make_float2(__uint_as_float(pa[j & 1].w[e]), __uint_as_float(pb[j & 1].w[e]));
-                const int qn = t * kG + j + 2;
-                if (qn < nslots) fetch(qn, pa[j & 1], pb[j & 1]);
+                    for (int e = 0; e < 8; ++e) {
+                        float va = (e & 1) ? 0.f : 2.f * __uint_as_float(pa[bi].w[sub + (e >> 1)]);
+                        float vb = (e & 1) ? 0.f : 2.f * __uint_as_float(pb[bi].w[sub + (e >> 1)]);
+                        if (tail) { if (q0 + e >= a.n_in) va = hold; if (q1 + e >= a.n_in) vb = hold; }
+                        x[e] = make_float2(va, vb);
+                    }
+                    if (j & 1) {                               // both slots of the pair consumed: refill its buffer
+                        const int qn = (t * kG + j) / 2 + 2;
+                        if (qn < nslots / 2) fetch2(qn, pa[bi], pb[bi]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = make_float2(__uint_as_float(pa[j & 1].w[e]), __uint_as_float(pb[j & 1].w[e]));
+                    const int qn = t * kG + j + 2;
+                    if (qn < nslots) fetch(qn, pa[j & 1], pb[j & 1]);
+                }
 #pragma unroll
                 for (int ee = 0; ee < 8; ++ee) { const int e = 7 - ee; x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl); }
                 if (store) {
@@ -495,9 +556,9 @@ int launch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
     kern<<<(unsigned)grid, kSeqWarps * 32, smem, st>>>(a, k);
     return ct_check_launch("ct_filter_fwd_kernel");
 }
-template <int NSEC, bool STATS>
+template <int NSEC, bool STATS, bool DEC2>
 int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    auto kern = ct_filter_bwd_kernel<NSEC, STATS>;
+    auto kern = ct_filter_bwd_kernel<NSEC, STATS, DEC2>;
     const int smem = kSeqWarps * kOutBytes;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int occ = 0;
@@ -514,13 +575,13 @@ int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
 
 template <typename InT, int MODE>
 int dispatch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    if (sizeof(InT) == 2 && MODE == kFwdScratch && a.cw_out) {
+    if (sizeof(InT) == 2 && MODE != kFwdFinal && a.cw_out) {
         switch (k.nsec) {
-            case 1: return launch_fwd<1, uint16_t, kFwdScratch, true>(a, k, st);
-            case 2: return launch_fwd<2, uint16_t, kFwdScratch, true>(a, k, st);
-            case 3: return launch_fwd<3, uint16_t, kFwdScratch, true>(a, k, st);
-            case 4: return launch_fwd<4, uint16_t, kFwdScratch, true>(a, k, st);
-            case 5: return launch_fwd<5, uint16_t, kFwdScratch, true>(a, k, st);
+            case 1: return launch_fwd<1, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
+            case 2: return launch_fwd<2, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
+            case 3: return launch_fwd<3, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
+            case 4: return launch_fwd<4, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
+            case 5: return launch_fwd<5, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
         }
     }
     switch (k.nsec) {
@@ -533,17 +594,38 @@ int dispatch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
     ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
     return CT_ERR_ARG;
 }
+template <bool DEC2>
 int dispatch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
     const bool stats = a.st_cnt != nullptr;
     switch (k.nsec) {
-        case 1: return stats ? launch_bwd<1, true>(a, k, st) : launch_bwd<1, false>(a, k, st);
-        case 2: return stats ? launch_bwd<2, true>(a, k, st) : launch_bwd<2, false>(a, k, st);
-        case 3: return stats ? launch_bwd<3, true>(a, k, st) : launch_bwd<3, false>(a, k, st);
-        case 4: return stats ? launch_bwd<4, true>(a, k, st) : launch_bwd<4, false>(a, k, st);
-        case 5: return stats ? launch_bwd<5, true>(a, k, st) : launch_bwd<5, false>(a, k, st);
+        case 1: return stats ? launch_bwd<1, true, DEC2>(a, k, st) : launch_bwd<1, false, DEC2>(a, k, st);
+        case 2: return stats ? launch_bwd<2, true, DEC2>(a, k, st) : launch_bwd<2, false, DEC2>(a, k, st);
+        case 3: return stats ? launch_bwd<3, true, DEC2>(a, k, st) : launch_bwd<3, false, DEC2>(a, k, st);
+        case 4: return stats ? launch_bwd<4, true, DEC2>(a, k, st) : launch_bwd<4, false, DEC2>(a, k, st);
+        case 5: return stats ? launch_bwd<5, true, DEC2>(a, k, st) : launch_bwd<5, false, DEC2>(a, k, st);
     }
     ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
     return CT_ERR_ARG;
+}
+
+// The forward output is band-limited by the filter itself.  If the cascade's gain is below eps everywhere in
+// [fs/4, fs/2], every second sample carries all the information (aliasing < eps) and the backward pass can
+// rebuild the rest by zero stuffing (its own stop band removes the images): the scratch then crosses HBM at
+// half rate.  Evaluated from the coefficients on the host (a few hundred complex multiplications).
+bool half_rate_ok(const CtFilterCoef& k) {
+    double worst = 0.0;
+    for (int i = 0; i <= 256; ++i) {
+        const double w = 1.5707963267948966 * (1.0 + i / 256.0);
+        const double cr = cos(w), ci = -sin(w), c2r = cos(2 * w), c2i = -sin(2 * w);   // z^-1, z^-2
+        double mag = fabs((double)k.gain);
+        for (int s = 0; s < k.nsec; ++s) {
+            const double nr = 1.0 + k.n1[s] * cr + k.n2[s] * c2r, ni = k.n1[s] * ci + k.n2[s] * c2i;
+            const double dr = 1.0 - k.na1[s] * cr - k.na2[s] * c2r, di = -k.na1[s] * ci - k.na2[s] * c2i;
+            mag *= sqrt((nr * nr + ni * ni) / (dr * dr + di * di));
+        }
+        if (mag > worst) worst = mag;
+    }
+    return worst < 1e-7;
 }
 
 // Run length for a trace of n samples: long runs amortise the warm-up, but there must be enough
@@ -620,7 +702,11 @@ int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, f
         a.cw_lo = cw_lo; a.cw_sh = __builtin_ctz(cw_step); a.cw_out = (unsigned long long*)counts9;
         a.cw_p0 = cw_begin < 0 ? 0 : cw_begin; a.cw_p1 = cw_end > n ? n : cw_end;
     }
-    auto go = [&](const SeqArgs& x) { return in_kind ? dispatch_fwd<float, kFwdScratch>(x, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch>(x, *coef, st); };
+    const bool half = half_rate_ok(*coef);
+    auto go = [&](const SeqArgs& x) {
+        if (half) return in_kind ? dispatch_fwd<float, kFwdScratch2>(x, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch2>(x, *coef, st);
+        return in_kind ? dispatch_fwd<float, kFwdScratch>(x, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch>(x, *coef, st);
+    };
     if (part == 0) { a.g_first = 0; a.ngroups = p.ng_fwd; return go(a); }
     if (part == 2) {
         // streaming: the groups whose input [.., group end) lies below to_pos (all remaining ones once to_pos >= n)
@@ -661,7 +747,7 @@ int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, co
         b.st_c0 = stats->c0; b.st_scale = ldexpf(1.f, stats->shift);
         b.st_cnt = (long long*)stats->cnt; b.st_s1 = (long long*)stats->s1; b.st_s2 = (long long*)stats->s2;
     }
-    return dispatch_bwd(b, *coef, st);
+    return half_rate_ok(*coef) ? dispatch_bwd<true>(b, *coef, st) : dispatch_bwd<false>(b, *coef, st);
 }
 
 // One call: forward (+ backward).  stats (may be NULL): fused baseline block sums of the output.
