@@ -204,7 +204,8 @@ class TraceAnalyzer:
                  baseline_min: float, baseline_max: float, padding: int = 1000, event_padding: int = 100,
                  minpoints: int = 8, maxpoints: int = 100_000, cusum_delta: float | None = None,
                  cusum_h: float | None = None, max_levels: int = cusum.DEFAULT_MAX_LEVELS,
-                 event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = False):
+                 event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = False,
+                 fused_count: bool = False):
         self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
         self.n_own = self.n_ext - self.lo_halo - self.hi_halo
         self.n_det = self.n_ext
@@ -225,6 +226,7 @@ class TraceAnalyzer:
         self.design = bessel_lowpass(self.order, 2.0 * self.cutoff / float(np.floor(np.squeeze(settings["ADCSAMPLERATE"]))))
         # baseline block sums ride on the filter's epilogue when the block is a whole number of its warp groups
         self.fuse_stats = bool(fuse_stats) and self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0
+        self.fused_count = bool(fused_count)     # tally the exact-median window inside the forward pass (measured slower)
         self.filter_ws = None
         self.H = max(1, self.design.impulse_tail(filters.DEFAULT_HALO_EPS))
         self.ws_bytes = int(L.ct_detect_workspace_bytes(self.n_det))
@@ -305,15 +307,21 @@ class TraceAnalyzer:
         # ---- forward pass with the estimate; it tallies the window counts of the owned codes on the side
         counts = torch.zeros(9, dtype=torch.int64, device=self.device)
         fused = plan.exact is None
-        pieces = [(0, 0, 0)] if _arrivals is None else [(2, a, b) for a, b in zip(_arrivals[0][:-1], _arrivals[0][1:])]
+        pieces = [(0, 0, self.n_ext)] if _arrivals is None else [(2, a, b) for a, b in zip(_arrivals[0][:-1], _arrivals[0][1:])]
         for i, (part, a, b) in enumerate(pieces):
             if _arrivals is not None:
                 cur.wait_event(_arrivals[1][i])
             rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask, 0.0,
                                          C.byref(coef), self.H, origin, part, plan.lo, plan.step, lo, lo + n_own,
-                                         counts.data_ptr() if fused else None, a, b, self.filter_ws.data_ptr(),
-                                         self.filter_ws.numel(), st)
+                                         counts.data_ptr() if (fused and self.fused_count) else None, a, b,
+                                         self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
             _lib.check(rc, "ct_filter_forward_u16")
+            if fused and not self.fused_count:     # the window count of this piece's owned codes, as its own (ALU-bound) kernel
+                ca, cb = max(a, lo), min(b, lo + n_own)
+                if cb > ca:
+                    rc = L.ct_count_window_u16(raw_ext[ca:cb].data_ptr(), cb - ca, self.mask, plan.lo, plan.step,
+                                               counts.data_ptr(), st)
+                    _lib.check(rc, "ct_count_window_u16")
         # ---- median, phase 2: exact order statistics (one small read; retries only if the window missed)
         c1, c2 = median_search(n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
                                first_counts=counts if fused else None)

@@ -148,7 +148,7 @@ def test_analyzer_filter_with_estimated_median_matches_the_oracle_at_the_trace_e
     from oracle import trace_oracle as to
     codes, _ = synth.c1_trace(n=n, n_events=min(1000, (n - 4000) // synth.EVENT_PERIOD), seed=n % 97)
     raw = torch.from_numpy(codes).cuda()
-    an = pipeline.TraceAnalyzer(n, S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=65536, **KW)
+    an = pipeline.TraceAnalyzer(n, S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=65536, fused_count=(n % 2 == 0), **KW)
     r = an.run(raw)
     own = codes[lo:n - hi]
     srt = np.sort(own & np.uint16(filters.chimera_bitmask(S)))
