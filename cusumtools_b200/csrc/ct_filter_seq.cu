@@ -43,6 +43,14 @@ constexpr int kRuns = 64;           // runs per warp (32 lanes x 2 halves)
 constexpr int kRowF = kK + 4;       // float row stride: conflict-free LDS.128 / STS.128
 constexpr int kRowH = kK + 8;       // uint16 row stride in halfwords ((kK+8)/2 words = 4 mod 16: conflict-free LDS.128)
 constexpr int kSeqWarps = 2;
+#ifndef CT_SEQ_BWD_UNROLL
+#define CT_SEQ_BWD_UNROLL 4
+#endif
+#ifndef CT_SEQ_FWD_UNROLL
+#define CT_SEQ_FWD_UNROLL 2
+#endif
+constexpr int kFwdUnroll = CT_SEQ_FWD_UNROLL;   // same for the forward tile loop (even: the half-rate scratch pairs slots)
+constexpr int kBwdUnroll = CT_SEQ_BWD_UNROLL;   // slots of the backward tile loop unrolled together (multiple of 4: static buffer indices)
 
 enum { kFwdScratch = 0, kFwdFinal = 1, kFwdScratch2 = 2 };   // Scratch2: the scratch holds every second sample
 
@@ -288,7 +296,7 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
             };
             load_group(0);
             f2 keep[4];
-#pragma unroll
+#pragma unroll (kFwdUnroll)
             for (int jj = 0; jj < kG; ++jj) {
                 f2 x[8];
                 if (sizeof(InT) == 4) {
@@ -476,7 +484,7 @@ ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
         const int nslots = ntiles * kG;
         for (int t = 0; t < ntiles; ++t) {
             const bool store = t >= wt;
-#pragma unroll
+#pragma unroll (kBwdUnroll)
             for (int j = 0; j < kG; ++j) {
                 const int jj = kG - 1 - j;
                 f2 x[8];
