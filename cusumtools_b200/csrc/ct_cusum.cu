@@ -342,6 +342,10 @@ __global__ void __launch_bounds__(128, 4) ct_cusum_warp_kernel(CusumArgs a) {
 // float64 mean / std are produced by ct_cusum_finalize from the integer sums the lanes
 // leave (bit-cast) in the mean / std arrays.
 // =====================================================================================
+#ifndef CT_CUSUM_SEQ_GROUP
+#define CT_CUSUM_SEQ_GROUP 8
+#endif
+constexpr int kS = CT_CUSUM_SEQ_GROUP;   // samples a lane processes per (unrolled) group: 4 or 8
 constexpr int kSeqMax = 16384;         // longest window a single lane takes
 constexpr int kSeqMinEvents = 16384;   // below this one event per lane cannot fill the GPU: warps take everything
 constexpr unsigned char kRawSums = 0x80;   // overflow[] bit: level rows hold raw integer sums (finalize pending)
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
     const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
     const float dq = __fmul_rn(a.delta, kQ);
     const float hq = __fmul_rn(dq, 0.5f);
-    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & (4 * kS - 1)) == 0;
     long long nev = a.nev;
     if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
     const int ML = a.max_levels;
@@ -388,18 +392,21 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
     int k0 = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0, overflow = 0;
     long long Sq = 0, Sqq = 0;           // sums over [k0, k]
     long long Lp = 0, Lpp = 0;           // sums over [e0, k0): the part of the open level before the anchor
-    float nx[kE];                        // the lane's next group of samples (software prefetch)
+    float nx[kS];                        // the lane's next group of samples (software prefetch)
 #pragma unroll
-    for (int e = 0; e < kE; ++e) nx[e] = 0.f;
-    auto load_group = [&](long long pa, float (&x)[kE]) {
-        if (aligned && pa >= 0 && pa + kE <= a.ntot) {
+    for (int e = 0; e < kS; ++e) nx[e] = 0.f;
+    auto load_group = [&](long long pa, float (&x)[kS]) {
+        if (aligned && pa >= 0 && pa + kS <= a.ntot) {
             const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
-            const uint4 lo = __ldg(p4), hi = __ldg(p4 + 1);
-            x[0] = __uint_as_float(lo.x); x[1] = __uint_as_float(lo.y); x[2] = __uint_as_float(lo.z); x[3] = __uint_as_float(lo.w);
-            x[4] = __uint_as_float(hi.x); x[5] = __uint_as_float(hi.y); x[6] = __uint_as_float(hi.z); x[7] = __uint_as_float(hi.w);
+#pragma unroll
+            for (int u = 0; u < kS / 4; ++u) {
+                const uint4 w = __ldg(p4 + u);
+                x[4 * u] = __uint_as_float(w.x); x[4 * u + 1] = __uint_as_float(w.y);
+                x[4 * u + 2] = __uint_as_float(w.z); x[4 * u + 3] = __uint_as_float(w.w);
+            }
         } else {
 #pragma unroll
-            for (int e = 0; e < kE; ++e) { const long long p = pa + e; x[e] = (p >= 0 && p < a.ntot) ? a.y[p] : 0.f; }
+            for (int e = 0; e < kS; ++e) { const long long p = pa + e; x[e] = (p >= 0 && p < a.ntot) ? a.y[p] : 0.f; }
         }
     };
 
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
                     else if (nn > seq_limit) a.pending[atomicAdd(a.counter + 1, 1ULL)] = (int)ev;
                     else {
                         n = (int)nn;
-                        gk = -(int)(p0 & 7);
+                        gk = -(int)(p0 & (kS - 1));
                         k0 = 0; gp = gn = 0; rp = rn = 0; nedge = 1; e0 = 0; overflow = 0;
                         Sq = Sqq = 0; Lp = Lpp = 0;
                         a.edges[ev * (ML + 1)] = 0;
@@ -438,13 +445,13 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
         }
         if (active) {
             // ---- one group of 8 consecutive samples of this lane's event (the next group is already on its way)
-            float xv[kE];
+            float xv[kS];
 #pragma unroll
-            for (int e = 0; e < kE; ++e) xv[e] = nx[e];
-            if (gk + kE < n) load_group(p0 + gk + kE, nx);
+            for (int e = 0; e < kS; ++e) xv[e] = nx[e];
+            if (gk + kS < n) load_group(p0 + gk + kS, nx);
             const unsigned nlim = overflow ? 0u : (unsigned)n;
 #pragma unroll
-            for (int e = 0; e < kE; ++e) {
+            for (int e = 0; e < kS; ++e) {
                 const int k = gk + e;
                 if ((unsigned)k >= nlim) continue;       // before the window (k < 0 wraps), behind it, or frozen by overflow
                 x0 = k == 0 ? xv[e] : x0;
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
                     k0 = k; Sq = q; Sqq = (long long)q * q; gp = gn = 0; rp = rn = k;
                 }
             }
-            gk += kE;
+            gk += kS;
             if (gk >= n || overflow) {
                 if (overflow) {                          // the rest of the window belongs to the last level
                     long long T = 0, TT = 0;
