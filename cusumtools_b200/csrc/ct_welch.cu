@@ -20,6 +20,7 @@
 // FFT passes are Stockham autosort radix-8/4/2.  Every trigonometric factor (window, Stockham and
 // four-step twiddles, real-FFT split) comes from ONE table T[j] = e^{-2 pi i j / L}, j < L, built once per
 // call with sincospif (8 MB for L = 2^20, L2 resident); the sub-FFT twiddles are staged in shared memory.
+#include <cstdlib>
 #include "ct_common.cuh"
 #include "cusumtools_b200.h"
 
@@ -101,6 +102,7 @@ struct WelchArgs {
     float c; int use_abs;
     const cpx* T;              // T[j] = e^{-2 pi i j / L}, j < L
     int rsplit;                // the segments of a batch are split over this many CTAs per row pair
+    int ssplit;                // ... and over this many CTAs per column group (register-resident kernels)
     cpx* Y;                    // [nseg][N1][N2]
     double* segsum;            // [nseg] sum of (x - c) over the segment
     double* acc;               // [N+1]
@@ -222,6 +224,369 @@ __global__ void __launch_bounds__(kThreads) ct_welch_rows(WelchArgs a) {
     }
 }
 
+
+// =====================================================================================
+// Register-resident FFT kernels (the production path for 2^15 <= L <= 2^22).
+//
+// The shared-memory Stockham kernels above keep every pass in shared memory and issue
+// their global loads one dependent iteration at a time: ncu shows them waiting on L2/HBM
+// latency (long_scoreboard 7-11 per issued instruction), not on bandwidth or math.  Here a
+// thread owns 8 points of a transform for the whole FFT: its 8 global loads are independent
+// and in flight together, the first pass reads them straight from registers, the last pass
+// leaves its results in registers for the fused epilogue, and shared memory only carries
+// the transposes between passes (one write + one read per pass boundary, conflict-free by
+// swizzled rows, double-buffered so there is a single barrier per exchange).  No
+// trigonometric table: the per-thread twiddle bases are computed once per CTA with
+// sincospif from exactly reduced integer arguments, the rest are products with 8th/16th
+// roots of unity and small powers.  A CTA loops over several segments so the set-up is
+// amortised.
+//
+// Index algebra (Stockham autosort, radix 8 while possible, one radix-4 or -2 pass last):
+// before a pass thread j holds in[j + r N/8], r < 8.  A radix-8 pass with Ns = 8^p finished
+// points multiplies input r by e^{-2 pi i (j mod Ns) r / (8 Ns)}, does the 8-point DFT and owns
+// out[(j / Ns) 8 Ns + (j mod Ns) + q Ns]; the final radix-R pass (R Ns = N) works on the
+// butterflies jj = j + s N/8, s < 8/R, whose inputs are the registers s + (8/R) q and whose
+// outputs land in the same registers.  After the last pass thread j holds X[j + r N/8].
+// =====================================================================================
+constexpr int kFastCols = 8;                 // columns per CTA in the column kernel (64 B of each input row)
+constexpr float kH = 0.70710678118654752f;
+
+template <int LOGN> struct FftPlan {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int T = N / 8;                       // threads per transform
+    static constexpr int n8 = LOGN / 3;                   // radix-8 passes
+    static constexpr int rem = LOGN % 3;                  // 1: final radix-2 pass, 2: final radix-4 pass
+    static constexpr int nbase = n8 - 1 + (rem ? 1 : 0);  // per-thread twiddle bases
+    static constexpr int pad = N / 8;                     // swizzle head-room of an exchange buffer (points)
+};
+
+// e^{-2 pi i num / den} for integers 0 <= num < den (den a power of two): exact argument reduction
+__device__ __forceinline__ cpx root(int num, int den) { return expmi(2.0f * (float)num / (float)den); }
+
+template <int LOGN> __device__ __forceinline__ void fft_bases(cpx* wb, int j) {
+    using P = FftPlan<LOGN>;
+    int Ns = 8;
+#pragma unroll
+    for (int p = 1; p < P::n8; ++p) { wb[p - 1] = root(j % Ns, 8 * Ns); Ns *= 8; }
+    if (P::rem) wb[P::n8 - 1] = root(j, P::N);
+}
+
+// v[r] *= w^r, r = 1..7 (powers by squaring: depth 3)
+__device__ __forceinline__ void twiddle8(cpx* v, cpx w) {
+    const cpx w2 = cmul(w, w), w4 = cmul(w2, w2), w3 = cmul(w2, w);
+    v[1] = cmul(v[1], w); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], cmul(w4, w)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+}
+
+// a * e^{-2 pi i s / 8}
+template <int S> __device__ __forceinline__ cpx rot8(cpx a) {
+    if (S == 0) return a;
+    if (S == 1) return make_float2(kH * (a.x + a.y), kH * (a.y - a.x));
+    if (S == 2) return mul_mi(a);
+    return make_float2(kH * (a.y - a.x), -kH * (a.x + a.y));           // S == 3
+}
+
+// Exchange layouts.  Every exchange is written along out[i0 + q Ns] and read along in[j + r T];
+// the swizzles below keep a half-warp's 64-bit accesses on distinct banks AND stay affine along
+// both patterns, so each thread needs one base per exchange and the rest are immediates.
+//   column kernel (a warp = 4 values of j x 8 columns, rows of 8 points = 16 banks): phi(i) = i + (i >> 3)
+//   row kernel (a warp = 32 consecutive j): after pass 0 phi(i) = i + (i >> 4), after pass 1
+//   phi(i) = i + 8 (i >> 6) (when N/8 is a multiple of 64), identity afterwards.
+template <int LOGN> struct ColsLay {
+    using P = FftPlan<LOGN>;
+    static constexpr int unit = kFastCols;
+    static __device__ __forceinline__ int phi(int, int i) { return i + (i >> 3); }
+    static __host__ __device__ constexpr int wstride(int p, int Ns) { return p == 0 ? 1 : Ns + Ns / 8; }
+    static __host__ __device__ constexpr int rstride(int) { return P::T + P::T / 8; }
+};
+template <int LOGN> struct RowsLay {
+    using P = FftPlan<LOGN>;
+    static constexpr int unit = 1;
+    static constexpr bool sw1 = (P::T % 64) == 0;
+    static __device__ __forceinline__ int phi(int p, int i) {
+        return p == 0 ? i + (i >> 4) : ((p == 1 && sw1) ? i + ((i >> 6) << 3) : i);
+    }
+    static __host__ __device__ constexpr int wstride(int p, int Ns) { return p == 0 ? 1 : Ns; }
+    static __host__ __device__ constexpr int rstride(int p) { return p == 0 ? P::T + P::T / 16 : ((p == 1 && sw1) ? P::T + P::T / 8 : P::T); }
+};
+template <int LOGN> struct FftX {                       // exchanges inside one transform
+    static constexpr int n = FftPlan<LOGN>::n8 - 1 + (FftPlan<LOGN>::rem ? 1 : 0);
+};
+
+// per-thread exchange bases (in points, before the `unit` scaling and the slot/column offset)
+template <int LOGN, class Lay> __device__ __forceinline__ void fft_exchange_bases(int* wbs, int* rbs, int j, int off) {
+    int Ns = 1;
+#pragma unroll
+    for (int p = 0; p < FftX<LOGN>::n; ++p) {
+        const int i0 = (j / Ns) * Ns * 8 + (j % Ns);
+        wbs[p] = Lay::phi(p, i0) * Lay::unit + off;
+        rbs[p] = Lay::phi(p, j) * Lay::unit + off;
+        Ns *= 8;
+    }
+}
+
+// Full transform of the 8 points in v (see the index algebra above).  Exchange e uses buffer
+// e & 1 (callers keep the number of exchanges per loop iteration even, or add a barrier).
+template <int LOGN, class Lay>
+__device__ __forceinline__ void fft_reg(cpx (&v)[8], const cpx* wb, cpx* buf0, cpx* buf1, const int* wbs, const int* rbs) {
+    using P = FftPlan<LOGN>;
+    int Ns = 1;
+#pragma unroll
+    for (int p = 0; p < P::n8; ++p) {
+        if (p > 0) twiddle8(v, wb[p - 1]);
+        dft<8>(v);
+        if (p + 1 < P::n8 || P::rem) {
+            cpx* b = (p & 1) ? buf1 : buf0;
+            cpx* w = b + wbs[p];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q * Lay::wstride(p, Ns) * Lay::unit] = v[q];
+            __syncthreads();
+            const cpx* rd = b + rbs[p];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[r] = rd[r * Lay::rstride(p) * Lay::unit];
+        }
+        Ns *= 8;
+    }
+    if (P::rem == 2) {
+        const cpx w0 = wb[P::n8 - 1], w1 = rot8<1>(w0);
+        {   cpx t[4] = {v[0], v[2], v[4], v[6]};
+            const cpx w2 = cmul(w0, w0);
+            t[1] = cmul(t[1], w0); t[2] = cmul(t[2], w2); t[3] = cmul(t[3], cmul(w2, w0));
+            dft<4>(t); v[0] = t[0]; v[2] = t[1]; v[4] = t[2]; v[6] = t[3]; }
+        {   cpx t[4] = {v[1], v[3], v[5], v[7]};
+            const cpx w2 = cmul(w1, w1);
+            t[1] = cmul(t[1], w1); t[2] = cmul(t[2], w2); t[3] = cmul(t[3], cmul(w2, w1));
+            dft<4>(t); v[1] = t[0]; v[3] = t[1]; v[5] = t[2]; v[7] = t[3]; }
+    } else if (P::rem == 1) {
+        const cpx w0 = wb[P::n8 - 1];
+        const cpx ws[4] = {w0, rot8<1>(w0), rot8<2>(w0), rot8<3>(w0)};
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+            const cpx a = v[s2], b = cmul(v[s2 + 4], ws[s2]);
+            v[s2] = cadd(a, b); v[s2 + 4] = csub(a, b);
+        }
+    }
+}
+
+// Column kernel: window + pack + length-N1 FFT down kFastCols adjacent columns + four-step twiddle.
+// Thread (j, c): column n2 = 8 g + c, points n1 = j + r N1/8.  The next segment's 8 loads are issued
+// before the current segment is transformed.
+template <int LOG1>
+__global__ void __launch_bounds__((1 << LOG1) / 8 * kFastCols) ct_welch_cols_fast(WelchArgs a) {
+    using P = FftPlan<LOG1>;
+    using Lay = ColsLay<LOG1>;
+    constexpr int N1 = P::N, T1 = P::T, NX = FftX<LOG1>::n;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    cpx* buf0 = reinterpret_cast<cpx*>(smraw);
+    cpx* buf1 = buf0 + (size_t)(N1 + P::pad) * kFastCols;
+    __shared__ double wsum[2][32];
+    const int N2 = 1 << a.logn2;
+    const long long N = (long long)N1 * N2;
+    const int tid = threadIdx.x, c = tid % kFastCols, j = tid / kFastCols;
+    const int groups = N2 / kFastCols;
+    const int g = blockIdx.x % groups, sp = blockIdx.x / groups;
+    const int n2 = g * kFastCols + c;
+    // ---- per-thread constants
+    cpx wb[P::nbase > 0 ? P::nbase : 1];
+    fft_bases<LOG1>(wb, j);
+    int wbs[NX > 0 ? NX : 1], rbs[NX > 0 ? NX : 1];
+    fft_exchange_bases<LOG1, Lay>(wbs, rbs, j, c);
+    // periodic Hann at the samples 2J, 2J+1 of point J = N2 (j + r T1) + n2: the angle advances by pi/4 per r
+    const long long J0 = (long long)N2 * j + n2;
+    float ce, se, co, so;
+    sincospif(2.0f * (float)(2 * J0) / (float)a.L, &se, &ce);
+    sincospif(2.0f * (float)(2 * J0 + 1) / (float)a.L, &so, &co);
+    // four-step twiddle W_N^(n2 k1), k1 = j + r T1
+    cpx ot[8];
+    {
+        const cpx base = root((int)(((long long)n2 * j) % N), (int)N), step = root((int)(((long long)n2 * T1) % N), (int)N);
+        const cpx s2 = cmul(step, step), s4 = cmul(s2, s2);
+        ot[0] = base; ot[1] = cmul(base, step); ot[2] = cmul(base, s2); ot[3] = cmul(ot[1], s2);
+        ot[4] = cmul(base, s4); ot[5] = cmul(ot[1], s4); ot[6] = cmul(ot[2], s4); ot[7] = cmul(ot[3], s4);
+    }
+    const long long rstep = 2 * (long long)N2 * T1;        // floats between a thread's consecutive points
+    const float* x0p = a.x + a.seg0 * (long long)(a.L / 2) + 2 * J0;
+    float2 in[8], nx[8];
+    if (sp < a.nseg) {
+        const float* xs = x0p + sp * (long long)(a.L / 2);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = __ldg(reinterpret_cast<const float2*>(xs + rstep * r));
+    }
+    for (int s = sp, it = 0; s < a.nseg; s += a.ssplit, ++it) {
+        if (s + a.ssplit < a.nseg) {
+            const float* xs = x0p + (s + a.ssplit) * (long long)(a.L / 2);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) nx[r] = __ldg(reinterpret_cast<const float2*>(xs + rstep * r));
+        }
+        cpx v[8];
+        float part = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float x0 = in[r].x, x1 = in[r].y;
+            if (a.use_abs) { x0 = fabsf(x0); x1 = fabsf(x1); }
+            x0 -= a.c; x1 -= a.c;
+            part += x0 + x1;
+            // cos(theta0 + r pi/4) for the even and the odd sample
+            float cer, cor;
+            switch (r) {
+                case 0: cer = ce; cor = co; break;
+                case 1: cer = kH * (ce - se); cor = kH * (co - so); break;
+                case 2: cer = -se; cor = -so; break;
+                case 3: cer = -kH * (ce + se); cor = -kH * (co + so); break;
+                case 4: cer = -ce; cor = -co; break;
+                case 5: cer = -kH * (ce - se); cor = -kH * (co - so); break;
+                case 6: cer = se; cor = so; break;
+                default: cer = kH * (ce + se); cor = kH * (co + so); break;
+            }
+            v[r] = make_float2(x0 * (0.5f - 0.5f * cer), x1 * (0.5f - 0.5f * cor));
+        }
+        // segment sum for the mean: warp, CTA, one atomic per CTA and segment.  The partial sums ride
+        // on the FFT's barriers (written before its first exchange, read after its last); two copies
+        // because a fast warp may already be one segment ahead.
+        double dp = (double)part;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dp += __shfl_xor_sync(CT_FULL, dp, o);
+        double* wsm = wsum[it & 1];
+        if ((tid & 31) == 0) wsm[tid >> 5] = dp;
+        fft_reg<LOG1, Lay>(v, wb, buf0, buf1, wbs, rbs);
+        if (NX & 1) __syncthreads();                       // keep the buffer parity of the next iteration safe
+        if (tid == 0) {
+            double t = 0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += wsm[i];
+            atomicAdd(a.segsum + s, t);
+        }
+        cpx* Y = a.Y + (size_t)s * N + n2;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) Y[(size_t)(j + r * T1) * N2] = cmul(v[r], ot[r]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = nx[r];
+    }
+}
+
+// Row kernel: length-N2 FFT along the row pair (k1, N1 - k1), real-FFT split, |X|^2 accumulated over the
+// CTA's segments in registers.  Thread (p, j): row p of the pair, bins k2 = j + r N2/8.
+template <int LOG2>
+__global__ void __launch_bounds__(2 * (1 << LOG2) / 8) ct_welch_rows_fast(WelchArgs a) {
+    using P = FftPlan<LOG2>;
+    using Lay = RowsLay<LOG2>;
+    constexpr int N2 = P::N, T2 = P::T, kSlot = N2 + P::pad, NX = FftX<LOG2>::n;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    cpx* buf0 = reinterpret_cast<cpx*>(smraw);
+    cpx* buf1 = buf0 + 2 * kSlot;
+    const int N1 = 1 << a.logn1;
+    const long long N = (long long)N1 * N2;
+    const int tid = threadIdx.x, p = tid / T2, j = tid % T2;
+    const int r0 = blockIdx.x / a.rsplit, part = blockIdx.x % a.rsplit;
+    const int r1 = (r0 == 0) ? 0 : N1 - r0;        // partner row (== r0 for rows 0 and N1/2)
+    const bool self = (r1 == r0);
+    const int row = p ? r1 : r0;
+    cpx wb[P::nbase > 0 ? P::nbase : 1];
+    fft_bases<LOG2>(wb, j);
+    int wbs[NX > 0 ? NX : 1], rbs[NX > 0 ? NX : 1];
+    fft_exchange_bases<LOG2, Lay>(wbs, rbs, j, p * kSlot);
+    // split twiddle e^{-2 pi i k / L} at k = row + N1 (j + r T2): the factor per r is a 16th root of unity
+    const cpx tb = root(row + N1 * j, a.L);
+    const int mine = p * kSlot + j;
+    // partner bin of k2 = j + r T2: N2 - 1 - k2 in the other row; (N2 - k2) mod N2 in the same row for row 0
+    const int other = (1 - p) * kSlot + N2 - (r0 == 0 ? 0 : 1) - j;
+    const bool owner = !(self && p == 1);          // the second slot of a self-paired row only mirrors the first
+    const bool nyq = self && p == 1 && r0 == 0 && j == 0;
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    const float hl = 0.5f * (float)a.L, ql = 0.25f * (float)a.L;
+    const cpx* Y0 = a.Y + (size_t)row * N2 + j;
+    cpx in[8], nx[8];
+    if (part < a.nseg) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = Y0[(size_t)part * N + r * T2];
+    }
+    for (int s = part; s < a.nseg; s += a.rsplit) {
+        if (s + a.rsplit < a.nseg) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) nx[r] = Y0[(size_t)(s + a.rsplit) * N + r * T2];
+        }
+        cpx v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = in[r];
+        const float dmu = (float)(a.segsum[s] * a.mu_scale);     // mu - c for this segment
+        fft_reg<LOG2, Lay>(v, wb, buf0, buf1, wbs, rbs);
+        cpx* b = (NX & 1) ? buf1 : buf0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) b[mine + r * T2] = v[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int mi = other - r * T2;
+            if (r == 0 && r0 == 0 && j == 0) mi -= N2;            // (N2 - 0) mod N2
+            const cpx Zk = v[r], Zm = b[mi];
+            const cpx E = cadd(Zk, cconj(Zm)), O = csub(Zk, cconj(Zm));
+            // tw = tb * e^{-2 pi i r / 16}
+            cpx tw;
+            {
+                const float c16 = 0.92387953251128674f, s16 = 0.38268343236508977f;
+                const cpx h = (r & 1) ? make_float2(tb.x * c16 + tb.y * s16, tb.y * c16 - tb.x * s16) : tb;   // * e^{-i pi/8}
+                switch (r >> 1) { case 0: tw = h; break; case 1: tw = rot8<1>(h); break; case 2: tw = rot8<2>(h); break; default: tw = rot8<3>(h); break; }
+            }
+            cpx X = cadd(make_float2(0.5f * E.x, 0.5f * E.y), cmul(make_float2(0.5f * O.y, -0.5f * O.x), tw));
+            if (r == 0) {
+                const long long k = row + (long long)N1 * j;
+                if (k == 0) X.x -= dmu * hl;
+                if (k == 1) X.x += dmu * ql;
+                if (nyq) X = make_float2(Zk.x - Zk.y, 0.f);      // bin N lives in Z[0]
+            }
+            acc[r] += X.x * X.x + X.y * X.y;
+        }
+        if (!(NX & 1)) __syncthreads();                           // odd number of exchanges per segment
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = nx[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long long k = row + (long long)N1 * (j + r * T2);
+        if (owner) atomicAdd(a.acc + k, (double)acc[r]);
+        else if (nyq && r == 0) atomicAdd(a.acc + N, (double)acc[r]);
+    }
+}
+
+template <int LOG1> static int launch_cols_fast(const WelchArgs& a, int N2, cudaStream_t st) {
+    using P = FftPlan<LOG1>;
+    const size_t sm = (size_t)2 * (P::N + P::pad) * kFastCols * sizeof(cpx);
+    cudaFuncSetAttribute(ct_welch_cols_fast<LOG1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    CT_COUNT_LAUNCH();
+    ct_welch_cols_fast<LOG1><<<(unsigned)((N2 / kFastCols) * a.ssplit), P::T * kFastCols, sm, st>>>(a);
+    return ct_check_launch("ct_welch_cols_fast");
+}
+template <int LOG2> static int launch_rows_fast(const WelchArgs& a, int N1, cudaStream_t st) {
+    using P = FftPlan<LOG2>;
+    const size_t sm = (size_t)2 * 2 * (P::N + P::pad) * sizeof(cpx);
+    cudaFuncSetAttribute(ct_welch_rows_fast<LOG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    CT_COUNT_LAUNCH();
+    ct_welch_rows_fast<LOG2><<<(unsigned)((N1 / 2 + 1) * a.rsplit), 2 * P::T, sm, st>>>(a);
+    return ct_check_launch("ct_welch_rows_fast");
+}
+static bool fast_sizes(int logn1, int logn2) { return logn1 >= 7 && logn1 <= 10 && logn2 >= 7 && logn2 <= 12; }
+static int cols_fast(const WelchArgs& a, cudaStream_t st) {
+    const int N2 = 1 << a.logn2;
+    switch (a.logn1) {
+        case 7: return launch_cols_fast<7>(a, N2, st);
+        case 8: return launch_cols_fast<8>(a, N2, st);
+        case 9: return launch_cols_fast<9>(a, N2, st);
+        default: return launch_cols_fast<10>(a, N2, st);
+    }
+}
+static int rows_fast(const WelchArgs& a, cudaStream_t st) {
+    const int N1 = 1 << a.logn1;
+    switch (a.logn2) {
+        case 7: return launch_rows_fast<7>(a, N1, st);
+        case 8: return launch_rows_fast<8>(a, N1, st);
+        case 9: return launch_rows_fast<9>(a, N1, st);
+        case 10: return launch_rows_fast<10>(a, N1, st);
+        case 11: return launch_rows_fast<11>(a, N1, st);
+        default: return launch_rows_fast<12>(a, N1, st);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -234,8 +599,8 @@ int64_t ct_welch_workspace_bytes(int32_t nperseg, int32_t batch) {
 int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_t use_abs, int32_t batch,
                  void* workspace, int64_t workspace_bytes, double* acc, int64_t* nseg_out, void* stream) {
     if (!x || !workspace || !acc || !nseg_out) { ct_set_error("welch: null pointer"); return CT_ERR_ARG; }
-    if (nperseg < 256 || (nperseg & (nperseg - 1)) || nperseg > (1 << 24)) {
-        ct_set_error("welch: nperseg must be a power of two in [256, 2^24] (got %d)", nperseg); return CT_ERR_UNSUPPORTED;
+    if (nperseg < 256 || (nperseg & (nperseg - 1)) || nperseg > (1 << 23)) {
+        ct_set_error("welch: nperseg must be a power of two in [256, 2^23] (got %d)", nperseg); return CT_ERR_UNSUPPORTED;
     }
     if ((reinterpret_cast<uintptr_t>(x) & 7) != 0) { ct_set_error("welch: input must be 8-byte aligned"); return CT_ERR_ARG; }
     const int L = nperseg, hop = L / 2;
@@ -250,6 +615,7 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
     int logn = 0; while ((1LL << logn) < N) ++logn;
     int logn2 = (logn + 1) / 2, logn1 = logn - logn2;      // N2 >= N1
     if (logn1 < 3) { logn1 = 3; logn2 = logn - 3; }
+    if (logn1 > 10) { logn1 = 10; logn2 = logn - 10; }    // the column kernel holds 8 columns of N1 <= 1024 points
     if (logn2 > 12 || logn1 > 12 || (1 << logn2) < kCols) { ct_set_error("welch: unsupported segment length"); return CT_ERR_UNSUPPORTED; }
     WelchArgs a;
     a.x = x; a.n = n; a.L = L; a.logn1 = logn1; a.logn2 = logn2; a.c = shift; a.use_abs = use_abs;
@@ -259,21 +625,36 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
     a.T = T;
     a.acc = acc; a.mu_scale = 1.0 / (double)L;
     const int N1 = 1 << logn1, N2 = 1 << logn2;
-    CT_COUNT_LAUNCH();
-    ct_welch_table<<<(L + 255) / 256, 256, 0, st>>>(T, L);
-    { int rc = ct_check_launch("ct_welch_table"); if (rc) return rc; }
+    const bool fast = fast_sizes(logn1, logn2);
     size_t smA = (size_t)(2 * N1 * kCols + N1) * sizeof(cpx), smB = (size_t)(2 * 2 * N2 + N2) * sizeof(cpx);
-    cudaFuncSetAttribute(ct_welch_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
-    cudaFuncSetAttribute(ct_welch_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
+    if (!fast) {
+        CT_COUNT_LAUNCH();
+        ct_welch_table<<<(L + 255) / 256, 256, 0, st>>>(T, L);
+        { int rc = ct_check_launch("ct_welch_table"); if (rc) return rc; }
+        cudaFuncSetAttribute(ct_welch_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
+        cudaFuncSetAttribute(ct_welch_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
+    }
+    const int target = 4 * ct_sm_count();
     for (long long s0 = 0; s0 < nseg; s0 += batch) {
         a.seg0 = s0; a.nseg = (int)((nseg - s0 < batch) ? nseg - s0 : batch);
         cudaMemsetAsync(a.segsum, 0, (size_t)a.nseg * 8, st);
+        // enough CTAs to fill the GPU: the segments of the batch are split over rsplit CTAs per row pair
+        // (and over ssplit CTAs per column group)
+        a.rsplit = 1;
+        while ((N1 / 2 + 1) * a.rsplit < target && a.rsplit * 2 <= a.nseg) a.rsplit *= 2;
+        a.ssplit = 1;
+        while ((N2 / kFastCols) * a.ssplit < target && a.ssplit * 2 <= a.nseg) a.ssplit *= 2;
+        if (const char* e = getenv("CT_WELCH_SSPLIT")) { int v = atoi(e); if (v >= 1) a.ssplit = v < a.nseg ? v : a.nseg; }
+        if (const char* e = getenv("CT_WELCH_RSPLIT")) { int v = atoi(e); if (v >= 1) a.rsplit = v < a.nseg ? v : a.nseg; }
+        int rc;
+        if (fast) {
+            rc = cols_fast(a, st); if (rc) return rc;
+            rc = rows_fast(a, st); if (rc) return rc;
+            continue;
+        }
         CT_COUNT_LAUNCH();
         ct_welch_cols<<<(unsigned)(a.nseg * (N2 / kCols)), kThreads, smA, st>>>(a);
-        int rc = ct_check_launch("ct_welch_cols"); if (rc) return rc;
-        // enough CTAs to fill the GPU: the segments of the batch are split over rsplit CTAs per row pair
-        a.rsplit = 1;
-        while ((N1 / 2 + 1) * a.rsplit < 4 * ct_sm_count() && a.rsplit * 2 <= a.nseg) a.rsplit *= 2;
+        rc = ct_check_launch("ct_welch_cols"); if (rc) return rc;
         CT_COUNT_LAUNCH();
         ct_welch_rows<<<(unsigned)((N1 / 2 + 1) * a.rsplit), kThreads, smB, st>>>(a);
         rc = ct_check_launch("ct_welch_rows"); if (rc) return rc;

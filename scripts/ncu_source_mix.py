@@ -9,7 +9,10 @@ iS, iE, iSt = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index
 mix = collections.Counter(); stall = collections.Counter(); tot = 0; tots = 0
 lines = []
 for r in rows[2:]:
-    if len(r) <= iE: continue
+    if len(r) <= iE:
+        if r and r[0] == 'Kernel Name': break      # only the first launch of the page
+        continue
+    if r[iE] == 'Instructions Executed': continue
     src = r[iS].strip(); n = int(r[iE] or 0); s = int(r[iSt] or 0)
     parts = src.split()
     op = parts[1] if parts and parts[0].startswith('@') and len(parts) > 1 else (parts[0] if parts else '?')

@@ -20,7 +20,7 @@ def check(P, want):
     assert not bad.any(), (np.nonzero(bad)[0][:10], (np.abs(P - want) / tol).max())
 
 
-@pytest.mark.parametrize("L", [256, 512, 1024, 4096, 1 << 15, 1 << 17])
+@pytest.mark.parametrize("L", [256, 512, 1024, 4096, 1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19])
 def test_white_noise_all_sizes(L):
     rng = np.random.default_rng(L)
     x = (5000 + 150 * rng.standard_normal(5 * L + 123)).astype(np.float32)
@@ -29,6 +29,17 @@ def test_white_noise_all_sizes(L):
     assert np.allclose(f, fw, rtol=1e-14)
     check(P, Pw)
     assert np.allclose(psd.integrate_noise(f, P), to.integrate_noise(fw, Pw), rtol=1e-6)
+
+
+@pytest.mark.parametrize("L", [1 << 21, 1 << 22, 1 << 23])
+def test_long_segments(L):
+    """Both kernel families at their largest sizes (register-resident FFT up to 2^22, shared-memory
+    Stockham beyond), 4 segments, with |x| as noise-fit.py:92 passes it."""
+    rng = np.random.default_rng(L + 1)
+    x = (40 * rng.standard_normal(5 * L // 2 + 17)).astype(np.float32)
+    f, P = psd.welch(torch.from_numpy(x).cuda(), 5.0e5, L, use_abs=True)
+    fw, Pw = to.welch_psd(np.abs(x.astype(np.float64)), 5.0e5, L)
+    check(P, Pw)
 
 
 def test_reference_fixture(golden_dir):
