@@ -1,4 +1,4 @@
-// Batched Welch periodogram with a hand-written shared-memory FFT (no cuFFT).
+// Batched Welch periodogram with a hand-written FFT (no cuFFT).
 //
 // Replaces scipy.signal.welch(x, fs, nperseg=L) as the reference calls it
 // (plot-trace.py:442, noise-fit.py:92, legacy/minimal_psd.py:255): periodic Hann window,
@@ -7,20 +7,23 @@
 //
 // A real segment of L samples is packed as N = L/2 complex points (z[j] = x[2j] + i x[2j+1])
 // and transformed by the four-step algorithm, N = N1 x N2:
-//   kernel A  window + pack + N2 column FFTs of length N1 (16 columns per CTA, data never
-//             leaves shared memory) + twiddle W_N^(n2 k1) -> Y[k1][n2]      (4 B/sample in)
+//   kernel A  window + pack + N2 column FFTs of length N1 + twiddle W_N^(n2 k1) -> Y[k1][n2]
 //   kernel B  row FFTs of length N2 for the row pair (k1, N1-k1), the real-FFT split
-//             X[k] = (Z[k]+Z*[N-k])/2 - (i/2) e^(-i pi k/N) (Z[k]-Z*[N-k]) inside shared
-//             memory, |X|^2 accumulated over the segments of the batch in registers and
-//             added once per bin into the float64 accumulator.
-// The intermediate Y (8 B per complex point) of a batch of segments is sized to stay in
-// the 126 MB L2.  Mean removal is applied in the spectrum: with the input shifted by a
-// constant c near the mean (for float32 headroom), FFT(w (x - mu)) = FFT(w (x - c)) -
-// (mu - c) FFT(w) and FFT(w) of the periodic Hann is L/2 at bin 0 and -L/4 at bins +-1.
-// FFT passes are Stockham autosort radix-8/4/2.  Every trigonometric factor (window, Stockham and
-// four-step twiddles, real-FFT split) comes from ONE table T[j] = e^{-2 pi i j / L}, j < L, built once per
-// call with sincospif (8 MB for L = 2^20, L2 resident); the sub-FFT twiddles are staged in shared memory.
-#include <cstdlib>
+//             X[k] = (Z[k]+Z*[N-k])/2 - (i/2) e^(-i pi k/N) (Z[k]-Z*[N-k]), |X|^2 accumulated
+//             over the segments of the batch in registers and added once per bin into the
+//             float64 accumulator.
+// Mean removal is applied in the spectrum: with the input shifted by a constant c near the
+// mean (for float32 headroom), FFT(w (x - mu)) = FFT(w (x - c)) - (mu - c) FFT(w) and FFT(w)
+// of the periodic Hann is L/2 at bin 0 and -L/4 at bins +-1.
+//
+// Two kernel families:
+//   * 2^15 <= L <= 2^23: register-resident FFTs (second half of this file) - 8 points per
+//     thread, shared memory only for the transposes between passes, no trigonometric table,
+//     the next segment's loads in flight while the current one is transformed.  The batch is
+//     as large as the workspace allows (more segments per CTA amortise the per-thread set-up;
+//     whether the intermediate Y stays in L2 turned out not to matter).
+//   * shorter segments: shared-memory Stockham radix-8/4/2 passes, 8 columns per CTA; every
+//     trigonometric factor from ONE table T[j] = e^{-2 pi i j / L} built once per call.
 #include "ct_common.cuh"
 #include "cusumtools_b200.h"
 
@@ -634,7 +637,7 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
         cudaFuncSetAttribute(ct_welch_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
         cudaFuncSetAttribute(ct_welch_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
     }
-    const int target = 4 * ct_sm_count();
+    const int target = 2 * ct_sm_count();
     for (long long s0 = 0; s0 < nseg; s0 += batch) {
         a.seg0 = s0; a.nseg = (int)((nseg - s0 < batch) ? nseg - s0 : batch);
         cudaMemsetAsync(a.segsum, 0, (size_t)a.nseg * 8, st);
@@ -644,8 +647,6 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
         while ((N1 / 2 + 1) * a.rsplit < target && a.rsplit * 2 <= a.nseg) a.rsplit *= 2;
         a.ssplit = 1;
         while ((N2 / kFastCols) * a.ssplit < target && a.ssplit * 2 <= a.nseg) a.ssplit *= 2;
-        if (const char* e = getenv("CT_WELCH_SSPLIT")) { int v = atoi(e); if (v >= 1) a.ssplit = v < a.nseg ? v : a.nseg; }
-        if (const char* e = getenv("CT_WELCH_RSPLIT")) { int v = atoi(e); if (v >= 1) a.rsplit = v < a.nseg ? v : a.nseg; }
         int rc;
         if (fast) {
             rc = cols_fast(a, st); if (rc) return rc;

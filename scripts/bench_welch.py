@@ -5,6 +5,7 @@ import torch
 from cusumtools_b200 import psd, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+psd.L2_BUDGET_BYTES = int(os.environ.get("CT_L2", psd.L2_BUDGET_BYTES))   # intermediate budget (sets the batch)
 g = torch.Generator(device="cuda"); g.manual_seed(3)
 x = torch.randn(n, generator=g, device="cuda") * 24 + 5000
 acc, nseg = psd.welch_sums(x, L); torch.cuda.synchronize()
