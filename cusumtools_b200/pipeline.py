@@ -276,9 +276,11 @@ class TraceAnalyzer:
                 events.append(e)
         return self.run(self.raw_dev, stage_hook=stage_hook, _arrivals=(bounds, events))
 
-    def run(self, raw_ext: torch.Tensor, stage_hook=None, _arrivals=None) -> AnalysisResult:
+    def run(self, raw_ext: torch.Tensor, stage_hook=None, _arrivals=None, _fixed=None) -> AnalysisResult:
         """One pass of stages 1-3.  `stage_hook(name)` (optional) is called after the launches of each
-        stage have been enqueued: 'median', 'filter', 'baseline', 'detect', 'cusum' (profiling only)."""
+        stage have been enqueued: 'median', 'filter', 'baseline', 'detect', 'cusum' (profiling only).
+        `_fixed = (MedianPlan, pad_x, (c1, c2))` (StreamingAnalyzer) skips the median stages: the filter
+        subtracts `plan.est` and pads with `pad_x` = median - estimate."""
         hook = stage_hook or (lambda name: None)
         if raw_ext.numel() != self.n_ext:
             raise ValueError(f"analyzer was planned for {self.n_ext} samples, got {raw_ext.numel()}")
@@ -289,7 +291,9 @@ class TraceAnalyzer:
         cur = torch.cuda.current_stream(self.device)
         # ---- median, phase 1: estimate (subtraction constant of the filter, verification window)
         hist_fn, count_fn = _median_kernels(owned, self.mask)
-        if _arrivals is None:
+        if _fixed is not None:
+            plan = _fixed[0]
+        elif _arrivals is None:
             plan = median_estimate(n_own, self.mask, hist_fn, self.group, self.device)
         else:                                                  # only the first chunk has arrived: estimate from it
             bounds, events = _arrivals
@@ -305,13 +309,14 @@ class TraceAnalyzer:
         alpha, _ = filters.chimera_affine(self.settings)
         origin = 0
         # ---- forward pass with the estimate; it tallies the window counts of the owned codes on the side
-        counts = torch.zeros(9, dtype=torch.int64, device=self.device)
-        fused = plan.exact is None
+        counts = torch.zeros(9, dtype=torch.int64, device=self.device) if _fixed is None else None
+        fused = plan.exact is None and _fixed is None
         pieces = [(0, 0, self.n_ext)] if _arrivals is None else [(2, a, b) for a, b in zip(_arrivals[0][:-1], _arrivals[0][1:])]
+        pad_first = float(_fixed[1]) if _fixed is not None else 0.0
         for i, (part, a, b) in enumerate(pieces):
             if _arrivals is not None:
                 cur.wait_event(_arrivals[1][i])
-            rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask, 0.0,
+            rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask, pad_first,
                                          C.byref(coef), self.H, origin, part, plan.lo, plan.step, lo, lo + n_own,
                                          counts.data_ptr() if (fused and self.fused_count) else None, a, b,
                                          self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
@@ -323,10 +328,13 @@ class TraceAnalyzer:
                                                counts.data_ptr(), st)
                     _lib.check(rc, "ct_count_window_u16")
         # ---- median, phase 2: exact order statistics (one small read; retries only if the window missed)
-        c1, c2 = median_search(n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
-                               first_counts=counts if fused else None)
+        if _fixed is not None:
+            c1, c2 = _fixed[2]
+        else:
+            c1, c2 = median_search(n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
+                                   first_counts=counts if fused else None)
         self.last_median = (c1, c2)
-        pad_x = 0.5 * (c1 + c2) - plan.est
+        pad_x = 0.5 * (c1 + c2) - plan.est if _fixed is None else 0.0
         if pad_x != 0.0:        # the pad holds median - estimate: redo the groups at the two ends of the trace
             rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask,
                                          float(pad_x), C.byref(coef), self.H, origin, 1, 0, 1, 0, 0, None, 0, 0,
@@ -387,7 +395,7 @@ class TraceAnalyzer:
         lv = None
         if self.delta is not None:
             lv = cusum.LevelTable(self.nl[:nk], self.ed[:nk], self.mu[:nk], self.sd[:nk], self.ov[:nk], self.max_levels)
-        first_id, total = event_id_offsets(nk, self.group, self.device)
+        first_id, total = event_id_offsets(nk, self.group, self.device) if _fixed is None else (0, nk)
         return AnalysisResult(filtered=y[lo:lo + n_own], detect_trace=yd, lo_halo=lo, baseline=bl, events=ev,
                               win_start=self.w0[:nk], win_end=self.w1[:nk], types=self.typ[:nk], levels=lv,
                               pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id, total_events=total)
@@ -414,6 +422,196 @@ class TraceAnalyzer:
             out[k] = h
         torch.cuda.current_stream(self.device).synchronize()
         return {k: v.numpy() for k, v in out.items()}
+
+
+@dataclass
+class StreamResult:
+    """What `StreamingAnalyzer.run_from_host` leaves behind: the filtered trace and the baseline
+    table on the device, the event / level tables already in (pinned) host memory."""
+    filtered: torch.Tensor          # float32 CUDA, the rank's owned samples
+    baseline: detect.Baseline       # blocks of the owned range
+    tables: dict                    # numpy: starts, ends (relative to the first owned sample), types[, n_levels, edges, mean, std, overflow]
+    pad_value: float
+    median_codes: tuple[int, int]
+    first_event_id: int = 0
+    total_events: int = 0
+    redone: str = ""                # "", "first" (first sub-shard redone with the exact pad) or "all"
+
+
+class StreamingAnalyzer:
+    """Stages 1-3 over a trace that is still in pinned host memory, overlapped with its own
+    host->device copy: the owned range is cut into time sub-shards (the multi-GPU sharding of
+    SURVEY.md 8e applied in sequence on one GPU: halo of `required_halo` samples on each side,
+    events owned by the sub-shard that holds their start), the copy is cut at the points where
+    a sub-shard becomes complete, and each sub-shard is filtered, detected, segmented and its
+    tables are sent back while the next pieces are still arriving.  When the last byte lands only
+    the last sub-shard is left to do.
+
+    The exact median (the reference's pad value, plot-trace.py:319) is known only at the end; the
+    filter needs it only as the pad at the two true ends of the trace (`filtfilt(code - c) + c`
+    does not depend on c otherwise), so every sub-shard subtracts the estimate from the first
+    piece, the last one is padded with the exact value, and the (small) first one is redone if the
+    estimate turns out to be off.  Interior sub-shard boundaries differ from a whole-trace run only by
+    the IIR warm-up error (< 1e-7 of the signal range, as between GPUs).  Blocks without enough
+    baseline samples inherit the nearest earlier valid block of their own sub-shard."""
+
+    def __init__(self, n_ext: int, settings, cutoff: float, order: int = 8, *, lo_halo: int = 0, hi_halo: int = 0,
+                 shards: int = 16, first_blocks: int = 4, group=None, device="cuda", **kw):
+        self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
+        self.n_own = self.n_ext - self.lo_halo - self.hi_halo
+        self.settings, self.cutoff, self.order = settings, float(cutoff), int(order)
+        self.group, self.device, self.kw = group, torch.device(device), dict(kw)
+        self.block = int(kw.get("baseline_block", detect.DEFAULT_BASELINE_BLOCK))
+        self.padding = int(kw.get("padding", 1000))
+        self.mask = filters.chimera_bitmask(settings)
+        self.max_levels = int(kw.get("max_levels", cusum.DEFAULT_MAX_LEVELS))
+        self.with_levels = kw.get("cusum_delta") is not None
+        fs = float(np.floor(np.squeeze(settings["ADCSAMPLERATE"])))
+        max_event = int(kw.get("maxpoints", 100_000)) + 2 * int(kw.get("event_padding", 100))
+        self.h = required_halo(self.cutoff, self.order, fs, max_event, self.padding, block=self.block)
+        if self.lo_halo % self.block:
+            raise ValueError("lo_halo must be a multiple of the baseline block (pipeline.required_halo(..., block=))")
+        a0, b_end = self.lo_halo, self.lo_halo + self.n_own
+        cuts = [a0]
+        if first_blocks * self.block < self.n_own and shards > 1:
+            cuts.append(a0 + first_blocks * self.block)
+        per = max(self.block, -(-(b_end - cuts[-1]) // max(1, int(shards)) // self.block) * self.block)
+        while cuts[-1] < b_end:
+            cuts.append(min(b_end, cuts[-1] + per))
+        # (a, b, ea, eb): owned [a, b) and extended [ea, eb) ranges of each sub-shard, in raw_ext coordinates
+        self.sub = [(a, b, max(0, a - self.h), min(self.n_ext, b + self.h)) for a, b in zip(cuts[:-1], cuts[1:])]
+        self.analyzers: dict = {}
+        self.y = torch.empty(self.n_own, dtype=torch.float32, device=self.device)
+        self.raw_dev = None
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bmin, self.bmax = float(kw["baseline_min"]), float(kw["baseline_max"])
+        self._pin, self._pin_cap = {}, 0
+        self._whole = None
+
+    # -- helpers -------------------------------------------------------------------
+    def _analyzer(self, a, b, ea, eb) -> TraceAnalyzer:
+        key = (eb - ea, a - ea, eb - b)
+        if key not in self.analyzers:
+            self.analyzers[key] = TraceAnalyzer(eb - ea, self.settings, self.cutoff, self.order, lo_halo=a - ea,
+                                                hi_halo=eb - b, group=None, device=self.device, **self.kw)
+        return self.analyzers[key]
+
+    def _pinned(self, name: str, like: torch.Tensor, rows: int) -> torch.Tensor:
+        """Row-capacity-managed pinned host column (grown geometrically, contents kept)."""
+        t = self._pin.get(name)
+        if t is None or t.shape[0] < rows:
+            cap = max(rows, 2 * (t.shape[0] if t is not None else 0), 4096, self.n_own // 2048)
+            new = torch.empty((cap,) + tuple(like.shape[1:]), dtype=like.dtype, pin_memory=True)
+            if t is not None:
+                torch.cuda.current_stream(self.device).synchronize()
+                new[:t.shape[0]] = t
+            self._pin[name] = t = new
+        return t
+
+    def _process(self, i: int, plan: MedianPlan, pad_x: float, med: tuple[int, int], row0: int, bl: detect.Baseline) -> int:
+        """Analyse sub-shard i (its data must be resident), store its owned samples, blocks and table rows
+        (from row `row0`); returns its event count."""
+        a, b, ea, eb = self.sub[i]
+        an = self._analyzer(a, b, ea, eb)
+        r = an.run(self.raw_dev[ea:eb], _fixed=(plan, pad_x, med))
+        a0 = self.lo_halo
+        self.y[a - a0:b - a0].copy_(r.filtered)
+        k0, nbk, g0 = (a - ea) // self.block, -(-(b - a) // self.block), (a - a0) // self.block
+        for name in ("cnt", "s1", "s2", "mean", "std", "sign", "t_start", "t_end"):
+            bl.dev[name][g0:g0 + nbk].copy_(r.baseline.dev[name][k0:k0 + nbk])
+        nk = int(r.events.starts.numel())
+        cols = {"starts": r.events.starts + (a - a0), "ends": r.events.ends + (a - a0), "types": r.types}
+        if r.levels is not None:
+            cols.update(n_levels=r.levels.n_levels, edges=r.levels.edges, mean=r.levels.mean, std=r.levels.std,
+                        overflow=r.levels.overflow)
+        for name, t in cols.items():
+            self._pinned(name, t, row0 + nk)[row0:row0 + nk].copy_(t, non_blocking=True)
+        return nk
+
+    def run_from_host(self, host_codes: torch.Tensor) -> StreamResult:
+        """`host_codes`: CPU (ideally pinned) uint16/int16 tensor [lo_halo | owned | hi_halo].  One
+        host synchronisation per sub-shard (its event count), all hidden under the copy except the last."""
+        if host_codes.numel() != self.n_ext or host_codes.dtype not in (torch.uint16, torch.int16) or host_codes.is_cuda:
+            raise ValueError("host_codes must be a CPU uint16/int16 tensor of the planned length")
+        if self.raw_dev is None or self.raw_dev.dtype != host_codes.dtype:
+            self.raw_dev = torch.empty(self.n_ext, dtype=host_codes.dtype, device=self.device)
+        L = _lib.lib()
+        cur = torch.cuda.current_stream(self.device)
+        a0, b_end = self.lo_halo, self.lo_halo + self.n_own
+        # ---- the copy, cut where each sub-shard's extended range is complete
+        ends = [eb for (_, _, _, eb) in self.sub]
+        ends[-1] = self.n_ext
+        arrivals = []
+        self.copy_stream.wait_stream(cur)                      # the previous step may still read raw_dev
+        with torch.cuda.stream(self.copy_stream):
+            prev = 0
+            for e in ends:
+                if e > prev:
+                    self.raw_dev[prev:e].copy_(host_codes[prev:e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                arrivals.append((prev, e, ev))
+                prev = max(prev, e)
+        # ---- median estimate from the first piece
+        cur.wait_event(arrivals[0][2])
+        first = self.raw_dev[a0:max(a0 + 1, min(arrivals[0][1], b_end))]
+        plan = median_estimate(self.n_own, self.mask, _median_kernels(first, self.mask)[0], self.group, self.device,
+                               n_sampled=first.numel())
+        self.last_plan = plan
+        counts = torch.zeros(9, dtype=torch.int64, device=self.device)
+        hist_fn, count_fn = _median_kernels(self.raw_dev[a0:b_end], self.mask)
+        bl = detect.new_baseline(self.n_own, self.block, self.bmin, self.bmax, self.device)
+        st = filters._stream_ptr(self.raw_dev)
+        rows, counts_per = 0, []
+        med, pad_x, redone = (0, 0), 0.0, ""
+        try:
+            for i, (pa, pe, ev) in enumerate(arrivals):
+                cur.wait_event(ev)
+                ca, cb = max(pa, a0), min(pe, b_end)
+                if plan.exact is None and cb > ca:           # exact-median window count of this piece's owned codes
+                    rc = L.ct_count_window_u16(self.raw_dev[ca:cb].data_ptr(), cb - ca, self.mask, plan.lo, plan.step,
+                                               counts.data_ptr(), st)
+                    _lib.check(rc, "ct_count_window_u16")
+                last = i == len(arrivals) - 1
+                if last:                                      # everything has arrived: exact order statistics
+                    med = median_search(self.n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
+                                        first_counts=counts if plan.exact is None else None)
+                    pad_x = 0.5 * (med[0] + med[1]) - plan.est
+                nk = self._process(i, plan, pad_x if last else 0.0, med, rows, bl)
+                counts_per.append(nk)
+                rows += nk
+            if pad_x != 0.0 and self.lo_halo == 0 and len(self.sub) > 1:
+                # the trace starts in this rank's first sub-shard and its pad was the estimate: redo it
+                nk = self._process(0, plan, pad_x, med, 0, bl)
+                redone = "first"
+                if nk != counts_per[0]:                       # an event (dis)appeared in the first samples: redo all rows
+                    rows, redone = 0, "all"
+                    for i in range(len(self.sub)):
+                        rows += self._process(i, plan, pad_x, med, rows, bl)
+        except ValueError as e:
+            if "baseline block" not in str(e):
+                raise
+            return self._run_whole(host_codes)                # a sub-shard without a single valid baseline block
+        first_id, total = event_id_offsets(rows, self.group, self.device)
+        cur.synchronize()
+        bl.dev["have_thresholds"] = True
+        bl._checked = True
+        bl.threshold, bl.hysteresis = float(self.kw.get("threshold", 5.0)), float(self.kw.get("hysteresis", 1.0))
+        pad_value = float(np.median(filters.scale_codes_host(np.array(med, dtype=np.uint16), self.settings)))
+        tables = {k: v[:rows].numpy() for k, v in self._pin.items()}
+        return StreamResult(filtered=self.y, baseline=bl, tables=tables, pad_value=pad_value, median_codes=tuple(med),
+                            first_event_id=first_id, total_events=total, redone=redone)
+
+    def _run_whole(self, host_codes: torch.Tensor) -> StreamResult:
+        """Fallback: the whole range through one TraceAnalyzer (baseline inheritance across the whole trace)."""
+        if self._whole is None:
+            self._whole = TraceAnalyzer(self.n_ext, self.settings, self.cutoff, self.order, lo_halo=self.lo_halo,
+                                        hi_halo=self.hi_halo, group=self.group, device=self.device, **self.kw)
+        r = self._whole.run_from_host(host_codes)
+        t = self._whole.tables_to_host(r)
+        return StreamResult(filtered=r.filtered, baseline=r.baseline, tables=t, pad_value=r.pad_value,
+                            median_codes=r.median_codes, first_event_id=r.first_event_id, total_events=r.total_events,
+                            redone="whole")
 
 
 def analyze_shard(raw_ext: torch.Tensor, settings, cutoff: float, order: int, *, lo_halo: int, hi_halo: int,

@@ -184,6 +184,43 @@ def test_streamed_run_from_host_equals_the_resident_run():
         assert (ra.events.starts - rb.events.starts).abs().max().item() <= 1
 
 
+@pytest.mark.parametrize("shift_first", [0, 64])
+def test_streaming_analyzer_equals_the_resident_run(shift_first):
+    """StreamingAnalyzer (time sub-shards processed while the copy is still running, tables sent back per
+    sub-shard) against one TraceAnalyzer.run over the whole trace: same medians, same events and levels,
+    samples equal to the IIR warm-up error.  With `shift_first` the first piece's median is a poor estimate of
+    the global one, so the first sub-shard has to be redone with the exact pad."""
+    codes, _ = synth.c1_trace(n=3_400_000, n_events=800, seed=32)
+    if shift_first:
+        codes[:200_000] += np.uint16(shift_first)
+    host = torch.from_numpy(codes).pin_memory()
+    kw = dict(baseline_block=65536, cusum_delta=400.0, cusum_h=10.0, **KW)
+    a = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, **kw)
+    ra = a.run(host.cuda())
+    ta = a.tables_to_host(ra)
+    for shards, first_blocks in ((5, 2), (1, 4), (16, 1)):
+        b = pipeline.StreamingAnalyzer(len(codes), S, 1e5, 8, shards=shards, first_blocks=first_blocks, **kw)
+        for _ in range(2):                                   # buffers are reused from run to run
+            rb = b.run_from_host(host)
+        assert tuple(rb.median_codes) == tuple(ra.median_codes) and rb.pad_value == ra.pad_value
+        if shift_first and shards > 1:
+            assert rb.redone in ("first", "all")
+        assert torch.max(torch.abs(ra.filtered - rb.filtered)).item() < 0.02
+        tb = rb.tables
+        assert len(tb["starts"]) == len(ta["starts"]) == rb.total_events
+        assert np.abs(tb["starts"] - ta["starts"]).max() <= 1 and np.abs(tb["ends"] - ta["ends"]).max() <= 1
+        same = (tb["starts"] == ta["starts"]) & (tb["ends"] == ta["ends"])
+        assert same.mean() > 0.99
+        assert np.array_equal(tb["types"][same], ta["types"][same])
+        assert np.array_equal(tb["n_levels"][same], ta["n_levels"][same])
+        assert np.mean(np.all(tb["edges"][same] == ta["edges"][same], axis=1)) > 0.99
+        bl_a, bl_b = ra.baseline, rb.baseline
+        assert len(bl_b) == len(bl_a)
+        # a different subtraction constant moves the samples by the float32 DC-gain error (1e-5 of the difference)
+        assert np.allclose(bl_b.mean, bl_a.mean, rtol=0, atol=1e-2) and np.allclose(bl_b.std, bl_a.std, rtol=5e-3)
+        assert np.array_equal(bl_b.count, bl_a.count) or np.abs(bl_b.count - bl_a.count).max() <= 2
+
+
 def test_config_c1_end_to_end_against_the_cpu_path():
     """BASELINE.json configs[0]: 1 s synthetic Chimera trace (4 166 666 samples), 8-pole 100 kHz Bessel,
     1000 injected two-level events, threshold detection + CUSUM+.  The GPU path runs on the codes; the CPU
