@@ -158,7 +158,7 @@ def run_reference(args):
                                        "reference is pure Python over numpy/scipy (nothing to compile into "
                                        "oracle/_ref), so the oracle port of its call sequence is timed"},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def side_kernels(torch, dev, peak):
@@ -372,12 +372,30 @@ def run_ours(args):
         line["other_kernels"] = side_kernels(torch, dev, peak)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if group is not None:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # stdout must carry exactly one JSON line: libraries that write to file descriptor 1 (NCCL prints its
+    # version banner there) are sent to stderr for the whole run, the result goes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

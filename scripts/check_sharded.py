@@ -33,6 +33,18 @@ if len({int(s.item()) for s in sizes}) != 1:                       # ragged: pad
     buf = [torch.zeros((m, 3), dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(buf, pad)
     parts = [bb[:int(s.item())] for bb, s in zip(buf, sizes)]
+# the streamed form of the same shard (time sub-shards overlapped with the host->device copy) must agree with it
+san = pipeline.StreamingAnalyzer(b - a, S, 1e5, 8, lo_halo=lo - a, hi_halo=b - hi, shards=3, first_blocks=2,
+                                 group=dist.group.WORLD, device=dev, **kw)
+rs = san.run_from_host(torch.from_numpy(codes[a:b].copy()).pin_memory())
+gs, ge = r.events.starts.cpu().numpy(), r.events.ends.cpu().numpy()
+stream_ok = (tuple(rs.median_codes) == tuple(r.median_codes) and rs.first_event_id == r.first_event_id
+             and rs.total_events == r.total_events and len(rs.tables["starts"]) == len(gs)
+             and np.abs(rs.tables["starts"] - gs).max(initial=0) <= 1 and np.abs(rs.tables["ends"] - ge).max(initial=0) <= 1
+             and torch.max(torch.abs(rs.filtered - r.filtered)).item() < 0.02)
+flag = torch.tensor([int(stream_ok)], dtype=torch.int64, device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+stream_ok = bool(flag.item())
 first = torch.tensor([r.first_event_id, r.total_events], dtype=torch.int64, device=dev)
 firsts = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
 dist.all_gather(firsts, first)
@@ -45,8 +57,8 @@ if rank == 0:
     ids = [int(f[0]) for f in firsts]
     ok = (r.median_codes == ref.median_codes and allev.shape == want.shape and np.array_equal(allev[:, :2], want[:, :2])
           and np.mean(allev[:, 2] == want[:, 2]) > 0.999 and ids == list(np.cumsum([0] + [int(s.item()) for s in sizes[:-1]]))
-          and int(firsts[0][1]) == want.shape[0])
+          and int(firsts[0][1]) == want.shape[0] and stream_ok)
     print(f"sharded over {world} GPUs: {allev.shape[0]} events vs {want.shape[0]} unsharded, median {r.median_codes} vs "
-          f"{ref.median_codes}, ids {ids}: {'OK' if ok else 'MISMATCH'}")
+          f"{ref.median_codes}, ids {ids}, streamed form {'agrees' if stream_ok else 'DIFFERS'}: {'OK' if ok else 'MISMATCH'}")
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
