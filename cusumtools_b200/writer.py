@@ -175,6 +175,24 @@ def event_table_from_result(an, r, *, samplerate: float, time_offset_s: float = 
                              block_offset=r.lo_halo)
 
 
+def event_table_from_stream(san, rs, *, samplerate: float, time_offset_s: float = 0.0, index_offset: int = 0) -> EventTable:
+    """Event table of one `pipeline.StreamingAnalyzer.run_from_host` result: the tables are already on
+    the host; only the per-event extrema are taken from the device-resident filtered trace (windows =
+    event +- event_padding, clipped to the rank's owned samples)."""
+    t = rs.tables
+    pad, n = int(san.kw.get("event_padding", 100)), int(rs.filtered.numel())
+    dev = rs.filtered.device
+    w0 = torch.from_numpy(np.clip(t["starts"] - pad, 0, n)).to(dev)
+    w1 = torch.from_numpy(np.clip(t["ends"] + pad, 0, n)).to(dev)
+    lo, hi = event_extrema(rs.filtered, w0, w1)
+    return build_event_table(starts=t["starts"], ends=t["ends"], types=t["types"], n_levels=t["n_levels"],
+                             edges=t["edges"], level_mean=t["mean"], level_std=t["std"], overflow=t["overflow"],
+                             xmin=lo.cpu().numpy(), xmax=hi.cpu().numpy(), samplerate=samplerate,
+                             threshold=float(san.kw.get("threshold", 5.0)), baseline_mean=rs.baseline.mean,
+                             baseline_std=rs.baseline.std, baseline_block=san.block, padding=pad,
+                             first_id=rs.first_event_id, time_offset_s=time_offset_s, index_offset=index_offset)
+
+
 def _write_csv(path: str, columns, table: dict) -> None:
     import pandas as pd
     df = pd.DataFrame({c: table[c] for c in columns}, columns=columns)

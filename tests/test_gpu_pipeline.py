@@ -221,6 +221,27 @@ def test_streaming_analyzer_equals_the_resident_run(shift_first):
         assert np.array_equal(bl_b.count, bl_a.count) or np.abs(bl_b.count - bl_a.count).max() <= 2
 
 
+def test_event_table_from_the_streamed_result_equals_the_resident_one():
+    """writer.event_table_from_stream over a StreamingAnalyzer result against writer.event_table_from_result
+    over the whole-trace run (same subtraction constant here: the estimate is exact for this trace's first piece)."""
+    from cusumtools_b200 import writer
+    codes, _ = synth.c1_trace(n=2_000_000, n_events=300, seed=33)
+    host = torch.from_numpy(codes).pin_memory()
+    kw = dict(baseline_block=65536, cusum_delta=400.0, cusum_h=10.0, **KW)
+    a = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, **kw)
+    ra = a.run(host.cuda())
+    ta = writer.event_table_from_result(a, ra, samplerate=synth.FS)
+    b = pipeline.StreamingAnalyzer(len(codes), S, 1e5, 8, shards=4, **kw)
+    rb = b.run_from_host(host)
+    tb = writer.event_table_from_stream(b, rb, samplerate=synth.FS)
+    assert list(tb.events) == list(ta.events) and list(tb.rate) == list(ta.rate)
+    assert np.array_equal(tb.rate["id"], ta.rate["id"]) and np.array_equal(tb.rate["type"], ta.rate["type"])
+    assert np.allclose(tb.rate["start_time_s"], ta.rate["start_time_s"], rtol=0, atol=1.01 / synth.FS)
+    assert np.array_equal(tb.events["id"], ta.events["id"]) and np.array_equal(tb.events["n_levels"], ta.events["n_levels"])
+    for col in ("effective_baseline_pA", "average_blockage_pA", "max_blockage_pA", "max_deviation_pA", "residual_pA"):
+        assert np.allclose(tb.events[col], ta.events[col], rtol=1e-3, atol=0.5), col
+
+
 def test_config_c1_end_to_end_against_the_cpu_path():
     """BASELINE.json configs[0]: 1 s synthetic Chimera trace (4 166 666 samples), 8-pole 100 kHz Bessel,
     1000 injected two-level events, threshold detection + CUSUM+.  The GPU path runs on the codes; the CPU
