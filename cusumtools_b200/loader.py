@@ -90,9 +90,10 @@ class ChimeraSeries:
         pieces.append(Piece(self.maps[end_f][:end_index - fsi[end_f]], self.settings[end_f], end_f))
         return pieces
 
-    def load_codes(self, start_s=None, end_s=None, device="cuda"):
-        """Raw codes of the window on the device plus the settings; requires one gain for the
-        whole window (the common case).  Returns (uint16 tensor, settings)."""
+    def host_codes(self, start_s=None, end_s=None):
+        """Raw codes of the window gathered into ONE pinned host tensor (what
+        pipeline.StreamingAnalyzer.run_from_host streams to the GPU) plus the settings; requires one
+        gain for the whole window (the common case).  Returns (uint16 CPU tensor, settings)."""
         pieces = self.window(start_s, end_s)
         if not all(_settings_equal(p.settings, pieces[0].settings) for p in pieces):
             raise ValueError("files in the window have different gain settings: use load_pA()")
@@ -103,7 +104,12 @@ class ChimeraSeries:
         for p in pieces:
             hv[o:o + len(p.codes)] = p.codes
             o += len(p.codes)
-        return host.to(device, non_blocking=True), pieces[0].settings
+        return host, pieces[0].settings
+
+    def load_codes(self, start_s=None, end_s=None, device="cuda"):
+        """`host_codes` copied to the device.  Returns (uint16 tensor, settings)."""
+        host, settings = self.host_codes(start_s, end_s)
+        return host.to(device, non_blocking=True), settings
 
     def load_pA(self, start_s=None, end_s=None, device="cuda") -> torch.Tensor:
         """load_mapped_data itself: every piece scaled with its own file's settings
