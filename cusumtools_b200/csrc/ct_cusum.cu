@@ -345,6 +345,9 @@ __global__ void __launch_bounds__(128, 4) ct_cusum_warp_kernel(CusumArgs a) {
 #ifndef CT_CUSUM_SEQ_GROUP
 #define CT_CUSUM_SEQ_GROUP 8
 #endif
+#ifndef CT_CUSUM_SEQ_CTAS
+#define CT_CUSUM_SEQ_CTAS 3
+#endif
 constexpr int kS = CT_CUSUM_SEQ_GROUP;   // samples a lane processes per (unrolled) group: 4 or 8
 constexpr int kSeqMax = 16384;         // longest window a single lane takes
 constexpr int kSeqMinEvents = 16384;   // below this one event per lane cannot fill the GPU: warps take everything
@@ -373,7 +376,7 @@ __device__ __forceinline__ SeqOut seq_increments(const double* __restrict__ rcta
     return o;
 }
 
-__global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
+__global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(CusumArgs a) {
     const int lane = ct_lane();
     const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
     const float dq = __fmul_rn(a.delta, kQ);
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
     bool active = false, exhausted = false;
     long long ev = 0, p0 = 0;
     int n = 0, gk = 0;                   // window length; relative index of the current 8-sample group
-    float x0 = 0.f;
+    float x0 = 0.f, nx0 = 0.f;           // the window's first sample and -64 x0 (quantisation: (x - x0) * 64, one FFMA)
     int k0 = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0, overflow = 0;
     long long Sq = 0, Sqq = 0;           // sums over [k0, k]
     long long Lp = 0, Lpp = 0;           // sums over [e0, k0): the part of the open level before the anchor
@@ -434,6 +437,8 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
                         Sq = Sqq = 0; Lp = Lpp = 0;
                         a.edges[ev * (ML + 1)] = 0;
                         load_group(p0 + gk, nx);
+                        x0 = a.y[p0];
+                        nx0 = __fmul_rn(x0, -kQ);
                         active = true;
                     }
                 }
@@ -454,8 +459,8 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
             for (int e = 0; e < kS; ++e) {
                 const int k = gk + e;
                 if ((unsigned)k >= nlim) continue;       // before the window (k < 0 wraps), behind it, or frozen by overflow
-                x0 = k == 0 ? xv[e] : x0;
-                const int q = quantise(xv[e], x0);
+                // == quantise(xv[e], x0): scaling by 2^6 commutes with the rounding of the difference
+                const int q = __float2int_rn(fminf(fmaxf(__fmaf_rn(xv[e], kQ, nx0), -kQMax), kQMax));
                 Sq += q; Sqq += (long long)q * q;
                 const SeqOut s = seq_increments(a.rctab, Sq, Sqq, k - k0 + 1, q, dq, hq);
                 gp = max(gp + s.sp, 0); rp = gp == 0 ? k : rp;
@@ -464,6 +469,7 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
                     if (nedge >= ML) { overflow = 1; continue; }
                     const int edge = ((gp >= gn) ? rp : rn) + 1;
                     long long T = 0, TT = 0;             // sums over [edge, k]
+#pragma unroll 1
                     for (int j = edge; j <= k; ++j) {
                         const long long qj = quantise(a.y[p0 + j], x0);
                         T += qj; TT += qj * qj;
@@ -481,6 +487,7 @@ __global__ void __launch_bounds__(256, 3) ct_cusum_seq_kernel(CusumArgs a) {
             if (gk >= n || overflow) {
                 if (overflow) {                          // the rest of the window belongs to the last level
                     long long T = 0, TT = 0;
+#pragma unroll 1
                     for (int j = e0; j < n; ++j) { const long long qj = quantise(a.y[p0 + j], x0); T += qj; TT += qj * qj; }
                     Lp = T; Lpp = TT; Sq = 0; Sqq = 0;
                 }
