@@ -50,28 +50,6 @@ struct CusumArgs {
     int* pending;                      // events left to the warp-cooperative kernel
 };
 
-__device__ __forceinline__ int warp_excl_add(int v, int lane, int& total) {
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(CT_FULL, inc, d); if (lane >= d) inc += t; }
-    total = __shfl_sync(CT_FULL, inc, 31);
-    return inc - v;
-}
-__device__ __forceinline__ long long warp_excl_add(long long v, int lane, long long& total) {
-    long long inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { long long t = __shfl_up_sync(CT_FULL, inc, d); if (lane >= d) inc += t; }
-    total = __shfl_sync(CT_FULL, inc, 31);
-    return inc - v;
-}
-__device__ __forceinline__ int warp_excl_min(int v, int lane, int& total) {
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(CT_FULL, inc, d); if (lane >= d) inc = min(inc, t); }
-    total = __shfl_sync(CT_FULL, inc, 31);
-    int ex = __shfl_up_sync(CT_FULL, inc, 1);
-    return lane == 0 ? kBig : ex;
-}
 // fused exclusive scan of an int32 and an int64 lane total (one shuffle round trip per step)
 __device__ __forceinline__ void warp_excl_add2(int v, long long w, int lane, int& exv, long long& exw, int& totv,
                                                long long& totw) {
