@@ -221,6 +221,23 @@ def test_streaming_analyzer_equals_the_resident_run(shift_first):
         assert np.array_equal(bl_b.count, bl_a.count) or np.abs(bl_b.count - bl_a.count).max() <= 2
 
 
+@pytest.mark.parametrize("n", [30_000, 100_000, 700_001])
+def test_streaming_analyzer_small_and_ragged_traces(n):
+    """Traces shorter than a baseline block, shorter than the first sub-shard, and not a multiple of the block."""
+    codes, _ = synth.c1_trace(n=n, n_events=max(2, n // 5000), seed=n)
+    host = torch.from_numpy(codes).pin_memory()
+    kw = dict(baseline_block=65536, cusum_delta=400.0, cusum_h=10.0, **KW)
+    ra_an = pipeline.TraceAnalyzer(n, S, 1e5, 8, **kw)
+    ra = ra_an.run(host.cuda())
+    ta = ra_an.tables_to_host(ra)
+    rb = pipeline.StreamingAnalyzer(n, S, 1e5, 8, shards=16, **kw).run_from_host(host)
+    assert tuple(rb.median_codes) == tuple(ra.median_codes)
+    assert rb.filtered.numel() == n and torch.max(torch.abs(ra.filtered - rb.filtered)).item() < 0.02
+    assert len(rb.tables["starts"]) == len(ta["starts"])
+    assert np.abs(rb.tables["starts"] - ta["starts"]).max(initial=0) <= 1
+    assert len(rb.baseline) == len(ra.baseline) == -(-n // 65536)
+
+
 def test_event_table_from_the_streamed_result_equals_the_resident_one():
     """writer.event_table_from_stream over a StreamingAnalyzer result against writer.event_table_from_result
     over the whole-trace run (same subtraction constant here: the estimate is exact for this trace's first piece)."""
