@@ -106,6 +106,19 @@ static __device__ __forceinline__ void tally(const SeqArgs& a, StatAcc& acc, flo
     const int q = in ? __float2int_rn(__fmul_rn(__fsub_rn(v, a.st_c0), a.st_scale)) : 0;
     acc.c += in ? 1 : 0; acc.s1 += q; acc.s2 += (long long)q * q;
 }
+// Four independent partial tallies (one per component of the float4 a lane stores): no serial
+// dependency on one accumulator, 32-bit count and sum (a tile gives a lane 128 samples and fused
+// blocks are >= 2^16 samples, so |q| < 2^23 and the partial sum stays below 2^30).
+struct StatAcc4 { int c[4]; int s1[4]; long long s2[4]; };
+static __device__ __forceinline__ void tally4(const SeqArgs& a, StatAcc4& t, const float4& v) {
+    const float w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool in = w[e] >= a.st_min && w[e] <= a.st_max;
+        const int q = in ? __float2int_rn(__fmul_rn(__fsub_rn(w[e], a.st_c0), a.st_scale)) : 0;
+        t.c[e] += in ? 1 : 0; t.s1[e] += q; t.s2[e] += (long long)q * q;
+    }
+}
 
 struct u8x { unsigned w[8]; };
 static __device__ __forceinline__ u8x ldg256(const void* p) {
@@ -206,13 +219,21 @@ __device__ __forceinline__ void store_tile(const SeqArgs& a, const float* outb, 
         float* dst = a.out + first + (long long)(lane / LPR) * a.R + (lane % LPR) * 4;
         const float* src = outb + (lane / LPR) * kRowF + (lane % LPR) * 4;
         const long long dstep = (long long)RPI * a.R;
+        StatAcc4 t4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { t4.c[e] = 0; t4.s1[e] = 0; t4.s2[e] = 0; }
 #pragma unroll
         for (int u = 0; u < kRuns / RPI; ++u) {
             float4 v = *reinterpret_cast<const float4*>(src + u * RPI * kRowF);
             v.x = fmaf(v.x, a.scale, a.offset); v.y = fmaf(v.y, a.scale, a.offset);
             v.z = fmaf(v.z, a.scale, a.offset); v.w = fmaf(v.w, a.scale, a.offset);
             ct_stg_stream(dst + u * dstep, v);
-            if (STATS) { tally(a, acc, v.x); tally(a, acc, v.y); tally(a, acc, v.z); tally(a, acc, v.w); }
+            if (STATS) tally4(a, t4, v);
+        }
+        if (STATS) {
+            acc.c += (t4.c[0] + t4.c[1]) + (t4.c[2] + t4.c[3]);
+            acc.s1 += ((long long)t4.s1[0] + t4.s1[1]) + ((long long)t4.s1[2] + t4.s1[3]);
+            acc.s2 += (t4.s2[0] + t4.s2[1]) + (t4.s2[2] + t4.s2[3]);
         }
         return;
     }
@@ -746,6 +767,10 @@ int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, co
             ct_set_error("filter: fused block statistics need block %% %lld == 0 and the grid origin (block = %lld)", p.G,
                          (long long)stats->block);
             return CT_ERR_ARG;
+        }
+        if (stats->block < 65536) {       // the epilogue's 32-bit partial sums: |q| < 2^31 / sqrt(block) must stay below 2^23
+            ct_set_error("filter: fused block statistics need blocks of at least 65536 samples (got %lld)", (long long)stats->block);
+            return CT_ERR_UNSUPPORTED;
         }
         const long long nb = (n - stats->origin + stats->block - 1) / stats->block;
         if (nb > 0) {

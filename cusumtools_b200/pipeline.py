@@ -204,7 +204,7 @@ class TraceAnalyzer:
                  baseline_min: float, baseline_max: float, padding: int = 1000, event_padding: int = 100,
                  minpoints: int = 8, maxpoints: int = 100_000, cusum_delta: float | None = None,
                  cusum_h: float | None = None, max_levels: int = cusum.DEFAULT_MAX_LEVELS,
-                 event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = False,
+                 event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = True,
                  fused_count: bool = False):
         self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
         self.n_own = self.n_ext - self.lo_halo - self.hi_halo
@@ -225,7 +225,8 @@ class TraceAnalyzer:
         self.y = torch.empty(self.n_ext, dtype=torch.float32, device=self.device)
         self.design = bessel_lowpass(self.order, 2.0 * self.cutoff / float(np.floor(np.squeeze(settings["ADCSAMPLERATE"]))))
         # baseline block sums ride on the filter's epilogue when the block is a whole number of its warp groups
-        self.fuse_stats = bool(fuse_stats) and self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0
+        self.fuse_stats = (bool(fuse_stats) and self.block >= 65536
+                           and self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0)
         self.fused_count = bool(fused_count)     # tally the exact-median window inside the forward pass (measured slower)
         self.filter_ws = None
         self.H = max(1, self.design.impulse_tail(filters.DEFAULT_HALO_EPS))

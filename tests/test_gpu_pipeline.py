@@ -127,7 +127,7 @@ def test_block_sums_fused_into_the_filter_equal_the_standalone_kernel(origin):
     codes, _ = synth.c1_trace(n=900_000, n_events=200, seed=17)
     raw = torch.from_numpy(codes).cuda()
     g = filters.stats_granule(len(codes), 1000, bessel_lowpass(8, 2 * 1e5 / synth.FS))
-    block = 2 * g
+    block = g * max(2, 65536 // g)             # a whole number of warp groups, at least 65536 samples
     n_det = len(codes) - origin
     bl = detect.new_baseline(n_det, block, 4700.0, 5300.0, raw.device)
     y = filters.dequant_filtfilt(raw, S, 1e5, 8, stats=detect.stats_args(bl, origin=origin))
@@ -136,6 +136,19 @@ def test_block_sums_fused_into_the_filter_equal_the_standalone_kernel(origin):
     ref = detect.baseline_blocks(y[origin:], block, 4700.0, 5300.0)
     for k in ("cnt", "s1", "s2"):
         assert torch.equal(bl.dev[k], ref.dev[k]), k
+
+
+def test_fused_block_sums_refuse_small_blocks():
+    from cusumtools_b200 import detect, filters
+    from cusumtools_b200.design import bessel_lowpass
+    codes, _ = synth.c1_trace(n=900_000, n_events=200, seed=17)
+    raw = torch.from_numpy(codes).cuda()
+    g = filters.stats_granule(len(codes), 1000, bessel_lowpass(8, 2 * 1e5 / synth.FS))
+    if g >= 65536:
+        pytest.skip("the run grid of this trace is already coarser than the limit")
+    bl = detect.new_baseline(len(codes), g, 4700.0, 5300.0, raw.device)
+    with pytest.raises(RuntimeError, match="at least 65536"):
+        filters.dequant_filtfilt(raw, S, 1e5, 8, stats=detect.stats_args(bl, origin=0))
 
 
 @pytest.mark.parametrize("n,lo,hi", [(300_001, 0, 0), (300_000, 0, 0), (5_000_000, 0, 0), (5_000_001, 65536, 8192)])
