@@ -288,16 +288,26 @@ def run_ours(args):
     # the dominant kernel pair alone (forward + backward filter pass, no host round trip in between),
     # timed with CUDA events on the launching stream: the roofline entry
     med = an.last_median if hasattr(an, "last_median") else filters.code_median(raw[lo_h:lo_h + n_own], filters.chimera_bitmask(S))
-    for _ in range(2):
-        filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y, workspace=an.filter_ws)
-    fa = torch.cuda.Event(enable_timing=True); fb = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    fa.record()
-    for _ in range(3):
-        filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y, workspace=an.filter_ws)
-    fb.record()
-    torch.cuda.synchronize()
-    filt_ms = fa.elapsed_time(fb) / 3
+
+    def time_pair(stats):
+        for _ in range(2):
+            filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y, workspace=an.filter_ws, stats=stats)
+        fa = torch.cuda.Event(enable_timing=True); fb = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        fa.record()
+        for _ in range(3):
+            filters.dequant_filtfilt(raw, S, CUTOFF, ORDER, median_codes=med, out=an.y, workspace=an.filter_ws, stats=stats)
+        fb.record()
+        torch.cuda.synchronize()
+        return fa.elapsed_time(fb) / 3
+
+    filt_plain_ms = time_pair(None)
+    # the pair as the step runs it: the backward pass also tallies the baseline block sums of its output
+    fused_stats = bool(getattr(an, "fuse_stats", False))
+    filt_ms = filt_plain_ms
+    if fused_stats:
+        bl_tmp = detect.new_baseline(raw.numel(), BASELINE_BLOCK, BASELINE_MIN, BASELINE_MAX, dev)
+        filt_ms = time_pair(detect.stats_args(bl_tmp, origin=0))
     ms_per_step = dev_ms / args.steps
     total = n_own * world
     value = total / (ms_per_step / 1e3) / 1e6
@@ -354,11 +364,15 @@ def run_ours(args):
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms": stage_ms,
         "roofline": {"kernel": "ct_filter_fwd_kernel + ct_filter_bwd_kernel (fused dequantise + median pad + zero-phase "
-                               "Bessel as two lane-sequential passes; timed alone, 3 back-to-back calls)", "bound": "hbm",
+                               "Bessel as two lane-sequential passes" + (", baseline block sums tallied in the backward "
+                               "pass's epilogue" if fused_stats else "") + "; timed alone, 3 back-to-back calls)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "kernel_ms": filt_ms,
                      "algorithmic_bytes_per_sample": FILTER_BYTES_PER_SAMPLE,
                      "share_of_step": filt_ms / ms_per_step,
+                     "filter_only": {"kernel_ms": filt_plain_ms, "frac": FILTER_BYTES_PER_SAMPLE * raw.numel() / (filt_plain_ms / 1e3) / 1e9 / peak,
+                                     "note": "the same pair without the fused block sums (the separate ct_block_stats kernel "
+                                             "it replaces reads 4 B/sample more and takes 2.2 ms)"},
                      "note": "traffic = ncu dram bytes per launch pair (profiles/): the forward output crosses HBM "
                              "once at half rate (2 B/sample written + 2 B/sample read) on top of the 6 algorithmic bytes"},
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(raw.numel() * 2 * world),
