@@ -45,6 +45,15 @@ stream_ok = (tuple(rs.median_codes) == tuple(r.median_codes) and rs.first_event_
 flag = torch.tensor([int(stream_ok)], dtype=torch.int64, device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 stream_ok = bool(flag.item())
+# stage 4 sharded: every rank transforms its contiguous block of Welch segments of the filtered trace (its samples
+# filtered here with a warm-up halo and the GLOBAL median), one all_reduce of the L/2+1 sums
+from cusumtools_b200 import filters, psd
+Lw = 1 << 16
+s0, s1, p0, p1 = psd.segment_share(n, Lw, world, rank)
+hw = 4096
+qa, qb = max(0, p0 - hw), min(n, p1 + hw)
+yl = filters.dequant_filtfilt(torch.from_numpy(codes[qa:qb]).to(dev), S, 1e5, 8, median_codes=r.median_codes)[p0 - qa:p1 - qa]
+fP, P = psd.welch_sharded(yl, synth.FS, Lw, shift=float(r.pad_value), group=dist.group.WORLD)
 first = torch.tensor([r.first_event_id, r.total_events], dtype=torch.int64, device=dev)
 firsts = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
 dist.all_gather(firsts, first)
@@ -58,7 +67,10 @@ if rank == 0:
     ok = (r.median_codes == ref.median_codes and allev.shape == want.shape and np.array_equal(allev[:, :2], want[:, :2])
           and np.mean(allev[:, 2] == want[:, 2]) > 0.999 and ids == list(np.cumsum([0] + [int(s.item()) for s in sizes[:-1]]))
           and int(firsts[0][1]) == want.shape[0] and stream_ok)
+    fW, PW = psd.welch(ref.filtered, synth.FS, Lw)
+    psd_ok = bool(np.allclose(fP, fW) and np.all(np.abs(P - PW) <= 2e-5 * PW + 1e-9 * PW.max()))
+    ok = ok and psd_ok
     print(f"sharded over {world} GPUs: {allev.shape[0]} events vs {want.shape[0]} unsharded, median {r.median_codes} vs "
-          f"{ref.median_codes}, ids {ids}, streamed form {'agrees' if stream_ok else 'DIFFERS'}: {'OK' if ok else 'MISMATCH'}")
+          f"{ref.median_codes}, ids {ids}, streamed form {'agrees' if stream_ok else 'DIFFERS'}, sharded PSD {'agrees' if psd_ok else 'DIFFERS'}: {'OK' if ok else 'MISMATCH'}")
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
