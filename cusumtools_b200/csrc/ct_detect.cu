@@ -391,6 +391,65 @@ __global__ void ct_event_windows_kernel(const long long* __restrict__ starts, co
     }
 }
 
+
+// ---------------------------- intra-event threshold crossings --------------------------
+// The consumer draws two more lines inside every event (readevents.py:1363-1366: local_baseline -
+// intra_threshold * local_stdev and local_baseline - (intra_threshold - intra_hysteresis) * local_stdev,
+// sign-mirrored) and shades the (start, end) pairs of rate.csv's intra_crossing_times_us
+// (readevents.py:1340-1343, 1366-1367).  Definition of record: oracle/events_oracle.py::intra_crossings -
+// the detector's own two-state automaton run over the event window with those lines (of the baseline
+// block that holds the event start), starting outside; a crossing still open at the end of the window
+// ends there.  One warp per event: 32 samples per ballot pair, the same adder-carry evaluation.
+__global__ void __launch_bounds__(256)
+ct_intra_crossings_kernel(const float* __restrict__ y, long long ntot, const long long* __restrict__ w0,
+                          const long long* __restrict__ w1, const long long* __restrict__ es, long long nev,
+                          const long long* __restrict__ nev_dev, long long block, long long nblocks,
+                          const int* __restrict__ sign, const float* __restrict__ ts, const float* __restrict__ te,
+                          int K, int* __restrict__ count, int* __restrict__ pairs) {
+    if (nev_dev) { const long long d = *nev_dev; nev = d < nev ? d : nev; }
+    const int lane = ct_lane();
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long ev = gw; ev < nev; ev += nw) {
+        long long a = w0[ev], b = w1[ev];
+        const long long org = a;                       // indices are reported relative to the window start
+        if (a < 0) a = 0;
+        if (b > ntot) b = ntot;
+        long long kb = es[ev] / block;
+        if (kb < 0) kb = 0;
+        if (kb >= nblocks) kb = nblocks - 1;
+        const float sg = sign[kb] > 0 ? 1.f : -1.f;
+        const float tst = sg * ts[kb], ten = sg * te[kb];      // mirrored: "beyond" is always "below"
+        unsigned c = 0;
+        int cnt = 0;
+        int* out = pairs + ev * 2 * (long long)K;
+        for (long long p = a; p < b; p += 32) {
+            const long long i = p + lane;
+            const bool valid = i < b;
+            const float v = valid ? sg * y[i] : 0.f;
+            const unsigned A = __ballot_sync(CT_FULL, valid && v < tst);
+            const unsigned B = __ballot_sync(CT_FULL, valid && v > ten);
+            const unsigned before = c;
+            const unsigned I = automaton_word(A, B, c);
+            const unsigned prev = (I << 1) | before;
+            unsigned m = (I & ~prev) | (~I & prev);    // starts and ends, alternating in time
+            if (lane == 0) {
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int idx = (int)(p - org) + bit;
+                    if ((I >> bit) & 1u) { if (cnt < K) out[2 * cnt] = idx; }
+                    else { if (cnt < K) out[2 * cnt + 1] = idx; ++cnt; }
+                }
+            }
+        }
+        if (lane == 0) {
+            if (c) { if (cnt < K) out[2 * cnt + 1] = (int)(b - org); ++cnt; }
+            count[ev] = cnt;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -492,5 +551,25 @@ int ct_event_windows(const int64_t* starts, const int64_t* ends, const uint64_t*
         padding, minpoints, maxpoints, (long long*)win_start, (long long*)win_end, type, (long long*)out2);
     return ct_check_launch("ct_event_windows_kernel");
 }
+
+int ct_intra_crossings_f32(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                           const int64_t* ev_start, int64_t n_events, const int64_t* n_events_dev, int64_t block,
+                           int64_t n_blocks, const int32_t* sign, const float* t_start, const float* t_end,
+                           int32_t max_pairs, int32_t* count, int32_t* pairs, void* stream) {
+    if (!y || !win_start || !win_end || !ev_start || !sign || !t_start || !t_end || !count || !pairs || n_events < 0) {
+        ct_set_error("intra_crossings: bad argument"); return CT_ERR_ARG;
+    }
+    if (block <= 0 || n_blocks <= 0 || max_pairs < 1) { ct_set_error("intra_crossings: need block > 0, n_blocks > 0, max_pairs >= 1"); return CT_ERR_ARG; }
+    if (n_events == 0) return CT_OK;
+    long long grid = (n_events + 7) / 8;
+    const long long cap = (long long)ct_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    CT_COUNT_LAUNCH();
+    ct_intra_crossings_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        y, n_total, (const long long*)win_start, (const long long*)win_end, (const long long*)ev_start, n_events,
+        (const long long*)n_events_dev, block, n_blocks, sign, t_start, t_end, max_pairs, count, pairs);
+    return ct_check_launch("ct_intra_crossings_kernel");
+}
+
 
 }  // extern "C"

@@ -43,6 +43,9 @@ constexpr int kRuns = 64;           // runs per warp (32 lanes x 2 halves)
 constexpr int kRowF = kK + 4;       // float row stride: conflict-free LDS.128 / STS.128
 constexpr int kRowH = kK + 8;       // uint16 row stride in halfwords ((kK+8)/2 words = 4 mod 16: conflict-free LDS.128)
 constexpr int kSeqWarps = 2;
+#ifndef CT_SEQ_STATS_UNROLL
+#define CT_SEQ_STATS_UNROLL 4
+#endif
 #ifndef CT_SEQ_BWD_UNROLL
 #define CT_SEQ_BWD_UNROLL 4
 #endif
@@ -74,7 +77,7 @@ struct SeqArgs {
     unsigned cw_lo; int cw_sh; unsigned long long* cw_out;
     long long cw_p0, cw_p1; // only codes at positions [cw_p0, cw_p1) are tallied (a shard's owned samples)
     // optional fused baseline block statistics of the final output (ct_block_stats_f32 semantics)
-    long long st_origin, st_block; float st_min, st_max, st_c0, st_scale;
+    long long st_origin, st_block; float st_min, st_max, st_c0, st_scale, st_nc0s;   // st_nc0s = -c0 * scale (exact)
     long long* st_cnt; long long* st_s1; long long* st_s2;
 };
 
@@ -115,7 +118,8 @@ static __device__ __forceinline__ void tally4(const SeqArgs& a, StatAcc4& t, con
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const bool in = w[e] >= a.st_min && w[e] <= a.st_max;
-        const int q = in ? __float2int_rn(__fmul_rn(__fsub_rn(w[e], a.st_c0), a.st_scale)) : 0;
+        // (v - c0) * 2^s in one FFMA: scaling by a power of two commutes with the rounding of the difference
+        const int q = in ? __float2int_rn(__fmaf_rn(w[e], a.st_scale, a.st_nc0s)) : 0;
         t.c[e] += in ? 1 : 0; t.s1[e] += q; t.s2[e] += (long long)q * q;
     }
 }
@@ -222,7 +226,9 @@ __device__ __forceinline__ void store_tile(const SeqArgs& a, const float* outb, 
         StatAcc4 t4;
 #pragma unroll
         for (int e = 0; e < 4; ++e) { t4.c[e] = 0; t4.s1[e] = 0; t4.s2[e] = 0; }
-#pragma unroll
+        // with the tallies the fully unrolled loop is ~1500 instructions: instruction-cache misses became the top stall
+        constexpr int kStoreUnroll = STATS ? CT_SEQ_STATS_UNROLL : kRuns / RPI;
+#pragma unroll (kStoreUnroll)
         for (int u = 0; u < kRuns / RPI; ++u) {
             float4 v = *reinterpret_cast<const float4*>(src + u * RPI * kRowF);
             v.x = fmaf(v.x, a.scale, a.offset); v.y = fmaf(v.y, a.scale, a.offset);
@@ -703,7 +709,7 @@ void init_args(SeqArgs& a) {
     a.scratch_runs = 0; a.base = 0; a.g_first = 0; a.pad_x = 0.f; a.cw_lo = 0; a.cw_sh = 0; a.cw_out = nullptr;
     a.cw_p0 = 0; a.cw_p1 = 0;
     a.st_cnt = nullptr; a.st_s1 = nullptr; a.st_s2 = nullptr; a.st_origin = 0; a.st_block = 1;
-    a.st_min = a.st_max = a.st_c0 = a.st_scale = 0.f; a.n_out = 0; a.sub = 0.f; a.mask = 0xffffu; a.scale = 1.f; a.offset = 0.f;
+    a.st_min = a.st_max = a.st_c0 = a.st_scale = a.st_nc0s = 0.f; a.n_out = 0; a.sub = 0.f; a.mask = 0xffffu; a.scale = 1.f; a.offset = 0.f;
 }
 int check_ws(const void* workspace, int64_t workspace_bytes, int64_t n, int64_t pad, int H) {
     if (!workspace || workspace_bytes < ct_filtfilt_workspace_bytes(n, pad, H) || (reinterpret_cast<uintptr_t>(workspace) & 31)) {
@@ -777,7 +783,7 @@ int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, co
             cudaMemsetAsync(stats->cnt, 0, nb * 8, st); cudaMemsetAsync(stats->s1, 0, nb * 8, st); cudaMemsetAsync(stats->s2, 0, nb * 8, st);
         }
         b.st_origin = stats->origin; b.st_block = stats->block; b.st_min = stats->bmin; b.st_max = stats->bmax;
-        b.st_c0 = stats->c0; b.st_scale = ldexpf(1.f, stats->shift);
+        b.st_c0 = stats->c0; b.st_scale = ldexpf(1.f, stats->shift); b.st_nc0s = -ldexpf(stats->c0, stats->shift);
         b.st_cnt = (long long*)stats->cnt; b.st_s1 = (long long*)stats->s1; b.st_s2 = (long long*)stats->s2;
     }
     return half_rate_ok(*coef) ? dispatch_bwd<true>(b, *coef, st) : dispatch_bwd<false>(b, *coef, st);

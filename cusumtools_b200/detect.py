@@ -122,6 +122,51 @@ class Baseline:
                 torch.from_numpy(np.ascontiguousarray(self._t_end, np.float32)).to(device))
 
 
+def lines_for(bl: Baseline, threshold: float, hysteresis: float):
+    """(sign, t_start, t_end) device tensors for ANOTHER pair of thresholds over the same block sums
+    (the intra-event lines), leaving the table's own detector lines untouched."""
+    d = bl.dev
+    if d is None:
+        raise ValueError("lines_for needs a device-resident baseline table")
+    nb = d["mean"].numel()
+    dev = d["mean"].device
+    f64 = torch.empty((2, max(nb, 1)), dtype=torch.float64, device=dev)
+    lines = torch.empty((2, max(nb, 1)), dtype=torch.float32, device=dev)
+    sign = torch.empty(max(nb, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = _lib.lib().ct_baseline_finalize(d["cnt"].data_ptr(), d["s1"].data_ptr(), d["s2"].data_ptr(), nb, float(d["c0"]),
+                                         int(d["shift"]), int(d["min_count"]), float(threshold), float(hysteresis),
+                                         f64[0].data_ptr(), f64[1].data_ptr(), sign.data_ptr(), lines[0].data_ptr(),
+                                         lines[1].data_ptr(), status.data_ptr(), _stream_ptr(d["mean"]))
+    _lib.check(rc, "ct_baseline_finalize")
+    return sign[:nb], lines[0, :nb], lines[1, :nb]
+
+
+def intra_crossings(y: torch.Tensor, win_start: torch.Tensor, win_end: torch.Tensor, ev_start: torch.Tensor, bl: Baseline,
+                    intra_threshold: float, intra_hysteresis: float, *, max_pairs: int = 8, n_events_dev=None,
+                    out=None):
+    """Intra-event threshold crossings of every event window (oracle/events_oracle.py::intra_crossings;
+    readevents.py:1340-1343,1363-1367): (count int32 [E], pairs int32 [E, 2*max_pairs]) device tensors,
+    pairs relative to the window start, valid for k < min(count, max_pairs).  `ev_start` (same coordinates
+    as the windows) selects the baseline block whose mean/std define the lines.  `n_events_dev`: event
+    count still on the device (rows beyond it are not written); `out`: preallocated (count, pairs)."""
+    E = int(win_start.numel())
+    dev = y.device
+    sign, ts, te = lines_for(bl, intra_threshold, intra_hysteresis)
+    if out is None:
+        count = torch.zeros(E, dtype=torch.int32, device=dev)
+        pairs = torch.full((E, 2 * int(max_pairs)), -1, dtype=torch.int32, device=dev)
+    else:
+        count, pairs = out
+    if E:
+        rc = _lib.lib().ct_intra_crossings_f32(y.data_ptr(), y.numel(), win_start.data_ptr(), win_end.data_ptr(),
+                                               ev_start.data_ptr(), E, n_events_dev.data_ptr() if n_events_dev is not None else None,
+                                               bl.block, len(bl), sign.data_ptr(), ts.data_ptr(), te.data_ptr(), int(max_pairs),
+                                               count.data_ptr(), pairs.data_ptr(), _stream_ptr(y))
+        _lib.check(rc, "ct_intra_crossings_f32")
+    return count, pairs
+
+
 def new_baseline(n: int, block: int, baseline_min: float, baseline_max: float, device, min_count: int = 16) -> Baseline:
     """An empty device-resident baseline table for a trace of `n` samples; the block sums are
     filled either by `baseline_blocks` (own kernel) or by the filter (`stats_args`)."""

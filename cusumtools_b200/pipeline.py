@@ -185,6 +185,7 @@ class AnalysisResult:
     median_codes: tuple[int, int]
     first_event_id: int = 0
     total_events: int = 0
+    intra: "tuple[torch.Tensor, torch.Tensor] | None" = None     # (count int32 [E], pairs int32 [E, 2K]) crossings
 
 
 class TraceAnalyzer:
@@ -205,7 +206,8 @@ class TraceAnalyzer:
                  minpoints: int = 8, maxpoints: int = 100_000, cusum_delta: float | None = None,
                  cusum_h: float | None = None, max_levels: int = cusum.DEFAULT_MAX_LEVELS,
                  event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = True,
-                 fused_count: bool = False):
+                 fused_count: bool = False, intra_threshold: float = 0.0, intra_hysteresis: float = 0.0,
+                 max_crossings: int = 8):
         self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
         self.n_own = self.n_ext - self.lo_halo - self.hi_halo
         self.n_det = self.n_ext
@@ -216,6 +218,9 @@ class TraceAnalyzer:
         self.block, self.bmin, self.bmax = int(baseline_block), float(baseline_min), float(baseline_max)
         self.event_padding, self.minpoints, self.maxpoints = int(event_padding), int(minpoints), int(maxpoints)
         self.delta, self.h, self.max_levels = cusum_delta, cusum_h, int(max_levels)
+        # intra-event threshold crossings (readevents.py:1340-1343, 1363-1367); 0 = off, as in summary.txt
+        self.intra_threshold, self.intra_hysteresis = float(intra_threshold), float(intra_hysteresis)
+        self.max_crossings = int(max_crossings)
         self.group = group
         self.device = torch.device(device)
         self.mask = filters.chimera_bitmask(settings)
@@ -243,6 +248,9 @@ class TraceAnalyzer:
         self.w1 = torch.empty(cap, dtype=torch.int64, device=dev)
         self.typ = torch.empty(cap, dtype=torch.int32, device=dev)
         self.scalars = torch.zeros(4, dtype=torch.int64, device=dev)     # n_starts, n_ends, n_kept, first kept index
+        if self.intra_threshold > 0:
+            self.ic = torch.zeros(cap, dtype=torch.int32, device=dev)
+            self.ip = torch.full((cap, 2 * self.max_crossings), -1, dtype=torch.int32, device=dev)
         if self.delta is not None:
             self.nl = torch.empty(cap, dtype=torch.int32, device=dev)
             self.ed = torch.empty((cap, ML + 1), dtype=torch.int32, device=dev)
@@ -378,6 +386,11 @@ class TraceAnalyzer:
                                           self.mu.data_ptr(), self.sd.data_ptr(), self.ov.data_ptr(), self.cws.data_ptr(),
                                           self.cws_bytes, st)
                 _lib.check(rc, "ct_cusum_batch_dev")
+            if self.intra_threshold > 0:
+                # the block of the event start: win_start + padding (windows are compacted, the start list is not)
+                detect.intra_crossings(yd, self.w0, self.w1, self.w0 + self.event_padding, bl, self.intra_threshold,
+                                       self.intra_hysteresis, max_pairs=self.max_crossings, n_events_dev=sc[2:],
+                                       out=(self.ic, self.ip))
             hook("cusum")
             host = torch.cat((sc[:4], bl.dev["status"].to(torch.int64))).cpu().numpy()   # the step's one sync
             ns, ne, nk, i0 = int(host[0]), int(host[1]), int(host[2]), int(host[3])
@@ -399,7 +412,8 @@ class TraceAnalyzer:
         first_id, total = event_id_offsets(nk, self.group, self.device) if _fixed is None else (0, nk)
         return AnalysisResult(filtered=y[lo:lo + n_own], detect_trace=yd, lo_halo=lo, baseline=bl, events=ev,
                               win_start=self.w0[:nk], win_end=self.w1[:nk], types=self.typ[:nk], levels=lv,
-                              pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id, total_events=total)
+                              pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id, total_events=total,
+                              intra=(self.ic[:nk], self.ip[:nk]) if self.intra_threshold > 0 else None)
 
 
     def tables_to_host(self, r: AnalysisResult) -> dict:
@@ -414,6 +428,8 @@ class TraceAnalyzer:
         if r.levels is not None:
             src.update(n_levels=r.levels.n_levels, edges=r.levels.edges, mean=r.levels.mean, std=r.levels.std,
                        overflow=r.levels.overflow)
+        if r.intra is not None:
+            src.update(intra_count=r.intra[0], intra_pairs=r.intra[1])
         out = {}
         for k, t in src.items():
             if k not in self._pinned:
@@ -525,6 +541,8 @@ class StreamingAnalyzer:
         if r.levels is not None:
             cols.update(n_levels=r.levels.n_levels, edges=r.levels.edges, mean=r.levels.mean, std=r.levels.std,
                         overflow=r.levels.overflow)
+        if r.intra is not None:
+            cols.update(intra_count=r.intra[0], intra_pairs=r.intra[1])
         for name, t in cols.items():
             self._pinned(name, t, row0 + nk)[row0:row0 + nk].copy_(t, non_blocking=True)
         return nk

@@ -20,8 +20,10 @@ fixed here (SURVEY.md Appendix A.4 lists the open points):
 * `type`: 0 accepted (CUSUM fit; 3-column event file), 2 too short, 3 too long, 4 padding
   overlaps a neighbour or leaves the trace, 5 CUSUM+ found no sub-level, 6 more levels than
   the table holds; types > 1 appear in rate.csv only (`plot-trace.py:354-357`);
-* this tool has no intra-event threshold pass and no step-response fit: `intra_crossings`
-  = 0, `rc_const1_us` = `rc_const2_us` = 0, `intra_threshold` = `intra_hysteresis` = 0.
+* intra-event threshold crossings (`intra_crossings`, rate.csv `intra_crossing_times_us`) are
+  produced when the analyzer is given `intra_threshold` > 0 (detect.intra_crossings; the lines the
+  consumer draws at readevents.py:1363-1366); at most `max_crossings` pairs are listed per event,
+  the count is complete.  No step-response fit: `rc_const1_us` = `rc_const2_us` = 0.
 
 Everything here is O(events) host arithmetic on tables that came from the device; the only
 device work is the per-event extrema kernel (ct_event_extrema_f32).
@@ -80,7 +82,7 @@ def _fmt_list(v) -> str:
 def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level_std, overflow, xmin, xmax,
                       samplerate: float, threshold: float, baseline_mean, baseline_std, baseline_block: int,
                       padding: int, first_id: int = 0, time_offset_s: float = 0.0, index_offset: int = 0,
-                      block_offset: int = 0) -> EventTable:
+                      block_offset: int = 0, intra_count=None, intra_pairs=None) -> EventTable:
     """Per-event columns from the detector / CUSUM+ tables (numpy arrays, one row per detected
     event).  `index_offset` is the global sample index of the shard's first owned sample,
     `first_id` the global id of its first event (multi-GPU: pipeline.AnalysisResult)."""
@@ -100,8 +102,17 @@ def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level
     t_end = time_offset_s + (index_offset + ends) / fs
     # `block_offset`: samples the baseline table starts before the first owned sample (a shard's left halo)
     blk = np.minimum((starts + int(block_offset)) // int(baseline_block), len(baseline_mean) - 1) if E else np.zeros(0, np.int64)
+    # intra-event crossings: ';'-joined start;end;start;end... in us on the event file's time axis (0 = window start)
+    crossing_txt = np.array([""] * E, dtype=object)
+    ic = np.zeros(E, np.int64)
+    if intra_count is not None and E:
+        ic = np.asarray(intra_count, np.int64)
+        ip = np.asarray(intra_pairs, np.int64).reshape(E, -1)
+        kmax = ip.shape[1] // 2
+        for i in np.nonzero(ic > 0)[0]:
+            crossing_txt[i] = ";".join("%.16g" % (v * (1e6 / fs)) for v in ip[i, :2 * min(int(ic[i]), kmax)])
     rate = {"id": ids, "type": types, "start_time_s": t_start, "end_time_s": t_end,
-            "intra_crossing_times_us": np.array([""] * E, dtype=object),
+            "intra_crossing_times_us": crossing_txt,
             "local_stdev": np.asarray(baseline_std, np.float64)[blk] if E else np.zeros(0),
             "local_baseline": np.asarray(baseline_mean, np.float64)[blk] if E else np.zeros(0)}
 
@@ -154,7 +165,7 @@ def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level
                   "area_pC": avg_block * dur_in / fs, "average_blockage_pA": avg_block,
                   "relative_average_blockage": avg_block / aeff, "max_blockage_pA": max_block,
                   "relative_max_blockage": max_block / aeff, "max_blockage_duration_us": length[rows, imax] * us,
-                  "n_levels": L - 1, "intra_crossings": np.zeros(n, np.int64), "rc_const1_us": np.zeros(n),
+                  "n_levels": L - 1, "intra_crossings": ic[ok], "rc_const1_us": np.zeros(n),
                   "rc_const2_us": np.zeros(n), "residual_pA": residual, "max_deviation_pA": max_dev,
                   "min_blockage_pA": min_block, "relative_min_blockage": min_block / aeff,
                   "min_blockage_duration_us": length[rows, imin] * us, **lists}
@@ -172,7 +183,7 @@ def event_table_from_result(an, r, *, samplerate: float, time_offset_s: float = 
                              samplerate=samplerate, threshold=an.threshold, baseline_mean=r.baseline.mean,
                              baseline_std=r.baseline.std, baseline_block=an.block, padding=an.event_padding,
                              first_id=r.first_event_id, time_offset_s=time_offset_s, index_offset=index_offset,
-                             block_offset=r.lo_halo)
+                             block_offset=r.lo_halo, intra_count=tabs.get("intra_count"), intra_pairs=tabs.get("intra_pairs"))
 
 
 def event_table_from_stream(san, rs, *, samplerate: float, time_offset_s: float = 0.0, index_offset: int = 0) -> EventTable:
@@ -190,7 +201,8 @@ def event_table_from_stream(san, rs, *, samplerate: float, time_offset_s: float 
                              xmin=lo.cpu().numpy(), xmax=hi.cpu().numpy(), samplerate=samplerate,
                              threshold=float(san.kw.get("threshold", 5.0)), baseline_mean=rs.baseline.mean,
                              baseline_std=rs.baseline.std, baseline_block=san.block, padding=pad,
-                             first_id=rs.first_event_id, time_offset_s=time_offset_s, index_offset=index_offset)
+                             first_id=rs.first_event_id, time_offset_s=time_offset_s, index_offset=index_offset,
+                             intra_count=t.get("intra_count"), intra_pairs=t.get("intra_pairs"))
 
 
 def _write_csv(path: str, columns, table: dict) -> None:
@@ -205,7 +217,7 @@ def _write_csv(path: str, columns, table: dict) -> None:
 def write_analysis_dir(path: str, table: EventTable, *, baseline_mean, baseline_std, baseline_block: int,
                        samplerate: float, threshold: float, hysteresis: float, cutoff: float, poles: int,
                        extra_summary: dict | None = None, event_samples=None, time_offset_s: float = 0.0,
-                       append: bool = False) -> None:
+                       append: bool = False, intra_threshold: float = 0.0, intra_hysteresis: float = 0.0) -> None:
     """Write `events.csv`, `rate.csv`, `baseline.csv`, `summary.txt` and (if `event_samples`
     is given) `events/event_%08d.csv` under `path`.
 
@@ -224,7 +236,8 @@ def write_analysis_dir(path: str, table: EventTable, *, baseline_mean, baseline_
     # summary.txt: consumers parse by SUBSTRING (plot-trace.py:190-203, readevents.py:73-79), so no
     # other key may contain 'threshold', 'hysteresis', 'cutoff' or 'poles'
     summary = {"threshold": repr(float(threshold)), "hysteresis": repr(float(hysteresis)), "cutoff": str(int(cutoff)),
-               "poles": str(int(poles)), "intra_threshold": "0", "intra_hysteresis": "0", "samplerate": repr(fs),
+               "poles": str(int(poles)), "intra_threshold": repr(float(intra_threshold)) if intra_threshold else "0",
+               "intra_hysteresis": repr(float(intra_hysteresis)) if intra_hysteresis else "0", "samplerate": repr(fs),
                "baseline_block_samples": str(int(baseline_block)), "events_detected": str(len(table.rate["id"])),
                "events_accepted": str(len(table))}
     for k, v in (extra_summary or {}).items():

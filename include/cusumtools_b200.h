@@ -182,6 +182,18 @@ int ct_cusum_batch_dev(const float* y, int64_t n_total, const int64_t* win_start
                        int max_levels, int32_t* n_levels, int32_t* edges, double* level_mean, double* level_std,
                        uint8_t* overflow, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Intra-event threshold crossings (rate.csv intra_crossing_times_us / events.csv intra_crossings;
+ * consumer: readevents.py:1340-1343,1363-1367, summary.txt keys intra_threshold / intra_hysteresis
+ * readevents.py:73-79).  The detector's automaton over each event window with the lines
+ * t_start / t_end (per baseline block, built from intra_threshold / intra_hysteresis by
+ * ct_baseline_finalize) of the block holding ev_start; starts outside, an open crossing ends at
+ * the window end.  count[i] = crossings of event i; pairs[i][2k], pairs[i][2k+1] = start / end
+ * sample relative to win_start[i] for k < min(count[i], max_pairs).  n_events_dev may be NULL. */
+int ct_intra_crossings_f32(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
+                           const int64_t* ev_start, int64_t n_events, const int64_t* n_events_dev, int64_t block,
+                           int64_t n_blocks, const int32_t* sign, const float* t_start, const float* t_end,
+                           int32_t max_pairs, int32_t* count, int32_t* pairs, void* stream);
+
 /* Minimum and maximum sample of every event window (max_deviation_pA of events.csv,
  * mosaicConverter.py:105 / readevents.py:1499); n_events_dev may be NULL.                  */
 int ct_event_extrema_f32(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,

@@ -154,6 +154,23 @@ def detect_events_sequential(y, block, sign, t_start, t_end, state_in=False):
     return (np.array(starts, np.int64), np.array(ends, np.int64), start if inside else -1)
 
 
+def intra_crossings(x, local_baseline, local_stdev, intra_threshold, intra_hysteresis):
+    """Intra-event threshold crossings of one event window (consumer side: readevents.py:1340-1343 reads
+    rate.csv's `intra_crossing_times_us` as start/end pairs and shades them, :1363-1366 draws the lines
+    local_baseline - intra_threshold*local_stdev and local_baseline - (intra_threshold -
+    intra_hysteresis)*local_stdev, sign-mirrored; the thresholds come from summary.txt, :73-79).
+
+    Definition: the detector's own automaton (`detect_events`) over the window samples with those two
+    lines (float32, `thresholds`), starting outside; a crossing still open at the end of the window ends
+    there.  Returns int64 [C, 2] (start, end) sample indices relative to the window start."""
+    x = np.asarray(x, dtype=np.float32)
+    sign, ts, te = thresholds(np.array([float(local_baseline)]), np.array([float(local_stdev)]), intra_threshold, intra_hysteresis)
+    s, e, open_start = detect_events(x, max(1, x.size), sign, ts, te)
+    if open_start >= 0:
+        s, e = np.append(s, open_start), np.append(e, x.size)
+    return np.stack((s, e), axis=1).astype(np.int64) if s.size else np.zeros((0, 2), np.int64)
+
+
 def event_windows(starts, ends, n, padding, minpoints, maxpoints):
     """Event sample windows handed to CUSUM+: [start - padding, end + padding), and the
     `type` column of rate.csv (plot-trace.py:354-357: 0/1 accepted, >1 rejected):
