@@ -313,8 +313,7 @@ ct_baseline_finalize_kernel(const long long* __restrict__ cnt, const long long* 
                             double* __restrict__ sd, int* __restrict__ sign, float* __restrict__ t_start,
                             float* __restrict__ t_end, int* __restrict__ status) {
     __shared__ long long s_first;
-    if (threadIdx.x == 0) s_first = -1;
-    __syncthreads();
+    __shared__ long long s_warp_last[32], s_warp_first[32];
     for (long long k = threadIdx.x; k < nb; k += blockDim.x) {
         const long long c = cnt[k];
         double m = __longlong_as_double(0x7ff8000000000000LL), s = m;
@@ -329,18 +328,47 @@ ct_baseline_finalize_kernel(const long long* __restrict__ cnt, const long long* 
         mean[k] = m; sd[k] = s;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                       // inheritance is a sequential fill (nb is small)
-        long long first = -1;
-        for (long long k = 0; k < nb; ++k) if (mean[k] == mean[k]) { first = k; break; }
-        s_first = first;
-        if (first >= 0) {
-            long long last = first;
-            for (long long k = 0; k < nb; ++k) {
-                if (mean[k] == mean[k]) last = k;
-                else { mean[k] = mean[last]; sd[k] = sd[last]; }
-            }
+    // Inheritance (a block without enough samples takes the nearest earlier valid block, leading ones the
+    // first valid block) as a max-scan of "index of the last valid block": every thread owns a contiguous
+    // chunk, the chunks' last/first valid indices are scanned over the CTA, then each chunk is filled.
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const long long per = (nb + blockDim.x - 1) / blockDim.x;
+    const long long lo = (long long)threadIdx.x * per, hi = lo + per < nb ? lo + per : nb;
+    const long long kNone = 0x7fffffffffffffffLL;
+    long long last = -1, first = kNone;
+    for (long long k = lo; k < hi; ++k)
+        if (cnt[k] >= min_count) { last = k; if (first == kNone) first = k; }
+    long long inc = last, fmin = first;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long t = __shfl_up_sync(CT_FULL, inc, d);
+        if (lane >= d && t > inc) inc = t;
+        const long long u = __shfl_xor_sync(CT_FULL, fmin, d);
+        if (u < fmin) fmin = u;
+    }
+    if (lane == 31) s_warp_last[wid] = inc;
+    if (lane == 0) s_warp_first[wid] = fmin;
+    __syncthreads();
+    long long before = -1;                         // last valid block of the earlier warps
+    for (int w = 0; w < wid; ++w) if (s_warp_last[w] > before) before = s_warp_last[w];
+    long long prev = __shfl_up_sync(CT_FULL, inc, 1);
+    if (lane == 0) prev = -1;
+    if (before > prev) prev = before;              // last valid block before this thread's chunk
+    if (threadIdx.x == 0) {
+        long long f = kNone;
+        for (int w = 0; w < nwarp; ++w) if (s_warp_first[w] < f) f = s_warp_first[w];
+        s_first = f == kNone ? -1 : f;
+        *status = f == kNone ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_first < 0) return;
+    {
+        long long run = prev >= 0 ? prev : s_first;
+        double rm = mean[run], rs = sd[run];       // valid blocks are never overwritten
+        for (long long k = lo; k < hi; ++k) {
+            if (cnt[k] >= min_count) { rm = mean[k]; rs = sd[k]; }
+            else { mean[k] = rm; sd[k] = rs; }
         }
-        *status = first < 0 ? 1 : 0;
     }
     __syncthreads();
     if (s_first < 0) return;

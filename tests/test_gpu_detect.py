@@ -80,3 +80,31 @@ def test_random_symbol_streams_match_sequential_definition():
             ev = detect.detect_events(torch.from_numpy(y).cuda(), bl, state_in=state_in)
             s, e, o = c_twin.detect_events(y, block, bl.sign, bl.t_start, bl.t_end, state_in=state_in)
             assert ev.starts.tolist() == s.tolist() and ev.ends.tolist() == e.tolist() and ev.open_start == o
+
+
+@pytest.mark.parametrize("block,nb", [(4096, 37), (4096, 2500), (8192, 1)])
+def test_blocks_without_baseline_samples_inherit_the_nearest_earlier_valid_block(block, nb):
+    """Blocks whose samples all lie outside [baseline_min, baseline_max] (a clogged pore, a long event) take the
+    table row of the nearest earlier valid block, leading ones that of the first valid block
+    (oracle/events_oracle.py::baseline_from_stats) - many blocks, runs of invalid blocks across thread chunks."""
+    rng = np.random.default_rng(block + nb)
+    n = block * nb - 17
+    y = (5000.0 + rng.normal(0, 20, n)).astype(np.float32)
+    bad = rng.random(nb) < 0.4
+    bad[0] = nb > 1                                    # leading invalid blocks
+    if nb > 40:
+        bad[5:30] = True; bad[1000:2100] = True        # long runs
+    for k in np.nonzero(bad)[0]:
+        y[k * block:(k + 1) * block] -= np.float32(2000.0)
+    if nb == 1:
+        bad[:] = False
+        y[:] = (5000.0 + rng.normal(0, 20, n)).astype(np.float32)
+    bl = detect.baseline_blocks(torch.from_numpy(y).cuda(), block, 4700.0, 5300.0, threshold=5.0, hysteresis=1.0)
+    c0 = np.float32(5000.0)
+    shift = eo.stats_shift(300.0, block)
+    cnt, s1, s2 = c_twin.block_stats(y, block, 4700.0, 5300.0, c0, shift)
+    mean, std = eo.baseline_from_stats(cnt, s1, s2, c0, shift)
+    assert (cnt < 16).sum() == bad.sum()
+    assert np.array_equal(bl.mean, mean) and np.array_equal(bl.std, std)
+    sign, ts, te = eo.thresholds(mean, std, 5.0, 1.0)
+    assert np.array_equal(bl.sign, sign) and np.array_equal(bl.t_start, ts) and np.array_equal(bl.t_end, te)
