@@ -58,8 +58,11 @@ def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n
     """Phase 1: a strided-sample histogram (summed over `group`) locates the median code.  `n_sampled`:
     the histogram covers only that many of the rank's samples (streaming: the first chunk), so it
     is an estimate even for small traces."""
-    nt = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
-    n = int(_all_reduce_(nt, group).item())
+    if group is None:
+        n = int(n_local)
+    else:
+        nt = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+        n = int(_all_reduce_(nt, group).item())
     if n == 0:
         raise ValueError("median of an empty trace")
     shift = 0
@@ -68,12 +71,13 @@ def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n
     step = 1 << shift
     k1, k2 = (n - 1) // 2, n // 2
     stride = max(1, (n if n_sampled is None else int(n_sampled)) // (1 << 20))      # ~1 M samples: median s.e. < 0.1 code
-    h = _all_reduce_(hist_fn(stride).to(torch.int64), group)
-    cdf = np.cumsum(h.cpu().numpy())
+    # the rank search runs where the histogram lives (device): 8 bytes come back instead of 65 536 bins
+    cdf = torch.cumsum(_all_reduce_(hist_fn(stride).to(torch.int64), group), 0)
     if stride == 1 and n_sampled is None:
-        c1, c2 = int(np.searchsorted(cdf, k1 + 1)), int(np.searchsorted(cdf, k2 + 1))
+        want = torch.tensor([k1 + 1, k2 + 1], dtype=torch.int64, device=cdf.device)
+        c1, c2 = (int(v) for v in torch.searchsorted(cdf, want).tolist())
         return MedianPlan(n, k1, k2, step, shift, c1, max(0, c1 - 3 * step), exact=(c1, c2))
-    est = (int(np.searchsorted(cdf, (cdf[-1] + 1) // 2)) >> shift) * step
+    est = (int(torch.searchsorted(cdf, (cdf[-1:] + 1) // 2).item()) >> shift) * step
     return MedianPlan(n, k1, k2, step, shift, est, max(0, est - 3 * step))
 
 
