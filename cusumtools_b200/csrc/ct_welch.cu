@@ -590,6 +590,167 @@ static int rows_fast(const WelchArgs& a, cudaStream_t st) {
     }
 }
 
+
+// =====================================================================================
+// One segment of ARBITRARY length (plot-trace.py:437: nperseg = min(2^20, len) is the window
+// length itself whenever the displayed window is shorter than 2^20 samples, and the psd-length
+// branch caps at len, :433-435): the length-n DFT by Bluestein's chirp-z identity
+//     X[k] = c_k * sum_j (x_j c_j) conj(c)_(k-j),   c_m = e^{-i pi m^2 / n},
+// i.e. one circular convolution of length M = 2^m >= 2n - 1 = three power-of-two complex FFTs
+// built from the same register-resident transform (four-step N1 x N2, generic load / store
+// stages).  |c_k| = 1, so the power spectrum needs no final chirp.  Not a hot path: one
+// segment, n < 2^21, once per call.
+// =====================================================================================
+struct CfftArgs {
+    const cpx* in; const cpx* mul; long long n_valid; int conj_in;   // input (zero beyond n_valid), optional pointwise factor
+    cpx* Y;                                                           // four-step intermediate [N1][N2]
+    cpx* out; int conj_out; float scale;                              // natural-order result
+    int logn1, logn2;
+};
+
+template <int LOG1>
+__global__ void __launch_bounds__((1 << LOG1) / 8 * kFastCols) ct_cfft_cols(CfftArgs a) {
+    using P = FftPlan<LOG1>;
+    using Lay = ColsLay<LOG1>;
+    constexpr int N1 = P::N, T1 = P::T, NX = FftX<LOG1>::n;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    cpx* buf0 = reinterpret_cast<cpx*>(smraw);
+    cpx* buf1 = buf0 + (size_t)(N1 + P::pad) * kFastCols;
+    const int N2 = 1 << a.logn2;
+    const long long N = (long long)N1 * N2;
+    const int tid = threadIdx.x, c = tid % kFastCols, j = tid / kFastCols;
+    const int n2 = blockIdx.x * kFastCols + c;
+    cpx wb[P::nbase > 0 ? P::nbase : 1];
+    fft_bases<LOG1>(wb, j);
+    int wbs[NX > 0 ? NX : 1], rbs[NX > 0 ? NX : 1];
+    fft_exchange_bases<LOG1, Lay>(wbs, rbs, j, c);
+    cpx v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long long J = (long long)N2 * (j + r * T1) + n2;
+        cpx x = make_float2(0.f, 0.f);
+        if (J < a.n_valid) {
+            x = a.in[J];
+            if (a.mul) x = cmul(x, a.mul[J]);
+            if (a.conj_in) x = cconj(x);
+        }
+        v[r] = x;
+    }
+    fft_reg<LOG1, Lay>(v, wb, buf0, buf1, wbs, rbs);
+    const cpx base = root((int)(((long long)n2 * j) % N), (int)N), step = root((int)(((long long)n2 * T1) % N), (int)N);
+    cpx tw = base;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        a.Y[(size_t)(j + r * T1) * N2 + n2] = cmul(v[r], tw);
+        tw = cmul(tw, step);
+    }
+}
+
+template <int LOG2>
+__global__ void __launch_bounds__(2 * (1 << LOG2) / 8) ct_cfft_rows(CfftArgs a) {
+    using P = FftPlan<LOG2>;
+    using Lay = RowsLay<LOG2>;
+    constexpr int N2 = P::N, T2 = P::T, kSlot = N2 + P::pad, NX = FftX<LOG2>::n;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    cpx* buf0 = reinterpret_cast<cpx*>(smraw);
+    cpx* buf1 = buf0 + 2 * kSlot;
+    const int N1 = 1 << a.logn1;
+    const int tid = threadIdx.x, p = tid / T2, j = tid % T2;
+    const int row = 2 * blockIdx.x + p;                      // N1 is even: two rows per CTA
+    cpx wb[P::nbase > 0 ? P::nbase : 1];
+    fft_bases<LOG2>(wb, j);
+    int wbs[NX > 0 ? NX : 1], rbs[NX > 0 ? NX : 1];
+    fft_exchange_bases<LOG2, Lay>(wbs, rbs, j, p * kSlot);
+    cpx v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = a.Y[(size_t)row * N2 + j + r * T2];
+    fft_reg<LOG2, Lay>(v, wb, buf0, buf1, wbs, rbs);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        cpx z = make_float2(v[r].x * a.scale, v[r].y * a.scale);
+        if (a.conj_out) z = cconj(z);
+        a.out[row + (size_t)N1 * (j + r * T2)] = z;
+    }
+}
+
+template <int LOG1> static int launch_cfft_cols(const CfftArgs& a, cudaStream_t st) {
+    using P = FftPlan<LOG1>;
+    const size_t sm = (size_t)2 * (P::N + P::pad) * kFastCols * sizeof(cpx);
+    cudaFuncSetAttribute(ct_cfft_cols<LOG1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    CT_COUNT_LAUNCH();
+    ct_cfft_cols<LOG1><<<(unsigned)((1 << a.logn2) / kFastCols), P::T * kFastCols, sm, st>>>(a);
+    return ct_check_launch("ct_cfft_cols");
+}
+template <int LOG2> static int launch_cfft_rows(const CfftArgs& a, cudaStream_t st) {
+    using P = FftPlan<LOG2>;
+    const size_t sm = (size_t)2 * 2 * (P::N + P::pad) * sizeof(cpx);
+    cudaFuncSetAttribute(ct_cfft_rows<LOG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    CT_COUNT_LAUNCH();
+    ct_cfft_rows<LOG2><<<(unsigned)((1 << a.logn1) / 2), 2 * P::T, sm, st>>>(a);
+    return ct_check_launch("ct_cfft_rows");
+}
+// complex FFT of M = 2^(logn1+logn2) points, 6 <= logn1 <= 10, 7 <= logn2 <= 12
+static int cfft(const CfftArgs& a, cudaStream_t st) {
+    int rc;
+    switch (a.logn1) {
+        case 6: rc = launch_cfft_cols<6>(a, st); break;
+        case 7: rc = launch_cfft_cols<7>(a, st); break;
+        case 8: rc = launch_cfft_cols<8>(a, st); break;
+        case 9: rc = launch_cfft_cols<9>(a, st); break;
+        default: rc = launch_cfft_cols<10>(a, st); break;
+    }
+    if (rc) return rc;
+    switch (a.logn2) {
+        case 7: return launch_cfft_rows<7>(a, st);
+        case 8: return launch_cfft_rows<8>(a, st);
+        case 9: return launch_cfft_rows<9>(a, st);
+        case 10: return launch_cfft_rows<10>(a, st);
+        case 11: return launch_cfft_rows<11>(a, st);
+        default: return launch_cfft_rows<12>(a, st);
+    }
+}
+
+// c[j] = e^{-i pi j^2 / n}: j^2 reduced mod 2n in integers, the angle in float64
+__global__ void ct_bluestein_chirp(cpx* __restrict__ c, long long n) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long r = ((unsigned long long)j * (unsigned long long)j) % (unsigned long long)(2 * n);
+    double sn, cs;
+    sincospi((double)r / (double)n, &sn, &cs);
+    c[j] = make_float2((float)cs, (float)(-sn));
+}
+// the convolution kernel conj(c)_(m) wrapped to length M: b[m] = conj(c[|m|]) for |m| < n (indices mod M), else 0
+__global__ void ct_bluestein_kernel(cpx* __restrict__ b, const cpx* __restrict__ c, long long n, long long M) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    cpx v = make_float2(0.f, 0.f);
+    if (m < n) v = cconj(c[m]);
+    else if (M - m < n) v = cconj(c[M - m]);
+    b[m] = v;
+}
+// a[j] = hann_n(j) (x_j - mean) c[j]   (periodic Hann; |x| first if use_abs)
+__global__ void ct_bluestein_input(cpx* __restrict__ a, const float* __restrict__ x, const cpx* __restrict__ c, long long n,
+                                   double mean, int use_abs) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double v = (double)x[j];
+    if (use_abs) v = fabs(v);
+    const double w = 0.5 - 0.5 * cospi(2.0 * (double)j / (double)n);
+    const float s = (float)(w * (v - mean));
+    a[j] = make_float2(s * c[j].x, s * c[j].y);
+}
+__global__ void ct_bluestein_power(double* __restrict__ acc, const cpx* __restrict__ z, long long nout) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nout) return;
+    const double re = (double)z[k].x, im = (double)z[k].y;
+    acc[k] = re * re + im * im;
+}
+static int bluestein_logm(long long n) {
+    int m = 13;
+    while ((1LL << m) < 2 * n - 1) ++m;
+    return m;
+}
+
 }  // namespace
 
 extern "C" {
@@ -662,5 +823,48 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
     }
     return CT_OK;
 }
+
+int64_t ct_welch_single_workspace_bytes(int64_t n) {
+    if (n < 2 || n > (1LL << 21)) return -1;
+    const long long M = 1LL << bluestein_logm(n);
+    return (int64_t)((n + 3 * M) * 8 + 256);
+}
+
+int ct_welch_single_f32(const float* x, int64_t n, double mean, int32_t use_abs, void* workspace, int64_t workspace_bytes,
+                        double* acc, void* stream) {
+    if (!x || !workspace || !acc) { ct_set_error("welch_single: null pointer"); return CT_ERR_ARG; }
+    if (n < 2 || n > (1LL << 21)) { ct_set_error("welch_single: segment length must be in [2, 2^21] (got %lld)", (long long)n); return CT_ERR_UNSUPPORTED; }
+    if (workspace_bytes < ct_welch_single_workspace_bytes(n)) { ct_set_error("welch_single: workspace too small"); return CT_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = bluestein_logm(n);
+    const long long M = 1LL << m;
+    const int logn1 = m / 2 < 10 ? m / 2 : 10, logn2 = m - logn1;
+    cpx* c = (cpx*)workspace;
+    cpx* bufA = (cpx*)((char*)workspace + (((size_t)n * 8 + 255) / 256) * 256);
+    cpx* bufB = bufA + M;
+    cpx* Y = bufB + M;
+    const int T = 256;
+    CT_COUNT_LAUNCH();
+    ct_bluestein_chirp<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(c, n);
+    CT_COUNT_LAUNCH();
+    ct_bluestein_kernel<<<(unsigned)((M + T - 1) / T), T, 0, st>>>(bufA, c, n, M);
+    int rc = ct_check_launch("ct_bluestein_kernel"); if (rc) return rc;
+    CfftArgs a;
+    a.logn1 = logn1; a.logn2 = logn2; a.Y = Y;
+    a.in = bufA; a.mul = nullptr; a.n_valid = M; a.conj_in = 0; a.out = bufB; a.conj_out = 0; a.scale = 1.f;
+    rc = cfft(a, st); if (rc) return rc;                       // bufB = FFT(kernel)
+    CT_COUNT_LAUNCH();
+    ct_bluestein_input<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(bufA, x, c, n, mean, use_abs);
+    rc = ct_check_launch("ct_bluestein_input"); if (rc) return rc;
+    a.in = bufA; a.n_valid = n; a.out = bufA;
+    rc = cfft(a, st); if (rc) return rc;                       // bufA = FFT(x w c)
+    a.in = bufA; a.mul = bufB; a.n_valid = M; a.conj_in = 1; a.out = bufA; a.conj_out = 1; a.scale = 1.0f / (float)M;
+    rc = cfft(a, st); if (rc) return rc;                       // bufA = IFFT(A B) = conj(FFT(conj(A B))) / M
+    const long long nout = n / 2 + 1;
+    CT_COUNT_LAUNCH();
+    ct_bluestein_power<<<(unsigned)((nout + T - 1) / T), T, 0, st>>>(acc, bufA, nout);
+    return ct_check_launch("ct_bluestein_power");
+}
+
 
 }  // extern "C"

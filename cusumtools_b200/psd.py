@@ -38,7 +38,7 @@ def welch_sums(x: torch.Tensor, nperseg: int, *, use_abs: bool = False, shift: f
     if L != nperseg or L & (L - 1) or L < 256:
         raise NotImplementedError(
             f"nperseg={nperseg}: the GPU Welch path needs a power-of-two segment >= 256 (the reference's default "
-            "2**20 and its 2**ceil(log2(.)) lengths are; a window shorter than the segment is not)")
+            "2**20 and its 2**ceil(log2(.)) lengths are) or nperseg == len(x) (one segment of arbitrary length)")
     lib = _lib.lib()
     batch = max(1, min(1024, L2_BUDGET_BYTES // (L // 2 * 8)))
     wsb = int(lib.ct_welch_workspace_bytes(L, batch))
@@ -65,11 +65,39 @@ def scale_sums(acc: np.ndarray, nseg: int, samplerate: float, nperseg: int):
     return f, P
 
 
+def welch_single_sums(x: torch.Tensor, *, use_abs: bool = False) -> torch.Tensor:
+    """|rfft(hann(n) (x - mean x))|^2 of ONE segment of arbitrary length n = len(x) (float64 CUDA tensor
+    [n//2+1]): the case nperseg == len(x) of plot-trace.py:433-437 when the window is not a power of two.
+    Bluestein chirp-z over the power-of-two FFT kernels (ct_welch_single_f32)."""
+    _require_cuda(x, "x", torch.float32)
+    n = int(x.numel())
+    lib = _lib.lib()
+    wsb = int(lib.ct_welch_single_workspace_bytes(n))
+    if wsb < 0:
+        raise NotImplementedError(f"a single Welch segment of {n} samples: the chirp-z path covers 2 <= n <= 2**21")
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    acc = torch.empty(n // 2 + 1, dtype=torch.float64, device=x.device)
+    xm = x.abs() if use_abs else x
+    mean = float(xm.sum(dtype=torch.float64).item()) / n         # scipy's detrend='constant' of the segment
+    rc = lib.ct_welch_single_f32(x.data_ptr(), n, mean, int(bool(use_abs)), ws.data_ptr(), wsb, acc.data_ptr(), _stream_ptr(x))
+    _lib.check(rc, "ct_welch_single_f32")
+    return acc
+
+
 def welch(x: torch.Tensor, samplerate: float, nperseg, *, use_abs: bool = False):
     """`f, Pxx = welch(x, fs, nperseg=L)` with x a float32 CUDA tensor; returns numpy
-    float64 arrays of length L/2+1 like scipy.  `nperseg` may be a float (the reference
-    passes 2**np.ceil(...), plot-trace.py:433, noise-fit.py:138)."""
+    float64 arrays of length L//2+1 like scipy.  `nperseg` may be a float (the reference
+    passes 2**np.ceil(...), plot-trace.py:433, noise-fit.py:138).  L is a power of two, or the
+    length of `x` itself (plot-trace.py:435,437: one segment of arbitrary length)."""
     L = int(nperseg)
+    if (L & (L - 1) or L < 256) and L == x.numel() and L >= 16:
+        acc = welch_single_sums(x, use_abs=use_abs).cpu().numpy()
+        P = acc / (float(samplerate) * (3.0 * L / 8.0))          # sum(w^2) = 3L/8 for the periodic Hann, one segment
+        if L % 2 == 0:
+            P[1:-1] *= 2.0
+        else:
+            P[1:] *= 2.0
+        return np.arange(L // 2 + 1, dtype=np.float64) * (float(samplerate) / L), P
     acc, nseg = welch_sums(x, L, use_abs=use_abs)
     return scale_sums(acc.cpu().numpy(), nseg, samplerate, L)
 

@@ -213,6 +213,14 @@ int64_t ct_welch_workspace_bytes(int32_t nperseg, int32_t batch);
 int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_t use_abs, int32_t batch,
                  void* workspace, int64_t workspace_bytes, double* acc, int64_t* nseg_out, void* stream);
 
+/* One segment of arbitrary length n (2 <= n <= 2^21): the reference passes nperseg = len(data) whenever the
+ * window is shorter than 2^20 samples or than the requested PSD length (plot-trace.py:433-437), i.e. ONE periodic-
+ * Hann segment that is not a power of two.  Bluestein chirp-z on the same register-resident FFT.  `mean` = the
+ * segment mean the caller computed (float64; of |x| if use_abs); acc[k] = |rfft(w (x - mean))[k]|^2, k = 0..n/2.   */
+int64_t ct_welch_single_workspace_bytes(int64_t n);
+int ct_welch_single_f32(const float* x, int64_t n, double mean, int32_t use_abs, void* workspace, int64_t workspace_bytes,
+                        double* acc, void* stream);
+
 /* ---- loaders: the byte formats either side of the path ---------------------------
  * ".bin" records (>f8 curr_pA, >f8 volt_mV), print_trace.py:33-34 / noise-fit.py:90-91:
  * n records of 16 bytes -> float32 current.  Legacy (>i2, >i2) records times savegain,

@@ -42,6 +42,33 @@ def test_long_segments(L):
     check(P, Pw)
 
 
+@pytest.mark.parametrize("n", [17, 255, 1000, 4097, 65536 + 1, 300_001, 1_000_000, 999_983, (1 << 20) - 1, 1_500_000])
+def test_single_segment_of_arbitrary_length(n):
+    """nperseg == len(x), not a power of two: what plot-trace.py:433-437 passes for a window shorter than 2^20
+    samples (or than the requested PSD length).  Chirp-z over the float32 FFT: |dP| <= 5e-5 P + 1e-8 max(P)
+    (three transforms instead of one; 999 983 is prime)."""
+    rng = np.random.default_rng(n)
+    t = np.arange(n)
+    x = (5000 + 24 * rng.standard_normal(n) + 40 * np.sin(2 * np.pi * 0.01 * t)).astype(np.float32)
+    f, P = psd.welch(torch.from_numpy(x).cuda(), synth.FS, n)
+    fw, Pw = to.welch_psd(x.astype(np.float64), synth.FS, n)
+    assert f.shape == fw.shape and np.allclose(f, fw, rtol=1e-14)
+    tol = 5e-5 * Pw + 1e-8 * Pw.max()
+    bad = np.abs(P - Pw) > tol
+    assert not bad.any(), (np.nonzero(bad)[0][:10], (np.abs(P - Pw) / tol).max())
+    assert np.allclose(psd.integrate_noise(f, P), to.integrate_noise(fw, Pw), rtol=1e-5)
+
+
+def test_update_psd_on_a_short_window():
+    """App.update_psd on 0.1 s of data (416 666 samples < 2^20): length = len(data), plot-trace.py:437."""
+    rng = np.random.default_rng(8)
+    x = (5000 + 24 * rng.standard_normal(416_666)).astype(np.float32)
+    f, P, rms, cur = psd.update_psd(torch.from_numpy(x).cuda(), synth.FS)
+    fw, Pw = to.welch_psd(x.astype(np.float64), synth.FS, len(x))
+    assert len(f) == len(x) // 2 + 1 and np.allclose(f, fw)
+    assert np.allclose(rms, to.integrate_noise(fw, Pw), rtol=1e-5) and np.isclose(cur, x.astype(np.float64).mean(), rtol=1e-9)
+
+
 def test_reference_fixture(golden_dir):
     z = np.load(os.path.join(golden_dir, "psd_fixture.npz"))
     x = z["x"].astype(np.float32)
@@ -91,7 +118,9 @@ def test_update_psd_and_spectrum_sample(golden_dir):
 def test_unsupported_lengths_fail_loudly():
     x = torch.zeros(5000, dtype=torch.float32, device="cuda")
     with pytest.raises(NotImplementedError):
-        psd.welch(x, 1e6, 5000)
+        psd.welch(x, 1e6, 3000)      # neither a power of two nor the whole input (the reference never asks for it)
+    with pytest.raises(NotImplementedError):
+        psd.welch(torch.zeros((1 << 21) + 5, dtype=torch.float32, device="cuda"), 1e6, (1 << 21) + 5)
     f, P = None, None
     with pytest.raises(ValueError):
         psd.welch(x, 1e6, 8192)      # shorter than one segment
