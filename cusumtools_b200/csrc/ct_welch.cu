@@ -3,27 +3,28 @@
 // Replaces scipy.signal.welch(x, fs, nperseg=L) as the reference calls it
 // (plot-trace.py:442, noise-fit.py:92, legacy/minimal_psd.py:255): periodic Hann window,
 // hop L/2, tail dropped, per-segment mean removal, density scaling, one-sided spectrum
-// (scipy/signal/_spectral_py.py:515 -> csd -> ShortTimeFFT).  L is a power of two.
+// (scipy/signal/_spectral_py.py:515 -> csd -> ShortTimeFFT).
 //
-// A real segment of L samples is packed as N = L/2 complex points (z[j] = x[2j] + i x[2j+1])
-// and transformed by the four-step algorithm, N = N1 x N2:
-//   kernel A  window + pack + N2 column FFTs of length N1 + twiddle W_N^(n2 k1) -> Y[k1][n2]
-//   kernel B  row FFTs of length N2 for the row pair (k1, N1-k1), the real-FFT split
-//             X[k] = (Z[k]+Z*[N-k])/2 - (i/2) e^(-i pi k/N) (Z[k]-Z*[N-k]), |X|^2 accumulated
-//             over the segments of the batch in registers and added once per bin into the
-//             float64 accumulator.
-// Mean removal is applied in the spectrum: with the input shifted by a constant c near the
-// mean (for float32 headroom), FFT(w (x - mu)) = FFT(w (x - c)) - (mu - c) FFT(w) and FFT(w)
-// of the periodic Hann is L/2 at bin 0 and -L/4 at bins +-1.
+// A real segment of L samples (L a power of two) is packed as N = L/2 complex points
+// (z[j] = x[2j] + i x[2j+1]), transformed, and split into the real spectrum
+// X[k] = (Z[k]+Z*[N-k])/2 - (i/2) e^(-i pi k/N) (Z[k]-Z*[N-k]); |X|^2 is accumulated over
+// segments in registers and added once per bin into a float64 accumulator.  Mean removal
+// is applied in the spectrum: with the input shifted by a constant c near the mean (for
+// float32 headroom), FFT(w (x - mu)) = FFT(w (x - c)) - (mu - c) FFT(w) and FFT(w) of the
+// periodic Hann is L/2 at bin 0 and -L/4 at bins +-1.
 //
-// Two kernel families:
-//   * 2^15 <= L <= 2^23: register-resident FFTs (second half of this file) - 8 points per
-//     thread, shared memory only for the transposes between passes, no trigonometric table,
-//     the next segment's loads in flight while the current one is transformed.  The batch is
-//     as large as the workspace allows (more segments per CTA amortise the per-thread set-up;
-//     whether the intermediate Y stays in L2 turned out not to matter).
-//   * shorter segments: shared-memory Stockham radix-8/4/2 passes, 8 columns per CTA; every
-//     trigonometric factor from ONE table T[j] = e^{-2 pi i j / L} built once per call.
+// ONE transform engine (fft_reg): a thread owns 8 points for the whole FFT - radix 8 while
+// possible, one radix-4/2 pass last - shared memory carries only the transposes between
+// passes (swizzled, double-buffered), no trigonometric table.  Three kernel families use it:
+//   * 256 <= L <= 2^14   ct_welch_seg_kernel: a segment is one transform; window, FFT, split
+//                        and accumulation without leaving the CTA (4 B/sample of traffic);
+//   * 2^15 <= L <= 2^23  four-step N = N1 x N2: ct_welch_cols_fast (window + pack + column
+//                        FFTs + twiddle -> Y[k1][n2]) and ct_welch_rows_fast (row FFTs of the
+//                        row pair (k1, N1-k1), split, accumulation); the next segment's loads
+//                        are in flight while the current one is transformed; batches as large
+//                        as the workspace allows (more segments per CTA amortise the set-up);
+//   * one segment of ARBITRARY length (nperseg = len(data)): Bluestein chirp-z over generic
+//                        complex four-step stages (ct_cfft_cols / ct_cfft_rows).
 #include "ct_common.cuh"
 #include "cusumtools_b200.h"
 
@@ -38,7 +39,6 @@ __device__ __forceinline__ cpx mul_mi(cpx a) { return make_float2(a.y, -a.x); } 
 __device__ __forceinline__ cpx expmi(float t) { float s, c; sincospif(t, &s, &c); return make_float2(c, -s); }  // e^{-i pi t}
 
 template <int R> __device__ __forceinline__ void dft(cpx* v);
-template <> __device__ __forceinline__ void dft<2>(cpx* v) { cpx a = v[0]; v[0] = cadd(a, v[1]); v[1] = csub(a, v[1]); }
 template <> __device__ __forceinline__ void dft<4>(cpx* v) {
     cpx a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = mul_mi(csub(v[1], v[3]));
     v[0] = cadd(a, c); v[1] = cadd(b, d); v[2] = csub(a, c); v[3] = csub(b, d);
@@ -54,56 +54,11 @@ template <> __device__ __forceinline__ void dft<8>(cpx* v) {
     for (int i = 0; i < 4; ++i) { v[i] = cadd(e[i], o[i]); v[i + 4] = csub(e[i], o[i]); }
 }
 
-// One Stockham radix-R pass over `batch` interleaved FFTs of length N held as
-// [index][batch] (batch fastest): in -> out.  Ns = product of the radices already done.
-// tws[m] = e^{-2 pi i m / N} (shared memory): the pass twiddle e^{-2 pi i k r / (Ns R)} is tws[k r N/(Ns R)].
-template <int R>
-__device__ __forceinline__ void stockham_pass(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tws,
-                                              int N, int Ns, int batch, int tid, int nthreads) {
-    const int work = (N / R) * batch;
-    const int tstride = N / (Ns * R);
-    for (int w = tid; w < work; w += nthreads) {
-        const int b = w % batch, j = w / batch;
-        const int k = j % Ns;
-        cpx v[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            cpx x = in[(j + r * (N / R)) * batch + b];
-            v[r] = (r == 0 || Ns == 1) ? x : cmul(x, tws[k * r * tstride]);
-        }
-        dft<R>(v);
-        const int j0 = (j / Ns) * Ns * R + k;
-#pragma unroll
-        for (int r = 0; r < R; ++r) out[(j0 + r * Ns) * batch + b] = v[r];
-    }
-}
-
-// full FFT of length N = 2^logn for `batch` interleaved transforms; result pointer returned
-__device__ cpx* fft_smem(cpx* a, cpx* b, const cpx* tws, int logn, int batch, int tid, int nthreads) {
-    const int N = 1 << logn;
-    int Ns = 1, rem = logn;
-    while (rem > 0) {
-        if (rem >= 3 && rem != 4) { stockham_pass<8>(a, b, tws, N, Ns, batch, tid, nthreads); Ns *= 8; rem -= 3; }
-        else if (rem >= 2) { stockham_pass<4>(a, b, tws, N, Ns, batch, tid, nthreads); Ns *= 4; rem -= 2; }
-        else { stockham_pass<2>(a, b, tws, N, Ns, batch, tid, nthreads); Ns *= 2; rem -= 1; }
-        __syncthreads();
-        cpx* t = a; a = b; b = t;
-    }
-    return a;
-}
-
-#ifndef CT_WELCH_COLS
-#define CT_WELCH_COLS 8
-#endif
-constexpr int kCols = CT_WELCH_COLS;      // columns per CTA in kernel A (smem: 2 x N1 x kCols complex)
-constexpr int kThreads = 256;
-
 struct WelchArgs {
     const float* x; long long n;
     int L, logn1, logn2;       // N = L/2 = 2^logn1 * 2^logn2
     long long seg0; int nseg;  // segments [seg0, seg0+nseg) in this launch
     float c; int use_abs;
-    const cpx* T;              // T[j] = e^{-2 pi i j / L}, j < L
     int rsplit;                // the segments of a batch are split over this many CTAs per row pair
     int ssplit;                // ... and over this many CTAs per column group (register-resident kernels)
     cpx* Y;                    // [nseg][N1][N2]
@@ -112,137 +67,21 @@ struct WelchArgs {
     double mu_scale;           // 1/L
 };
 
-__global__ void ct_welch_table(cpx* T, int L) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < L) T[j] = expmi(2.0f * (float)j / (float)L);
-}
-
-__global__ void __launch_bounds__(kThreads) ct_welch_cols(WelchArgs a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    const int N1 = 1 << a.logn1, N2 = 1 << a.logn2;
-    cpx* A = reinterpret_cast<cpx*>(smraw);
-    cpx* B = A + (size_t)N1 * kCols;
-    cpx* tws = B + (size_t)N1 * kCols;             // e^{-2 pi i m / N1} = T[m * L / N1]
-    for (int m = threadIdx.x; m < N1; m += kThreads) tws[m] = a.T[(size_t)m * (a.L / N1)];
-    const int groups = N2 / kCols;
-    const int s = blockIdx.x / groups, g = blockIdx.x % groups;
-    const long long base = (a.seg0 + s) * (long long)(a.L / 2);   // hop = L/2
-    const int tid = threadIdx.x;
-    double part = 0.0;
-    // load + window + pack: element (n1, col) is z[N2*n1 + g*16 + col] = x[2j], x[2j+1]
-    for (int w = tid; w < N1 * kCols; w += kThreads) {
-        const int col = w % kCols, n1 = w / kCols;
-        const int j = N2 * n1 + g * kCols + col;
-        float2 v = *reinterpret_cast<const float2*>(a.x + base + 2 * (long long)j);
-        if (a.use_abs) { v.x = fabsf(v.x); v.y = fabsf(v.y); }
-        v.x -= a.c; v.y -= a.c;
-        part += (double)v.x + (double)v.y;
-        const float4 t01 = *reinterpret_cast<const float4*>(a.T + 2 * j);      // T[2j], T[2j+1]: cos = .x, .z
-        A[w] = make_float2(v.x * (0.5f - 0.5f * t01.x), v.y * (0.5f - 0.5f * t01.z));
-    }
-    // segment sum for the mean (warp + block reduction, one atomic per CTA)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(CT_FULL, part, o);
-    __shared__ double wsum[kThreads / 32];
-    if ((tid & 31) == 0) wsum[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0; for (int i = 0; i < kThreads / 32; ++i) t += wsum[i];
-        atomicAdd(a.segsum + s, t);
-    }
-    cpx* R = fft_smem(A, B, tws, a.logn1, kCols, tid, kThreads);
-    // twiddle W_N^(n2 k1) and store Y[k1][n2]
-    cpx* Y = a.Y + (size_t)s * N1 * N2;
-    for (int w = tid; w < N1 * kCols; w += kThreads) {
-        const int col = w % kCols, k1 = w / kCols;
-        const int n2 = g * kCols + col;
-        // W_N^(n2 k1) = T[2 (n2 k1 mod N)]   (n2 k1 < N1 N2 = N always)
-        Y[(size_t)k1 * N2 + n2] = cmul(R[w], a.T[2 * (size_t)n2 * k1]);
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) ct_welch_rows(WelchArgs a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    const int N1 = 1 << a.logn1, N2 = 1 << a.logn2;
-    const long long N = (long long)N1 * N2;
-    cpx* A = reinterpret_cast<cpx*>(smraw);       // [N2][2] interleaved pair of rows
-    cpx* B = A + (size_t)N2 * 2;
-    cpx* tws = B + (size_t)N2 * 2;                 // e^{-2 pi i m / N2} = T[m * L / N2]
-    for (int m = threadIdx.x; m < N2; m += kThreads) tws[m] = a.T[(size_t)m * (a.L / N2)];
-    const int r = blockIdx.x / a.rsplit;           // 0 .. N1/2
-    const int part = blockIdx.x % a.rsplit;
-    const int r2 = (r == 0) ? 0 : N1 - r;          // partner row (== r for r = 0 and N1/2)
-    const bool self = (r2 == r);
-    const int tid = threadIdx.x;
-    // each thread owns bins k2 = tid, tid+256, ... of the row pair across all segments
-    constexpr int kMaxOwn = 16;                    // N2 <= 4096
-    float accA[kMaxOwn], accB[kMaxOwn];
-#pragma unroll
-    for (int i = 0; i < kMaxOwn; ++i) { accA[i] = 0.f; accB[i] = 0.f; }
-    for (int s = part; s < a.nseg; s += a.rsplit) {
-        const cpx* Y = a.Y + (size_t)s * N1 * N2;
-        for (int w = tid; w < N2; w += kThreads) {
-            A[2 * w] = Y[(size_t)r * N2 + w];
-            A[2 * w + 1] = Y[(size_t)r2 * N2 + w];
-        }
-        __syncthreads();
-        cpx* Z = fft_smem(A, B, tws, a.logn2, 2, tid, kThreads);
-        const float dmu = (float)(a.segsum[s] * a.mu_scale);     // mu - c for this segment
-        int own = 0;
-        for (int k2 = tid; k2 < N2; k2 += kThreads, ++own) {
-            // bin k = r + N1*k2 from row r, its mirror N-k from the partner row
-            const long long k = r + (long long)N1 * k2;
-            int m2; cpx Zk = Z[2 * k2], Zm;
-            if (r == 0) { m2 = (N2 - k2) % N2; Zm = Z[2 * m2]; }
-            else { m2 = N2 - 1 - k2; Zm = Z[2 * m2 + 1]; }
-            cpx E = cadd(Zk, cconj(Zm)), O = csub(Zk, cconj(Zm));
-            const cpx tw = a.T[k];                                // e^{-i pi k / N} = e^{-2 pi i k / L}
-            cpx X = cadd(make_float2(0.5f * E.x, 0.5f * E.y), cmul(make_float2(0.5f * O.y, -0.5f * O.x), tw));
-            // (-i/2) O tw  ==  (0.5*O.y, -0.5*O.x) * tw
-            if (k == 0) X.x -= dmu * 0.5f * (float)a.L;
-            if (k == 1) X.x += dmu * 0.25f * (float)a.L;
-            accA[own] += X.x * X.x + X.y * X.y;
-            // mirror bin N-k (k != 0): swap roles
-            cpx E2 = cadd(Zm, cconj(Zk)), O2 = csub(Zm, cconj(Zk));
-            const cpx tw2 = make_float2(-tw.x, tw.y);             // e^{-i pi (N-k)/N} = -conj(e^{-i pi k/N})
-            cpx X2 = cadd(make_float2(0.5f * E2.x, 0.5f * E2.y), cmul(make_float2(0.5f * O2.y, -0.5f * O2.x), tw2));
-            if (k == 0) {                                         // bin N (Nyquist) lives here
-                X2 = make_float2(Zk.x - Zk.y, 0.f);
-            }
-            if (N - k == 1) X2.x += dmu * 0.25f * (float)a.L;
-            accB[own] += X2.x * X2.x + X2.y * X2.y;
-        }
-        __syncthreads();
-    }
-    int own = 0;
-    for (int k2 = tid; k2 < N2; k2 += kThreads, ++own) {
-        const long long k = r + (long long)N1 * k2;
-        const long long km = N - k;
-        // every bin 0..N must be added exactly once per segment: row r owns k; the mirror
-        // N-k is added here only if it belongs to the partner row of a non-self pair, or
-        // (self-paired rows) if it is the Nyquist bin
-        atomicAdd(a.acc + k, (double)accA[own]);
-        if (!self) atomicAdd(a.acc + km, (double)accB[own]);
-        else if (k == 0) atomicAdd(a.acc + N, (double)accB[own]);
-    }
-}
-
-
 // =====================================================================================
-// Register-resident FFT kernels (the production path for 2^15 <= L <= 2^22).
+// The register-resident transform.
 //
-// The shared-memory Stockham kernels above keep every pass in shared memory and issue
-// their global loads one dependent iteration at a time: ncu shows them waiting on L2/HBM
-// latency (long_scoreboard 7-11 per issued instruction), not on bandwidth or math.  Here a
-// thread owns 8 points of a transform for the whole FFT: its 8 global loads are independent
-// and in flight together, the first pass reads them straight from registers, the last pass
-// leaves its results in registers for the fused epilogue, and shared memory only carries
-// the transposes between passes (one write + one read per pass boundary, conflict-free by
-// swizzled rows, double-buffered so there is a single barrier per exchange).  No
-// trigonometric table: the per-thread twiddle bases are computed once per CTA with
-// sincospif from exactly reduced integer arguments, the rest are products with 8th/16th
-// roots of unity and small powers.  A CTA loops over several segments so the set-up is
-// amortised.
+// The first version of this file kept every Stockham pass in shared memory and took its
+// trigonometric factors from an 8 MB table: ncu showed it waiting on L2/HBM latency
+// (long_scoreboard 7-11 per issued instruction: one dependent global load per loop iteration,
+// scattered table gathers), not on bandwidth or math.  Here a thread owns 8 points of a
+// transform for the whole FFT: its 8 global loads are independent and in flight together, the
+// first pass reads them straight from registers, the last pass leaves its results in
+// registers for the fused epilogue, and shared memory only carries the transposes between
+// passes (one write + one read per pass boundary, conflict-free by swizzled rows,
+// double-buffered so there is a single barrier per exchange).  No trigonometric table: the
+// per-thread twiddle bases are computed once per CTA with sincospif from exactly reduced
+// integer arguments, the rest are products with 8th/16th roots of unity and small powers.
+// A CTA loops over several segments so the set-up is amortised.
 //
 // Index algebra (Stockham autosort, radix 8 while possible, one radix-4 or -2 pass last):
 // before a pass thread j holds in[j + r N/8], r < 8.  A radix-8 pass with Ns = 8^p finished
@@ -552,6 +391,141 @@ __global__ void __launch_bounds__(2 * (1 << LOG2) / 8) ct_welch_rows_fast(WelchA
     }
 }
 
+// Whole-segment kernel (256 <= L <= 2^14): the N = L/2 packed points of a segment fit one transform, so a
+// segment is windowed, transformed, split and accumulated without leaving the CTA.  A CTA holds S slots
+// (S T >= 128 threads for the short lengths) and walks the segments S at a time; slot p, thread j owns the
+// points / bins j + r N/8.
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / 8 >= 128 ? (1 << LOGN) / 8 : 128) ct_welch_seg_kernel(WelchArgs a) {
+    using P = FftPlan<LOGN>;
+    using Lay = RowsLay<LOGN>;
+    constexpr int N = P::N, T = P::T, kSlot = N + P::pad, NX = FftX<LOGN>::n;
+    constexpr int S = T >= 128 ? 1 : 128 / T;                 // slots per CTA
+    constexpr int WPS = T >= 32 ? T / 32 : 1;                 // warps per slot
+    extern __shared__ __align__(16) unsigned char smraw[];
+    cpx* buf0 = reinterpret_cast<cpx*>(smraw);
+    cpx* buf1 = buf0 + S * kSlot;
+    __shared__ float wsum[2][S * WPS];
+    const int tid = threadIdx.x, p = tid / T, j = tid % T;
+    const int lane = ct_lane();
+    cpx wb[P::nbase > 0 ? P::nbase : 1];
+    fft_bases<LOGN>(wb, j);
+    int wbs[NX > 0 ? NX : 1], rbs[NX > 0 ? NX : 1];
+    fft_exchange_bases<LOGN, Lay>(wbs, rbs, j, p * kSlot);
+    // periodic Hann at samples 2J, 2J+1, J = j + r T: the angle advances by pi/4 per r
+    float ce, se, co, so;
+    sincospif(2.0f * (float)(2 * j) / (float)a.L, &se, &ce);
+    sincospif(2.0f * (float)(2 * j + 1) / (float)a.L, &so, &co);
+    const cpx tb = root(j, a.L);                              // split twiddle e^{-2 pi i k / L} at k = j (+ r T: 16th roots)
+    const int mine = p * kSlot + j;
+    const int other = p * kSlot + N - j;                      // partner bin (N - k) mod N of k = j + r T
+    float acc[8], accn = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    const float hl = 0.5f * (float)a.L, ql = 0.25f * (float)a.L;
+    const int stride = gridDim.x * S;
+    const int iters = (a.nseg + stride - 1) / stride;         // every slot runs the same number of barriers
+    for (int it = 0; it < iters; ++it) {
+        const int sg = blockIdx.x * S + p + it * stride;
+        const bool live = sg < a.nseg;
+        cpx v[8];
+        float part = 0.f;
+        const float* xs = a.x + (a.seg0 + (live ? sg : 0)) * (long long)(a.L / 2) + 2 * j;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float2 in = make_float2(a.c, a.c);
+            if (live) in = __ldg(reinterpret_cast<const float2*>(xs + 2 * T * r));
+            float x0 = in.x, x1 = in.y;
+            if (a.use_abs) { x0 = fabsf(x0); x1 = fabsf(x1); }
+            x0 -= a.c; x1 -= a.c;
+            part += x0 + x1;
+            float cer, cor;
+            switch (r) {
+                case 0: cer = ce; cor = co; break;
+                case 1: cer = kH * (ce - se); cor = kH * (co - so); break;
+                case 2: cer = -se; cor = -so; break;
+                case 3: cer = -kH * (ce + se); cor = -kH * (co + so); break;
+                case 4: cer = -ce; cor = -co; break;
+                case 5: cer = -kH * (ce - se); cor = -kH * (co - so); break;
+                case 6: cer = se; cor = so; break;
+                default: cer = kH * (ce + se); cor = kH * (co + so); break;
+            }
+            v[r] = make_float2(x0 * (0.5f - 0.5f * cer), x1 * (0.5f - 0.5f * cor));
+        }
+        // segment sum: shuffles inside the slot's lanes, then across its warps through shared memory
+        // (written before the transform's first barrier, read after its last; two copies per parity)
+#pragma unroll
+        for (int o = (T < 32 ? T : 32) / 2; o > 0; o >>= 1) part += __shfl_xor_sync(CT_FULL, part, o);
+        float* wsm = wsum[it & 1];
+        if (T >= 32) { if (lane == 0) wsm[p * WPS + (j >> 5)] = part; }
+        fft_reg<LOGN, Lay>(v, wb, buf0, buf1, wbs, rbs);
+        cpx* b = (NX & 1) ? buf1 : buf0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) b[mine + r * T] = v[r];
+        __syncthreads();
+        float tot = part;
+        if (T >= 32) {
+            tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPS; ++w) tot += wsm[p * WPS + w];
+        }
+        const float dmu = tot / (float)a.L;                   // mu - c of this segment
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int mi = other - r * T;
+            if (r == 0 && j == 0) mi -= N;
+            const cpx Zk = v[r], Zm = b[mi];
+            const cpx E = cadd(Zk, cconj(Zm)), O = csub(Zk, cconj(Zm));
+            cpx tw;
+            {
+                const float c16 = 0.92387953251128674f, s16 = 0.38268343236508977f;
+                const cpx h = (r & 1) ? make_float2(tb.x * c16 + tb.y * s16, tb.y * c16 - tb.x * s16) : tb;
+                switch (r >> 1) { case 0: tw = h; break; case 1: tw = rot8<1>(h); break; case 2: tw = rot8<2>(h); break; default: tw = rot8<3>(h); break; }
+            }
+            cpx X = cadd(make_float2(0.5f * E.x, 0.5f * E.y), cmul(make_float2(0.5f * O.y, -0.5f * O.x), tw));
+            if (r == 0) {
+                if (j == 0) {
+                    X.x -= dmu * hl;                                        // bin 0
+                    if (live) accn += (Zk.x - Zk.y) * (Zk.x - Zk.y);       // bin N (Nyquist) lives in Z[0]
+                }
+                if (j == 1) X.x += dmu * ql;                               // bin 1
+            }
+            if (live) acc[r] += X.x * X.x + X.y * X.y;
+        }
+        if (!(NX & 1)) __syncthreads();                       // odd number of exchanges per iteration
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) atomicAdd(a.acc + j + r * T, (double)acc[r]);
+    if (j == 0) atomicAdd(a.acc + N, (double)accn);
+}
+
+template <int LOGN> static int launch_seg(const WelchArgs& a, cudaStream_t st) {
+    using P = FftPlan<LOGN>;
+    constexpr int S = P::T >= 128 ? 1 : 128 / P::T;
+    const size_t sm = (size_t)2 * S * (P::N + P::pad) * sizeof(cpx);
+    cudaFuncSetAttribute(ct_welch_seg_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_welch_seg_kernel<LOGN>, S * P::T, sm);
+    if (occ < 1) occ = 1;
+    long long grid = (long long)ct_sm_count() * occ;
+    const long long want = (a.nseg + S - 1) / S;
+    if (grid > want) grid = want;
+    CT_COUNT_LAUNCH();
+    ct_welch_seg_kernel<LOGN><<<(unsigned)grid, S * P::T, sm, st>>>(a);
+    return ct_check_launch("ct_welch_seg_kernel");
+}
+static int seg_path(const WelchArgs& a, int logn, cudaStream_t st) {
+    switch (logn) {
+        case 7: return launch_seg<7>(a, st);
+        case 8: return launch_seg<8>(a, st);
+        case 9: return launch_seg<9>(a, st);
+        case 10: return launch_seg<10>(a, st);
+        case 11: return launch_seg<11>(a, st);
+        case 12: return launch_seg<12>(a, st);
+        default: return launch_seg<13>(a, st);
+    }
+}
+
 template <int LOG1> static int launch_cols_fast(const WelchArgs& a, int N2, cudaStream_t st) {
     using P = FftPlan<LOG1>;
     const size_t sm = (size_t)2 * (P::N + P::pad) * kFastCols * sizeof(cpx);
@@ -568,7 +542,6 @@ template <int LOG2> static int launch_rows_fast(const WelchArgs& a, int N1, cuda
     ct_welch_rows_fast<LOG2><<<(unsigned)((N1 / 2 + 1) * a.rsplit), 2 * P::T, sm, st>>>(a);
     return ct_check_launch("ct_welch_rows_fast");
 }
-static bool fast_sizes(int logn1, int logn2) { return logn1 >= 7 && logn1 <= 10 && logn2 >= 7 && logn2 <= 12; }
 static int cols_fast(const WelchArgs& a, cudaStream_t st) {
     const int N2 = 1 << a.logn2;
     switch (a.logn1) {
@@ -757,7 +730,8 @@ extern "C" {
 
 int64_t ct_welch_workspace_bytes(int32_t nperseg, int32_t batch) {
     if (nperseg < 256 || (nperseg & (nperseg - 1))) return -1;
-    return (int64_t)batch * (nperseg / 2) * 8 + (int64_t)batch * 8 + 256 + (int64_t)nperseg * 8;
+    if (nperseg <= (1 << 14)) return 256;                      // whole-segment kernel: no intermediate
+    return (int64_t)batch * (nperseg / 2) * 8 + (int64_t)batch * 8 + 256;
 }
 
 int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_t use_abs, int32_t batch,
@@ -777,49 +751,33 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
     if (batch < 1) batch = 1;
     if (workspace_bytes < ct_welch_workspace_bytes(nperseg, batch)) { ct_set_error("welch: workspace too small"); return CT_ERR_ARG; }
     int logn = 0; while ((1LL << logn) < N) ++logn;
-    int logn2 = (logn + 1) / 2, logn1 = logn - logn2;      // N2 >= N1
-    if (logn1 < 3) { logn1 = 3; logn2 = logn - 3; }
-    if (logn1 > 10) { logn1 = 10; logn2 = logn - 10; }    // the column kernel holds 8 columns of N1 <= 1024 points
-    if (logn2 > 12 || logn1 > 12 || (1 << logn2) < kCols) { ct_set_error("welch: unsupported segment length"); return CT_ERR_UNSUPPORTED; }
     WelchArgs a;
-    a.x = x; a.n = n; a.L = L; a.logn1 = logn1; a.logn2 = logn2; a.c = shift; a.use_abs = use_abs;
+    a.x = x; a.n = n; a.L = L; a.c = shift; a.use_abs = use_abs; a.acc = acc; a.mu_scale = 1.0 / (double)L;
+    a.rsplit = a.ssplit = 1; a.logn1 = a.logn2 = 0; a.Y = nullptr; a.segsum = nullptr;
+    if (logn <= 13) {                                          // L <= 2^14: a segment is one transform, no intermediate
+        if (nseg > 0x7fffffffLL) { ct_set_error("welch: too many segments"); return CT_ERR_UNSUPPORTED; }
+        a.seg0 = 0; a.nseg = (int)nseg;
+        return seg_path(a, logn, st);
+    }
+    // four-step N1 x N2: N2 >= N1, the column kernel holds 8 columns of N1 <= 1024 points
+    int logn2 = (logn + 1) / 2, logn1 = logn - logn2;
+    if (logn1 > 10) { logn1 = 10; logn2 = logn - 10; }
+    a.logn1 = logn1; a.logn2 = logn2;
     a.Y = (cpx*)workspace;
     a.segsum = (double*)((char*)workspace + (size_t)batch * N * 8);
-    cpx* T = (cpx*)((char*)workspace + (((size_t)batch * N * 8 + (size_t)batch * 8 + 255) / 256) * 256);
-    a.T = T;
-    a.acc = acc; a.mu_scale = 1.0 / (double)L;
     const int N1 = 1 << logn1, N2 = 1 << logn2;
-    const bool fast = fast_sizes(logn1, logn2);
-    size_t smA = (size_t)(2 * N1 * kCols + N1) * sizeof(cpx), smB = (size_t)(2 * 2 * N2 + N2) * sizeof(cpx);
-    if (!fast) {
-        CT_COUNT_LAUNCH();
-        ct_welch_table<<<(L + 255) / 256, 256, 0, st>>>(T, L);
-        { int rc = ct_check_launch("ct_welch_table"); if (rc) return rc; }
-        cudaFuncSetAttribute(ct_welch_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
-        cudaFuncSetAttribute(ct_welch_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
-    }
     const int target = 2 * ct_sm_count();
     for (long long s0 = 0; s0 < nseg; s0 += batch) {
         a.seg0 = s0; a.nseg = (int)((nseg - s0 < batch) ? nseg - s0 : batch);
         cudaMemsetAsync(a.segsum, 0, (size_t)a.nseg * 8, st);
         // enough CTAs to fill the GPU: the segments of the batch are split over rsplit CTAs per row pair
-        // (and over ssplit CTAs per column group)
+        // (and over ssplit CTAs per column group); more segments per CTA amortise its set-up
         a.rsplit = 1;
         while ((N1 / 2 + 1) * a.rsplit < target && a.rsplit * 2 <= a.nseg) a.rsplit *= 2;
         a.ssplit = 1;
         while ((N2 / kFastCols) * a.ssplit < target && a.ssplit * 2 <= a.nseg) a.ssplit *= 2;
-        int rc;
-        if (fast) {
-            rc = cols_fast(a, st); if (rc) return rc;
-            rc = rows_fast(a, st); if (rc) return rc;
-            continue;
-        }
-        CT_COUNT_LAUNCH();
-        ct_welch_cols<<<(unsigned)(a.nseg * (N2 / kCols)), kThreads, smA, st>>>(a);
-        rc = ct_check_launch("ct_welch_cols"); if (rc) return rc;
-        CT_COUNT_LAUNCH();
-        ct_welch_rows<<<(unsigned)((N1 / 2 + 1) * a.rsplit), kThreads, smB, st>>>(a);
-        rc = ct_check_launch("ct_welch_rows"); if (rc) return rc;
+        int rc = cols_fast(a, st); if (rc) return rc;
+        rc = rows_fast(a, st); if (rc) return rc;
     }
     return CT_OK;
 }

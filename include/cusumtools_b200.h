@@ -207,8 +207,8 @@ int ct_event_extrema_f32(const float* y, int64_t n_total, const int64_t* win_sta
  * the caller divides by nseg * fs * sum(w^2) = nseg * fs * 3L/8 and doubles bins 1..L/2-1.
  * `shift` is any constant near the signal mean (subtracted before the float32 FFT, exactly
  * compensated); `batch` segments are transformed per launch pair (intermediate
- * batch * L/2 * 8 bytes in the workspace; larger batches amortise the per-CTA set-up).
- * 256 <= L <= 2^23.                                                                     */
+ * batch * L/2 * 8 bytes in the workspace for L > 2^14; larger batches amortise the per-CTA set-up;
+ * shorter segments need no intermediate).  256 <= L <= 2^23.                            */
 int64_t ct_welch_workspace_bytes(int32_t nperseg, int32_t batch);
 int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_t use_abs, int32_t batch,
                  void* workspace, int64_t workspace_bytes, double* acc, int64_t* nseg_out, void* stream);
