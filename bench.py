@@ -368,6 +368,7 @@ def run_ours(args):
                                "pass's epilogue" if fused_stats else "") + "; timed alone, 3 back-to-back calls)", "bound": "hbm",
                      "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "kernel_ms": filt_ms,
+                     "frac_of_nominal_8000_GBps": ach / 8000.0,      # also against the nominal HBM3e figure
                      "algorithmic_bytes_per_sample": FILTER_BYTES_PER_SAMPLE,
                      "share_of_step": filt_ms / ms_per_step,
                      "filter_only": {"kernel_ms": filt_plain_ms, "frac": FILTER_BYTES_PER_SAMPLE * raw.numel() / (filt_plain_ms / 1e3) / 1e9 / peak,
