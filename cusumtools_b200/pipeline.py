@@ -456,7 +456,7 @@ class StreamResult:
     median_codes: tuple[int, int]
     first_event_id: int = 0
     total_events: int = 0
-    redone: str = ""                # "", "first" (first sub-shard redone with the exact pad) or "all"
+    redone: str = ""                # "", "first" (first sub-shard redone with the exact pad) or "whole" (fallback)
 
 
 class StreamingAnalyzer:
@@ -529,9 +529,10 @@ class StreamingAnalyzer:
             self._pin[name] = t = new
         return t
 
-    def _process(self, i: int, plan: MedianPlan, pad_x: float, med: tuple[int, int], row0: int, bl: detect.Baseline) -> int:
+    def _process(self, i: int, plan: MedianPlan, pad_x: float, med: tuple[int, int], row0: int, bl: detect.Baseline,
+                 end_at: int | None = None) -> int:
         """Analyse sub-shard i (its data must be resident), store its owned samples, blocks and table rows
-        (from row `row0`); returns its event count."""
+        (from row `row0`, or ending at row `end_at`); returns its event count (-1: more rows than `end_at`)."""
         a, b, ea, eb = self.sub[i]
         an = self._analyzer(a, b, ea, eb)
         r = an.run(self.raw_dev[ea:eb], _fixed=(plan, pad_x, med))
@@ -547,6 +548,10 @@ class StreamingAnalyzer:
                         overflow=r.levels.overflow)
         if r.intra is not None:
             cols.update(intra_count=r.intra[0], intra_pairs=r.intra[1])
+        if end_at is not None:
+            if nk > end_at:
+                return -1
+            row0 = end_at - nk
         for name, t in cols.items():
             self._pinned(name, t, row0 + nk)[row0:row0 + nk].copy_(t, non_blocking=True)
         return nk
@@ -585,7 +590,12 @@ class StreamingAnalyzer:
         hist_fn, count_fn = _median_kernels(self.raw_dev[a0:b_end], self.mask)
         bl = detect.new_baseline(self.n_own, self.block, self.bmin, self.bmax, self.device)
         st = filters._stream_ptr(self.raw_dev)
-        rows, counts_per = 0, []
+        # The first sub-shard holds the true start of the trace, whose pad needs the exact median: it is analysed
+        # with the estimate right away and again at the end if the estimate was off.  Its rows sit RIGHT-ALIGNED
+        # in a reserved head of the tables, so a different event count the second time moves nothing else.
+        head = self.lo_halo == 0 and len(self.sub) > 1
+        reserve = max(1024, (self.sub[0][3] - self.sub[0][2]) // 512) if head else 0
+        rows, first_rows = reserve, 0
         med, pad_x, redone = (0, 0), 0.0, ""
         try:
             for i, (pa, pe, ev) in enumerate(arrivals):
@@ -600,28 +610,28 @@ class StreamingAnalyzer:
                     med = median_search(self.n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
                                         first_counts=counts if plan.exact is None else None)
                     pad_x = 0.5 * (med[0] + med[1]) - plan.est
-                nk = self._process(i, plan, pad_x if last else 0.0, med, rows, bl)
-                counts_per.append(nk)
-                rows += nk
-            if pad_x != 0.0 and self.lo_halo == 0 and len(self.sub) > 1:
-                # the trace starts in this rank's first sub-shard and its pad was the estimate: redo it
-                nk = self._process(0, plan, pad_x, med, 0, bl)
+                if head and i == 0:
+                    first_rows = self._process(0, plan, 0.0, med, 0, bl, end_at=reserve)
+                else:
+                    rows += self._process(i, plan, pad_x if last else 0.0, med, rows, bl)
+            if head and (pad_x != 0.0 or first_rows < 0):
+                first_rows = self._process(0, plan, pad_x, med, 0, bl, end_at=reserve)
                 redone = "first"
-                if nk != counts_per[0]:                       # an event (dis)appeared in the first samples: redo all rows
-                    rows, redone = 0, "all"
-                    for i in range(len(self.sub)):
-                        rows += self._process(i, plan, pad_x, med, rows, bl)
+            if first_rows < 0:                                # more events at the very start than the reserved head holds
+                raise ValueError("baseline block / head reserve: fall back to the whole-trace analyzer")
         except ValueError as e:
             if "baseline block" not in str(e):
                 raise
             return self._run_whole(host_codes)                # a sub-shard without a single valid baseline block
-        first_id, total = event_id_offsets(rows, self.group, self.device)
+        start = reserve - first_rows                            # first row of the (right-aligned) head
+        n_rows = rows - start
+        first_id, total = event_id_offsets(n_rows, self.group, self.device)
         cur.synchronize()
         bl.dev["have_thresholds"] = True
         bl._checked = True
         bl.threshold, bl.hysteresis = float(self.kw.get("threshold", 5.0)), float(self.kw.get("hysteresis", 1.0))
         pad_value = float(np.median(filters.scale_codes_host(np.array(med, dtype=np.uint16), self.settings)))
-        tables = {k: v[:rows].numpy() for k, v in self._pin.items()}
+        tables = {k: v[start:rows].numpy() for k, v in self._pin.items()}
         return StreamResult(filtered=self.y, baseline=bl, tables=tables, pad_value=pad_value, median_codes=tuple(med),
                             first_event_id=first_id, total_events=total, redone=redone)
 

@@ -217,7 +217,7 @@ def test_streaming_analyzer_equals_the_resident_run(shift_first):
             rb = b.run_from_host(host)
         assert tuple(rb.median_codes) == tuple(ra.median_codes) and rb.pad_value == ra.pad_value
         if shift_first and shards > 1:
-            assert rb.redone in ("first", "all")
+            assert rb.redone == "first"
         assert torch.max(torch.abs(ra.filtered - rb.filtered)).item() < 0.02
         tb = rb.tables
         assert len(tb["starts"]) == len(ta["starts"]) == rb.total_events
@@ -249,6 +249,48 @@ def test_streaming_analyzer_small_and_ragged_traces(n):
     assert len(rb.tables["starts"]) == len(ta["starts"])
     assert np.abs(rb.tables["starts"] - ta["starts"]).max(initial=0) <= 1
     assert len(rb.baseline) == len(ra.baseline) == -(-n // 65536)
+
+
+def _tables_agree(ta, tb):
+    assert set(ta) == set(tb)
+    for k in ("starts", "ends", "types", "n_levels", "overflow", "intra_count"):
+        if k in ta:
+            assert ta[k].shape == tb[k].shape and np.mean(ta[k] == tb[k]) > 0.98, k
+    if "mean" in ta:
+        sel = (np.arange(ta["mean"].shape[1])[None, :] < ta["n_levels"][:, None]) & (ta["n_levels"] == tb["n_levels"])[:, None]
+        assert np.allclose(ta["mean"][sel], tb["mean"][sel], rtol=0, atol=0.5)
+        assert not sel.any() or np.mean(ta["edges"][:, 1:][sel] == tb["edges"][:, 1:][sel]) > 0.98
+
+
+@pytest.mark.parametrize("opts", [
+    {}, {"cusum_delta": 400.0, "cusum_h": 10.0}, {"cusum_delta": 400.0, "cusum_h": 10.0, "intra_threshold": 40.0, "intra_hysteresis": 4.0},
+    {"intra_threshold": 40.0, "intra_hysteresis": 4.0}, {"cusum_delta": 400.0, "cusum_h": 10.0, "event_capacity": 16},
+    {"cusum_delta": 400.0, "cusum_h": 10.0, "max_levels": 3}, {"cusum_delta": 400.0, "cusum_h": 10.0, "maxpoints": 1500}],
+    ids=["detect-only", "cusum", "cusum+intra", "intra-only", "regrow", "level-overflow", "too-long"])
+def test_streamed_and_resident_forms_agree_for_every_option_set(opts):
+    codes, _ = synth.c1_trace(n=2_000_000, n_events=400, seed=9)
+    host = torch.from_numpy(codes).pin_memory()
+    kw = dict(baseline_block=65536, **KW, **opts)
+    a = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, **kw)
+    ta = a.tables_to_host(a.run(host.cuda()))
+    rb = pipeline.StreamingAnalyzer(len(codes), S, 1e5, 8, shards=5, **kw).run_from_host(host)
+    assert len(ta["starts"]) == 400 and rb.redone in ("", "first")
+    _tables_agree(ta, rb.tables)
+
+
+def test_streaming_analyzer_over_a_shard_with_halos():
+    """A rank's extended range [left halo | owned | right halo] through the streamed form: the rows and the
+    filtered samples are those of the owned range only, as with TraceAnalyzer."""
+    codes, _ = synth.c1_trace(n=2_000_000, n_events=400, seed=9)
+    host = torch.from_numpy(codes).pin_memory()
+    kw = dict(baseline_block=65536, cusum_delta=400.0, cusum_h=10.0, lo_halo=131072, hi_halo=131072, **KW)
+    a = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, **kw)
+    ra = a.run(host.cuda())
+    ta = a.tables_to_host(ra)
+    rb = pipeline.StreamingAnalyzer(len(codes), S, 1e5, 8, shards=4, **kw).run_from_host(host)
+    assert rb.filtered.numel() == len(codes) - 2 * 131072 and rb.redone == ""
+    assert torch.max(torch.abs(rb.filtered - ra.filtered)).item() < 0.02
+    assert np.array_equal(ta["starts"], rb.tables["starts"]) and np.array_equal(ta["ends"], rb.tables["ends"])
 
 
 def test_event_table_from_the_streamed_result_equals_the_resident_one():
