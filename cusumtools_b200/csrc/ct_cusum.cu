@@ -333,17 +333,15 @@ constexpr unsigned char kRawSums = 0x80;   // overflow[] bit: level rows hold ra
 
 struct SeqOut { int sp, sn; };
 
-__device__ __forceinline__ SeqOut seq_increments(const double* __restrict__ rctab, long long Sq, long long Sqq,
-                                                 int cnt, int q, float dq, float hq) {
-    const double rc = __ldg(rctab + cnt);          // cnt <= kSeqMax < kRcTab
-    const double Sqd = (double)Sq;
-    const double m = __dmul_rn(Sqd, rc);
+// The increments of both tests from the running sums.  Split in two: the mean and the sample's deviation t
+// are needed for every sample; the variance, the IEEE division and the two products only matter when an
+// increment can change a statistic (see the quiet-sample shortcut in the kernel).
+__device__ __forceinline__ SeqOut seq_increments_tail(double Sqd, double m, double rc, long long Sqq, float t, float dq, float hq) {
     const double vv = __dmul_rn(__dsub_rn((double)Sqq, __dmul_rn(Sqd, m)), rc);
     const float v = __double2float_rn(vv);
     // branch-free: evaluate with a harmless divisor when the variance carries no information, then mask
     const bool ok = v > 0.f;
     const float r = __fdiv_rn(dq, ok ? v : 1.f);
-    const float t = __fsub_rn((float)q, __double2float_rn(m));
     float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
     float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
     fa = fminf(fmaxf(fa, -kSMax), kSMax);
@@ -440,7 +438,18 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
                 // == quantise(xv[e], x0): scaling by 2^6 commutes with the rounding of the difference
                 const int q = __float2int_rn(fminf(fmaxf(__fmaf_rn(xv[e], kQ, nx0), -kQMax), kQMax));
                 Sq += q; Sqq += (long long)q * q;
-                const SeqOut s = seq_increments(a.rctab, Sq, Sqq, k - k0 + 1, q, dq, hq);
+                const double rc = __ldg(a.rctab + (k - k0 + 1));      // k - k0 + 1 <= kSeqMax < kRcTab
+                const double Sqd = (double)Sq;
+                const double m = __dmul_rn(Sqd, rc);
+                const float t = __fsub_rn((float)q, __double2float_rn(m));
+                // Quiet sample: both statistics are 0 and |t| <= delta/2, so both increments are <= 0 whatever the
+                // variance is (r > 0 or masked; t - hq <= 0 and t + hq >= 0 survive every rounding and the clamps) and
+                // the statistics stay 0 with their argmin at k: exactly what the full evaluation would leave.  On the
+                // plateaus of an event almost every sample is quiet; the shortcut is taken when all the lanes that are
+                // at a sample agree (warp-uniform branch), the full evaluation is always valid.
+                const bool quiet = (gp | gn) == 0 && fabsf(t) <= hq;
+                if (__all_sync(__activemask(), quiet)) { rp = k; rn = k; continue; }
+                const SeqOut s = seq_increments_tail(Sqd, m, rc, Sqq, t, dq, hq);
                 gp = max(gp + s.sp, 0); rp = gp == 0 ? k : rp;
                 gn = max(gn + s.sn, 0); rn = gn == 0 ? k : rn;
                 if (max(gp, gn) > H) {
