@@ -431,6 +431,29 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
             for (int e = 0; e < kS; ++e) xv[e] = nx[e];
             if (gk + kS < n) load_group(p0 + gk + kS, nx);
             const unsigned nlim = overflow ? 0u : (unsigned)n;
+            // ---- quiet group: the whole group lies inside the window, both statistics are 0 and every sample of
+            // it is quiet (see below) in EVERY lane that is at a group: then only the running sums move.  The
+            // attempt costs ~20 instructions per sample with one vote per group; if it fails nothing has been
+            // committed and the group takes the per-sample path.
+            bool done = false;
+            if (__all_sync(__activemask(), gk >= 0 && gk + kS <= n && !overflow && (gp | gn) == 0)) {
+                const double* rcp = a.rctab + (gk - k0 + 1);             // counts gk-k0+1 .. gk-k0+kS <= kSeqMax < kRcTab
+                double rcv[kS];
+#pragma unroll
+                for (int e = 0; e < kS; ++e) rcv[e] = __ldg(rcp + e);
+                long long S1 = Sq, S2 = Sqq;
+                bool allq = true;
+#pragma unroll
+                for (int e = 0; e < kS; ++e) {
+                    const int q = __float2int_rn(fminf(fmaxf(__fmaf_rn(xv[e], kQ, nx0), -kQMax), kQMax));
+                    S1 += q; S2 += (long long)q * q;
+                    const double m = __dmul_rn((double)S1, rcv[e]);
+                    const float t = __fsub_rn((float)q, __double2float_rn(m));
+                    allq = allq && fabsf(t) <= hq;
+                }
+                if (__all_sync(__activemask(), allq)) { Sq = S1; Sqq = S2; rp = rn = gk + kS - 1; done = true; }
+            }
+            if (!done)
 #pragma unroll
             for (int e = 0; e < kS; ++e) {
                 const int k = gk + e;
