@@ -158,3 +158,48 @@ def test_summary_rejects_keys_the_consumers_would_misparse(tmp_path):
         writer.write_analysis_dir(str(tmp_path / "x"), tab, baseline_mean=d["mean"], baseline_std=d["std"],
                                   baseline_block=BLOCK, samplerate=FS, threshold=5.0, hysteresis=1.0, cutoff=1e5,
                                   poles=8, extra_summary={"cusum_threshold": 10})
+
+
+def test_intra_crossing_columns_round_trip_through_the_consumer(tmp_path):
+    """rate.csv `intra_crossing_times_us` / events.csv `intra_crossings` / summary keys from the oracle's
+    crossings, read back with the consumer's statements (readevents.py:73-79, 1310, 1340-1343)."""
+    y, _, d = make_tables()
+    E = len(d["s"])
+    K = 4
+    cnt = np.zeros(E, np.int32); pairs = np.full((E, 2 * K), -1, np.int32)
+    for i in range(E):
+        kb = min(d["s"][i] // BLOCK, len(d["mean"]) - 1)
+        c = eo.intra_crossings(y[max(d["w0"][i], 0):d["w1"][i]], d["mean"][kb], d["std"][kb], 50.0, 5.0)
+        cnt[i] = len(c)
+        pairs[i, :2 * min(len(c), K)] = c[:K].ravel()
+    assert (cnt == 1).mean() > 0.9                        # the deeper second level of every synthetic event
+    xmin = np.array([y[max(a, 0):b].min() for a, b in zip(d["w0"], d["w1"])], np.float32)
+    xmax = np.array([y[max(a, 0):b].max() for a, b in zip(d["w0"], d["w1"])], np.float32)
+    ov = np.zeros(E, np.uint8)
+    sdv = np.zeros_like(d["mu"])
+    tab = writer.build_event_table(starts=d["s"], ends=d["e"], types=d["typ"], n_levels=d["nl"], edges=d["ed"], level_mean=d["mu"],
+                                   level_std=sdv, overflow=ov, xmin=xmin, xmax=xmax, samplerate=FS, threshold=5.0,
+                                   baseline_mean=d["mean"], baseline_std=d["std"], baseline_block=BLOCK, padding=PAD,
+                                   intra_count=cnt, intra_pairs=pairs)
+    assert np.array_equal(tab.events["intra_crossings"], cnt[tab.rate["type"] == 0])
+    writer.write_analysis_dir(str(tmp_path), tab, baseline_mean=d["mean"], baseline_std=d["std"], baseline_block=BLOCK,
+                              samplerate=FS, threshold=5.0, hysteresis=1.0, cutoff=1e5, poles=8, intra_threshold=50.0,
+                              intra_hysteresis=5.0)
+    it = ih = thr = None
+    for line in open(tmp_path / "summary.txt"):
+        if "intra_threshold" in line:
+            it = float(re.split("=|\n", line)[1])
+        if "intra_hysteresis" in line:
+            ih = float(re.split("=|\n", line)[1])
+        if "threshold" in line and "intra" not in line:
+            thr = float(re.split("=|\n", line)[1])
+    assert (it, ih, thr) == (50.0, 5.0, 5.0)
+    ratedb = pd.read_csv(tmp_path / "rate.csv", encoding="utf-8")
+    for i in np.nonzero(cnt > 0)[0][:10]:
+        semilist = np.squeeze(ratedb.loc[ratedb["id"] == i, "intra_crossing_times_us"].values)
+        crossings = np.hstack([np.array(a, dtype=float) for a in str(semilist).split(";")]).astype(np.float64)
+        got = np.array(list(zip(crossings[::2], crossings[1::2])))
+        want = pairs[i, :2 * min(cnt[i], K)].reshape(-1, 2) * 1e6 / FS
+        assert np.allclose(got, want, rtol=1e-12)
+    evdb = pd.read_csv(tmp_path / "events.csv", encoding="utf-8")
+    assert np.array_equal(evdb["intra_crossings"].values, tab.events["intra_crossings"])
