@@ -106,12 +106,19 @@ def median_search(n_local: int, mask: int, hist_fn, count_fn, group=None, device
     if plan.exact is not None:
         return plan.exact
     counts = first_counts
-    for _ in range(16):
+    for attempt in range(16):
         if counts is None:
             counts = count_fn(plan.lo, plan.step)
         pair, plan.lo = median_verify(plan, counts, group)
         if pair is not None:
             return pair
+        if attempt == 0:
+            # the window missed: the estimate came from too small or too local a sample (streaming: the first
+            # piece of a drifting trace).  Re-estimate from a strided histogram of ALL the data before stepping.
+            again = median_estimate(n_local, mask, hist_fn, group, device)
+            if again.exact is not None:
+                return again.exact
+            plan.lo = again.lo                 # (plan.est stays: the filter has already subtracted it)
         counts = None
     cdf = np.cumsum(_all_reduce_(hist_fn(1).to(torch.int64), group).cpu().numpy())   # pathological distribution
     return int(np.searchsorted(cdf, plan.k1 + 1)), int(np.searchsorted(cdf, plan.k2 + 1))
