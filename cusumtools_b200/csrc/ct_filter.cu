@@ -574,6 +574,8 @@ static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
     return r;
 }
+// WIDE = false: only the first four window codes are counted (one counter word: 7 instead of 10 operations per code).
+template <bool WIDE>
 __global__ void __launch_bounds__(256)
 ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned mask, unsigned lo,
                        unsigned step, unsigned long long* __restrict__ out /*[1+kWin]*/) {
@@ -587,7 +589,7 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
         below += d >> 31;                                  // codes and lo are < 2^16: negative iff code < lo
         const unsigned amt = sh >= 3 ? d >> (sh - 3) : d << (3 - sh);   // 8 * (d / step): d is a multiple of step
         c0 += shl_clamp(1u, amt);
-        c1 += shl_clamp(1u, amt - 32u);
+        if (WIDE) c1 += shl_clamp(1u, amt - 32u);
     };
     auto flush = [&]() {
         tot[0] += below; below = 0;
@@ -604,10 +606,20 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
     if (aligned) {
         long long i = tid;
         int rounds = 0;
-        for (; i + 3 * nth < nvec; i += 4 * nth) {          // four independent 16-byte loads in flight
-            uint4 q[4];
+        // four independent 16-byte loads per batch, the next batch on its way while this one is tallied
+        uint4 q[4], nq[4];
+        bool have = i + 3 * nth < nvec;
+        if (have) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) q[u] = ct_ldg_stream(v + i + u * nth);
+        }
+        while (have) {
+            const long long inext = i + 4 * nth;
+            const bool more = inext + 3 * nth < nvec;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nq[u] = ct_ldg_stream(v + inext + u * nth);
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const unsigned ww[4] = {q[u].x & m2, q[u].y & m2, q[u].z & m2, q[u].w & m2};
@@ -615,6 +627,10 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
                 for (int j = 0; j < 4; ++j) { tally(ww[j] & 0xffffu); tally(ww[j] >> 16); }
             }
             if (++rounds == 7) { flush(); rounds = 0; }     // 32 tallies per round: an 8-bit counter holds 7 rounds
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = nq[u];
+            i = inext;
+            have = more;
         }
         flush();
         for (; i < nvec; i += nth) {
@@ -631,7 +647,7 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
     }
     flush();
 #pragma unroll
-    for (int i = 0; i < 1 + kWin; ++i) {
+    for (int i = 0; i < 1 + (WIDE ? kWin : kWin / 2); ++i) {
         unsigned long long sum = tot[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(CT_FULL, sum, o);
@@ -807,17 +823,31 @@ int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t
     return ct_check_launch("ct_hist_sampled_kernel");
 }
 
-int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
-                        uint64_t* counts9, void* stream) {
+static int count_window(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step, uint64_t* counts9,
+                        bool wide, void* stream) {
     if (!raw || !counts9 || n < 0 || step < 1) { ct_set_error("count_window: bad argument"); return CT_ERR_ARG; }
     if (n == 0) return CT_OK;
     long long blocks = (long long)ct_sm_count() * 8;
     long long want = (n / 8 + 255) / 256 + 1;
     if (blocks > want) blocks = want;
     CT_COUNT_LAUNCH();
-    ct_count_window_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        raw, n, mask, lo, step, reinterpret_cast<unsigned long long*>(counts9));
+    if (wide)
+        ct_count_window_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            raw, n, mask, lo, step, reinterpret_cast<unsigned long long*>(counts9));
+    else
+        ct_count_window_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            raw, n, mask, lo, step, reinterpret_cast<unsigned long long*>(counts9));
     return ct_check_launch("ct_count_window_kernel");
+}
+
+int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
+                        uint64_t* counts9, void* stream) {
+    return count_window(raw, n, mask, lo, step, counts9, true, stream);
+}
+
+int ct_count_window4_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
+                         uint64_t* counts9, void* stream) {
+    return count_window(raw, n, mask, lo, step, counts9, false, stream);
 }
 
 }  // extern "C"

@@ -114,11 +114,15 @@ int ct_filter_backward(int64_t n, int64_t pad, float scale, float offset, const 
 /* Exact global median of the masked codes, the value np.pad(mode='median') needs
  * (plot-trace.py:319): a strided-sample histogram to locate it and an exact count of
  * the codes below / inside a window of 8 codes {lo + i*step} to verify it.
- *   hist65536: uint32[65536], caller-zeroed; counts9: uint64[9], caller-zeroed.        */
+ *   hist65536: uint32[65536], caller-zeroed; counts9: uint64[9], caller-zeroed.
+ * ct_count_window4_u16 counts only the first four window codes (counts9[5..8] untouched): the
+ * cheaper first attempt when the estimate comes from a sample of the whole trace.         */
 int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t mask,
                         uint32_t* hist65536, void* stream);
 int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
                         uint64_t* counts9, void* stream);
+int ct_count_window4_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
+                         uint64_t* counts9, void* stream);
 
 /* ---- stage 2: baseline statistics + threshold/hysteresis detection ---------------
  * No reference implementation exists; semantics per plot-trace.py:379-414, definition in
