@@ -210,7 +210,7 @@ def run_ours(args):
     S = synth.CHIMERA_SETTINGS
     n_own = int(args.samples)
     n_own = n_own // BASELINE_BLOCK * BASELINE_BLOCK if world > 1 else n_own
-    halo = pipeline.required_halo(CUTOFF, ORDER, synth.FS, max_event=4096, block=BASELINE_BLOCK) if world > 1 else 0
+    halo = pipeline.required_halo(CUTOFF, ORDER, synth.FS, max_event=MAXPOINTS + 2 * EVENT_PAD, block=BASELINE_BLOCK) if world > 1 else 0
     lo_h = halo if rank > 0 else 0
     hi_h = halo if rank < world - 1 else 0
     raw = synth.device_trace(n_own + lo_h + hi_h, dev, seed=1234 + rank, start_index=rank * n_own - lo_h)

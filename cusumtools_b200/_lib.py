@@ -14,19 +14,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CT_LIB_PATH") or os.path.join(_HERE, "libcusumtools_b200.so")   # override: A/B builds
 
 CT_MAX_SECTIONS = 5
-CT_SCAN_STEPS = 5
 
 
 class CtFilterCoef(C.Structure):
     _fields_ = [
         ("nsec", C.c_int32),
-        ("tile_c", C.c_int32),
         ("na1", C.c_float * CT_MAX_SECTIONS),
         ("na2", C.c_float * CT_MAX_SECTIONS),
         ("n1", C.c_float * CT_MAX_SECTIONS),
         ("n2", C.c_float * CT_MAX_SECTIONS),
-        ("AC", (C.c_float * 4) * CT_MAX_SECTIONS),
-        ("M", ((C.c_float * 4) * CT_SCAN_STEPS) * CT_MAX_SECTIONS),
         ("ss", C.c_float * CT_MAX_SECTIONS),
         ("gain", C.c_float),
     ]
@@ -47,18 +43,18 @@ SIGNATURES = {
     "ct_launch_count": (C.c_uint64, []),
     "ct_launch_count_reset": (None, []),
     "ct_device_info": (C.c_int, [_vp, _vp, _vp, _vp]),
-    "ct_filter_tile": (C.c_int, []),
-    "ct_filter_chunk": (C.c_int, []),
     "ct_filter_seq_tile": (C.c_int, []),
+    "ct_filter_decimation": (C.c_int, [C.POINTER(CtFilterCoef), _i64, C.c_int]),
+    "ct_filter_summary_count": (_i64, [_i64, _i64, C.c_int]),
     "ct_filtfilt_workspace_bytes": (_i64, [_i64, _i64, C.c_int]),
     "ct_filtfilt_stats_granule": (_i64, [_i64, _i64, C.c_int]),
     "ct_filter_forward_u16": (C.c_int, [_vp, _i64, _i64, _f32, _u16, _f32, C.POINTER(CtFilterCoef), C.c_int, _i64, C.c_int,
                                         _u32, _u32, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
-    "ct_filter_backward": (C.c_int, [_i64, _i64, _f32, _f32, C.POINTER(CtFilterCoef), C.c_int, _i64, _vp, _vp, _i64,
-                                     C.POINTER(CtFilterStats), _vp]),
+    "ct_filter_backward": (C.c_int, [_i64, _i64, _f32, _f32, _f32, C.POINTER(CtFilterCoef), C.c_int, _i64, _vp, _vp, _i64,
+                                     C.POINTER(CtFilterStats), _vp, _vp]),
     "ct_filtfilt_u16": (C.c_int, [_vp, _i64, _i64, _f32, _u16, _f32, _f32, C.POINTER(CtFilterCoef),
-                                  C.c_int, C.c_int, C.c_int, _vp, _vp, _i64, C.POINTER(CtFilterStats), _vp]),
-    "ct_filtfilt_f32": (C.c_int, [_vp, _i64, _i64, _f32, C.POINTER(CtFilterCoef), C.c_int, C.c_int,
+                                  C.c_int, C.c_int, _vp, _vp, _i64, C.POINTER(CtFilterStats), _vp]),
+    "ct_filtfilt_f32": (C.c_int, [_vp, _i64, _i64, _f32, C.POINTER(CtFilterCoef), C.c_int,
                                   C.c_int, _vp, _vp, _i64, C.POINTER(CtFilterStats), _vp]),
     "ct_hist_sampled_u16": (C.c_int, [_vp, _i64, _i64, _u16, _vp, _vp]),
     "ct_count_window_u16": (C.c_int, [_vp, _i64, _u16, _u32, _u32, _vp, _vp]),
@@ -66,7 +62,7 @@ SIGNATURES = {
     "ct_block_stats_f32": (C.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, C.c_int, _vp, _vp, _vp, _vp]),
     "ct_detect_run": (C.c_int, []),
     "ct_detect_workspace_bytes": (_i64, [_i64]),
-    "ct_detect_f32": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "ct_detect_f32": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "ct_welch_workspace_bytes": (_i64, [_i32, _i32]),
     "ct_welch_f32": (C.c_int, [_vp, _i64, _i32, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "ct_bin_be_f64_to_f32": (C.c_int, [_vp, _i64, _vp, _vp]),

@@ -115,6 +115,97 @@ ct_detect_pass1(const float* __restrict__ y, long long n, long long block,
     }
 }
 
+// Pass 1 from chunk extrema.  The filter's backward pass leaves (min, max) of every 64-sample chunk of its output
+// (ct_filter_backward, chunk_minmax); against the block's two lines a chunk is almost always decided as a whole -
+// every sample back beyond the end line (baseline), every sample beyond the start line (inside a deep event) or
+// neither - and only the chunks that hold a crossing are read from the trace (32 lanes x 2 samples, four ballots).
+// Same masks, same run summaries as ct_detect_pass1, at 1/32 of its traffic.  One warp per run of 4096 samples;
+// lane l owns chunks 2l, 2l+1 = mask words 4l .. 4l+3.
+__global__ void __launch_bounds__(kDetWarps * 32)
+ct_detect_pass1_minmax(const float* __restrict__ y, long long n, long long block,
+                       const int* __restrict__ sign, const float* __restrict__ t_start,
+                       const float* __restrict__ t_end, const float2* __restrict__ mm, long long mm_shift,
+                       uint2* __restrict__ masks, RunSummary* __restrict__ summ, long long nruns) {
+    const int lane = ct_lane();
+    const int wib = threadIdx.x >> 5;
+    const long long run = (long long)blockIdx.x * kDetWarps + wib;
+    if (run >= nruns) return;
+    const long long base = run * kRun;
+    const long long kb = base / block;
+    const float sgn = sign[kb] > 0 ? 1.f : -1.f;
+    const float ts = sgn * t_start[kb], te = sgn * t_end[kb];
+    const long long c0 = (base + mm_shift) >> 6;             // first chunk of the run
+    unsigned A[4], B[4];
+    bool mixed[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const long long cb = base + (2 * lane + k) * 64;     // first sample of the chunk
+        bool mix = true;
+        unsigned a = 0, b = 0;
+        if (cb + 64 <= n) {
+            const float2 e = mm[c0 + 2 * lane + k];
+            const float lo = sgn > 0.f ? e.x : -e.y, hi = sgn > 0.f ? e.y : -e.x;     // extrema of sgn * v
+            if (hi < ts) { a = 0xffffffffu; mix = false; }                // every sample beyond the start line
+            else if (lo >= ts && lo > te) { b = 0xffffffffu; mix = false; }   // every sample back beyond the end line
+            else if (lo >= ts && hi <= te) mix = false;                   // no symbol at all
+        } else if (cb >= n) mix = false;                                  // past the data: no symbol
+        A[2 * k] = A[2 * k + 1] = a; B[2 * k] = B[2 * k + 1] = b;
+        mixed[k] = mix;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        unsigned todo = __ballot_sync(CT_FULL, mixed[k]);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long p0 = base + (2 * src + k) * 64 + lane, p1 = p0 + 32;
+            const float v0 = p0 < n ? sgn * y[p0] : te, v1 = p1 < n ? sgn * y[p1] : te;   // == te is neither symbol
+            const unsigned a0 = __ballot_sync(CT_FULL, v0 < ts), b0 = __ballot_sync(CT_FULL, v0 > te);
+            const unsigned a1 = __ballot_sync(CT_FULL, v1 < ts), b1 = __ballot_sync(CT_FULL, v1 > te);
+            if (lane == src) { A[2 * k] = a0; B[2 * k] = b0; A[2 * k + 1] = a1; B[2 * k + 1] = b1; }
+        }
+    }
+    uint4* mout = reinterpret_cast<uint4*>(masks + run * kRunWords + 4 * lane);
+    mout[0] = make_uint4(A[0], B[0], A[1], B[1]);
+    mout[1] = make_uint4(A[2], B[2], A[3], B[3]);
+    // the lane's four words as one map on the state: identity, or constant = its last symbol
+    unsigned lastIn = 0, firstIn = 0, any = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const unsigned nz = A[w] | B[w];
+        if (nz) {
+            if (!any) firstIn = (A[w] >> (__ffs(nz) - 1)) & 1u;
+            lastIn = (A[w] >> (31 - __clz(nz))) & 1u;
+            any = 1;
+        }
+    }
+    const unsigned nzmask = __ballot_sync(CT_FULL, any != 0);
+    const unsigned lastmask = __ballot_sync(CT_FULL, lastIn != 0);
+    const unsigned firstmask = __ballot_sync(CT_FULL, firstIn != 0);
+    const unsigned lower = nzmask & ((1u << lane) - 1u);
+    unsigned c = lower ? ((lastmask >> (31 - __clz(lower))) & 1u) : 0u;     // a run is evaluated as if it began outside
+    unsigned ns = 0, ne = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const unsigned cprev = c;
+        const unsigned I = automaton_word(A[w], B[w], c);
+        const unsigned prev = (I << 1) | cprev;
+        ns += __popc(I & ~prev);
+        ne += __popc(~I & prev);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(CT_FULL, ns, o); ne += __shfl_xor_sync(CT_FULL, ne, o); }
+    if (lane == 0) {
+        unsigned first = 0, last = 0;
+        if (nzmask) {
+            first = ((firstmask >> (__ffs(nzmask) - 1)) & 1u) ? 1u : 2u;
+            last = ((lastmask >> (31 - __clz(nzmask))) & 1u) ? 1u : 2u;
+        }
+        RunSummary s; s.first_last = first | (last << 2); s.ns0 = ns; s.ne0 = ne; s.pad = 0;
+        summ[run] = s;
+    }
+}
+
 // ---- hierarchical chained scan over run summaries -----------------------------------
 // counts of a summary given the true incoming state (1 = inside)
 __device__ __forceinline__ void adjusted(const RunSummary& s, unsigned st, unsigned& a, unsigned& b) {
@@ -509,8 +600,8 @@ int ct_block_stats_f32(const float* y, int64_t n, int64_t block, float bmin, flo
 }
 
 int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign, const float* t_start,
-                  const float* t_end, int state_in, void* workspace, int64_t workspace_bytes,
-                  int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream) {
+                  const float* t_end, int state_in, const float* chunk_minmax, int64_t minmax_shift, void* workspace,
+                  int64_t workspace_bytes, int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream) {
     if (!y || !sign || !t_start || !t_end || !workspace || !starts || !ends || !counts2 || n < 0) {
         ct_set_error("detect: bad argument"); return CT_ERR_ARG;
     }
@@ -530,8 +621,16 @@ int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign,
     uint4* ginfo = (uint4*)w;            w += al(ng * 16);
     unsigned long long* goffs = (unsigned long long*)w;
     long long g1 = (nruns + kDetWarps - 1) / kDetWarps;
+    if (chunk_minmax && (minmax_shift < 0 || minmax_shift % 64 || (reinterpret_cast<uintptr_t>(chunk_minmax) & 7))) {
+        ct_set_error("detect: chunk extrema need an 8-byte aligned array and a shift that is a multiple of 64"); return CT_ERR_ARG;
+    }
     CT_COUNT_LAUNCH();
-    ct_detect_pass1<<<(unsigned)g1, kDetWarps * 32, 0, st>>>(y, n, block, sign, t_start, t_end, masks, summ, nruns);
+    if (chunk_minmax)
+        ct_detect_pass1_minmax<<<(unsigned)g1, kDetWarps * 32, 0, st>>>(y, n, block, sign, t_start, t_end,
+                                                                        reinterpret_cast<const float2*>(chunk_minmax), minmax_shift,
+                                                                        masks, summ, nruns);
+    else
+        ct_detect_pass1<<<(unsigned)g1, kDetWarps * 32, 0, st>>>(y, n, block, sign, t_start, t_end, masks, summ, nruns);
     int rc = ct_check_launch("ct_detect_pass1"); if (rc) return rc;
     CT_COUNT_LAUNCH();
     ct_detect_scan_groups<<<(unsigned)((ng + 127) / 128), 128, 0, st>>>(summ, nruns, gsum, ng);

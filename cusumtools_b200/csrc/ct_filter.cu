@@ -1,557 +1,10 @@
-// Fused dequantise + median-pad + zero-phase Bessel (filtfilt) for sm_100a.
-//
-// Replaces, for the hot path of reference plot-trace.py:
-//   scale_raw_data (:272-287)  ->  affine map folded into the load / the epilogue FMA
-//   np.pad(mode='median', 1000) (:318-319)  ->  "virtual" pad: the kernel works on
-//       x' = code - median_code, which is 0 in the pad, so the pad is never materialised
-//   filtfilt(b, a, padded, padtype=None) (:320)  ->  forward + backward cascade of
-//       all-pole second-order sections with (1+z^-1)^2 numerators, in ONE kernel:
-//       HBM sees one 2-byte read and one 4-byte write per sample.
-//
-// Parallelisation of the sequential IIR (DESIGN.md "filter kernel"):
-//   * a WARP owns a sub-segment of S output samples and sweeps it in tiles of 32*C
-//     samples (lane l holds C consecutive samples in registers);
-//   * per section: every lane runs the recursion over its chunk from zero state, the
-//     32 chunk-final states are combined by a warp-shuffle Kogge-Stone scan over the
-//     2x2 affine state maps (the matrices A^(C*2^k) are constants), the tile-to-tile
-//     carry is injected at lane 0, and the lanes re-run their chunk from the now exact
-//     incoming state, emitting the section output in place;
-//   * the forward result of the sub-segment (+ H warm-up samples to its right) stays
-//     in shared memory (bank-conflict-free XOR-swizzled 16-byte units); the backward
-//     sweep consumes it top-down and writes the final samples to global memory;
-//   * sub-segments are independent: each starts its recursions H samples early from
-//     zero state, H chosen on the host so the truncated natural response is < eps.
-//
-// Boundary semantics identical to the reference (scipy/_signaltools.py:4897-4913):
-// forward initial state = steady state of padded[0] (the median => zero in x'),
-// backward initial state = steady state of the last forward output.
+// C-ABI entry points of stage 1 (dequantise + median pad + zero-phase Bessel; plot-trace.py:272-287, 313-320)
+// and the exact median of the masked codes that np.pad(mode='median') needs (plot-trace.py:319).
+// The filter passes themselves live in ct_filter_seq.cu.
 #include "ct_common.cuh"
 #include "cusumtools_b200.h"
 
 namespace {
-
-constexpr int kC = 16;              // samples per lane per tile
-constexpr int kT = 32 * kC;         // tile = 512 samples
-constexpr int kWarpsPerCta = 4;
-
-struct FilterArgs {
-    const void* in;
-    float* out;
-    long long n;          // samples
-    long long pad;        // reference's constant pad length (1000)
-    int S;                // sub-segment length (multiple of kT)
-    int H;                // warm-up halo (multiple of kT)
-    float sub;            // value subtracted from the input (median code / pad value)
-    unsigned mask2;       // ADC bitmask replicated in both halves (u16 input)
-    float out_scale;      // pA per code (alpha) or 1
-    float out_offset;     // pad value in output units
-    int in_aligned;       // input base 16-byte aligned
-    int out_aligned;      // output base 16-byte aligned
-};
-
-template <int C>
-__device__ __forceinline__ int swz(int lane) {
-    constexpr int U = C / 4;                 // 16-byte units per lane chunk
-    return (lane / (8 / U)) & (U - 1);
-}
-
-// ---- one cascade pass (all sections) over the C samples a lane holds ----------------
-template <int NSEC, int C>
-__device__ __forceinline__ void cascade_tile(float (&x)[C], float (&carry)[NSEC][2],
-                                             const CtFilterCoef& k, int lane) {
-#pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        const float na1 = k.na1[s], na2 = k.na2[s];
-        // (1) zero-state run: only the chunk-final state is needed
-        float v1 = 0.f, v2 = 0.f;
-#pragma unroll
-        for (int e = 0; e < C; ++e) {
-            float v = fmaf(na1, v1, fmaf(na2, v2, x[e]));
-            v2 = v1; v1 = v;
-        }
-        // (2) inject the tile carry at lane 0: f_0 += A^C * carry
-        if (lane == 0) {
-            v1 = fmaf(k.AC[s][0], carry[s][0], fmaf(k.AC[s][1], carry[s][1], v1));
-            v2 = fmaf(k.AC[s][2], carry[s][0], fmaf(k.AC[s][3], carry[s][1], v2));
-        }
-        // (3) inclusive Kogge-Stone scan of the affine maps across lanes
-#pragma unroll
-        for (int st = 0; st < 5; ++st) {
-            const int d = 1 << st;
-            float t1 = __shfl_up_sync(CT_FULL, v1, d);
-            float t2 = __shfl_up_sync(CT_FULL, v2, d);
-            if (lane >= d) {
-                v1 = fmaf(k.M[s][st][0], t1, fmaf(k.M[s][st][1], t2, v1));
-                v2 = fmaf(k.M[s][st][2], t1, fmaf(k.M[s][st][3], t2, v2));
-            }
-        }
-        // (4) incoming state of this lane = end state of the previous lane
-        float i1 = __shfl_up_sync(CT_FULL, v1, 1);
-        float i2 = __shfl_up_sync(CT_FULL, v2, 1);
-        if (lane == 0) { i1 = carry[s][0]; i2 = carry[s][1]; }
-        carry[s][0] = __shfl_sync(CT_FULL, v1, 31);
-        carry[s][1] = __shfl_sync(CT_FULL, v2, 31);
-        // (5) exact run from the incoming state, numerator applied on the way out
-        const float n1 = k.n1[s], n2 = k.n2[s];
-        v1 = i1; v2 = i2;
-        if (s == NSEC - 1) {
-            const float g = k.gain, g1 = n1 * k.gain, g2 = n2 * k.gain;
-#pragma unroll
-            for (int e = 0; e < C; ++e) {
-                float v = fmaf(na1, v1, fmaf(na2, v2, x[e]));
-                x[e] = fmaf(g1, v1, fmaf(g2, v2, g * v));
-                v2 = v1; v1 = v;
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < C; ++e) {
-                float v = fmaf(na1, v1, fmaf(na2, v2, x[e]));
-                x[e] = fmaf(n1, v1, fmaf(n2, v2, v));
-                v2 = v1; v1 = v;
-            }
-        }
-    }
-}
-
-// ---- input tile: positions p0 .. p0+C-1 of the virtual (median-subtracted) signal ---
-template <int C>
-__device__ __forceinline__ void load_chunk(const FilterArgs& a, const uint16_t* in, long long p0,
-                                           float (&x)[C]) {
-    if (a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
-#pragma unroll
-        for (int u = 0; u < C / 8; ++u) {
-            uint4 w = ct_ldg_stream(in + p0 + u * 8);
-            unsigned ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                unsigned m = ww[j] & a.mask2;
-                x[u * 8 + 2 * j]     = (float)(int)(m & 0xffffu) - a.sub;
-                x[u * 8 + 2 * j + 1] = (float)(int)(m >> 16) - a.sub;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < C; ++e) {
-            long long p = p0 + e;
-            x[e] = (p >= 0 && p < a.n) ? (float)(int)(in[p] & (a.mask2 & 0xffffu)) - a.sub : 0.f;
-        }
-    }
-}
-template <int C>
-__device__ __forceinline__ void load_chunk(const FilterArgs& a, const float* in, long long p0,
-                                           float (&x)[C]) {
-    if (a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
-#pragma unroll
-        for (int u = 0; u < C / 4; ++u) {
-            uint4 w = ct_ldg_stream(in + p0 + u * 4);
-            x[u * 4 + 0] = __uint_as_float(w.x) - a.sub;
-            x[u * 4 + 1] = __uint_as_float(w.y) - a.sub;
-            x[u * 4 + 2] = __uint_as_float(w.z) - a.sub;
-            x[u * 4 + 3] = __uint_as_float(w.w) - a.sub;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < C; ++e) {
-            long long p = p0 + e;
-            x[e] = (p >= 0 && p < a.n) ? in[p] - a.sub : 0.f;
-        }
-    }
-}
-
-// output chunk for positions p0..p0+C-1, values given in position order
-template <int C>
-__device__ __forceinline__ void store_chunk(const FilterArgs& a, long long p0, const float (&y)[C]) {
-    if (a.out_aligned && p0 >= 0 && p0 + C <= a.n) {
-#pragma unroll
-        for (int u = 0; u < C / 4; ++u) {
-            float4 v;
-            v.x = fmaf(y[u * 4 + 0], a.out_scale, a.out_offset);
-            v.y = fmaf(y[u * 4 + 1], a.out_scale, a.out_offset);
-            v.z = fmaf(y[u * 4 + 2], a.out_scale, a.out_offset);
-            v.w = fmaf(y[u * 4 + 3], a.out_scale, a.out_offset);
-            ct_stg_stream(a.out + p0 + u * 4, v);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < C; ++e) {
-            long long p = p0 + e;
-            if (p >= 0 && p < a.n) a.out[p] = fmaf(y[e], a.out_scale, a.out_offset);
-        }
-    }
-}
-
-// swizzled shared-memory index of relative position r (>= 0) inside the warp's y1 store
-template <int C>
-__device__ __forceinline__ int y1_index(int r) {
-    constexpr int T = 32 * C;
-    int tile = r / T, w = r % T, l = w / C, e = w % C;
-    return tile * T + l * C + (((e >> 2) ^ swz<C>(l)) << 2) + (e & 3);
-}
-
-template <int NSEC, int C, typename InT, bool FWD_ONLY>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-ct_filtfilt_kernel(FilterArgs a, CtFilterCoef k, long long nseg) {
-    constexpr int T = 32 * C;
-    extern __shared__ __align__(16) float smem[];
-    const int lane = ct_lane();
-    const int wib = threadIdx.x >> 5;
-    float* y1 = smem + (size_t)wib * (size_t)(a.S + a.H);
-    const InT* in = reinterpret_cast<const InT*>(a.in);
-    const long long gw = (long long)blockIdx.x * kWarpsPerCta + wib;
-    const long long nw = (long long)gridDim.x * kWarpsPerCta;
-    const long long top = ((a.n + a.pad + T - 1) / T) * T;
-    const int sw = swz<C>(lane);
-
-    for (long long seg = gw; seg < nseg; seg += nw) {
-        const long long s0 = seg * a.S, s1 = s0 + a.S;
-        long long q0 = s0 - a.H; if (q0 < 0) q0 = 0;
-        long long q1 = FWD_ONLY ? s1 : (s1 + a.H < top ? s1 + a.H : top);
-        if (FWD_ONLY && q1 > top) q1 = top;
-
-        float carry[NSEC][2];
-#pragma unroll
-        for (int s = 0; s < NSEC; ++s) { carry[s][0] = 0.f; carry[s][1] = 0.f; }
-
-        // ------------------------------ forward sweep ------------------------------
-        for (long long t = q0; t < q1; t += T) {
-            float x[C];
-            load_chunk<C>(a, in, t + (long long)lane * C, x);
-            cascade_tile<NSEC, C>(x, carry, k, lane);
-            if (FWD_ONLY) {
-                if (t >= s0) store_chunk<C>(a, t + (long long)lane * C, x);
-            } else if (t >= s0) {
-                float* dst = y1 + (size_t)(t - s0) + lane * C;
-#pragma unroll
-                for (int u = 0; u < C / 4; ++u)
-                    *reinterpret_cast<float4*>(dst + ((u ^ sw) << 2)) =
-                        make_float4(x[u * 4], x[u * 4 + 1], x[u * 4 + 2], x[u * 4 + 3]);
-            }
-        }
-        if (FWD_ONLY) continue;
-
-        // ---- right end: the forward output is held constant beyond the pad (that is
-        // ---- what "steady-state initial condition zi*y[-1]" means for the backward pass)
-        __syncwarp();
-        float c = 0.f;
-        const long long last = a.n + a.pad - 1;
-        if (q1 > last + 1) {
-            c = y1[y1_index<C>((int)(last - s0))];
-            __syncwarp();
-            for (long long p = last + 1 + lane; p < q1; p += 32) y1[y1_index<C>((int)(p - s0))] = c;
-            __syncwarp();
-        }
-#pragma unroll
-        for (int s = 0; s < NSEC; ++s) { carry[s][0] = c * k.ss[s]; carry[s][1] = carry[s][0]; }
-
-        // ------------------------------ backward sweep -----------------------------
-        for (long long t = q1 - T; t >= s0; t -= T) {
-            // lane j walks the chunk of forward lane 31-j in decreasing time
-            const int fl = 31 - lane;
-            const int fsw = swz<C>(fl);
-            const float* src = y1 + (size_t)(t - s0) + fl * C;
-            float x[C];
-#pragma unroll
-            for (int u = 0; u < C / 4; ++u) {
-                float4 v = *reinterpret_cast<const float4*>(src + ((u ^ fsw) << 2));
-                x[C - 1 - (u * 4 + 0)] = v.x;
-                x[C - 1 - (u * 4 + 1)] = v.y;
-                x[C - 1 - (u * 4 + 2)] = v.z;
-                x[C - 1 - (u * 4 + 3)] = v.w;
-            }
-            cascade_tile<NSEC, C>(x, carry, k, lane);
-            if (t < s1 && t < a.n) {      // halo tiles (t >= s1) only warm the recursion up
-                float y[C];
-#pragma unroll
-                for (int e = 0; e < C; ++e) y[e] = x[C - 1 - e];
-                store_chunk<C>(a, t + (long long)fl * C, y);
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// =====================================================================================
-// Dual-stream zero-phase kernel (the production filtfilt path).
-//
-// A warp walks its contiguous run of sub-segments as a software pipeline: in phase k it
-// runs the FORWARD sweep of segment k and the BACKWARD sweep of segment k-1 in lock step,
-// one tile of each per super-step.  The two sweeps execute the same cascade, so they are
-// packed into the two halves of float2 registers and issued as FFMA2 (fma.rn.f32x2, new
-// in sm_100): half the issue slots for the same work, and two independent dependency
-// chains per warp.  They also run in anti-phase on the shared-memory store of forward
-// results: the backward sweep drains slot i in the same super-step in which the forward
-// sweep refills it, so ONE (S+H)-float buffer serves both segments (twice as many
-// streams per SM as buffer-per-segment).
-// Global traffic uses 256-bit LDG/STG (32 B = one sector per lane per instruction).
-// =====================================================================================
-typedef float2 f2;
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 splat(float v) { return make_float2(v, v); }
-__device__ __forceinline__ f2 shfl_up2(f2 v, int d) {
-    return make_float2(__shfl_up_sync(CT_FULL, v.x, d), __shfl_up_sync(CT_FULL, v.y, d));
-}
-__device__ __forceinline__ f2 shfl_idx2(f2 v, int l) {
-    return make_float2(__shfl_sync(CT_FULL, v.x, l), __shfl_sync(CT_FULL, v.y, l));
-}
-
-struct u8x { unsigned w[8]; };
-static __device__ __forceinline__ u8x ldg256(const void* p) {
-    u8x r;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
-                   "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
-    return r;
-}
-static __device__ __forceinline__ void stg256(void* p, const float* f) {
-    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
-                 : "memory");
-}
-
-// Per-lane masked scan matrices: entry [s][st][0] is zero, [s][st][1] is A^(C*2^st) (st < 5)
-// or A^C (st == 5, the tile-carry injection).  A lane reads [lane >= 2^st] (or [lane == 0]),
-// so the Kogge-Stone update "v += M t for lanes >= d" becomes four UNCONDITIONAL FFMA2 with
-// no predicate, select or move, and the coefficients arrive with one LDS.128.
-struct ScanTab { float4 m[CT_MAX_SECTIONS][6][2]; };
-
-__device__ __forceinline__ void scan_fma(f2& v1, f2& v2, f2 t1, f2 t2, float4 m) {
-    v1 = fma2(splat(m.x), t1, fma2(splat(m.y), t2, v1));
-    v2 = fma2(splat(m.z), t1, fma2(splat(m.w), t2, v2));
-}
-
-template <int NSEC, int C>
-__device__ __forceinline__ void cascade_tile2(f2 (&x)[C], f2 (&carry)[NSEC][2], const CtFilterCoef& k,
-                                              int lane, const float4* const (&tp)[6]) {
-#pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        const f2 na1 = splat(k.na1[s]), na2 = splat(k.na2[s]);
-        // zero-state run (the first two steps have no history)
-        f2 v2 = x[0], v1 = fma2(na1, x[0], x[1]);
-#pragma unroll
-        for (int e = 2; e < C; ++e) {
-            f2 v = fma2(na1, v1, fma2(na2, v2, x[e]));
-            v2 = v1; v1 = v;
-        }
-        scan_fma(v1, v2, carry[s][0], carry[s][1], tp[5][s * 12]);
-#pragma unroll
-        for (int st = 0; st < 5; ++st) {
-            f2 t1 = shfl_up2(v1, 1 << st), t2 = shfl_up2(v2, 1 << st);
-            scan_fma(v1, v2, t1, t2, tp[st][s * 12]);
-        }
-        f2 i1 = shfl_up2(v1, 1), i2 = shfl_up2(v2, 1);
-        if (lane == 0) { i1 = carry[s][0]; i2 = carry[s][1]; }
-        carry[s][0] = shfl_idx2(v1, 31);
-        carry[s][1] = shfl_idx2(v2, 31);
-        v1 = i1; v2 = i2;
-        if (s == NSEC - 1) {
-            const f2 g = splat(k.gain), g1 = splat(k.n1[s] * k.gain), g2 = splat(k.n2[s] * k.gain);
-#pragma unroll
-            for (int e = 0; e < C; ++e) {
-                f2 v = fma2(na1, v1, fma2(na2, v2, x[e]));
-                x[e] = fma2(g1, v1, fma2(g2, v2, mul2(g, v)));
-                v2 = v1; v1 = v;
-            }
-        } else {
-            const f2 n1 = splat(k.n1[s]), n2 = splat(k.n2[s]);
-#pragma unroll
-            for (int e = 0; e < C; ++e) {
-                f2 v = fma2(na1, v1, fma2(na2, v2, x[e]));
-                x[e] = fma2(n1, v1, fma2(n2, v2, v));
-                v2 = v1; v1 = v;
-            }
-        }
-    }
-}
-
-// raw (unconverted) input chunk of a lane, so the next tile can be prefetched cheaply
-template <int C, typename InT> struct Raw;
-template <int C> struct Raw<C, uint16_t> { u8x v[C / 16]; unsigned valid; };
-template <int C> struct Raw<C, float> { u8x v[C / 8]; unsigned valid; };
-
-template <int C>
-__device__ __forceinline__ void fetch(const FilterArgs& a, const uint16_t* in, long long p0, bool active,
-                                      Raw<C, uint16_t>& r) {
-    if (active && a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
-#pragma unroll
-        for (int u = 0; u < C / 16; ++u) r.v[u] = ldg256(in + p0 + u * 16);
-        r.valid = 0xffffffffu;
-    } else {
-        unsigned valid = 0;
-#pragma unroll
-        for (int u = 0; u < C / 16; ++u)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                long long pa = p0 + u * 16 + 2 * j, pb = pa + 1;
-                bool oa = active && pa >= 0 && pa < a.n, ob = active && pb >= 0 && pb < a.n;
-                unsigned ca = oa ? in[pa] : 0u, cb = ob ? in[pb] : 0u;
-                r.v[u].w[j] = ca | (cb << 16);
-                valid |= (oa ? 1u : 0u) << (u * 16 + 2 * j);
-                valid |= (ob ? 1u : 0u) << (u * 16 + 2 * j + 1);
-            }
-        r.valid = valid;
-    }
-}
-template <int C>
-__device__ __forceinline__ void fetch(const FilterArgs& a, const float* in, long long p0, bool active,
-                                      Raw<C, float>& r) {
-    if (active && a.in_aligned && p0 >= 0 && p0 + C <= a.n) {
-#pragma unroll
-        for (int u = 0; u < C / 8; ++u) r.v[u] = ldg256(in + p0 + u * 8);
-        r.valid = 0xffffffffu;
-    } else {
-        unsigned valid = 0;
-#pragma unroll
-        for (int u = 0; u < C / 8; ++u)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                long long p = p0 + u * 8 + j;
-                bool ok = active && p >= 0 && p < a.n;
-                r.v[u].w[j] = ok ? __float_as_uint(in[p]) : 0u;
-                valid |= (ok ? 1u : 0u) << (u * 8 + j);
-            }
-        r.valid = valid;
-    }
-}
-// converted, median-subtracted samples into the .x halves
-template <int C>
-__device__ __forceinline__ void unpack(const FilterArgs& a, const Raw<C, uint16_t>& r, f2 (&x)[C]) {
-#pragma unroll
-    for (int u = 0; u < C / 16; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            unsigned m = r.v[u].w[j] & a.mask2;
-            const int e = u * 16 + 2 * j;
-            x[e].x = (float)(int)(m & 0xffffu) - a.sub;
-            x[e + 1].x = (float)(int)(m >> 16) - a.sub;
-        }
-    if (r.valid != 0xffffffffu) {            // trace edges only
-#pragma unroll
-        for (int e = 0; e < C; ++e) if (!((r.valid >> e) & 1)) x[e].x = 0.f;
-    }
-}
-template <int C>
-__device__ __forceinline__ void unpack(const FilterArgs& a, const Raw<C, float>& r, f2 (&x)[C]) {
-#pragma unroll
-    for (int u = 0; u < C / 8; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[u * 8 + j].x = __uint_as_float(r.v[u].w[j]) - a.sub;
-    if (r.valid != 0xffffffffu) {
-#pragma unroll
-        for (int e = 0; e < C; ++e) if (!((r.valid >> e) & 1)) x[e].x = 0.f;
-    }
-}
-
-// forward results live in shared memory element-major ([e][lane]) so that every scalar
-// LDS/STS of a warp is bank-conflict free and lands directly in the right register half
-template <int C>
-__device__ __forceinline__ int buf_index(int r, int par, int NB) {
-    constexpr int T = 32 * C;
-    int tile = r / T, w = r % T, l = w / C, e = w % C;
-    int slot = par ? NB - 1 - tile : tile;
-    return slot * T + e * 32 + l;
-}
-
-template <int NSEC, int C, typename InT>
-__global__ void __launch_bounds__(128)
-ct_filtfilt2_kernel(FilterArgs a, CtFilterCoef k, long long nseg) {
-    static_assert(C == 16, "the lane chunk is 16 samples (one 256-bit load of codes)");
-    constexpr int T = 32 * C;
-    extern __shared__ __align__(16) float smem[];
-    const int lane = ct_lane();
-    // warp-uniform by construction: the shuffle lets the compiler keep everything derived
-    // from it (loop bounds, coefficients) in uniform registers
-    const int wib = __shfl_sync(CT_FULL, threadIdx.x >> 5, 0);
-    const int wpc = blockDim.x >> 5;
-    float* buf = smem + (size_t)wib * (size_t)(a.S + a.H);
-    const InT* in = reinterpret_cast<const InT*>(a.in);
-    const long long gw = (long long)blockIdx.x * wpc + wib;
-    const long long nw = (long long)gridDim.x * wpc;
-    const long long per = (nseg + nw - 1) / nw;
-    const long long sb = gw * per;
-    const long long cnt = (sb + per <= nseg ? per : nseg - sb);
-    const int HT = a.H / T, NB = (a.S + a.H) / T, NF = NB + HT;
-    const int fl = 31 - lane;
-    const long long last = a.n + a.pad - 1;
-    float cB = 0.f;   // constant the forward output of the backward stream's segment is held at
-
-    __shared__ ScanTab tab;
-    if (threadIdx.x < NSEC * 6) {
-        const int s = threadIdx.x / 6, st = threadIdx.x % 6;
-        const float* M = st < 5 ? k.M[s][st] : k.AC[s];
-        tab.m[s][st][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        tab.m[s][st][1] = make_float4(M[0], M[1], M[2], M[3]);
-    }
-    __syncthreads();
-    const float4* tp[6];
-#pragma unroll
-    for (int st = 0; st < 5; ++st) tp[st] = &tab.m[0][st][lane >= (1 << st) ? 1 : 0];
-    tp[5] = &tab.m[0][5][lane == 0 ? 1 : 0];
-    if (cnt <= 0) return;
-
-    for (long long ph = 0; ph <= cnt; ++ph) {
-        const bool vF = ph < cnt, vB = ph >= 1;
-        const long long s0F = (sb + ph) * (long long)a.S;
-        const long long s0B = s0F - a.S;
-        const int par = (int)(ph & 1);
-        f2 carry[NSEC][2];
-#pragma unroll
-        for (int s = 0; s < NSEC; ++s) { carry[s][0] = make_float2(0.f, cB * k.ss[s]); carry[s][1] = carry[s][0]; }
-
-        Raw<C, InT> pre;
-        fetch<C>(a, in, s0F - a.H + (long long)lane * C, vF, pre);
-        for (int u = 0; u < NF; ++u) {
-            f2 x[C];
-            unpack<C>(a, pre, x);
-            if (u + 1 < NF) fetch<C>(a, in, s0F - a.H + (long long)(u + 1) * T + (long long)lane * C, vF, pre);
-            const int ai = u - HT;                       // stored forward tile == backward tile index
-            const bool st = ai >= 0;
-            float* tb = buf + (size_t)(par ? NB - 1 - ai : ai) * T;
-            if (st && vB) {
-#pragma unroll
-                for (int e = 0; e < C; ++e) x[C - 1 - e].y = tb[e * 32 + fl];
-            } else {
-#pragma unroll
-                for (int e = 0; e < C; ++e) x[e].y = 0.f;
-            }
-            __syncwarp();
-            cascade_tile2<NSEC, C>(x, carry, k, lane, tp);
-            if (st && vF) {
-#pragma unroll
-                for (int e = 0; e < C; ++e) tb[e * 32 + lane] = x[e].x;
-            }
-            if (st && vB) {
-                const long long tB = s0B + a.S + a.H - (long long)(ai + 1) * T;
-                if (tB < s0B + a.S && tB < a.n) {          // owned tile (halo tiles only warm up)
-                    const long long p0 = tB + (long long)fl * C;
-                    float y[C];
-#pragma unroll
-                    for (int e = 0; e < C; ++e) y[e] = fmaf(x[C - 1 - e].y, a.out_scale, a.out_offset);
-                    if (a.out_aligned && p0 + C <= a.n) {
-                        stg256(a.out + p0, y);
-                        stg256(a.out + p0 + 8, y + 8);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < C; ++e) if (p0 + e < a.n) a.out[p0 + e] = y[e];
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        // right end of the trace: hold the forward output constant beyond the pad, which is
-        // what the steady-state initial condition zi*y[-1] of the backward pass means
-        cB = 0.f;
-        if (vF && s0F + a.S + a.H > last + 1) {
-            float c = buf[buf_index<C>((int)(last - s0F), par, NB)];
-            __syncwarp();
-            for (long long p = last + 1 + lane; p < s0F + a.S + a.H; p += 32)
-                buf[buf_index<C>((int)(p - s0F), par, NB)] = c;
-            __syncwarp();
-            cB = c;
-        }
-    }
-}
-
 // ------------------------------ exact median of u16 codes ----------------------------
 // Sampled histogram (estimate) + exact window count (verification); the host replays the
 // reference's scale_raw_data on the selected code(s) so the pad value is bit-identical
@@ -655,73 +108,6 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
     }
 }
 
-template <int NSEC, typename InT, bool FWD>
-int launch_filter(const FilterArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    long long nseg = (a.n + a.S - 1) / a.S;
-    if (FWD) {
-        auto kern = ct_filtfilt_kernel<NSEC, kC, InT, true>;
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, 0);
-        if (occ < 1) occ = 1;
-        long long want = (nseg + kWarpsPerCta - 1) / kWarpsPerCta;
-        long long grid = (long long)ct_sm_count() * occ;
-        if (grid > want) grid = want;
-        if (grid < 1) grid = 1;
-        CT_COUNT_LAUNCH();
-        kern<<<(unsigned)grid, kWarpsPerCta * 32, 0, st>>>(a, k, nseg);
-        return ct_check_launch("ct_filtfilt_kernel");
-    }
-    auto kern = ct_filtfilt2_kernel<NSEC, kC, InT>;
-    // warps per CTA: as many resident warps per SM as the shared-memory buffers allow
-    const size_t per_warp = (size_t)(a.S + a.H) * sizeof(float);
-    int best_w = 0, best_occ = 0, best_total = 0;
-    for (int w = 4; w >= 1; w >>= 1) {
-        size_t smem = per_warp * w;
-        if (smem > (size_t)ct_max_smem_optin()) continue;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, smem);
-        if (occ * w > best_total) { best_total = occ * w; best_w = w; best_occ = occ; }
-    }
-    if (!best_w) {
-        ct_set_error("filter: sub-segment + halo (%d + %d samples) does not fit in shared memory", a.S, a.H);
-        return CT_ERR_UNSUPPORTED;
-    }
-    size_t smem = per_warp * best_w;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long grid = (long long)ct_sm_count() * best_occ;
-    long long want = (nseg + best_w - 1) / best_w;
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
-    CT_COUNT_LAUNCH();
-    kern<<<(unsigned)grid, best_w * 32, smem, st>>>(a, k, nseg);
-    return ct_check_launch("ct_filtfilt2_kernel");
-}
-
-template <typename InT, bool FWD>
-int dispatch_nsec(const FilterArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    switch (k.nsec) {
-        case 1: return launch_filter<1, InT, FWD>(a, k, st);
-        case 2: return launch_filter<2, InT, FWD>(a, k, st);
-        case 3: return launch_filter<3, InT, FWD>(a, k, st);
-        case 4: return launch_filter<4, InT, FWD>(a, k, st);
-        case 5: return launch_filter<5, InT, FWD>(a, k, st);
-    }
-    ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
-    return CT_ERR_ARG;
-}
-
-int check_common(const void* in, const float* out, long long n, long long pad, int S, int H,
-                 const CtFilterCoef* k) {
-    if (!in || !out || !k) { ct_set_error("filter: null pointer"); return CT_ERR_ARG; }
-    if (n < 0 || pad < 0) { ct_set_error("filter: negative length"); return CT_ERR_ARG; }
-    if (S <= 0 || H < 0 || S % kT || H % kT) {
-        ct_set_error("filter: S and H must be multiples of %d (got %d, %d)", kT, S, H);
-        return CT_ERR_ARG;
-    }
-    if (k->tile_c != kC) { ct_set_error("filter: coefficients built for C=%d, kernel uses %d", k->tile_c, kC); return CT_ERR_ARG; }
-    return CT_OK;
-}
 
 }  // namespace
 
@@ -729,14 +115,13 @@ int check_common(const void* in, const float* out, long long n, long long pad, i
 int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float scale,
                     float offset, const CtFilterCoef* coef, int H, int forward_only, float* out, void* workspace,
                     int64_t workspace_bytes, const CtFilterStats* stats, cudaStream_t st);
-
 int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float pad_x,
                           const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t cw_lo, uint32_t cw_step,
                           int64_t cw_begin, int64_t cw_end, uint64_t* counts9, int64_t from_pos, int64_t to_pos,
                           void* workspace, int64_t workspace_bytes, cudaStream_t st);
-int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H,
+int ct_filter_backward_seq(int64_t n, int64_t pad, float sub, float scale, float offset, const CtFilterCoef* coef, int H,
                            int64_t origin, float* out, const void* workspace, int64_t workspace_bytes,
-                           const CtFilterStats* stats, cudaStream_t st);
+                           const CtFilterStats* stats, float* summaries, cudaStream_t st);
 
 extern "C" {
 
@@ -750,63 +135,33 @@ int ct_filter_forward_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub
                                  (cudaStream_t)stream);
 }
 
-int ct_filter_backward(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H, int64_t origin,
-                       float* out, const void* workspace, int64_t workspace_bytes, const CtFilterStats* stats, void* stream) {
+int ct_filter_backward(int64_t n, int64_t pad, float sub_code, float scale, float offset, const CtFilterCoef* coef, int H,
+                       int64_t origin, float* out, const void* workspace, int64_t workspace_bytes, const CtFilterStats* stats,
+                       float* chunk_minmax, void* stream) {
     if (!out || !coef || n <= 0 || pad < 0 || H < 0 || origin < 0) { ct_set_error("filter_backward: bad argument"); return CT_ERR_ARG; }
-    return ct_filter_backward_seq(n, pad, scale, offset, coef, H, origin, out, workspace, workspace_bytes, stats,
-                                  (cudaStream_t)stream);
+    return ct_filter_backward_seq(n, pad, sub_code, scale, offset, coef, H, origin, out, workspace, workspace_bytes, stats,
+                                  chunk_minmax, (cudaStream_t)stream);
 }
 
-int ct_filter_tile(void) { return kT; }
-int ct_filter_seq_tile(void) { return 32; }
-int ct_filter_chunk(void) { return kC; }
+int ct_filter_seq_tile(void) { return 64; }
 
 int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_code, uint16_t mask,
-                    float alpha, float pad_value, const CtFilterCoef* coef, int S, int H,
+                    float alpha, float pad_value, const CtFilterCoef* coef, int H,
                     int forward_only, float* out, void* workspace, int64_t workspace_bytes, const CtFilterStats* stats,
                     void* stream) {
-    if (S != 0 && stats) { ct_set_error("filter: fused block statistics need the S == 0 path"); return CT_ERR_UNSUPPORTED; }
-    if (S == 0) {                       // lane-sequential passes (the default path)
-        if (!raw || !out || !coef || n < 0 || pad < 0 || H < 0) { ct_set_error("filter: bad argument"); return CT_ERR_ARG; }
-        if (n == 0) return CT_OK;
-        return ct_filtfilt_seq(raw, 0, n, pad, median_code, mask, alpha, pad_value, coef, H, forward_only, out, workspace,
-                               workspace_bytes, stats, (cudaStream_t)stream);
-    }
-    int rc = check_common(raw, out, n, pad, S, H, coef);
-    if (rc) return rc;
+    if (!raw || !out || !coef || n < 0 || pad < 0 || H < 0) { ct_set_error("filter: bad argument"); return CT_ERR_ARG; }
     if (n == 0) return CT_OK;
-    FilterArgs a;
-    a.in = raw; a.out = out; a.n = n; a.pad = pad; a.S = S; a.H = H;
-    a.sub = median_code; a.mask2 = (unsigned)mask | ((unsigned)mask << 16);
-    a.out_scale = alpha; a.out_offset = pad_value;
-    a.in_aligned = (reinterpret_cast<uintptr_t>(raw) & 31) == 0;
-    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    return forward_only ? dispatch_nsec<uint16_t, true>(a, *coef, st)
-                        : dispatch_nsec<uint16_t, false>(a, *coef, st);
+    return ct_filtfilt_seq(raw, 0, n, pad, median_code, mask, alpha, pad_value, coef, H, forward_only, out, workspace,
+                           workspace_bytes, stats, (cudaStream_t)stream);
 }
 
 int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, const CtFilterCoef* coef,
-                    int S, int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
+                    int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
                     const CtFilterStats* stats, void* stream) {
-    if (S != 0 && stats) { ct_set_error("filter: fused block statistics need the S == 0 path"); return CT_ERR_UNSUPPORTED; }
-    if (S == 0) {
-        if (!x || !out || !coef || n < 0 || pad < 0 || H < 0) { ct_set_error("filter: bad argument"); return CT_ERR_ARG; }
-        if (n == 0) return CT_OK;
-        return ct_filtfilt_seq(x, 1, n, pad, pad_value, 0xffff, 1.f, pad_value, coef, H, forward_only, out, workspace,
-                               workspace_bytes, stats, (cudaStream_t)stream);
-    }
-    int rc = check_common(x, out, n, pad, S, H, coef);
-    if (rc) return rc;
+    if (!x || !out || !coef || n < 0 || pad < 0 || H < 0) { ct_set_error("filter: bad argument"); return CT_ERR_ARG; }
     if (n == 0) return CT_OK;
-    FilterArgs a;
-    a.in = x; a.out = out; a.n = n; a.pad = pad; a.S = S; a.H = H;
-    a.sub = pad_value; a.mask2 = 0xffffffffu; a.out_scale = 1.f; a.out_offset = pad_value;
-    a.in_aligned = (reinterpret_cast<uintptr_t>(x) & 31) == 0;
-    a.out_aligned = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    return forward_only ? dispatch_nsec<float, true>(a, *coef, st)
-                        : dispatch_nsec<float, false>(a, *coef, st);
+    return ct_filtfilt_seq(x, 1, n, pad, pad_value, 0xffff, 1.f, pad_value, coef, H, forward_only, out, workspace,
+                           workspace_bytes, stats, (cudaStream_t)stream);
 }
 
 int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t mask,

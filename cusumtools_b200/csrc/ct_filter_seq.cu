@@ -1,343 +1,387 @@
-// Zero-phase Bessel as two LANE-SEQUENTIAL passes (forward, then backward) for sm_100a.
+// Zero-phase Bessel (plot-trace.py:313-320: filtfilt(b, a, np.pad(data, 1000, 'median'), padtype=None)) as
+// two LANE-SEQUENTIAL passes for sm_100a, staged with TMA.
 //
-// Why: the warp-scan formulation in ct_filter.cu resolves the lane-to-lane carries with a
-// zero-state run + Kogge-Stone scan + exact re-run, ~75 FP32 lane-operations per sample, and
-// is bound by the FMA pipe at 0.26 of the HBM roofline.  Here every lane owns whole RUNS of
-// R consecutive samples and simply executes the recurrence (the reference's own dataflow,
-// scipy _linear_filter, in cascade form): 4 FMA per section and sample, nothing else.  The
-// price is an IIR warm-up of Hw samples per run (|h| tail < eps, Hw/R ~ 6 %) and that the
-// forward output has to live somewhere until the backward pass reads it: an HBM scratch
-// (4 B/sample written + 4 B/sample read).
+// Every lane owns whole RUNS of R consecutive samples and simply executes the recurrence (the reference's
+// own dataflow, scipy _linear_filter, in cascade form): 4 FMA per section and sample.  A run starts Hw
+// samples early (IIR warm-up, |h| tail < eps).  A warp owns 64 adjacent runs: lane l executes run l in the
+// .x halves and run 32+l in the .y halves of float2 registers (FFMA2: two recurrences per issue slot, the
+// only way to the 128 FMA/clk/SM of the B200).
 //
-// Mapping: a warp owns 64 adjacent runs; lane l executes run l in the .x halves and run
-// 32+l in the .y halves of float2 registers (FFMA2: one issue slot for two recurrences).
-//
-// Data movement (the part that decides the speed: a lane-sequential kernel needs a
-// transposition between "lane = run" and "lane = consecutive address"):
-//   * the INPUT of the forward pass (natural layout) is fetched as whole 64/128-byte pieces
-//     with cp.async, one tile ahead, into a per-warp shared-memory tile whose row stride is
-//     bank-conflict free; lanes then walk their own row;
-//   * the SCRATCH between the passes is ours, so it is kept in a lane-interleaved layout:
-//     block ((group, tile, 8-sample slot, half)) = 32 lanes x 8 floats = 1 KB.  The forward
-//     pass writes it and the backward pass reads it with 256-bit accesses straight from /
-//     into registers, fully coalesced, with no shared memory at all;
-//   * the FINAL output (natural layout) is transposed back through shared memory and leaves
-//     as coalesced 128-byte pieces.
+// What decides the speed is the transposition between "lane = run" and "lane = consecutive address":
+//   * forward INPUT (natural layout): one TMA 2-D tile copy per stage (cp.async.bulk.tensor.2d, box =
+//     64 rows (runs, row stride R) x 128 bytes, SWIZZLE_128B, completion on an mbarrier), two stages per
+//     warp; a lane then reads its own row with conflict-free LDS.128.  No per-lane copy instructions, no
+//     address arithmetic, 16 KB of shared memory per warp (14 warps per SM).
+//   * the SCRATCH between the passes is ours: it is kept lane-interleaved (unit = two 8-sample slots of the
+//     32 lanes of one half-warp group, contiguous) so both passes move it with coalesced 128/256-bit accesses
+//     straight from / into registers.  The forward output is band-limited by the filter itself, so only every
+//     D-th sample is kept (D = 1, 2, 4, chosen on the host from the cascade's frequency response: the aliasing
+//     error of "decimate, zero-stuff, filter backward" is max_f |H(f)| |H(f - k fs/D)|, required < 1e-7) and
+//     the backward pass zero-stuffs it; the gain D rides on the forward pass's last section.
+//   * final OUTPUT (natural layout): lanes write their rows into a swizzled half-tile (64 rows x 128 bytes)
+//     and one TMA tile store per half-tile sends it out; dequantisation (offset + alpha*y) is folded into the
+//     last section of the backward cascade (no extra instruction per sample).
+// Groups of 64 runs that touch the ends of the trace (the median pad, partial tiles) take an EDGE
+// instantiation with all the guards; everything else runs guard-free, straight-line code.
 //
 // Section arithmetic:  v[n] = x[n] + na1 v[n-1] + na2 v[n-2]        (all-pole part)
 //                      y[n] = x[n] + (na1+n1) v[n-1] + (na2+n2) v[n-2]   (= v + n1 v1 + n2 v2)
-// so the section output does not wait for v[n]: the cascade's dependent chain is 2 FMA per
-// section, and v[n] is off the critical path.
+// so the section output does not wait for v[n]: the cascade's dependent chain is 2 FMA per section.
+//
+// On its way out the backward pass can also (a) tally the baseline block sums of the final samples
+// (ct_block_stats_f32 semantics, exact integers) and (b) leave the minimum / maximum of every 64-sample
+// chunk, from which the detector classifies whole chunks without re-reading the trace (ct_detect.cu).
 #include "ct_common.cuh"
 #include "cusumtools_b200.h"
+#include <cuda.h>
 #include <math.h>
+#include <string.h>
 
 namespace {
 
-#ifndef CT_SEQ_K
-#define CT_SEQ_K 64
-#endif
-constexpr int kK = CT_SEQ_K;        // samples per run per tile (one contiguous piece of global memory)
-constexpr int kG = kK / 8;          // 8-sample slots per tile
+constexpr int kK = 64;              // samples per run per tile
+constexpr int kG = 8;               // 8-sample slots per tile
 constexpr int kRuns = 64;           // runs per warp (32 lanes x 2 halves)
-constexpr int kRowF = kK + 4;       // float row stride: conflict-free LDS.128 / STS.128
-constexpr int kRowH = kK + 8;       // uint16 row stride in halfwords ((kK+8)/2 words = 4 mod 16: conflict-free LDS.128)
-constexpr int kSeqWarps = 2;
-#ifndef CT_SEQ_STATS_UNROLL
-#define CT_SEQ_STATS_UNROLL 4
-#endif
-#ifndef CT_SEQ_BWD_UNROLL
-#define CT_SEQ_BWD_UNROLL 4
-#endif
-#ifndef CT_SEQ_FWD_UNROLL
-#define CT_SEQ_FWD_UNROLL 2
-#endif
-constexpr int kFwdUnroll = CT_SEQ_FWD_UNROLL;   // same for the forward tile loop (even: the half-rate scratch pairs slots)
-constexpr int kBwdUnroll = CT_SEQ_BWD_UNROLL;   // slots of the backward tile loop unrolled together (multiple of 4: static buffer indices)
-
-enum { kFwdScratch = 0, kFwdFinal = 1, kFwdScratch2 = 2 };   // Scratch2: the scratch holds every second sample
+constexpr int kStage = 8192;        // bytes per shared-memory stage / output half-tile: 64 rows x 128 B
+constexpr int kWarps = 4;           // warps per CTA, one per SM sub-partition; 3 CTAs per SM (16 KB of shared memory per warp)
+constexpr int kCtasPerSm = 3;       // 12 warps per SM: three per scheduler, up to 168 registers each
 
 typedef float2 f2;
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ f2 splat(float v) { return make_float2(v, v); }
 
 struct SeqArgs {
-    const void* in;        // FWD: codes (uint16) or samples (float), natural layout; BWD: interleaved scratch
-    float* out;            // kFwdScratch: interleaved scratch; otherwise the final output, natural layout
+    const void* in;        // FWD: codes (uint16) or samples (float), natural layout; BWD: scratch
+    float* out;            // scratch (FWD) or the final output, natural layout
+    float2* summ;          // BWD, optional: (min, max) of every 64-sample chunk of the output, chunk c = positions base + 64c ..
     long long n_in;        // valid input positions [0, n_in): FWD n, BWD n + pad
     long long n_out;       // final output positions [0, n_out)
-    long long ngroups;     // groups of 64 runs this launch processes
-    long long scratch_runs;// runs the scratch holds (BWD: reads beyond are the held value)
+    long long ngroups;     // groups [g_first, ngroups) are processed
+    long long g_first;
+    long long scratch_runs;// runs the scratch holds
+    long long base;        // position of run 0 (<= 0): aligns groups with baseline blocks
+    unsigned long long* next_group;   // work counter (zeroed by the host): warps fetch groups g_first + counter++ (NULL: static round robin)
     int R, Hw;             // run length, warm-up (multiples of kK, Hw <= R)
-    float sub; unsigned mask; float scale, offset;   // input x' = (code & mask) - sub ; out = offset + scale*y
-    long long base;        // position of run 0 (<= 0): shifts the run grid so that groups align with baseline blocks
-    long long g_first;     // first group to process (partial re-runs of the trace ends)
-    float pad_x;           // FWD: value of x' in the pad and beyond (0 when `sub` is the exact median)
+    int isub; unsigned mask; float fsub;   // uint16: x' = (code & mask) - isub; float: x' = x - fsub
+    float pad_x;           // FWD: x' in the pad and beyond
+    float scale, offset;   // gain / offset folded into the last section (FWD scratch: D, 0)
+    int tma_in, tma_out;   // tensor maps usable (alignment)
     // optional fused window count for the exact median (ct_count_window_u16 semantics), FWD uint16 only
-    unsigned cw_lo; int cw_sh; unsigned long long* cw_out;
-    long long cw_p0, cw_p1; // only codes at positions [cw_p0, cw_p1) are tallied (a shard's owned samples)
+    unsigned cw_lo; int cw_sh; unsigned long long* cw_out; long long cw_p0, cw_p1;
     // optional fused baseline block statistics of the final output (ct_block_stats_f32 semantics)
-    long long st_origin, st_block; float st_min, st_max, st_c0, st_scale, st_nc0s;   // st_nc0s = -c0 * scale (exact)
+    long long st_origin, st_block; float st_min, st_max, st_scale, st_nc0s;
     long long* st_cnt; long long* st_s1; long long* st_s2;
 };
 
-// |q| < 2^31 by construction of the shift (detect.stats_shift: (half_width 2^shift + 1)^2 block < 2^62), so the
-// quantised value fits an int32 (full-rate F2I) and q*q + s2 is one IMAD.WIDE
-// window count for the exact median: see ct_count_window_kernel (ct_filter.cu)
-static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
-    unsigned r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
+// ------------------------------------------------------------------ PTX helpers
+static __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+static __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+static __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(map), "r"(x), "r"(y), "r"(src) : "memory");
+}
+static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> static __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+static __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+static __device__ __forceinline__ uint4 lds128(unsigned addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
-static __device__ __forceinline__ void cw_tally(unsigned code, const SeqArgs& a, unsigned& below, unsigned& c0, unsigned& c1) {
-    const unsigned d = code - a.cw_lo;
-    below += d >> 31;
-    const unsigned amt = a.cw_sh >= 3 ? d >> (a.cw_sh - 3) : d << (3 - a.cw_sh);
-    c0 += shl_clamp(1u, amt);
-    c1 += shl_clamp(1u, amt - 32u);
+static __device__ __forceinline__ void sts128(unsigned addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-static __device__ __forceinline__ void cw_flush(unsigned (&tot)[9], unsigned& below, unsigned& c0, unsigned& c1) {
-    tot[0] += below; below = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { tot[1 + i] += (c0 >> (8 * i)) & 0xffu; tot[5 + i] += (c1 >> (8 * i)) & 0xffu; }
-    c0 = 0; c1 = 0;
-}
+// swizzled (SWIZZLE_128B) byte offset of the 16-byte chunk c of row r inside a stage
+static __device__ __forceinline__ unsigned swz(int r, int c) { return (unsigned)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-struct StatAcc { int c; long long s1, s2; };
-static __device__ __forceinline__ void tally(const SeqArgs& a, StatAcc& acc, float v) {
-    const bool in = v >= a.st_min && v <= a.st_max;
-    const int q = in ? __float2int_rn(__fmul_rn(__fsub_rn(v, a.st_c0), a.st_scale)) : 0;
-    acc.c += in ? 1 : 0; acc.s1 += q; acc.s2 += (long long)q * q;
+template <int F> struct Vec { float v[F]; };
+template <int F> static __device__ __forceinline__ void ldg_vec(const float* p, Vec<F>& r);
+template <> __device__ __forceinline__ void ldg_vec<4>(const float* p, Vec<4>& r) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
 }
-// Four independent partial tallies (one per component of the float4 a lane stores): no serial
-// dependency on one accumulator, 32-bit count and sum (a tile gives a lane 128 samples and fused
-// blocks are >= 2^16 samples, so |q| < 2^23 and the partial sum stays below 2^30).
-struct StatAcc4 { int c[4]; int s1[4]; long long s2[4]; };
-static __device__ __forceinline__ void tally4(const SeqArgs& a, StatAcc4& t, const float4& v) {
-    const float w[4] = {v.x, v.y, v.z, v.w};
+template <> __device__ __forceinline__ void ldg_vec<8>(const float* p, Vec<8>& r) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+}
+template <> __device__ __forceinline__ void ldg_vec<16>(const float* p, Vec<16>& r) {
+    Vec<8> a, b;
+    ldg_vec<8>(p, a); ldg_vec<8>(p + 8, b);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const bool in = w[e] >= a.st_min && w[e] <= a.st_max;
-        // (v - c0) * 2^s in one FFMA: scaling by a power of two commutes with the rounding of the difference
-        const int q = in ? __float2int_rn(__fmaf_rn(w[e], a.st_scale, a.st_nc0s)) : 0;
-        t.c[e] += in ? 1 : 0; t.s1[e] += q; t.s2[e] += (long long)q * q;
-    }
+    for (int i = 0; i < 8; ++i) { r.v[i] = a.v[i]; r.v[8 + i] = b.v[i]; }
 }
-
-struct u8x { unsigned w[8]; };
-static __device__ __forceinline__ u8x ldg256(const void* p) {
-    u8x r;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]),
-                   "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
-    return r;
+template <int F> static __device__ __forceinline__ void stg_vec(float* p, const float* f);
+template <> __device__ __forceinline__ void stg_vec<4>(float* p, const float* f) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
 }
-static __device__ __forceinline__ void stg256(float* p, const float (&f)[8]) {
+template <> __device__ __forceinline__ void stg_vec<8>(float* p, const float* f) {
     asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
 }
-static __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
-}
-static __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> static __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+template <> __device__ __forceinline__ void stg_vec<16>(float* p, const float* f) { stg_vec<8>(p, f); stg_vec<8>(p + 8, f + 8); }
 
-template <typename InT> struct Tile;
-template <> struct Tile<float> { static constexpr int kInBytes = kRuns * kRowF * 4; };
-template <> struct Tile<uint16_t> { static constexpr int kInBytes = kRuns * kRowH * 2; };
-constexpr int kOutBytes = kRuns * kRowF * 4;
-
-// float offset of the 8-sample slot (tile `to`, slot jj) of run `run` in the interleaved scratch
-static __device__ __forceinline__ long long scratch_off(long long run, int to, int jj, int TO) {
+// ------------------------------------------------------------------ scratch layout
+// Unit = the kept samples of one PAIR of slots (16 positions) of one run: F = 16/D floats.  Units of the 32
+// runs of a half-warp group are contiguous (lane-interleaved): float offset of (run, tile to, pair jp).
+template <int D>
+static __device__ __forceinline__ long long scratch_off(long long run, int to, int jp, int TO) {
+    constexpr int F = 16 / D;
     const long long g = run >> 6;
     const int h = (int)(run >> 5) & 1, l = (int)run & 31;
-    return ((((g * TO + to) * kG + jj) * 2 + h) << 8) + l * 8;
+    return ((((g * TO + to) * 4 + jp) * 2 + h) * 32 + l) * F;
 }
 
-// half-rate scratch: one 1 KB block holds the even-position samples of TWO consecutive slots (16 positions)
-static __device__ __forceinline__ long long scratch_off2(long long run, int to, int jp, int TO) {
-    const long long g = run >> 6;
-    const int h = (int)(run >> 5) & 1, l = (int)run & 31;
-    return ((((g * TO + to) * (kG / 2) + jp) * 2 + h) << 8) + l * 8;
-}
-
-// Forward-pass input tile: rows = the K-sample pieces [lo_r, lo_r + K) of the warp's 64 runs.
-// Fast path (whole tile inside the valid domain, 16-byte aligned): cp.async of 16-byte units;
-// otherwise guarded scalar fills (float: the pad value outside; uint16: codes, zeroed later).
-template <typename InT>
-__device__ __forceinline__ void fill_tile(const SeqArgs& a, char* buf, long long run0, long long off, int lane, bool in_aligned) {
-    const InT* in = reinterpret_cast<const InT*>(a.in);
-    constexpr int EPU = 16 / sizeof(InT);                 // elements per 16-byte unit
-    constexpr int LPR = kK / EPU, RPI = 32 / LPR;         // lanes per row, rows per instruction
-    constexpr int kRow = sizeof(InT) == 4 ? kRowF : kRowH;
-    InT* t = reinterpret_cast<InT*>(buf);
-    const long long first = a.base + run0 * a.R + off;
-    if (in_aligned && first >= 0 && first + (kRuns - 1) * (long long)a.R + kK <= a.n_in) {   // whole tile inside (warp-uniform)
-        const InT* src = in + first + (long long)(lane / LPR) * a.R + (lane % LPR) * EPU;
-        InT* dst = t + (lane / LPR) * kRow + (lane % LPR) * EPU;
-        const long long sstep = (long long)RPI * a.R;
-#pragma unroll
-        for (int u = 0; u < kRuns / RPI; ++u) cp_async16(dst + u * RPI * kRow, src + u * sstep);
-        return;
-    }
-#pragma unroll 1
-    for (int u = 0; u < kRuns / RPI; ++u) {                // trace edges: per 16-byte unit
-        const int row = u * RPI + lane / LPR, c = (lane % LPR) * EPU;
-        const long long p = a.base + (run0 + row) * a.R + off + c;
-        InT* dst = t + row * kRow + c;
-        if (in_aligned && p >= 0 && p + EPU <= a.n_in) cp_async16(dst, in + p);
-        else {                                             // float gets the pad value, codes are zeroed later
-#pragma unroll
-            for (int e = 0; e < EPU; ++e) {
-                const long long q = p + e;
-                if (sizeof(InT) == 4) dst[e] = (q >= 0 && q < a.n_in) ? in[q] : (InT)(a.sub + a.pad_x);
-                else dst[e] = (q >= 0 && q < a.n_in) ? in[q] : (InT)0;
-            }
-        }
-    }
-}
-
-// one cascade step for the sample pair u (both halves); returns the cascade output
+// ------------------------------------------------------------------ the cascade
+// one step for the sample pair u (both halves); the last section's output carries gain and offset
 template <int NSEC>
 __device__ __forceinline__ f2 cascade_step(f2 u, f2 (&v1)[NSEC], f2 (&v2)[NSEC], const f2 (&na1)[NSEC], const f2 (&na2)[NSEC],
-                                           const f2 (&c1)[NSEC], const f2 (&c2)[NSEC], const f2 gl) {
+                                           const f2 (&c1)[NSEC], const f2 (&c2)[NSEC], const f2 gl, const f2 off) {
 #pragma unroll
     for (int s = 0; s < NSEC; ++s) {
         const f2 vn = fma2(na1[s], v1[s], fma2(na2[s], v2[s], u));
-        const f2 yo = fma2(c1[s], v1[s], fma2(c2[s], v2[s], s == NSEC - 1 ? __fmul2_rn(gl, u) : u));
+        const f2 yo = fma2(c1[s], v1[s], fma2(c2[s], v2[s], s == NSEC - 1 ? fma2(gl, u, off) : u));
         v2[s] = v1[s]; v1[s] = vn;
         u = yo;
     }
     return u;
 }
-
-// cooperative, coalesced store of the 64 output pieces of one tile, natural layout; STATS: the stored
-// values are tallied into the lane's baseline-block accumulators on their way out
-template <bool STATS>
-__device__ __forceinline__ void store_tile(const SeqArgs& a, const float* outb, long long run0, long long off, int lane,
-                                           bool out_aligned, StatAcc& acc) {
-    constexpr int LPR = kK / 4, RPI = 32 / LPR;
-    const long long first = a.base + run0 * a.R + off;
-    if (out_aligned && first >= 0 && first + (kRuns - 1) * (long long)a.R + kK <= a.n_out) {  // whole tile inside (warp-uniform)
-        float* dst = a.out + first + (long long)(lane / LPR) * a.R + (lane % LPR) * 4;
-        const float* src = outb + (lane / LPR) * kRowF + (lane % LPR) * 4;
-        const long long dstep = (long long)RPI * a.R;
-        StatAcc4 t4;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { t4.c[e] = 0; t4.s1[e] = 0; t4.s2[e] = 0; }
-        // with the tallies the fully unrolled loop is ~1500 instructions: instruction-cache misses became the top stall
-        constexpr int kStoreUnroll = STATS ? CT_SEQ_STATS_UNROLL : kRuns / RPI;
-#pragma unroll (kStoreUnroll)
-        for (int u = 0; u < kRuns / RPI; ++u) {
-            float4 v = *reinterpret_cast<const float4*>(src + u * RPI * kRowF);
-            v.x = fmaf(v.x, a.scale, a.offset); v.y = fmaf(v.y, a.scale, a.offset);
-            v.z = fmaf(v.z, a.scale, a.offset); v.w = fmaf(v.w, a.scale, a.offset);
-            ct_stg_stream(dst + u * dstep, v);
-            if (STATS) tally4(a, t4, v);
-        }
-        if (STATS) {
-            acc.c += (t4.c[0] + t4.c[1]) + (t4.c[2] + t4.c[3]);
-            acc.s1 += ((long long)t4.s1[0] + t4.s1[1]) + ((long long)t4.s1[2] + t4.s1[3]);
-            acc.s2 += (t4.s2[0] + t4.s2[1]) + (t4.s2[2] + t4.s2[3]);
-        }
-        return;
-    }
-#pragma unroll 1
-    for (int u = 0; u < kRuns / RPI; ++u) {                // trace edges: per element
-        const int row = u * RPI + lane / LPR, c = (lane % LPR) * 4;
-        const long long p = a.base + (run0 + row) * a.R + off + c;
-        const float4 v = *reinterpret_cast<const float4*>(outb + row * kRowF + c);
-        const float w[4] = {fmaf(v.x, a.scale, a.offset), fmaf(v.y, a.scale, a.offset), fmaf(v.z, a.scale, a.offset),
-                            fmaf(v.w, a.scale, a.offset)};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (p + e >= 0 && p + e < a.n_out) { a.out[p + e] = w[e]; if (STATS) tally(a, acc, w[e]); }
-    }
-}
-
-// =============================== forward pass ========================================
-template <int NSEC, typename InT, int MODE, bool COUNT>
-__global__ void __launch_bounds__(kSeqWarps * 32)
-ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
-    extern __shared__ __align__(16) char smem[];
-    constexpr int kIn = Tile<InT>::kInBytes;
-    constexpr int kPerWarp = 2 * kIn + (MODE == kFwdFinal ? kOutBytes : 0);
-    static_assert(kG % 2 == 0, "the half-rate scratch pairs slots");
-    const int lane = ct_lane();
-    const int wib = threadIdx.x >> 5;
-    char* wbase = smem + (size_t)wib * kPerWarp;
-    float* outb = reinterpret_cast<float*>(wbase + 2 * kIn);
-    const long long gw = (long long)blockIdx.x * kSeqWarps + wib;
-    const long long nw = (long long)gridDim.x * kSeqWarps;
-    const bool in_aligned = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
-    const bool out_aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
-    const int ntiles = (a.Hw + a.R) / kK, wt = a.Hw / kK, TO = a.R / kK;
-
-    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC];
+template <int NSEC>
+__device__ __forceinline__ void load_coef(const CtFilterCoef& k, float out_gain, f2 (&na1)[NSEC], f2 (&na2)[NSEC], f2 (&c1)[NSEC],
+                                          f2 (&c2)[NSEC], f2& gl) {
 #pragma unroll
     for (int s = 0; s < NSEC; ++s) {
         na1[s] = splat(k.na1[s]); na2[s] = splat(k.na2[s]);
-        const float g = (s == NSEC - 1) ? k.gain : 1.f;   // the overall gain rides on the last section's output
+        const float g = (s == NSEC - 1) ? k.gain * out_gain : 1.f;   // the overall gain rides on the last section's output
         c1[s] = splat((k.na1[s] + k.n1[s]) * g); c2[s] = splat((k.na2[s] + k.n2[s]) * g);
     }
-    const f2 gl = splat(k.gain);
-    const unsigned m2 = a.mask | (a.mask << 16);
+    gl = splat(k.gain * out_gain);
+}
 
-    for (long long g = a.g_first + gw; g < a.ngroups; g += nw) {
-        const long long run0 = g * kRuns;
-        unsigned cw_tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, cw_below = 0, cw_c0 = 0, cw_c1 = 0;
-        int cw_since = 0;
-        f2 v1[NSEC], v2[NSEC];
-        {   // runs that begin in the left pad start from the steady state of the pad value (scipy: zi * x[0])
-            const float p0 = a.base + (run0 + lane) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
-            const float p1 = a.base + (run0 + lane + 32) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
+// ------------------------------------------------------------------ exact-median window count (optional, FWD)
+static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
+    return r;
+}
+struct CwAcc { unsigned tot[9], below, c0, c1; int since; };
+static __device__ __forceinline__ void cw_tally(unsigned code, const SeqArgs& a, CwAcc& w) {
+    const unsigned d = code - a.cw_lo;
+    w.below += d >> 31;
+    const unsigned amt = a.cw_sh >= 3 ? d >> (a.cw_sh - 3) : d << (3 - a.cw_sh);
+    w.c0 += shl_clamp(1u, amt);
+    w.c1 += shl_clamp(1u, amt - 32u);
+}
+static __device__ __forceinline__ void cw_flush(CwAcc& w) {
+    w.tot[0] += w.below; w.below = 0;
 #pragma unroll
-            for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(p0 * k.ss[s], p1 * k.ss[s]); v2[s] = v1[s]; }
+    for (int i = 0; i < 4; ++i) { w.tot[1 + i] += (w.c0 >> (8 * i)) & 0xffu; w.tot[5 + i] += (w.c1 >> (8 * i)) & 0xffu; }
+    w.c0 = 0; w.c1 = 0; w.since = 0;
+}
+
+// ------------------------------------------------------------------ output half-tiles (shared by FWD-final and BWD)
+// Row r (0..63) of half-tile hb holds 32 consecutive floats of run run0 + r.  A lane writes the 8 samples of slot s
+// (0..7 of the tile) of its two runs; after 4 slots the half-tile leaves through one TMA store (interior) or guarded
+// scalar stores (trace edges / unaligned output).
+static __device__ __forceinline__ void out_write_slot(unsigned outb, int lane, int s, const f2 (&y)[8]) {
+    const unsigned hb = (unsigned)(s >> 2) * kStage;
+    const int c = (s & 3) * 2;
+    const unsigned a0 = outb + hb + swz(lane, c), a1 = outb + hb + swz(lane, c + 1);
+    sts128(a0, y[0].x, y[1].x, y[2].x, y[3].x);
+    sts128(a1, y[4].x, y[5].x, y[6].x, y[7].x);
+    sts128(a0 + 32 * 128, y[0].y, y[1].y, y[2].y, y[3].y);
+    sts128(a1 + 32 * 128, y[4].y, y[5].y, y[6].y, y[7].y);
+}
+// guarded copy of half-tile hb (positions first + r*R + [0, 32), r = 0..63) to the natural-layout output
+static __device__ void out_store_guarded(const SeqArgs& a, unsigned outb, int hb, long long first, int lane) {
+    for (int r = 0; r < kRuns; ++r) {
+        const long long p = first + (long long)r * a.R + lane;
+        float v;
+        const unsigned addr = outb + (unsigned)hb * kStage + swz(r, lane >> 2) + (lane & 3) * 4;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+        if (p >= 0 && p < a.n_out) a.out[p] = v;
+    }
+}
+
+// ------------------------------------------------------------------ baseline block sums + chunk extrema (BWD epilogue)
+struct StatAcc { int c; long long s1, s2; };
+static __device__ __forceinline__ void tally(const SeqArgs& a, StatAcc& acc, float v) {
+    const bool in = v >= a.st_min && v <= a.st_max;
+    // (v - c0) * 2^s in one FFMA: scaling by a power of two commutes with the rounding of the difference
+    const int q = in ? __float2int_rn(__fmaf_rn(v, a.st_scale, a.st_nc0s)) : 0;
+    acc.c += in ? 1 : 0; acc.s1 += q; acc.s2 += (long long)q * q;
+}
+// Per-slot partial tallies: 32-bit count / sum (8 samples, |q| < 2^23: fused blocks are >= 2^16 samples), folded
+// into the 64-bit accumulators once per slot.
+static __device__ __forceinline__ void tally_slot(const SeqArgs& a, StatAcc& a0, StatAcc& a1, const f2 (&y)[8]) {
+    int c0 = 0, c1 = 0, s0 = 0, s1 = 0;
+    long long q0 = 0, q1 = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const bool in0 = y[e].x >= a.st_min && y[e].x <= a.st_max, in1 = y[e].y >= a.st_min && y[e].y <= a.st_max;
+        const int u0 = in0 ? __float2int_rn(__fmaf_rn(y[e].x, a.st_scale, a.st_nc0s)) : 0;
+        const int u1 = in1 ? __float2int_rn(__fmaf_rn(y[e].y, a.st_scale, a.st_nc0s)) : 0;
+        c0 += in0 ? 1 : 0; c1 += in1 ? 1 : 0; s0 += u0; s1 += u1;
+        q0 += (long long)u0 * u0; q1 += (long long)u1 * u1;
+    }
+    a0.c += c0; a0.s1 += s0; a0.s2 += q0;
+    a1.c += c1; a1.s1 += s1; a1.s2 += q1;
+}
+
+static __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+static __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// Work distribution: groups are handed out in order from a global counter (a warp that shares its scheduler with
+// fewer or faster neighbours simply takes more of them; neighbouring groups are in flight together, which keeps
+// their DRAM pages and L2 lines warm), or by static round robin when the caller gave no counter.
+static __device__ __forceinline__ long long next_group(const SeqArgs& a, long long static_next, int lane, bool first) {
+    if (!a.next_group) return first ? a.g_first + static_next : static_next;
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(a.next_group, 1ULL);
+    return a.g_first + (long long)__shfl_sync(CT_FULL, v, 0);
+}
+
+// =============================== forward pass ========================================
+// MODE: 1, 2, 4 = scratch output keeping every MODE-th sample; 0 = final output (causal filter only).
+template <int NSEC, typename InT, int MODE, bool COUNT, bool EDGE>
+__device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap* in_map, const CUtensorMap* out_map,
+                                          const long long g, const int lane, const unsigned stage0, const unsigned bar0,
+                                          const unsigned outb, unsigned& phase,
+                                          const f2 (&na1)[NSEC], const f2 (&na2)[NSEC], const f2 (&c1)[NSEC], const f2 (&c2)[NSEC],
+                                          const f2 gl, const f2 off2) {
+    constexpr bool U16 = sizeof(InT) == 2;
+    constexpr int SPT = U16 ? 1 : 2;             // stages per tile (a stage row is 128 bytes)
+    constexpr int SLOTS = kG / SPT;              // slots per stage
+    constexpr int SAMP = kK / SPT;               // samples per stage row
+    constexpr int D = MODE ? MODE : 1;
+    constexpr int F = 16 / D;
+    const long long run0 = g * kRuns;
+    const int ntiles = (a.Hw + a.R) / kK, wt = a.Hw / kK, TO = a.R / kK;
+    const int nstages = ntiles * SPT;
+    const InT* in = reinterpret_cast<const InT*>(a.in);
+    const unsigned m2 = a.mask | (a.mask << 16);
+    const f2 kmagic = splat(-(8388608.f + (float)a.isub));
+
+    f2 v1[NSEC], v2[NSEC];
+    {   // runs that begin in the left pad start from the steady state of the pad value (scipy: zi * x[0])
+        float p0 = 0.f, p1 = 0.f;
+        if (EDGE) {
+            p0 = a.base + (run0 + lane) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
+            p1 = a.base + (run0 + lane + 32) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
         }
-        __syncwarp();
-        fill_tile<InT>(a, wbase, run0, -(long long)a.Hw, lane, in_aligned);
-        cp_commit();
-        for (int t = 0; t < ntiles; ++t) {
-            const long long off = (long long)t * kK - a.Hw;          // tile t covers r*R + off + [0, K)
-            if (t + 1 < ntiles) fill_tile<InT>(a, wbase + (((t + 1) & 1) ? kIn : 0), run0, off + kK, lane, in_aligned);
-            cp_commit();
-            cp_wait<1>();
-            __syncwarp();
-            const bool store = t >= wt;
-            const long long lo0 = a.base + (run0 + lane) * a.R + off, lo1 = lo0 + 32LL * a.R;
-            const bool edge = sizeof(InT) == 2 && !(lo0 >= 0 && lo1 + kK <= a.n_in);
-            const char* ib = wbase + ((t & 1) ? kIn : 0);
-            uint4 ra[2], rb[2];
-            auto load_group = [&](int jj) {
-                if (sizeof(InT) == 4) {
-                    const float* t0 = reinterpret_cast<const float*>(ib) + lane * kRowF + jj * 8;
-                    const float* t1 = t0 + 32 * kRowF;
-                    ra[0] = *reinterpret_cast<const uint4*>(t0); ra[1] = *reinterpret_cast<const uint4*>(t0 + 4);
-                    rb[0] = *reinterpret_cast<const uint4*>(t1); rb[1] = *reinterpret_cast<const uint4*>(t1 + 4);
-                } else {
-                    const uint16_t* t0 = reinterpret_cast<const uint16_t*>(ib) + lane * kRowH + jj * 8;
-                    ra[0] = *reinterpret_cast<const uint4*>(t0);
-                    rb[0] = *reinterpret_cast<const uint4*>(t0 + 32 * kRowH);
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(p0 * k.ss[s], p1 * k.ss[s]); v2[s] = v1[s]; }
+    }
+    CwAcc cw;
+    if (COUNT) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cw.tot[i] = 0;
+        cw.below = cw.c0 = cw.c1 = 0; cw.since = 0;
+    }
+
+    // stage q covers the positions base + (run0 + r) R + off(q) + [0, SAMP), r = 0..63
+    auto stage_off = [&](int q) { return (long long)(q / SPT) * kK - a.Hw + (q % SPT) * SAMP; };
+    auto issue = [&](int q) {
+        const long long off = stage_off(q);
+        const unsigned buf = stage0 + (unsigned)(q & 1) * kStage, bar = bar0 + (unsigned)(q & 1) * 8;
+        bool tma = true;                             // interior groups: every stage is one tile copy
+        if (EDGE) {
+            const long long first = a.base + run0 * a.R + off;
+            tma = a.tma_in && first >= 0 && first + (long long)(kRuns - 1) * a.R + SAMP <= a.n_in;
+        }
+        if (tma) {
+            if (lane == 0) {
+                mbar_expect_tx(bar, kStage);
+                // warm-up pieces (off < 0) are the tail of the previous run: one row up, R further right
+                const int x = off >= 0 ? (int)off : (int)(a.R + off);
+                const int y = (int)(run0) - (off >= 0 ? 0 : 1);
+                tma_load_2d(buf, in_map, x, y, bar);
+            }
+        } else if (EDGE) {
+            // guarded fill of the same swizzled layout; float gets the pad value outside the data, codes are fixed up later
+            constexpr int EPC = 16 / (int)sizeof(InT);      // elements per 16-byte chunk
+            for (int r = 0; r < kRuns; ++r) {
+#pragma unroll
+                for (int half = 0; half < (SAMP > 32 ? 2 : 1); ++half) {
+                    const int col = lane + half * 32;
+                    const long long p = a.base + (run0 + r) * a.R + off + col;
+                    InT v;
+                    if (U16) v = (p >= 0 && p < a.n_in) ? in[p] : (InT)0;
+                    else v = (p >= 0 && p < a.n_in) ? in[p] : (InT)(a.fsub + a.pad_x);
+                    const unsigned addr = buf + swz(r, col / EPC) + (unsigned)(col % EPC) * (unsigned)sizeof(InT);
+                    if (U16) asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory");
+                    else asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"((float)v) : "memory");
                 }
-            };
-            load_group(0);
-            f2 keep[4];
-#pragma unroll (kFwdUnroll)
-            for (int jj = 0; jj < kG; ++jj) {
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        }
+    };
+
+    issue(0);
+    f2 keep[F];                                     // kept samples of the current slot pair (scratch modes)
+    for (int t = 0; t < ntiles; ++t) {
+        const bool store = t >= wt;
+        const long long toff = (long long)t * kK - a.Hw;
+        const long long lo0 = a.base + (run0 + lane) * a.R + toff, lo1 = lo0 + 32LL * a.R;
+        const bool edge = EDGE && U16 && !(lo0 >= 0 && lo1 + kK <= a.n_in);
+        const bool cw_part = COUNT && EDGE && !(lo0 >= a.cw_p0 && lo1 + kK <= a.cw_p1 && lo0 + kK <= a.cw_p1 && lo1 >= a.cw_p0);
+#pragma unroll
+        for (int hs = 0; hs < SPT; ++hs) {
+            const int q = t * SPT + hs;
+            if (q + 1 < nstages) issue(q + 1);
+            const unsigned buf = stage0 + (unsigned)(q & 1) * kStage;
+            mbar_wait(bar0 + (unsigned)(q & 1) * 8, (phase >> (q & 1)) & 1u);
+            phase ^= 1u << (q & 1);
+            const unsigned row0 = buf + (unsigned)lane * 128u;
+            const int sw = lane & 7;
+            if (MODE == 0 && store && hs == 0 && a.tma_out) {   // the half-tile about to be rewritten must have left
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+            }
+#pragma unroll 2
+            for (int j = 0; j < SLOTS; ++j) {
+                const int jj = hs * SLOTS + j;             // slot inside the tile
                 f2 x[8];
-                if (sizeof(InT) == 4) {
-                    const unsigned wa[8] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w, ra[1].x, ra[1].y, ra[1].z, ra[1].w};
-                    const unsigned wb[8] = {rb[0].x, rb[0].y, rb[0].z, rb[0].w, rb[1].x, rb[1].y, rb[1].z, rb[1].w};
+                if (U16) {
+                    const uint4 ra = lds128(row0 + (unsigned)((j ^ sw) << 4));
+                    const uint4 rb = lds128(row0 + 32 * 128 + (unsigned)((j ^ sw) << 4));
+                    const unsigned wa[4] = {ra.x & m2, ra.y & m2, ra.z & m2, ra.w & m2};
+                    const unsigned wb[4] = {rb.x & m2, rb.y & m2, rb.z & m2, rb.w & m2};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = make_float2(__uint_as_float(wa[e]) - a.sub, __uint_as_float(wb[e]) - a.sub);
-                } else {
-                    const unsigned wa[4] = {ra[0].x, ra[0].y, ra[0].z, ra[0].w}, wb[4] = {rb[0].x, rb[0].y, rb[0].z, rb[0].w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const unsigned ma = wa[q] & m2, mb = wb[q] & m2;
-                        x[2 * q] = make_float2((float)(int)(ma & 0xffffu) - a.sub, (float)(int)(mb & 0xffffu) - a.sub);
-                        x[2 * q + 1] = make_float2((float)(int)(ma >> 16) - a.sub, (float)(int)(mb >> 16) - a.sub);
+                    for (int w = 0; w < 4; ++w) {
+                        // 2^23 + code as a float (byte permute), minus (2^23 + isub): exact
+                        const f2 lo = make_float2(__uint_as_float(__byte_perm(wa[w], 0x4B000000u, 0x7410)),
+                                                  __uint_as_float(__byte_perm(wb[w], 0x4B000000u, 0x7410)));
+                        const f2 hi = make_float2(__uint_as_float(__byte_perm(wa[w], 0x4B000000u, 0x7432)),
+                                                  __uint_as_float(__byte_perm(wb[w], 0x4B000000u, 0x7432)));
+                        x[2 * w] = __fadd2_rn(lo, kmagic);
+                        x[2 * w + 1] = __fadd2_rn(hi, kmagic);
                     }
                     if (edge) {                            // x' = pad_x in the pad and beyond it
 #pragma unroll
@@ -348,325 +392,464 @@ ct_filter_fwd_kernel(SeqArgs a, CtFilterCoef k) {
                         }
                     }
                     if (COUNT && store) {                  // every code of [cw_p0, cw_p1) is tallied exactly once
-                        const bool part0 = !(lo0 >= a.cw_p0 && lo0 + kK <= a.cw_p1), part1 = !(lo1 >= a.cw_p0 && lo1 + kK <= a.cw_p1);
-                        if (!(part0 | part1)) {            // both pieces inside the counted range: no per-code tests
+                        if (!cw_part) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const unsigned ma = wa[q] & m2, mb = wb[q] & m2;
-                                cw_tally(ma & 0xffffu, a, cw_below, cw_c0, cw_c1); cw_tally(ma >> 16, a, cw_below, cw_c0, cw_c1);
-                                cw_tally(mb & 0xffffu, a, cw_below, cw_c0, cw_c1); cw_tally(mb >> 16, a, cw_below, cw_c0, cw_c1);
+                            for (int w = 0; w < 4; ++w) {
+                                cw_tally(wa[w] & 0xffffu, a, cw); cw_tally(wa[w] >> 16, a, cw);
+                                cw_tally(wb[w] & 0xffffu, a, cw); cw_tally(wb[w] >> 16, a, cw);
                             }
                         } else {
 #pragma unroll 1
-                            for (int q = 0; q < 4; ++q) {
-                                const unsigned ma = wa[q] & m2, mb = wb[q] & m2;
-                                const long long pa0 = lo0 + jj * 8 + 2 * q, pb0 = lo1 + jj * 8 + 2 * q;
-                                if (pa0 >= a.cw_p0 && pa0 < a.cw_p1) cw_tally(ma & 0xffffu, a, cw_below, cw_c0, cw_c1);
-                                if (pa0 + 1 >= a.cw_p0 && pa0 + 1 < a.cw_p1) cw_tally(ma >> 16, a, cw_below, cw_c0, cw_c1);
-                                if (pb0 >= a.cw_p0 && pb0 < a.cw_p1) cw_tally(mb & 0xffffu, a, cw_below, cw_c0, cw_c1);
-                                if (pb0 + 1 >= a.cw_p0 && pb0 + 1 < a.cw_p1) cw_tally(mb >> 16, a, cw_below, cw_c0, cw_c1);
+                            for (int w = 0; w < 4; ++w) {
+                                const long long pa0 = lo0 + jj * 8 + 2 * w, pb0 = lo1 + jj * 8 + 2 * w;
+                                if (pa0 >= a.cw_p0 && pa0 < a.cw_p1) cw_tally(wa[w] & 0xffffu, a, cw);
+                                if (pa0 + 1 >= a.cw_p0 && pa0 + 1 < a.cw_p1) cw_tally(wa[w] >> 16, a, cw);
+                                if (pb0 >= a.cw_p0 && pb0 < a.cw_p1) cw_tally(wb[w] & 0xffffu, a, cw);
+                                if (pb0 + 1 >= a.cw_p0 && pb0 + 1 < a.cw_p1) cw_tally(wb[w] >> 16, a, cw);
                             }
                         }
-                        if (++cw_since == 15) {            // 16 tallies per slot: an 8-bit counter holds 15 slots
-                            cw_flush(cw_tot, cw_below, cw_c0, cw_c1);
-                            cw_since = 0;
-                        }
-                    }
-                }
-                if (jj + 1 < kG) load_group(jj + 1);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl);
-                if (store) {
-                    if (MODE == kFwdScratch) {
-                        float oa[8], ob[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) { oa[e] = x[e].x; ob[e] = x[e].y; }
-                        float* dst = a.out + scratch_off(run0 + lane, t - wt, jj, TO);
-                        stg256(dst, oa);
-                        stg256(dst + 256, ob);
-                    } else if (MODE == kFwdScratch2) {      // band-limited output: keep the even positions only
-                        if ((jj & 1) == 0) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) keep[e] = x[2 * e];
-                        } else {
-                            float oa[8], ob[8];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { oa[e] = keep[e].x; ob[e] = keep[e].y; oa[4 + e] = x[2 * e].x; ob[4 + e] = x[2 * e].y; }
-                            float* dst = a.out + scratch_off2(run0 + lane, t - wt, jj >> 1, TO);
-                            stg256(dst, oa);
-                            stg256(dst + 256, ob);
-                        }
-                    } else {
-                        float* o0 = outb + lane * kRowF + jj * 8;
-                        float* o1 = o0 + 32 * kRowF;
-                        *reinterpret_cast<float4*>(o0) = make_float4(x[0].x, x[1].x, x[2].x, x[3].x);
-                        *reinterpret_cast<float4*>(o0 + 4) = make_float4(x[4].x, x[5].x, x[6].x, x[7].x);
-                        *reinterpret_cast<float4*>(o1) = make_float4(x[0].y, x[1].y, x[2].y, x[3].y);
-                        *reinterpret_cast<float4*>(o1 + 4) = make_float4(x[4].y, x[5].y, x[6].y, x[7].y);
-                    }
-                }
-            }
-            __syncwarp();
-            if (MODE == kFwdFinal && store) {
-                StatAcc none;
-                store_tile<false>(a, outb, run0, off, lane, out_aligned, none);
-                __syncwarp();
-            }
-        }
-        cp_wait<0>();
-        if (COUNT) {                                       // (a lane tallies < 2^32 codes per group)
-            cw_flush(cw_tot, cw_below, cw_c0, cw_c1);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                unsigned v = cw_tot[i];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CT_FULL, v, o);
-                if (lane == 0 && v) atomicAdd(a.cw_out + i, (unsigned long long)v);
-            }
-        }
-    }
-}
-
-// =============================== backward pass =======================================
-// Reads the interleaved scratch; run r processes positions r*R + R + Hw - 1 down to r*R, the first
-// Hw of them (the first Hw/K tiles of run r+1) only to warm the recursion up.
-template <int NSEC, bool STATS, bool DEC2>
-__global__ void __launch_bounds__(kSeqWarps * 32, 8)
-ct_filter_bwd_kernel(SeqArgs a, CtFilterCoef k) {
-    extern __shared__ __align__(16) char smem[];
-    const int lane = ct_lane();
-    const int wib = threadIdx.x >> 5;
-    float* outb = reinterpret_cast<float*>(smem + (size_t)wib * kOutBytes);
-    const float* y1 = reinterpret_cast<const float*>(a.in);
-    const long long gw = (long long)blockIdx.x * kSeqWarps + wib;
-    const long long nw = (long long)gridDim.x * kSeqWarps;
-    const bool out_aligned = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
-    const int ntiles = (a.Hw + a.R) / kK, wt = a.Hw / kK, TO = a.R / kK;
-
-    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC];
-#pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        na1[s] = splat(k.na1[s]); na2[s] = splat(k.na2[s]);
-        const float g = (s == NSEC - 1) ? k.gain : 1.f;
-        c1[s] = splat((k.na1[s] + k.n1[s]) * g); c2[s] = splat((k.na2[s] + k.n2[s]) * g);
-    }
-    const f2 gl = splat(k.gain);
-    // the forward output is held constant beyond n_in (scipy: zi * y[-1], _signaltools.py:4910-4913)
-    // (half-rate scratch: the last stored, i.e. even, position; the forward output is flat at the end of the pad)
-    const long long last = ((a.n_in - 1 - a.base) >> (DEC2 ? 1 : 0)) << (DEC2 ? 1 : 0);      // relative to the run grid
-    const float hold = DEC2
-        ? y1[scratch_off2(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 4), TO) + ((last & 15) >> 1)]
-        : y1[scratch_off(last / a.R, (int)((last % a.R) / kK), (int)((last % kK) >> 3), TO) + (last & 7)];
-
-    for (long long g = a.g_first + gw; g < a.ngroups; g += nw) {
-        const long long run0 = g * kRuns;
-        const long long r0 = run0 + lane, r1 = r0 + 32;
-        f2 v1[NSEC], v2[NSEC];
-        {   // runs whose first processed position lies beyond the data start from the steady state of `hold`
-            const float h0 = a.base + r0 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
-            const float h1 = a.base + r1 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
-#pragma unroll
-            for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(h0 * k.ss[s], h1 * k.ss[s]); v2[s] = v1[s]; }
-        }
-        // slot q (0 .. ntiles*kG-1) in processing order: tile t = q / kG, jj = kG-1 - q % kG (descending positions)
-        // half-rate scratch: pair qp (0 .. ntiles*kG/2-1) in processing order holds the even positions of two slots
-        auto fetch2 = [&](int qp, u8x& xa, u8x& xb) {
-            const int t = qp / (kG / 2), jp = kG / 2 - 1 - (qp % (kG / 2));
-            const bool warm = t < wt;
-            const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
-            const long long s0 = warm ? r0 + 1 : r0, s1 = warm ? r1 + 1 : r1;
-            // out-of-range blocks are never dereferenced; their values are replaced by `hold` position by position below
-            if (s0 < a.scratch_runs) xa = ldg256(y1 + scratch_off2(s0, to, jp, TO));
-            if (s1 < a.scratch_runs) xb = ldg256(y1 + scratch_off2(s1, to, jp, TO));
-        };
-        auto fetch = [&](int q, u8x& xa, u8x& xb) {
-            const int t = q / kG, jj = kG - 1 - (q % kG);
-            const bool warm = t < wt;
-            const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
-            const long long s0 = warm ? r0 + 1 : r0, s1 = warm ? r1 + 1 : r1;
-            const long long p0 = a.base + s0 * a.R + (long long)to * kK + jj * 8, p1 = a.base + s1 * a.R + (long long)to * kK + jj * 8;
-            if (s0 < a.scratch_runs && p0 + 8 <= a.n_in) xa = ldg256(y1 + scratch_off(s0, to, jj, TO));
-            else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    xa.w[e] = __float_as_uint((s0 < a.scratch_runs && p0 + e < a.n_in) ? y1[scratch_off(s0, to, jj, TO) + e] : hold);
-            }
-            if (s1 < a.scratch_runs && p1 + 8 <= a.n_in) xb = ldg256(y1 + scratch_off(s1, to, jj, TO));
-            else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    xb.w[e] = __float_as_uint((s1 < a.scratch_runs && p1 + e < a.n_in) ? y1[scratch_off(s1, to, jj, TO) + e] : hold);
-            }
-        };
-        // register pipeline two slots deep (slot q+1 in flight while slot q+2 is issued into the
-        // buffer slot q just released); buffer index = j & 1 is static because kG is even
-        StatAcc acc; acc.c = 0; acc.s1 = 0; acc.s2 = 0;
-        u8x pa[2], pb[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { pa[i].w[e] = 0u; pb[i].w[e] = 0u; }
-        if (DEC2) { fetch2(0, pa[0], pb[0]); fetch2(1, pa[1], pb[1]); }
-        else { fetch(0, pa[0], pb[0]); fetch(1, pa[1], pb[1]); }
-        const int nslots = ntiles * kG;
-        for (int t = 0; t < ntiles; ++t) {
-            const bool store = t >= wt;
-#pragma unroll (kBwdUnroll)
-            for (int j = 0; j < kG; ++j) {
-                const int jj = kG - 1 - j;
-                f2 x[8];
-                if (DEC2) {
-                    // slot jj of the pair buffer (j >> 1) & 1: the upper slot of a pair (jj odd) is processed first and
-                    // holds kept samples 4..7; x = 2 * kept at even positions, 0 at odd ones (zero stuffing: the
-                    // images sit above fs/4 where this very filter has no gain), `hold` beyond the forward output
-                    const int bi = (j >> 1) & 1, sub = (jj & 1) * 4;
-                    const bool warm = t < wt;
-                    const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
-                    const long long q0 = a.base + (warm ? r0 + 1 : r0) * a.R + (long long)to * kK + jj * 8, q1 = q0 + 32LL * a.R;
-                    const bool tail = q1 + 8 > a.n_in;         // (q0 < q1: both pieces inside the forward output)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float va = (e & 1) ? 0.f : 2.f * __uint_as_float(pa[bi].w[sub + (e >> 1)]);
-                        float vb = (e & 1) ? 0.f : 2.f * __uint_as_float(pb[bi].w[sub + (e >> 1)]);
-                        if (tail) { if (q0 + e >= a.n_in) va = hold; if (q1 + e >= a.n_in) vb = hold; }
-                        x[e] = make_float2(va, vb);
-                    }
-                    if (j & 1) {                               // both slots of the pair consumed: refill its buffer
-                        const int qn = (t * kG + j) / 2 + 2;
-                        if (qn < nslots / 2) fetch2(qn, pa[bi], pb[bi]);
+                        if (++cw.since == 15) cw_flush(cw);   // 16 tallies per slot: an 8-bit counter holds 15 slots
                     }
                 } else {
+                    const uint4 a0 = lds128(row0 + (unsigned)(((2 * j) ^ sw) << 4)), a1 = lds128(row0 + (unsigned)(((2 * j + 1) ^ sw) << 4));
+                    const uint4 b0 = lds128(row0 + 32 * 128 + (unsigned)(((2 * j) ^ sw) << 4));
+                    const uint4 b1 = lds128(row0 + 32 * 128 + (unsigned)(((2 * j + 1) ^ sw) << 4));
+                    const unsigned wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const unsigned wb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    const f2 nsub = splat(-a.fsub);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = make_float2(__uint_as_float(pa[j & 1].w[e]), __uint_as_float(pb[j & 1].w[e]));
-                    const int qn = t * kG + j + 2;
-                    if (qn < nslots) fetch(qn, pa[j & 1], pb[j & 1]);
+                    for (int e = 0; e < 8; ++e) x[e] = __fadd2_rn(make_float2(__uint_as_float(wa[e]), __uint_as_float(wb[e])), nsub);
                 }
 #pragma unroll
-                for (int ee = 0; ee < 8; ++ee) { const int e = 7 - ee; x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl); }
+                for (int e = 0; e < 8; ++e) x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl, off2);
                 if (store) {
-                    float* o0 = outb + lane * kRowF + jj * 8;
-                    float* o1 = o0 + 32 * kRowF;
-                    *reinterpret_cast<float4*>(o0) = make_float4(x[0].x, x[1].x, x[2].x, x[3].x);
-                    *reinterpret_cast<float4*>(o0 + 4) = make_float4(x[4].x, x[5].x, x[6].x, x[7].x);
-                    *reinterpret_cast<float4*>(o1) = make_float4(x[0].y, x[1].y, x[2].y, x[3].y);
-                    *reinterpret_cast<float4*>(o1 + 4) = make_float4(x[4].y, x[5].y, x[6].y, x[7].y);
+                    if (MODE == 0) {
+                        out_write_slot(outb, lane, jj, x);
+                        if ((jj & 3) == 3) {               // half-tile complete
+                            const int hb = jj >> 2;
+                            const long long first = a.base + run0 * a.R + toff + hb * 32;
+                            bool tma = true;
+                            if (EDGE) tma = a.tma_out && first >= 0 && first + (long long)(kRuns - 1) * a.R + 32 <= a.n_out;
+                            if (tma) {
+                                fence_async_smem();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(out_map, (int)(toff + hb * 32), (int)run0, outb + (unsigned)hb * kStage);
+                                    bulk_commit();
+                                }
+                                if (hb == 0) {             // the other half is rewritten next
+                                    if (lane == 0) bulk_wait_read<1>();
+                                    __syncwarp();
+                                }
+                            } else if (EDGE) {
+                                __syncwarp();
+                                out_store_guarded(a, outb, hb, first, lane);
+                                __syncwarp();
+                            }
+                        }
+                    } else {
+                        // keep every D-th sample; a pair of slots fills one scratch unit of F floats per half
+                        constexpr int PER = 8 / D;
+#pragma unroll
+                        for (int i = 0; i < PER; ++i) keep[(jj & 1) * PER + i] = x[i * D];
+                        if (jj & 1) {
+                            float oa[F], ob[F];
+#pragma unroll
+                            for (int i = 0; i < F; ++i) { oa[i] = keep[i].x; ob[i] = keep[i].y; }
+                            float* dst = a.out + scratch_off<D>(run0 + lane, t - wt, jj >> 1, TO);
+                            stg_vec<F>(dst, oa);
+                            stg_vec<F>(dst + 32 * F, ob);
+                        }
+                    }
                 }
             }
-            if (store) {
-                __syncwarp();
-                store_tile<STATS>(a, outb, run0, (long long)(TO - 1 - (t - wt)) * kK, lane, out_aligned, acc);
-                __syncwarp();
-            }
+            __syncwarp();                                  // every lane is done with the stage before it is refilled
         }
-        if (STATS) {                                       // the group lies inside one baseline block (grid aligned by `base`)
-            long long c = acc.c, s1 = acc.s1, s2 = acc.s2;   // (a group has < 2^31 samples per lane)
+    }
+    if (COUNT) {                                           // (a lane tallies < 2^32 codes per group)
+        cw_flush(cw);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                c += __shfl_xor_sync(CT_FULL, c, o); s1 += __shfl_xor_sync(CT_FULL, s1, o); s2 += __shfl_xor_sync(CT_FULL, s2, o);
-            }
-            const long long rel = a.base + run0 * a.R - a.st_origin;
-            if (lane == 0 && c && rel >= 0) {
-                const long long kb = rel / a.st_block;
-                atomicAdd(reinterpret_cast<unsigned long long*>(a.st_cnt + kb), (unsigned long long)c);
-                atomicAdd(reinterpret_cast<unsigned long long*>(a.st_s1 + kb), (unsigned long long)s1);
-                atomicAdd(reinterpret_cast<unsigned long long*>(a.st_s2 + kb), (unsigned long long)s2);
-            }
+        for (int i = 0; i < 9; ++i) {
+            unsigned v = cw.tot[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CT_FULL, v, o);
+            if (lane == 0 && v) atomicAdd(a.cw_out + i, (unsigned long long)v);
         }
     }
 }
 
 template <int NSEC, typename InT, int MODE, bool COUNT>
-int launch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    auto kern = ct_filter_fwd_kernel<NSEC, InT, MODE, COUNT>;
-    const int smem = kSeqWarps * (2 * Tile<InT>::kInBytes + (MODE == kFwdFinal ? kOutBytes : 0));
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+ct_filter_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map, SeqArgs a, CtFilterCoef k) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int kPerWarp = 2 * kStage + (MODE == 0 ? 2 * kStage : 0);
+    const int lane = ct_lane();
+    const int wib = threadIdx.x >> 5;
+    const unsigned sbase = smem_u32(smem);
+    const unsigned stage0 = sbase + (unsigned)wib * kPerWarp;
+    const unsigned outb = stage0 + 2 * kStage;
+    const unsigned bar0 = sbase + (unsigned)kWarps * kPerWarp + (unsigned)wib * 16;
+    if (lane == 0) {
+        if (sbase & 1023u) asm volatile("trap;");
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    __syncwarp();
+    const long long gw = (long long)blockIdx.x * kWarps + wib;
+    const long long nw = (long long)gridDim.x * kWarps;
+
+    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC], gl;
+    load_coef<NSEC>(k, a.scale, na1, na2, c1, c2, gl);
+    const f2 off2 = splat(a.offset);
+    unsigned phase = 0;
+    for (long long g = next_group(a, gw, lane, true); g < a.ngroups; g = next_group(a, g + nw, lane, false)) {
+        // interior groups (every stage and output piece of all 64 runs inside the data, the counted range too) run guard-free
+        const long long p_lo = a.base + g * kRuns * a.R - a.Hw, p_hi = a.base + (g + 1) * kRuns * a.R;
+        bool interior = a.tma_in && p_lo >= 0 && p_hi <= a.n_in;
+        if (MODE == 0) interior = interior && a.tma_out && p_hi <= a.n_out;
+        if (COUNT) interior = interior && p_lo + a.Hw >= a.cw_p0 && p_hi <= a.cw_p1;
+        if (interior) fwd_group<NSEC, InT, MODE, COUNT, false>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, na1, na2, c1, c2, gl, off2);
+        else fwd_group<NSEC, InT, MODE, COUNT, true>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, na1, na2, c1, c2, gl, off2);
+    }
+    if (MODE == 0 && lane == 0) bulk_wait_read<0>();         // shared memory must outlive the last tile store
+}
+
+// =============================== backward pass =======================================
+// Run r processes positions r*R + R + Hw - 1 down to r*R, the first Hw of them (the first Hw/K tiles of run
+// r + 1) only to warm the recursion up.  The scratch holds D * (forward output) at every D-th position.
+template <int NSEC, int D, bool STATS, bool SUMM, bool EDGE>
+__device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap* out_map, const long long g,
+                                          const int lane, const unsigned outb, const float hold,
+                                          const f2 (&na1)[NSEC], const f2 (&na2)[NSEC], const f2 (&c1)[NSEC], const f2 (&c2)[NSEC],
+                                          const f2 gl, const f2 off2) {
+    constexpr int F = 16 / D;
+    const float* y1 = reinterpret_cast<const float*>(a.in);
+    const long long run0 = g * kRuns;
+    const long long r0 = run0 + lane, r1 = r0 + 32;
+    const int ntiles = (a.Hw + a.R) / kK, wt = a.Hw / kK, TO = a.R / kK;
+    const int npairs = ntiles * 4;
+
+    f2 v1[NSEC], v2[NSEC];
+    {   // runs whose first processed position lies beyond the data start from the steady state of `hold`
+        // (scipy: zi * y[-1], _signaltools.py:4910-4913); the cascade's own gain/offset do not enter the state
+        float h0 = 0.f, h1 = 0.f;
+        if (EDGE) {
+            h0 = a.base + r0 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
+            h1 = a.base + r1 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
+        }
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(h0 * k.ss[s], h1 * k.ss[s]); v2[s] = v1[s]; }
+    }
+    // pair i (0 .. npairs-1) in processing order: tile t = i / 4, pair jp = 3 - i % 4 (descending positions)
+    auto fetch = [&](int i, Vec<F>& xa, Vec<F>& xb) {
+        const int t = i >> 2, jp = 3 - (i & 3);
+        const bool warm = t < wt;
+        const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
+        const long long s0 = warm ? r0 + 1 : r0, s1 = warm ? r1 + 1 : r1;
+        if (!EDGE) {
+            ldg_vec<F>(y1 + scratch_off<D>(s0, to, jp, TO), xa);
+            ldg_vec<F>(y1 + scratch_off<D>(s1, to, jp, TO), xb);
+        } else {
+            // units beyond the scratch are never dereferenced; positions beyond the forward output are replaced by `hold` below
+            if (s0 < a.scratch_runs) ldg_vec<F>(y1 + scratch_off<D>(s0, to, jp, TO), xa);
+            if (s1 < a.scratch_runs) ldg_vec<F>(y1 + scratch_off<D>(s1, to, jp, TO), xb);
+        }
+    };
+    StatAcc acc0, acc1;
+    acc0.c = 0; acc0.s1 = 0; acc0.s2 = 0; acc1 = acc0;
+    float2 sb0[4], sb1[4];                          // chunk extrema of four consecutive tiles (one 32-byte store each)
+    Vec<F> pa[2], pb[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int e = 0; e < F; ++e) { pa[i].v[e] = 0.f; pb[i].v[e] = 0.f; }
+    fetch(0, pa[0], pb[0]);
+    if (npairs > 1) fetch(1, pa[1], pb[1]);
+
+    for (int t = 0; t < ntiles; ++t) {
+        const bool warm = t < wt;
+        const bool store = !warm;
+        const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
+        const long long tpos0 = a.base + (warm ? r0 + 1 : r0) * a.R + (long long)to * kK;   // position of the tile's first sample, half 0
+        float mn0 = __int_as_float(0x7f800000), mx0 = __int_as_float(0xff800000), mn1 = mn0, mx1 = mx0;
+#pragma unroll 1
+        for (int jq = 0; jq < 4; ++jq) {
+            const int jp = 3 - jq;
+            // the unit of this pair -> x registers; shift the pipeline, issue the pair after next
+            Vec<F> ca = pa[0], cb = pb[0];
+            pa[0] = pa[1]; pb[0] = pb[1];
+            { const int nx = t * 4 + jq + 2; if (nx < npairs) fetch(nx, pa[1], pb[1]); }
+            if (store && (jq & 1) == 0 && a.tma_out) {     // this half-tile's previous store must have read it
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+            }
+#pragma unroll
+            for (int sl = 1; sl >= 0; --sl) {              // upper slot of the pair first
+                const int jj = jp * 2 + sl;
+                f2 x[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (e % D == 0) x[e] = make_float2(ca.v[sl * (8 / D) + e / D], cb.v[sl * (8 / D) + e / D]);
+                    else x[e] = make_float2(0.f, 0.f);     // zero stuffing: the images sit where this very filter has no gain
+                }
+                if (EDGE) {
+                    const long long q0 = tpos0 + jj * 8, q1 = q0 + 32LL * a.R;
+                    if (q1 + 8 > a.n_in) {                 // (q0 < q1) beyond the forward output: held value, at full rate
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (q0 + e >= a.n_in) x[e].x = hold;
+                            if (q1 + e >= a.n_in) x[e].y = hold;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int ee = 0; ee < 8; ++ee) { const int e = 7 - ee; x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl, off2); }
+                if (store) {
+                    out_write_slot(outb, lane, jj, x);
+                    if (!EDGE) {
+                        if (STATS) tally_slot(a, acc0, acc1, x);
+                        if (SUMM) {
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                mn0 = fmin3(mn0, x[e].x, x[e + 1].x); mx0 = fmax3(mx0, x[e].x, x[e + 1].x);
+                                mn1 = fmin3(mn1, x[e].y, x[e + 1].y); mx1 = fmax3(mx1, x[e].y, x[e + 1].y);
+                            }
+                        }
+                    } else {
+                        const long long p0 = a.base + r0 * a.R + (long long)to * kK + jj * 8, p1 = p0 + 32LL * a.R;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (p0 + e >= 0 && p0 + e < a.n_out) {
+                                if (STATS) tally(a, acc0, x[e].x);
+                                mn0 = fminf(mn0, x[e].x); mx0 = fmaxf(mx0, x[e].x);
+                            }
+                            if (p1 + e >= 0 && p1 + e < a.n_out) {
+                                if (STATS) tally(a, acc1, x[e].y);
+                                mn1 = fminf(mn1, x[e].y); mx1 = fmaxf(mx1, x[e].y);
+                            }
+                        }
+                    }
+                }
+            }
+            if (store && (jq & 1)) {                       // half-tile hb = jp >> 1 complete
+                const int hb = jp >> 1;
+                const long long first = a.base + run0 * a.R + (long long)to * kK + hb * 32;
+                bool tma = true;
+                if (EDGE) tma = a.tma_out && first >= 0 && first + (long long)(kRuns - 1) * a.R + 32 <= a.n_out;
+                if (tma) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(out_map, to * kK + hb * 32, (int)run0, outb + (unsigned)hb * kStage);
+                        bulk_commit();
+                    }
+                } else if (EDGE) {
+                    __syncwarp();
+                    out_store_guarded(a, outb, hb, first, lane);
+                    __syncwarp();
+                }
+            }
+        }
+        if (SUMM && store) {
+            // tiles descend: the newest chunk is the lowest one of its group of four
+            sb0[3] = sb0[2]; sb0[2] = sb0[1]; sb0[1] = sb0[0]; sb0[0] = make_float2(mn0, mx0);
+            sb1[3] = sb1[2]; sb1[2] = sb1[1]; sb1[1] = sb1[0]; sb1[0] = make_float2(mn1, mx1);
+            if ((to & 3) == 0) {
+                float2* d0 = a.summ + (r0 * TO + to);
+                float2* d1 = a.summ + (r1 * TO + to);
+                const float f0[8] = {sb0[0].x, sb0[0].y, sb0[1].x, sb0[1].y, sb0[2].x, sb0[2].y, sb0[3].x, sb0[3].y};
+                const float f1[8] = {sb1[0].x, sb1[0].y, sb1[1].x, sb1[1].y, sb1[2].x, sb1[2].y, sb1[3].x, sb1[3].y};
+                stg_vec<8>(reinterpret_cast<float*>(d0), f0);
+                stg_vec<8>(reinterpret_cast<float*>(d1), f1);
+            }
+        }
+    }
+    if (STATS) {                                           // the group lies inside one baseline block (grid aligned by `base`)
+        long long c = (long long)acc0.c + acc1.c, s1 = acc0.s1 + acc1.s1, s2 = acc0.s2 + acc1.s2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(CT_FULL, c, o); s1 += __shfl_xor_sync(CT_FULL, s1, o); s2 += __shfl_xor_sync(CT_FULL, s2, o);
+        }
+        const long long rel = a.base + run0 * a.R - a.st_origin;
+        if (lane == 0 && c && rel >= 0) {
+            const long long kb = rel / a.st_block;
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.st_cnt + kb), (unsigned long long)c);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.st_s1 + kb), (unsigned long long)s1);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.st_s2 + kb), (unsigned long long)s2);
+        }
+    }
+}
+
+template <int NSEC, int D, bool STATS, bool SUMM>
+__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+ct_filter_bwd_kernel(const __grid_constant__ CUtensorMap out_map, SeqArgs a, CtFilterCoef k) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int lane = ct_lane();
+    const int wib = threadIdx.x >> 5;
+    const unsigned sbase = smem_u32(smem);
+    const unsigned outb = sbase + (unsigned)wib * 2 * kStage;
+    if (lane == 0 && (sbase & 1023u)) asm volatile("trap;");
+    const float* y1 = reinterpret_cast<const float*>(a.in);
+    const long long gw = (long long)blockIdx.x * kWarps + wib;
+    const long long nw = (long long)gridDim.x * kWarps;
+    const int TO = a.R / kK;
+
+    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC], gl;
+    load_coef<NSEC>(k, a.scale, na1, na2, c1, c2, gl);
+    const f2 off2 = splat(a.offset);
+    // the forward output is held constant beyond n_in: its last kept sample (the output is flat at the end of the pad)
+    const long long last = (a.n_in - 1 - a.base) / D * D;                  // relative to the run grid
+    const int lo = (int)(last % a.R);
+    const float hold = y1[scratch_off<D>(last / a.R, lo / kK, (lo % kK) >> 4, TO) + (lo & 15) / D] * (1.f / (float)D);
+
+    for (long long g = next_group(a, gw, lane, true); g < a.ngroups; g = next_group(a, g + nw, lane, false)) {
+        const long long p_lo = a.base + g * kRuns * a.R, p_hi = a.base + (g + 1) * kRuns * a.R;
+        const bool interior = a.tma_out && p_lo >= 0 && p_hi + a.Hw <= a.n_in && p_hi <= a.n_out && (g + 1) * kRuns < a.scratch_runs;
+        if (interior) bwd_group<NSEC, D, STATS, SUMM, false>(a, k, &out_map, g, lane, outb, hold, na1, na2, c1, c2, gl, off2);
+        else bwd_group<NSEC, D, STATS, SUMM, true>(a, k, &out_map, g, lane, outb, hold, na1, na2, c1, c2, gl, off2);
+    }
+    if (lane == 0) bulk_wait_read<0>();                    // shared memory must outlive the last tile store
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+// 2-D view of a trace as rows = runs: row r holds the R samples base + r R .. (element (x, r)); box = 128 bytes x 64 rows.
+// Returns false when the view cannot be encoded (alignment); the kernels then take the guarded path everywhere.
+bool make_map(CUtensorMap* map, const void* ptr, int elem_bytes, long long base, int R, long long nrows, bool l2_256 = false) {
+    memset(map, 0, sizeof(*map));
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || !ptr || nrows < 1) return false;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(ptr) + (uintptr_t)(base * elem_bytes);   // base <= 0: may lie before the data; never read there
+    if (addr & 15) return false;
+    if (((long long)R * elem_bytes) & 15) return false;
+    if (nrows > 0x7fffffffLL) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)R, (cuuint64_t)nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)R * (cuuint64_t)elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)kRuns};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUresult rc = fn(map, dt, 2, reinterpret_cast<void*>(addr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, l2_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS;
+}
+
+long long grid_for(const void* kern, int smem, long long ngroups) {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSeqWarps * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem);
     if (occ < 1) occ = 1;
     long long grid = (long long)ct_sm_count() * occ;
-    const long long want = (a.ngroups - a.g_first + kSeqWarps - 1) / kSeqWarps;
+    const long long want = (ngroups + kWarps - 1) / kWarps;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
+    return grid;
+}
+
+template <int NSEC, typename InT, int MODE, bool COUNT>
+int launch_fwd(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap& im, const CUtensorMap& om, cudaStream_t st) {
+    auto kern = ct_filter_fwd_kernel<NSEC, InT, MODE, COUNT>;
+    const int smem = kWarps * (2 * kStage + (MODE == 0 ? 2 * kStage : 0)) + kWarps * 16;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const long long grid = grid_for(reinterpret_cast<const void*>(kern), smem, a.ngroups - a.g_first);
     CT_COUNT_LAUNCH();
-    kern<<<(unsigned)grid, kSeqWarps * 32, smem, st>>>(a, k);
+    kern<<<(unsigned)grid, kWarps * 32, smem, st>>>(im, om, a, k);
     return ct_check_launch("ct_filter_fwd_kernel");
 }
-template <int NSEC, bool STATS, bool DEC2>
-int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    auto kern = ct_filter_bwd_kernel<NSEC, STATS, DEC2>;
-    const int smem = kSeqWarps * kOutBytes;
+template <int NSEC, int D, bool STATS, bool SUMM>
+int launch_bwd(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap& om, cudaStream_t st) {
+    auto kern = ct_filter_bwd_kernel<NSEC, D, STATS, SUMM>;
+    const int smem = kWarps * 2 * kStage;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSeqWarps * 32, smem);
-    if (occ < 1) occ = 1;
-    long long grid = (long long)ct_sm_count() * occ;
-    const long long want = (a.ngroups - a.g_first + kSeqWarps - 1) / kSeqWarps;
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
+    const long long grid = grid_for(reinterpret_cast<const void*>(kern), smem, a.ngroups - a.g_first);
     CT_COUNT_LAUNCH();
-    kern<<<(unsigned)grid, kSeqWarps * 32, smem, st>>>(a, k);
+    kern<<<(unsigned)grid, kWarps * 32, smem, st>>>(om, a, k);
     return ct_check_launch("ct_filter_bwd_kernel");
 }
 
+#define CT_NSEC_SWITCH(nsec, CALL)                                                              \
+    switch (nsec) {                                                                             \
+        case 1: { constexpr int NS = 1; return CALL; }                                          \
+        case 2: { constexpr int NS = 2; return CALL; }                                          \
+        case 3: { constexpr int NS = 3; return CALL; }                                          \
+        case 4: { constexpr int NS = 4; return CALL; }                                          \
+        case 5: { constexpr int NS = 5; return CALL; }                                          \
+    }                                                                                           \
+    ct_set_error("filter: nsec must be 1..5, got %d", nsec);                                    \
+    return CT_ERR_ARG;
+
 template <typename InT, int MODE>
-int dispatch_fwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    if (sizeof(InT) == 2 && MODE != kFwdFinal && a.cw_out) {
-        switch (k.nsec) {
-            case 1: return launch_fwd<1, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
-            case 2: return launch_fwd<2, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
-            case 3: return launch_fwd<3, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
-            case 4: return launch_fwd<4, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
-            case 5: return launch_fwd<5, uint16_t, MODE == kFwdFinal ? kFwdScratch : MODE, true>(a, k, st);
-        }
+int dispatch_fwd(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap& im, const CUtensorMap& om, cudaStream_t st) {
+    if (sizeof(InT) == 2 && MODE != 0 && a.cw_out) {
+        CT_NSEC_SWITCH(k.nsec, (launch_fwd<NS, uint16_t, MODE == 0 ? 1 : MODE, true>(a, k, im, om, st)))
     }
-    switch (k.nsec) {
-        case 1: return launch_fwd<1, InT, MODE, false>(a, k, st);
-        case 2: return launch_fwd<2, InT, MODE, false>(a, k, st);
-        case 3: return launch_fwd<3, InT, MODE, false>(a, k, st);
-        case 4: return launch_fwd<4, InT, MODE, false>(a, k, st);
-        case 5: return launch_fwd<5, InT, MODE, false>(a, k, st);
-    }
-    ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
-    return CT_ERR_ARG;
+    CT_NSEC_SWITCH(k.nsec, (launch_fwd<NS, InT, MODE, false>(a, k, im, om, st)))
 }
-template <bool DEC2>
-int dispatch_bwd(const SeqArgs& a, const CtFilterCoef& k, cudaStream_t st) {
-    const bool stats = a.st_cnt != nullptr;
-    switch (k.nsec) {
-        case 1: return stats ? launch_bwd<1, true, DEC2>(a, k, st) : launch_bwd<1, false, DEC2>(a, k, st);
-        case 2: return stats ? launch_bwd<2, true, DEC2>(a, k, st) : launch_bwd<2, false, DEC2>(a, k, st);
-        case 3: return stats ? launch_bwd<3, true, DEC2>(a, k, st) : launch_bwd<3, false, DEC2>(a, k, st);
-        case 4: return stats ? launch_bwd<4, true, DEC2>(a, k, st) : launch_bwd<4, false, DEC2>(a, k, st);
-        case 5: return stats ? launch_bwd<5, true, DEC2>(a, k, st) : launch_bwd<5, false, DEC2>(a, k, st);
-    }
-    ct_set_error("filter: nsec must be 1..5, got %d", k.nsec);
-    return CT_ERR_ARG;
+template <int D>
+int dispatch_bwd(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap& om, cudaStream_t st) {
+    const bool stats = a.st_cnt != nullptr, summ = a.summ != nullptr;
+    if (stats && summ) { CT_NSEC_SWITCH(k.nsec, (launch_bwd<NS, D, true, true>(a, k, om, st))) }
+    if (stats) { CT_NSEC_SWITCH(k.nsec, (launch_bwd<NS, D, true, false>(a, k, om, st))) }
+    if (summ) { CT_NSEC_SWITCH(k.nsec, (launch_bwd<NS, D, false, true>(a, k, om, st))) }
+    CT_NSEC_SWITCH(k.nsec, (launch_bwd<NS, D, false, false>(a, k, om, st)))
 }
 
-// The forward output is band-limited by the filter itself.  If the cascade's gain is below eps everywhere in
-// [fs/4, fs/2], every second sample carries all the information (aliasing < eps) and the backward pass can
-// rebuild the rest by zero stuffing (its own stop band removes the images): the scratch then crosses HBM at
-// half rate.  Evaluated from the coefficients on the host (a few hundred complex multiplications).
-bool half_rate_ok(const CtFilterCoef& k) {
-    double worst = 0.0;
-    for (int i = 0; i <= 256; ++i) {
-        const double w = 1.5707963267948966 * (1.0 + i / 256.0);
-        const double cr = cos(w), ci = -sin(w), c2r = cos(2 * w), c2i = -sin(2 * w);   // z^-1, z^-2
-        double mag = fabs((double)k.gain);
-        for (int s = 0; s < k.nsec; ++s) {
-            const double nr = 1.0 + k.n1[s] * cr + k.n2[s] * c2r, ni = k.n1[s] * ci + k.n2[s] * c2i;
-            const double dr = 1.0 - k.na1[s] * cr - k.na2[s] * c2r, di = -k.na1[s] * ci - k.na2[s] * c2i;
-            mag *= sqrt((nr * nr + ni * ni) / (dr * dr + di * di));
-        }
-        if (mag > worst) worst = mag;
+// Decimation factor of the scratch.  Keeping every D-th sample of the forward output and zero-stuffing it in the
+// backward pass leaves, at output frequency f, the aliases conj(H(f)) H(f - k fs/D) X(f - k fs/D), k = 1..D-1: the error
+// gain is the PRODUCT of the cascade's gains at two frequencies fs/D apart.  D is the largest of 4, 2 for which that
+// product stays below eps everywhere (evaluated from the coefficients on the host), else 1.  (8-pole, fs = 4.17 MHz:
+// D = 4 up to ~150 kHz, D = 2 up to ~450 kHz, full rate above.)  A pad shorter than the warm-up keeps full rate: the
+// held value after the data is then not the settled output.
+double cascade_gain(const CtFilterCoef& k, double w) {
+    const double cr = cos(w), ci = -sin(w), c2r = cos(2 * w), c2i = -sin(2 * w);   // z^-1, z^-2
+    double mag = fabs((double)k.gain);
+    for (int s = 0; s < k.nsec; ++s) {
+        const double nr = 1.0 + k.n1[s] * cr + k.n2[s] * c2r, ni = k.n1[s] * ci + k.n2[s] * c2i;
+        const double dr = 1.0 - k.na1[s] * cr - k.na2[s] * c2r, di = -k.na1[s] * ci - k.na2[s] * c2i;
+        mag *= sqrt((nr * nr + ni * ni) / (dr * dr + di * di));
     }
-    return worst < 1e-7;
+    return mag;
+}
+int pick_decimation(const CtFilterCoef& k, long long pad, int Hw) {
+    if (pad < Hw) return 1;
+    static thread_local CtFilterCoef cached_k;
+    static thread_local int cached_d = 0;
+    if (cached_d && memcmp(&cached_k, &k, sizeof(k)) == 0) return cached_d;
+    constexpr int N = 1024;                       // frequencies on [0, 2 pi)
+    static thread_local double H[N];
+    const double two_pi = 6.283185307179586;
+    for (int i = 0; i < N; ++i) H[i] = cascade_gain(k, two_pi * i / N);
+    int best = 1;
+    for (int D = 4; D >= 2; D >>= 1) {
+        double worst = 0.0;
+        for (int kk = 1; kk < D; ++kk)
+            for (int i = 0; i < N; ++i) { const double v = H[i] * H[(i + kk * (N / D)) % N]; if (v > worst) worst = v; }
+        if (worst < 1e-7) { best = D; break; }
+    }
+    cached_k = k; cached_d = best;
+    return best;
 }
 
 // Run length for a trace of n samples: long runs amortise the warm-up, but there must be enough
-// runs to fill the GPU (64 runs per warp, several warps per SM sub-partition).  Hw <= R always.
+// runs to give every SM a CTA (64 runs per warp, 7 warps per CTA; doubling the warm-up share costs more than a
+// half-occupied SM).  Hw <= R always.
 int pick_run(long long n, int Hw) {
-    const long long target_runs = (long long)ct_sm_count() * 12 * kRuns;
+    const long long target_runs = (long long)ct_sm_count() * kWarps * kRuns;
     long long R = 4096;
     while (R > 256 && (n + R - 1) / R < target_runs) R >>= 1;
     while (R < Hw) R <<= 1;
@@ -688,6 +871,16 @@ extern "C" int64_t ct_filtfilt_stats_granule(int64_t n, int64_t pad, int H) {
     return (int64_t)pick_run(n + pad, Hw) * kRuns;
 }
 
+extern "C" int ct_filter_decimation(const CtFilterCoef* coef, int64_t pad, int H) {
+    if (!coef) { ct_set_error("filter_decimation: null coefficients"); return CT_ERR_ARG; }
+    return pick_decimation(*coef, pad, (H + kK - 1) / kK * kK);
+}
+
+/* float2 entries the chunk-extrema array of ct_filter_backward needs (one per 64 output samples of the run grid) */
+extern "C" int64_t ct_filter_summary_count(int64_t n, int64_t pad, int H) {
+    return ct_filtfilt_workspace_bytes(n, pad, H) / 4 / kK;
+}
+
 namespace {
 
 struct Plan { int Hw, R; long long G, base, n1, ng_fwd, ng_bwd, g_right; };
@@ -706,23 +899,30 @@ Plan make_plan(long long n, long long pad, int H, long long origin) {
     return p;
 }
 void init_args(SeqArgs& a) {
-    a.scratch_runs = 0; a.base = 0; a.g_first = 0; a.pad_x = 0.f; a.cw_lo = 0; a.cw_sh = 0; a.cw_out = nullptr;
-    a.cw_p0 = 0; a.cw_p1 = 0;
-    a.st_cnt = nullptr; a.st_s1 = nullptr; a.st_s2 = nullptr; a.st_origin = 0; a.st_block = 1;
-    a.st_min = a.st_max = a.st_c0 = a.st_scale = a.st_nc0s = 0.f; a.n_out = 0; a.sub = 0.f; a.mask = 0xffffu; a.scale = 1.f; a.offset = 0.f;
+    memset(&a, 0, sizeof(a));
+    a.st_block = 1; a.mask = 0xffffu; a.scale = 1.f;
 }
 int check_ws(const void* workspace, int64_t workspace_bytes, int64_t n, int64_t pad, int H) {
-    if (!workspace || workspace_bytes < ct_filtfilt_workspace_bytes(n, pad, H) || (reinterpret_cast<uintptr_t>(workspace) & 31)) {
-        ct_set_error("filter: workspace missing, too small or not 32-byte aligned"); return CT_ERR_ARG;
+    if (!workspace || workspace_bytes < ct_filtfilt_workspace_bytes(n, pad, H) || (reinterpret_cast<uintptr_t>(workspace) & 63)) {
+        ct_set_error("filter: workspace missing, too small or not 64-byte aligned"); return CT_ERR_ARG;
     }
     return CT_OK;
+}
+// x' = value - sub with an INTEGER constant inside the kernel (exact in the byte-permute conversion): the fractional
+// part of `sub` (0 or 0.5 for a median of codes) moves into the pad value and the output offset (the cascade's DC
+// gain is 1: filtfilt(x + f) = filtfilt(x) + f).
+void split_sub(SeqArgs& a, float sub, float pad_x) {
+    const float fl = floorf(sub);
+    a.isub = (int)fl;
+    a.fsub = sub;
+    a.pad_x = pad_x + (sub - fl);
 }
 
 }  // namespace
 
 // Forward pass into the scratch.  in_kind: 0 = uint16 codes, 1 = float32 samples.  part: 0 = whole
-// trace, 1 = only the groups whose result depends on pad_x (the two ends of the trace).
-// counts9 != NULL (uint16 only, part 0): also tally the window count for the exact median.
+// trace, 1 = only the groups whose result depends on pad_x (the two ends of the trace), 2 = streaming.
+// counts9 != NULL (uint16 only, part 0/2): also tally the window count for the exact median.
 int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float pad_x,
                           const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t cw_lo, uint32_t cw_step,
                           int64_t cw_begin, int64_t cw_end, uint64_t* counts9, int64_t from_pos, int64_t to_pos,
@@ -730,17 +930,31 @@ int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, f
     int rc = check_ws(workspace, workspace_bytes, n, pad, H); if (rc) return rc;
     const Plan p = make_plan(n, pad, H, origin);
     SeqArgs a; init_args(a);
-    a.in = in; a.n_in = n; a.sub = sub; a.mask = mask; a.pad_x = pad_x; a.Hw = p.Hw; a.R = p.R; a.base = p.base;
+    a.in = in; a.n_in = n; a.mask = mask; a.Hw = p.Hw; a.R = p.R; a.base = p.base;
+    if (in_kind == 0) split_sub(a, sub, pad_x); else { a.fsub = sub; a.pad_x = pad_x; }
     a.out = reinterpret_cast<float*>(workspace);
     if (counts9 && part != 1 && in_kind == 0) {
         if (!cw_step || (cw_step & (cw_step - 1))) { ct_set_error("filter: window step must be a power of two"); return CT_ERR_ARG; }
         a.cw_lo = cw_lo; a.cw_sh = __builtin_ctz(cw_step); a.cw_out = (unsigned long long*)counts9;
         a.cw_p0 = cw_begin < 0 ? 0 : cw_begin; a.cw_p1 = cw_end > n ? n : cw_end;
     }
-    const bool half = half_rate_ok(*coef);
+    const int D = pick_decimation(*coef, pad, p.Hw);
+    a.scale = (float)D; a.offset = 0.f;
+    CUtensorMap im, om;
+    memset(&om, 0, sizeof(om));
+    a.tma_in = make_map(&im, in, in_kind ? 4 : 2, p.base, p.R, p.ng_fwd * kRuns, true) ? 1 : 0;
+    // the work counter lives in the last 256 bytes of the workspace (never part of the scratch)
+    a.next_group = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + ct_filtfilt_workspace_bytes(n, pad, H) - 256);
     auto go = [&](const SeqArgs& x) {
-        if (half) return in_kind ? dispatch_fwd<float, kFwdScratch2>(x, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch2>(x, *coef, st);
-        return in_kind ? dispatch_fwd<float, kFwdScratch>(x, *coef, st) : dispatch_fwd<uint16_t, kFwdScratch>(x, *coef, st);
+        cudaMemsetAsync(x.next_group, 0, 8, st);
+        if (in_kind) {
+            if (D == 4) return dispatch_fwd<float, 4>(x, *coef, im, om, st);
+            if (D == 2) return dispatch_fwd<float, 2>(x, *coef, im, om, st);
+            return dispatch_fwd<float, 1>(x, *coef, im, om, st);
+        }
+        if (D == 4) return dispatch_fwd<uint16_t, 4>(x, *coef, im, om, st);
+        if (D == 2) return dispatch_fwd<uint16_t, 2>(x, *coef, im, om, st);
+        return dispatch_fwd<uint16_t, 1>(x, *coef, im, om, st);
     };
     if (part == 0) { a.g_first = 0; a.ngroups = p.ng_fwd; return go(a); }
     if (part == 2) {
@@ -759,15 +973,18 @@ int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, f
     return rc;
 }
 
-// Backward pass scratch -> out = offset + scale * y (+ optional fused baseline block sums).
-int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H,
+// Backward pass scratch -> out = offset + scale * y (+ optional fused baseline block sums and chunk extrema).
+int ct_filter_backward_seq(int64_t n, int64_t pad, float sub, float scale, float offset, const CtFilterCoef* coef, int H,
                            int64_t origin, float* out, const void* workspace, int64_t workspace_bytes,
-                           const CtFilterStats* stats, cudaStream_t st) {
+                           const CtFilterStats* stats, float* summaries, cudaStream_t st) {
     int rc = check_ws(workspace, workspace_bytes, n, pad, H); if (rc) return rc;
     const Plan p = make_plan(n, pad, H, origin);
     SeqArgs b; init_args(b);
-    b.in = workspace; b.n_in = p.n1; b.out = out; b.n_out = n; b.scale = scale; b.offset = offset;
+    b.in = workspace; b.n_in = p.n1; b.out = out; b.n_out = n; b.scale = scale;
+    b.offset = offset - scale * (sub - floorf(sub));      // see split_sub: the kernel subtracted floor(sub)
     b.Hw = p.Hw; b.R = p.R; b.base = p.base; b.scratch_runs = p.ng_fwd * kRuns; b.ngroups = p.ng_bwd;
+    b.summ = reinterpret_cast<float2*>(summaries);
+    if (summaries && (reinterpret_cast<uintptr_t>(summaries) & 31)) { ct_set_error("filter: chunk extrema must be 32-byte aligned"); return CT_ERR_ARG; }
     if (stats) {
         if (stats->block <= 0 || stats->block % p.G || stats->origin != origin || !stats->cnt || !stats->s1 || !stats->s2) {
             ct_set_error("filter: fused block statistics need block %% %lld == 0 and the grid origin (block = %lld)", p.G,
@@ -783,10 +1000,18 @@ int ct_filter_backward_seq(int64_t n, int64_t pad, float scale, float offset, co
             cudaMemsetAsync(stats->cnt, 0, nb * 8, st); cudaMemsetAsync(stats->s1, 0, nb * 8, st); cudaMemsetAsync(stats->s2, 0, nb * 8, st);
         }
         b.st_origin = stats->origin; b.st_block = stats->block; b.st_min = stats->bmin; b.st_max = stats->bmax;
-        b.st_c0 = stats->c0; b.st_scale = ldexpf(1.f, stats->shift); b.st_nc0s = -ldexpf(stats->c0, stats->shift);
+        b.st_scale = ldexpf(1.f, stats->shift); b.st_nc0s = -ldexpf(stats->c0, stats->shift);
         b.st_cnt = (long long*)stats->cnt; b.st_s1 = (long long*)stats->s1; b.st_s2 = (long long*)stats->s2;
     }
-    return half_rate_ok(*coef) ? dispatch_bwd<true>(b, *coef, st) : dispatch_bwd<false>(b, *coef, st);
+    CUtensorMap om;
+    b.tma_out = make_map(&om, out, 4, p.base, p.R, p.ng_bwd * kRuns) ? 1 : 0;
+    b.next_group = reinterpret_cast<unsigned long long*>(const_cast<char*>(reinterpret_cast<const char*>(workspace)) +
+                                                        ct_filtfilt_workspace_bytes(n, pad, H) - 256) + 1;
+    cudaMemsetAsync(b.next_group, 0, 8, st);
+    const int D = pick_decimation(*coef, pad, p.Hw);
+    if (D == 4) return dispatch_bwd<4>(b, *coef, om, st);
+    if (D == 2) return dispatch_bwd<2>(b, *coef, om, st);
+    return dispatch_bwd<1>(b, *coef, om, st);
 }
 
 // One call: forward (+ backward).  stats (may be NULL): fused baseline block sums of the output.
@@ -796,15 +1021,21 @@ int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float s
     if (forward_only) {
         if (stats) { ct_set_error("filter: block statistics are fused into the zero-phase path only"); return CT_ERR_UNSUPPORTED; }
         SeqArgs a; init_args(a);
-        a.in = in; a.n_in = n; a.sub = sub; a.mask = mask; a.scale = scale; a.offset = offset;
+        a.in = in; a.n_in = n; a.mask = mask;
+        if (in_kind == 0) split_sub(a, sub, 0.f); else { a.fsub = sub; a.pad_x = 0.f; }
+        a.scale = scale; a.offset = in_kind == 0 ? offset - scale * (sub - floorf(sub)) : offset;
         a.Hw = (H + kK - 1) / kK * kK; a.R = pick_run(n, a.Hw);
         a.ngroups = (n + (long long)a.R * kRuns - 1) / ((long long)a.R * kRuns);
         a.out = out; a.n_out = n;
-        return in_kind ? dispatch_fwd<float, kFwdFinal>(a, *coef, st) : dispatch_fwd<uint16_t, kFwdFinal>(a, *coef, st);
+        CUtensorMap im, om;
+        a.tma_in = make_map(&im, in, in_kind ? 4 : 2, 0, a.R, a.ngroups * kRuns) ? 1 : 0;
+        a.tma_out = make_map(&om, out, 4, 0, a.R, a.ngroups * kRuns) ? 1 : 0;
+        return in_kind ? dispatch_fwd<float, 0>(a, *coef, im, om, st) : dispatch_fwd<uint16_t, 0>(a, *coef, im, om, st);
     }
     const int64_t origin = stats ? stats->origin : 0;
     int rc = ct_filter_forward_seq(in, in_kind, n, pad, sub, mask, 0.f, coef, H, origin, 0, 0, 1, 0, 0, nullptr, 0, 0, workspace,
                                    workspace_bytes, st);
     if (rc) return rc;
-    return ct_filter_backward_seq(n, pad, scale, offset, coef, H, origin, out, workspace, workspace_bytes, stats, st);
+    return ct_filter_backward_seq(n, pad, in_kind == 0 ? sub : 0.f, scale, offset, coef, H, origin, out, workspace, workspace_bytes,
+                                  stats, nullptr, st);
 }

@@ -231,9 +231,10 @@ class EventList:
 
 
 def detect_events(y: torch.Tensor, baseline: Baseline, *, state_in: bool = False,
-                  capacity: int | None = None) -> EventList:
+                  capacity: int | None = None, chunk_minmax: torch.Tensor | None = None, minmax_shift: int = 0) -> EventList:
     """Threshold/hysteresis detection over the whole filtered trace `y` (device float32).
-    Event i occupies samples [starts[i], ends[i])."""
+    Event i occupies samples [starts[i], ends[i]).  `chunk_minmax`: the (min, max) pairs of the
+    64-sample chunks of `y` the filter's backward pass left (same result, 1/32 of the traffic)."""
     _require_cuda(y, "y", torch.float32)
     L = _lib.lib()
     n = y.numel()
@@ -249,9 +250,11 @@ def detect_events(y: torch.Tensor, baseline: Baseline, *, state_in: bool = False
         starts = torch.empty(cap, dtype=torch.int64, device=dev)
         ends = torch.empty(cap, dtype=torch.int64, device=dev)
         counts = torch.zeros(2, dtype=torch.int64, device=dev)
-        rc = L.ct_detect_f32(y.data_ptr(), n, baseline.block, sign.data_ptr(), ts.data_ptr(), te.data_ptr(),
-                             int(bool(state_in)), ws.data_ptr(), wsb, starts.data_ptr(), ends.data_ptr(), cap,
-                             counts.data_ptr(), _stream_ptr(y))
+        with torch.cuda.device(dev):
+            rc = L.ct_detect_f32(y.data_ptr(), n, baseline.block, sign.data_ptr(), ts.data_ptr(), te.data_ptr(),
+                                 int(bool(state_in)), chunk_minmax.data_ptr() if chunk_minmax is not None else None,
+                                 int(minmax_shift), ws.data_ptr(), wsb, starts.data_ptr(), ends.data_ptr(), cap,
+                                 counts.data_ptr(), _stream_ptr(y))
         _lib.check(rc, "ct_detect_f32")
         ns, ne = (int(v) for v in counts.cpu().numpy())
         if max(ns, ne) <= cap:

@@ -17,27 +17,14 @@ from . import _lib
 from .design import BesselDesign, bessel_lowpass
 
 DEFAULT_HALO_EPS = 1e-7      # truncated natural response relative to max |x - median|
-DEFAULT_SUBSEGMENT = 4096    # output samples per warp sub-segment
 
 
 # ------------------------------------------------------------------ coefficient packing
-def _mat_pow(A: np.ndarray, p: int) -> np.ndarray:
-    R = np.eye(2)
-    B = A.copy()
-    while p:
-        if p & 1:
-            R = R @ B
-        B = B @ B
-        p >>= 1
-    return R
-
-
 _coef_cache: dict[tuple[int, float], "_lib.CtFilterCoef"] = {}
 
 
 def make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
-    """Pack a design for the kernel: per-section taps, the constant state-transition
-    powers A^C and A^(C*2^k) used by the warp scan, steady-state factors, gain."""
+    """Pack a design for the kernel: per-section taps, steady-state factors, gain."""
     key = (design.order, design.wn)
     if key not in _coef_cache:
         _coef_cache[key] = _make_coef(design)
@@ -45,24 +32,14 @@ def make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
 
 
 def _make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
-    Cc = _lib.lib().ct_filter_chunk()
     k = _lib.CtFilterCoef()
     k.nsec = design.nsec
-    k.tile_c = Cc
     dc = 1.0  # DC gain of the cascade up to (not including) the current section
     for s in range(design.nsec):
         a1, a2 = design.sections[s]
         fo = bool(design.first_order[s])
         n1, n2 = (1.0, 0.0) if fo else (2.0, 1.0)
         k.na1[s], k.na2[s], k.n1[s], k.n2[s] = -a1, -a2, n1, n2
-        A = np.array([[-a1, -a2], [1.0, 0.0]])
-        AC = _mat_pow(A, Cc)
-        for i in range(4):
-            k.AC[s][i] = AC.flat[i]
-        for st in range(_lib.CT_SCAN_STEPS):
-            M = _mat_pow(A, Cc * (1 << st))
-            for i in range(4):
-                k.M[s][st][i] = M.flat[i]
         k.ss[s] = dc / (1.0 + a1 + a2)
         dc *= (1.0 + n1 + n2) / (1.0 + a1 + a2)
     k.gain = design.gain
@@ -72,34 +49,20 @@ def _make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
     return k
 
 
-_halo_cache: dict[tuple[int, float, float], int] = {}
+def warmup_samples(design: BesselDesign, eps: float = DEFAULT_HALO_EPS) -> int:
+    """IIR warm-up H of a run: the cascade's impulse response is below eps beyond it."""
+    return max(1, design.impulse_tail(eps))
 
 
-def halo_samples(design: BesselDesign, eps: float = DEFAULT_HALO_EPS) -> int:
-    """IIR warm-up halo H, rounded up to the kernel tile."""
-    key = (design.order, design.wn, float(eps))
-    if key not in _halo_cache:
-        T = _lib.lib().ct_filter_tile()
-        h = design.impulse_tail(eps)
-        _halo_cache[key] = max(T, (h + T - 1) // T * T)
-    return _halo_cache[key]
+def scratch_decimation(design: BesselDesign, padding: int = 1000, eps: float = DEFAULT_HALO_EPS) -> int:
+    """Every how-many-th forward sample the scratch between the two passes keeps (1, 2 or 4): the library's
+    choice from the cascade's stop band (aliasing error < 1e-7), reported for diagnostics and benchmarks."""
+    return int(_lib.lib().ct_filter_decimation(C.byref(make_coef(design)), int(padding), warmup_samples(design, eps)))
 
 
-def _plan(design: BesselDesign, halo_eps: float, subsegment: int | None):
-    """(S, H) for the kernel: subsegment None selects the lane-sequential passes (S = 0, H =
-    raw warm-up length), a number the warp-scan kernel with that sub-segment length."""
-    if not subsegment:
-        return 0, max(1, design.impulse_tail(halo_eps))
-    T = _lib.lib().ct_filter_tile()
-    H = halo_samples(design, halo_eps)
-    S = max(T, (int(subsegment) + T - 1) // T * T)
-    return S, H
-
-
-def _workspace(n: int, padding: int, S: int, H: int, forward_only: bool, device, workspace):
-    """Device scratch for the forward output of the lane-sequential path (caller may pass a
-    reusable uint8 tensor)."""
-    if S or forward_only:
+def _workspace(n: int, padding: int, H: int, forward_only: bool, device, workspace):
+    """Device scratch for the forward output (caller may pass a reusable uint8 tensor)."""
+    if forward_only:
         return None, 0
     need = int(_lib.lib().ct_filtfilt_workspace_bytes(n, padding, H))
     if workspace is None or workspace.numel() < need:
@@ -200,7 +163,7 @@ def code_median(raw: torch.Tensor, mask: int = 0xFFFF) -> tuple[int, int]:
 # ------------------------------------------------------------------------ entry points
 def filtfilt_codes(raw: torch.Tensor, *, alpha: float, pad_value: float, median_code: float, mask: int,
                    design: BesselDesign, padding: int = 1000, forward_only: bool = False,
-                   halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
+                   halo_eps: float = DEFAULT_HALO_EPS,
                    out: torch.Tensor | None = None, workspace: torch.Tensor | None = None, stats=None) -> torch.Tensor:
     """out = pad_value + alpha * filtfilt((raw & mask) - median_code) with the reference's
     boundary handling (dequantisation fused into the load and the store).  `stats`: a
@@ -216,19 +179,20 @@ def filtfilt_codes(raw: torch.Tensor, *, alpha: float, pad_value: float, median_
     if out.numel() != n:
         raise ValueError("out has the wrong length")
     coef = make_coef(design)
-    S, H = _plan(design, halo_eps, subsegment)
-    ws, wsb = _workspace(n, int(padding), S, H, forward_only, raw.device, workspace)
-    rc = _lib.lib().ct_filtfilt_u16(raw.data_ptr(), n, int(padding), float(median_code), int(mask),
-                                    float(alpha), float(pad_value), C.byref(coef), S, H,
-                                    int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
-                                    wsb, C.byref(stats) if stats is not None else None, _stream_ptr(raw))
+    H = warmup_samples(design, halo_eps)
+    ws, wsb = _workspace(n, int(padding), H, forward_only, raw.device, workspace)
+    with torch.cuda.device(raw.device):
+        rc = _lib.lib().ct_filtfilt_u16(raw.data_ptr(), n, int(padding), float(median_code), int(mask),
+                                        float(alpha), float(pad_value), C.byref(coef), H,
+                                        int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                        wsb, C.byref(stats) if stats is not None else None, _stream_ptr(raw))
     _lib.check(rc, "ct_filtfilt_u16")
     return out
 
 
 def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8, *,
                      samplerate: float | None = None, padding: int = 1000, forward_only: bool = False,
-                     halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
+                     halo_eps: float = DEFAULT_HALO_EPS,
                      median_codes: tuple[int, int] | None = None,
                      out: torch.Tensor | None = None, workspace: torch.Tensor | None = None, stats=None) -> torch.Tensor:
     """`App.scale_raw_data` + `App.filter_data` (plot-trace.py:272-287, 313-320) fused:
@@ -246,7 +210,7 @@ def dequant_filtfilt(raw: torch.Tensor, settings, cutoff: float, order: int = 8,
     pad_value = float(np.median(vals))
     return filtfilt_codes(raw, alpha=alpha, pad_value=pad_value, median_code=0.5 * (c1 + c2), mask=mask,
                           design=design, padding=padding, forward_only=forward_only, halo_eps=halo_eps,
-                          subsegment=subsegment, out=out, workspace=workspace, stats=stats)
+                          out=out, workspace=workspace, stats=stats)
 
 
 def stats_granule(n: int, padding: int, design: BesselDesign, halo_eps: float = DEFAULT_HALO_EPS) -> int:
@@ -285,7 +249,7 @@ def float_median(x: torch.Tensor, *, use_abs: bool = False) -> float:
 
 def bessel_filtfilt(x: torch.Tensor, samplerate: float, cutoff: float, order: int = 8, *,
                     pad_value: float | None = None, padding: int = 1000, forward_only: bool = False,
-                    halo_eps: float = DEFAULT_HALO_EPS, subsegment: int | None = None,
+                    halo_eps: float = DEFAULT_HALO_EPS,
                     out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """Zero-phase Bessel of an already-dequantised float32 trace (e.g. `.bin` data,
     print_trace.py:33): out = pad_value + filtfilt(x - pad_value) with `padding` samples
@@ -301,11 +265,12 @@ def bessel_filtfilt(x: torch.Tensor, samplerate: float, cutoff: float, order: in
     _require_cuda(out, "out", torch.float32)
     design = bessel_lowpass(int(order), 2.0 * float(cutoff) / float(samplerate))
     coef = make_coef(design)
-    S, H = _plan(design, halo_eps, subsegment)
-    ws, wsb = _workspace(n, int(padding), S, H, forward_only, x.device, workspace)
-    rc = _lib.lib().ct_filtfilt_f32(x.data_ptr(), n, int(padding), float(pad_value), C.byref(coef), S, H,
-                                    int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
-                                    wsb, None, _stream_ptr(x))
+    H = warmup_samples(design, halo_eps)
+    ws, wsb = _workspace(n, int(padding), H, forward_only, x.device, workspace)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ct_filtfilt_f32(x.data_ptr(), n, int(padding), float(pad_value), C.byref(coef), H,
+                                        int(bool(forward_only)), out.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                        wsb, None, _stream_ptr(x))
     _lib.check(rc, "ct_filtfilt_f32")
     return out
 
@@ -319,11 +284,11 @@ def bessel_lfilter(x: torch.Tensor, samplerate: float, cutoff: float, order: int
 
 
 def bessel_filtfilt_odd(x: torch.Tensor, samplerate: float, cutoff: float, poles: int) -> torch.Tensor:
-    """legacy/bessel-filter.py:124-131: np.pad(x, poles, mode='edge') followed by scipy's
-    default filtfilt (padtype='odd', padlen = 3*ntaps = 3*(poles+1)).  The odd extension is a
-    few dozen samples and is built on the device with torch; the kernel then runs without a
-    constant pad, its steady-state initial conditions being exactly scipy's zi*ext[0] and
-    zi*y[-1].  Returns the edge-padded length like the reference."""
+    """legacy/bessel-filter.py:124-131: `np.pad(x, poles, mode='edge')`, scipy's default filtfilt
+    (`method='pad', padlen=None`: padtype='odd', padlen = 3*ntaps = 3*(poles+1)) and `[poles:-poles]`,
+    so the result has the length of `x`.  The odd extension is a few dozen samples and is built on the
+    device with torch; the kernel then runs without a constant pad (which also keeps the scratch at full
+    rate), its steady-state initial conditions being exactly scipy's zi*ext[0] and zi*y[-1]."""
     _require_cuda(x, "x", torch.float32)
     p = int(poles)
     xe = torch.cat((x[:1].expand(p), x, x[-1:].expand(p)))
@@ -334,4 +299,4 @@ def bessel_filtfilt_odd(x: torch.Tensor, samplerate: float, cutoff: float, poles
     right = 2 * xe[-1] - torch.flip(xe[-edge - 1:-1], [0])
     ext = torch.cat((left, xe, right)).contiguous()
     y = bessel_filtfilt(ext, samplerate, cutoff, p, pad_value=float(ext[0].item()), padding=0)
-    return y[edge:-edge]
+    return y[edge + p:y.numel() - edge - p]

@@ -34,6 +34,11 @@ class TraceResult:
     total_events: int = 0
 
 
+def _world(group) -> int:
+    import torch.distributed as dist
+    return dist.get_world_size(group)
+
+
 def _all_reduce_(t: torch.Tensor, group) -> torch.Tensor:
     if group is not None:
         import torch.distributed as dist
@@ -58,21 +63,29 @@ def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n
     """Phase 1: a strided-sample histogram (summed over `group`) locates the median code.  `n_sampled`:
     the histogram covers only that many of the rank's samples (streaming: the first chunk), so it
     is an estimate even for small traces."""
-    if group is None:
-        n = int(n_local)
-    else:
-        nt = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
-        n = int(_all_reduce_(nt, group).item())
-    if n == 0:
-        raise ValueError("median of an empty trace")
     shift = 0
     while shift < 16 and not (mask >> shift) & 1:
         shift += 1
     step = 1 << shift
+    if group is None:
+        n = int(n_local)
+        if n == 0:
+            raise ValueError("median of an empty trace")
+        stride = max(1, (n if n_sampled is None else int(n_sampled)) // (1 << 20))  # ~1 M samples: median s.e. < 0.1 code
+        hist = hist_fn(stride).to(torch.int64)
+    else:
+        # every rank samples with the stride of ITS share (ranks own equal shares), and the sample count rides in the
+        # same all_reduce as the histogram: one collective for the phase
+        stride = max(1, (int(n_local) if n_sampled is None else int(n_sampled)) * _world(group) // (1 << 20))
+        h = hist_fn(stride).to(torch.int64)
+        packed = _all_reduce_(torch.cat((h, torch.tensor([int(n_local)], dtype=torch.int64, device=h.device))), group)
+        n = int(packed[-1].item())
+        if n == 0:
+            raise ValueError("median of an empty trace")
+        hist = packed[:-1]
     k1, k2 = (n - 1) // 2, n // 2
-    stride = max(1, (n if n_sampled is None else int(n_sampled)) // (1 << 20))      # ~1 M samples: median s.e. < 0.1 code
     # the rank search runs where the histogram lives (device): 8 bytes come back instead of 65 536 bins
-    cdf = torch.cumsum(_all_reduce_(hist_fn(stride).to(torch.int64), group), 0)
+    cdf = torch.cumsum(hist, 0)
     if stride == 1 and n_sampled is None:
         want = torch.tensor([k1 + 1, k2 + 1], dtype=torch.int64, device=cdf.device)
         c1, c2 = (int(v) for v in torch.searchsorted(cdf, want).tolist())
@@ -168,6 +181,22 @@ def event_id_offsets(n_local_events: int, group=None, device=None) -> tuple[int,
     return int(c[:rk].sum()), int(c.sum())
 
 
+def event_ids_and_status(n_local_events: int, status: int, group=None, device=None) -> tuple[int, int, int]:
+    """`event_id_offsets` with a status flag riding in the same all_reduce: (first id, total events, sum of the
+    ranks' flags).  A rank that hit an error passes status != 0 INSTEAD of raising before the collective, so that
+    every rank takes the same decision afterwards (raise together, fall back together) and nobody is left waiting
+    in a collective its peers never enter."""
+    if group is None:
+        return 0, int(n_local_events), int(status)
+    import torch.distributed as dist
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    v = torch.zeros(ws + 1, dtype=torch.int64, device=device)
+    v[rk] = int(n_local_events)
+    v[ws] = int(status != 0)
+    c = _all_reduce_(v, group).cpu().numpy()
+    return int(c[:rk].sum()), int(c[:ws].sum()), int(c[ws])
+
+
 def required_halo(cutoff: float, order: int, samplerate: float, max_event: int, padding: int = 1000,
                   eps: float = filters.DEFAULT_HALO_EPS, block: int = 1) -> int:
     """Samples a rank must read beyond each end of its owned range: IIR warm-up on both
@@ -218,12 +247,20 @@ class TraceAnalyzer:
                  cusum_h: float | None = None, max_levels: int = cusum.DEFAULT_MAX_LEVELS,
                  event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = True,
                  fused_count: bool = False, intra_threshold: float = 0.0, intra_hysteresis: float = 0.0,
-                 max_crossings: int = 8):
+                 max_crossings: int = 8, halos_clipped_by_trace_ends: bool = False):
         self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
         self.n_own = self.n_ext - self.lo_halo - self.hi_halo
         self.n_det = self.n_ext
         if self.lo_halo % int(baseline_block):
             raise ValueError("lo_halo must be a multiple of the baseline block (pipeline.required_halo(..., block=))")
+        # a halo (0 = a true end of the trace) must cover the IIR warm-up of both passes and one maximal event window
+        need = required_halo(cutoff, order, float(np.floor(np.squeeze(settings["ADCSAMPLERATE"]))),
+                             int(maxpoints) + 2 * int(event_padding), int(padding))
+        # (`halos_clipped_by_trace_ends`: the caller cut full halos at the true ends of the trace, where nothing is missing)
+        for name, h in (("lo_halo", self.lo_halo), ("hi_halo", self.hi_halo)):
+            if 0 < h < need and not halos_clipped_by_trace_ends:
+                raise ValueError(f"{name} = {h} samples is shorter than the {need} this configuration needs "
+                                 "(pipeline.required_halo(cutoff, order, fs, maxpoints + 2 * event_padding))")
         self.settings, self.cutoff, self.order, self.padding = settings, float(cutoff), int(order), int(padding)
         self.threshold, self.hysteresis = float(threshold), float(hysteresis)
         self.block, self.bmin, self.bmax = int(baseline_block), float(baseline_min), float(baseline_max)
@@ -245,6 +282,7 @@ class TraceAnalyzer:
                            and self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0)
         self.fused_count = bool(fused_count)     # tally the exact-median window inside the forward pass (measured slower)
         self.filter_ws = None
+        self.minmax = None                         # (min, max) of every 64-sample chunk of y, left by the backward pass
         self.H = max(1, self.design.impulse_tail(filters.DEFAULT_HALO_EPS))
         self.ws_bytes = int(L.ct_detect_workspace_bytes(self.n_det))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
@@ -297,6 +335,11 @@ class TraceAnalyzer:
         return self.run(self.raw_dev, stage_hook=stage_hook, _arrivals=(bounds, events))
 
     def run(self, raw_ext: torch.Tensor, stage_hook=None, _arrivals=None, _fixed=None) -> AnalysisResult:
+        # the library keys its per-device state on the CURRENT device: make it the tensors' device
+        with torch.cuda.device(self.device):
+            return self._run(raw_ext, stage_hook, _arrivals, _fixed)
+
+    def _run(self, raw_ext: torch.Tensor, stage_hook=None, _arrivals=None, _fixed=None) -> AnalysisResult:
         """One pass of stages 1-3.  `stage_hook(name)` (optional) is called after the launches of each
         stage have been enqueued: 'median', 'filter', 'baseline', 'detect', 'cusum' (profiling only).
         `_fixed = (MedianPlan, pad_x, (c1, c2))` (StreamingAnalyzer) skips the median stages: the filter
@@ -325,6 +368,8 @@ class TraceAnalyzer:
         if self.filter_ws is None:
             need = int(L.ct_filtfilt_workspace_bytes(self.n_ext, self.padding, self.H))
             self.filter_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.minmax = torch.empty(2 * int(L.ct_filter_summary_count(self.n_ext, self.padding, self.H)), dtype=torch.float32,
+                                      device=self.device)
         coef = filters.make_coef(self.design)
         alpha, _ = filters.chimera_affine(self.settings)
         origin = 0
@@ -369,9 +414,9 @@ class TraceAnalyzer:
         stats = detect.stats_args(bl, origin=0) if bl is not None else None
         offset = float(filters.scale_codes_host(np.array([plan.est], dtype=np.uint16), self.settings)[0])
         y = self.y
-        rc = L.ct_filter_backward(self.n_ext, self.padding, float(alpha), offset, C.byref(coef), self.H, origin,
+        rc = L.ct_filter_backward(self.n_ext, self.padding, float(plan.est), float(alpha), offset, C.byref(coef), self.H, origin,
                                   y.data_ptr(), self.filter_ws.data_ptr(), self.filter_ws.numel(),
-                                  C.byref(stats) if stats is not None else None, st)
+                                  C.byref(stats) if stats is not None else None, self.minmax.data_ptr(), st)
         _lib.check(rc, "ct_filter_backward")
         pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), self.settings)))
         yd = y
@@ -387,8 +432,8 @@ class TraceAnalyzer:
         while True:
             sc = self.scalars
             rc = L.ct_detect_f32(yd.data_ptr(), self.n_det, self.block, sign.data_ptr(), ts.data_ptr(), te.data_ptr(), 0,
-                                 self.ws.data_ptr(), self.ws_bytes, self.starts.data_ptr(), self.ends.data_ptr(),
-                                 self.cap, sc[0:].data_ptr(), st)
+                                 self.minmax.data_ptr(), 0, self.ws.data_ptr(), self.ws_bytes, self.starts.data_ptr(),
+                                 self.ends.data_ptr(), self.cap, sc[0:].data_ptr(), st)
             _lib.check(rc, "ct_detect_f32")
             rc = L.ct_event_windows(self.starts.data_ptr(), self.ends.data_ptr(), sc[0:].data_ptr(), self.cap, self.n_det,
                                     lo, lo + n_own, self.event_padding, self.minpoints, self.maxpoints, self.w0.data_ptr(),
@@ -413,8 +458,15 @@ class TraceAnalyzer:
             if max(ns, ne) <= self.cap:
                 break
             self._alloc_events(max(ns, ne))          # more events than planned: grow and redo stages 2-3
-        if int(host[4]) != 0:
-            raise ValueError("no baseline block has enough samples inside [baseline_min, baseline_max]")
+        status = int(host[4]) != 0
+        if _fixed is None:
+            # the error decision is collective: the flag rides with the event counts, then every rank raises
+            first_id, total, bad = event_ids_and_status(0 if status else nk, int(status), self.group, self.device)
+        else:
+            first_id, total, bad = 0, nk, int(status)
+        if bad:
+            raise ValueError("no baseline block has enough samples inside [baseline_min, baseline_max]"
+                             + ("" if status else " (on another rank)"))
         bl._checked = True
         open_start = -1
         if ns > ne:                                   # an event still open at the end of the data
@@ -425,7 +477,6 @@ class TraceAnalyzer:
         lv = None
         if self.delta is not None:
             lv = cusum.LevelTable(self.nl[:nk], self.ed[:nk], self.mu[:nk], self.sd[:nk], self.ov[:nk], self.max_levels)
-        first_id, total = event_id_offsets(nk, self.group, self.device) if _fixed is None else (0, nk)
         return AnalysisResult(filtered=y[lo:lo + n_own], detect_trace=yd, lo_halo=lo, baseline=bl, events=ev,
                               win_start=self.w0[:nk], win_end=self.w1[:nk], types=self.typ[:nk], levels=lv,
                               pad_value=pad_value, median_codes=(c1, c2), first_event_id=first_id, total_events=total,
@@ -526,7 +577,8 @@ class StreamingAnalyzer:
         key = (eb - ea, a - ea, eb - b)
         if key not in self.analyzers:
             self.analyzers[key] = TraceAnalyzer(eb - ea, self.settings, self.cutoff, self.order, lo_halo=a - ea,
-                                                hi_halo=eb - b, group=None, device=self.device, **self.kw)
+                                                hi_halo=eb - b, group=None, device=self.device,
+                                                halos_clipped_by_trace_ends=True, **self.kw)
         return self.analyzers[key]
 
     def _pinned(self, name: str, like: torch.Tensor, rows: int) -> torch.Tensor:
@@ -569,6 +621,10 @@ class StreamingAnalyzer:
         return nk
 
     def run_from_host(self, host_codes: torch.Tensor) -> StreamResult:
+        with torch.cuda.device(self.device):
+            return self._run_from_host(host_codes)
+
+    def _run_from_host(self, host_codes: torch.Tensor) -> StreamResult:
         """`host_codes`: CPU (ideally pinned) uint16/int16 tensor [lo_halo | owned | hi_halo].  One
         host synchronisation per sub-shard (its event count), all hidden under the copy except the last."""
         if host_codes.numel() != self.n_ext or host_codes.dtype not in (torch.uint16, torch.int16) or host_codes.is_cuda:
@@ -609,35 +665,48 @@ class StreamingAnalyzer:
         reserve = max(1024, (self.sub[0][3] - self.sub[0][2]) // 512) if head else 0
         rows, first_rows = reserve, 0
         med, pad_x, redone = (0, 0), 0.0, ""
-        try:
-            for i, (pa, pe, ev) in enumerate(arrivals):
-                cur.wait_event(ev)
-                ca, cb = max(pa, a0), min(pe, b_end)
-                if plan.exact is None and cb > ca:           # exact-median window count of this piece's owned codes
-                    rc = L.ct_count_window_u16(self.raw_dev[ca:cb].data_ptr(), cb - ca, self.mask, plan.lo, plan.step,
-                                               counts.data_ptr(), st)
-                    _lib.check(rc, "ct_count_window_u16")
-                last = i == len(arrivals) - 1
-                if last:                                      # everything has arrived: exact order statistics
-                    med = median_search(self.n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
-                                        first_counts=counts if plan.exact is None else None)
-                    pad_x = 0.5 * (med[0] + med[1]) - plan.est
-                if head and i == 0:
-                    first_rows = self._process(0, plan, 0.0, med, 0, bl, end_at=reserve)
-                else:
-                    rows += self._process(i, plan, pad_x if last else 0.0, med, rows, bl)
-            if head and (pad_x != 0.0 or first_rows < 0):
-                first_rows = self._process(0, plan, pad_x, med, 0, bl, end_at=reserve)
-                redone = "first"
-            if first_rows < 0:                                # more events at the very start than the reserved head holds
-                raise ValueError("baseline block / head reserve: fall back to the whole-trace analyzer")
-        except ValueError as e:
-            if "baseline block" not in str(e):
-                raise
-            return self._run_whole(host_codes)                # a sub-shard without a single valid baseline block
-        start = reserve - first_rows                            # first row of the (right-aligned) head
-        n_rows = rows - start
-        first_id, total = event_id_offsets(n_rows, self.group, self.device)
+        # A sub-shard without a single valid baseline block (or more events at the very start than the reserved head
+        # holds) sends this rank to the whole-trace analyzer.  That decision must be COLLECTIVE: the rank keeps taking
+        # part in the median collectives below, the flag rides with the event counts, and all ranks fall back together.
+        failed = False
+
+        def attempt(*args, **kwargs) -> int:
+            nonlocal failed
+            try:
+                return self._process(*args, **kwargs)
+            except ValueError as e:
+                if "baseline block" not in str(e):
+                    raise
+                failed = True
+                return 0
+
+        for i, (pa, pe, ev) in enumerate(arrivals):
+            cur.wait_event(ev)
+            ca, cb = max(pa, a0), min(pe, b_end)
+            if plan.exact is None and cb > ca:           # exact-median window count of this piece's owned codes
+                rc = L.ct_count_window_u16(self.raw_dev[ca:cb].data_ptr(), cb - ca, self.mask, plan.lo, plan.step,
+                                           counts.data_ptr(), st)
+                _lib.check(rc, "ct_count_window_u16")
+            last = i == len(arrivals) - 1
+            if last:                                      # everything has arrived: exact order statistics
+                med = median_search(self.n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
+                                    first_counts=counts if plan.exact is None else None)
+                pad_x = 0.5 * (med[0] + med[1]) - plan.est
+            if failed:
+                continue
+            if head and i == 0:
+                first_rows = attempt(0, plan, 0.0, med, 0, bl, end_at=reserve)
+            else:
+                rows += attempt(i, plan, pad_x if last else 0.0, med, rows, bl)
+        if head and not failed and (pad_x != 0.0 or first_rows < 0):
+            first_rows = attempt(0, plan, pad_x, med, 0, bl, end_at=reserve)
+            redone = "first"
+        if first_rows < 0:                                # more events at the very start than the reserved head holds
+            failed = True
+        start = reserve - max(first_rows, 0)
+        first_id, total, any_failed = event_ids_and_status(0 if failed else rows - start, int(failed), self.group, self.device)
+        if any_failed:
+            return self._run_whole(host_codes)
         cur.synchronize()
         bl.dev["have_thresholds"] = True
         bl._checked = True
@@ -685,7 +754,10 @@ def analyze_trace(raw: torch.Tensor, settings, cutoff: float, order: int = 8, *,
 def gather_tables(tables: dict, group=None, dst: int = 0) -> dict | None:
     """Gather per-rank event-table columns (tensors whose first dimension is the rank's event count) to rank
     `dst` in rank order = time order (the one data-sized collective of the path, O(events)).
-    Returns the concatenated columns on `dst`, None elsewhere; with `group=None` the input itself."""
+    One small all_reduce exchanges the row counts; every column then travels point to point, exactly its rows,
+    straight into its slice of the concatenated column on `dst` (one batched send/receive group, no padding and
+    nothing sent to ranks that do not need it).  Returns the concatenated columns on `dst`, None elsewhere; with
+    `group=None` the input itself."""
     if group is None:
         return tables
     import torch.distributed as dist
@@ -695,15 +767,22 @@ def gather_tables(tables: dict, group=None, dst: int = 0) -> dict | None:
     counts = torch.zeros(ws, dtype=torch.int64, device=dev)
     counts[rk] = first.shape[0]
     counts = _all_reduce_(counts, group).cpu().numpy()
-    m = int(counts.max())
-    out = {}
-    for name, t in tables.items():
-        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        pad[:t.shape[0]] = t
-        bufs = [torch.empty_like(pad) for _ in range(ws)]
-        dist.all_gather(bufs, pad, group=group)          # NCCL has no gatherv: pad to the longest table
+    offs = np.concatenate(([0], np.cumsum(counts)))
+    out, ops = {}, []
+    for name, t in tables.items():                       # same column order on every rank (dict order)
+        t = t.contiguous()
         if rk == dst:
-            out[name] = torch.cat([b[:int(c)] for b, c in zip(bufs, counts)])
+            full = torch.empty((int(offs[-1]),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            full[int(offs[rk]):int(offs[rk + 1])] = t
+            for src in range(ws):
+                if src != dst and counts[src]:
+                    ops.append(dist.P2POp(dist.irecv, full[int(offs[src]):int(offs[src + 1])], dist.get_global_rank(group, src), group))
+            out[name] = full
+        elif counts[rk]:
+            ops.append(dist.P2POp(dist.isend, t, dist.get_global_rank(group, dst), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
     return out if rk == dst else None
 
 

@@ -23,24 +23,19 @@
 extern "C" {
 #endif
 
-#define CT_ABI_VERSION 1
+#define CT_ABI_VERSION 2
 #define CT_MAX_SECTIONS 5
-#define CT_SCAN_STEPS 5
 
 /* Filter coefficients as the kernel consumes them (built on the host in float64 by
  * cusumtools_b200/design.py from the same Bessel design the reference requests with
  * scipy.signal.bessel(order, Wn, 'low') at plot-trace.py:317).
  *   section s: v[n] = x[n] + na1*v[n-1] + na2*v[n-2];  y[n] = v[n] + n1*v[n-1] + n2*v[n-2]
- *   AC  = A^C,  M[k] = A^(C*2^k)  with A = [[na1, na2], [1, 0]] (row-major 2x2)
  *   ss  = steady-state value of v for a unit constant at the cascade input
  *   gain = overall scale making the DC gain exactly 1 (applied in the last section)   */
 typedef struct CtFilterCoef {
     int32_t nsec;
-    int32_t tile_c;                               /* must equal ct_filter_chunk() */
     float na1[CT_MAX_SECTIONS], na2[CT_MAX_SECTIONS];
     float n1[CT_MAX_SECTIONS], n2[CT_MAX_SECTIONS];
-    float AC[CT_MAX_SECTIONS][4];
-    float M[CT_MAX_SECTIONS][CT_SCAN_STEPS][4];
     float ss[CT_MAX_SECTIONS];
     float gain;
 } CtFilterCoef;
@@ -58,12 +53,12 @@ int ct_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int6
  * steady-state initial conditions).  raw codes are masked with `mask` first
  * (plot-trace.py:281-282).  forward_only != 0 gives the causal pass only (scipy.signal.lfilter
  * with zi = lfilter_zi*pad_value), the primitive filtfilt is built from.
- *   S == 0 (default path): two lane-sequential passes; H = IIR warm-up per run (any value,
- *     rounded up to ct_filter_seq_tile()); workspace = ct_filtfilt_workspace_bytes(n, pad, H)
- *     bytes of device scratch (16-byte aligned) for the forward output, unused if forward_only.
- *   S > 0: the single-kernel warp-scan formulation; S (sub-segment) and H are multiples of
- *     ct_filter_tile(), no workspace needed.                                            */
-/* Optional fusion of ct_block_stats_f32 into the zero-phase filter (S == 0 path): the final
+ *   Two lane-sequential passes staged with TMA; H = IIR warm-up per run (any value, rounded up to
+ *   ct_filter_seq_tile()); workspace = ct_filtfilt_workspace_bytes(n, pad, H) bytes of device scratch
+ *   (64-byte aligned) for the forward output, unused if forward_only.  The scratch keeps every D-th
+ *   forward sample, D = ct_filter_decimation(coef, pad, H) in {1, 2, 4}, chosen from the cascade's
+ *   own stop band so that the aliasing error stays below 1e-7 of the signal.                    */
+/* Optional fusion of ct_block_stats_f32 into the zero-phase filter: the final
  * samples are tallied on their way out, which saves the separate 4 B/sample pass.  The block
  * grid starts at output sample `origin` (samples before it are not tallied; time shards put
  * their left halo there); `block` must be a multiple of ct_filtfilt_stats_granule(n, pad, H).
@@ -75,23 +70,22 @@ typedef struct CtFilterStats {
     int64_t* cnt; int64_t* s1; int64_t* s2;
 } CtFilterStats;
 
-int ct_filter_tile(void);
 int ct_filter_seq_tile(void);
+int ct_filter_decimation(const CtFilterCoef* coef, int64_t pad, int H);
 int64_t ct_filtfilt_stats_granule(int64_t n, int64_t pad, int H);
-int ct_filter_chunk(void);
 int64_t ct_filtfilt_workspace_bytes(int64_t n, int64_t pad, int H);
 int ct_filtfilt_u16(const uint16_t* raw, int64_t n, int64_t pad, float median_code, uint16_t mask,
-                    float alpha, float pad_value, const CtFilterCoef* coef, int S, int H,
+                    float alpha, float pad_value, const CtFilterCoef* coef, int H,
                     int forward_only, float* out, void* workspace, int64_t workspace_bytes,
                     const CtFilterStats* stats, void* stream);
 /* Same for already-dequantised float32 input (.bin traces, print_trace.py:33,
  * noise-fit.py:90; multi-gain file series, plot-trace.py:252-269):
  *   out = pad_value + filtfilt(x - pad_value).                                         */
 int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, const CtFilterCoef* coef,
-                    int S, int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
+                    int H, int forward_only, float* out, void* workspace, int64_t workspace_bytes,
                     const CtFilterStats* stats, void* stream);
 
-/* The two passes of the S == 0 path as separate calls, for callers that know the median only
+/* The two passes as separate calls, for callers that know the median only
  * approximately when the forward pass starts (streaming loads; fusing the exact count into the
  * pass that reads every code anyway).  With DC gain exactly 1,
  *     filtfilt(code - m) + m == filtfilt(code - c) + c      for ANY constant c,
@@ -99,17 +93,23 @@ int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, con
  * (`sub_code`) with pad_x = 0; it can tally, on the side, the window counts that pin the exact
  * median m (counts9: as ct_count_window_u16, zeroed by the caller); if m != c the caller re-runs
  * only the groups the pad influences (`part` = 1, pad_x = m - c) and then runs the backward
- * pass with offset = value(c).  `origin` (>= 0) aligns the run grid with baseline blocks counted
- * from that output sample; both passes must get the same value.  Only codes at positions
- * [count_begin, count_end) are tallied (a time shard counts its owned samples, not its halos).
+ * pass with the same sub_code and offset = value(sub_code).  `origin` (>= 0) aligns the run grid with
+ * baseline blocks counted from that output sample; both passes must get the same value.  Only codes at
+ * positions [count_begin, count_end) are tallied (a time shard counts its owned samples, not its halos).
  * part = 2 streams the pass while the codes are still arriving: each call processes the groups
- * whose input lies below to_pos and that the previous call (which ended at from_pos) did not. */
+ * whose input lies below to_pos and that the previous call (which ended at from_pos) did not.
+ * chunk_minmax (may be NULL): float[2 * ct_filter_summary_count(n, pad, H)], 32-byte aligned; entry c
+ * receives (min, max) of the output samples [64 c - shift, 64 c - shift + 64), shift = (G - origin % G) % G with
+ * G = ct_filtfilt_stats_granule (0 when origin is 0): what ct_detect_f32 needs to classify whole chunks
+ * without re-reading the trace.  Entries of chunks that are not entirely inside [0, n) are unspecified. */
+int64_t ct_filter_summary_count(int64_t n, int64_t pad, int H);
 int ct_filter_forward_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub_code, uint16_t mask, float pad_x,
                           const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t window_lo,
                           uint32_t window_step, int64_t count_begin, int64_t count_end, uint64_t* counts9, int64_t from_pos,
                           int64_t to_pos, void* workspace, int64_t workspace_bytes, void* stream);
-int ct_filter_backward(int64_t n, int64_t pad, float scale, float offset, const CtFilterCoef* coef, int H, int64_t origin,
-                       float* out, const void* workspace, int64_t workspace_bytes, const CtFilterStats* stats, void* stream);
+int ct_filter_backward(int64_t n, int64_t pad, float sub_code, float scale, float offset, const CtFilterCoef* coef, int H,
+                       int64_t origin, float* out, const void* workspace, int64_t workspace_bytes, const CtFilterStats* stats,
+                       float* chunk_minmax, void* stream);
 
 /* Exact global median of the masked codes, the value np.pad(mode='median') needs
  * (plot-trace.py:319): a strided-sample histogram to locate it and an exact count of
@@ -144,10 +144,13 @@ int ct_detect_run(void);                          /* `block` must be a multiple 
 int64_t ct_detect_workspace_bytes(int64_t n);
 /* starts/ends: int64[capacity] in time order; counts2 = {n_starts, n_ends} (may exceed
  * capacity: nothing is written past it).  With state_in == 0 event i is
- * [starts[i], ends[i]) for i < n_ends and starts[n_ends] (if any) is still open.       */
+ * [starts[i], ends[i]) for i < n_ends and starts[n_ends] (if any) is still open.
+ * chunk_minmax (may be NULL): the (min, max) pairs ct_filter_backward left for the 64-sample chunks of y,
+ * entry c covering samples [64 c - minmax_shift, 64 c - minmax_shift + 64); whole chunks are then classified
+ * against the block's lines and only chunks that hold a crossing are read from y (same result).   */
 int ct_detect_f32(const float* y, int64_t n, int64_t block, const int32_t* sign, const float* t_start,
-                  const float* t_end, int state_in, void* workspace, int64_t workspace_bytes,
-                  int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream);
+                  const float* t_end, int state_in, const float* chunk_minmax, int64_t minmax_shift, void* workspace,
+                  int64_t workspace_bytes, int64_t* starts, int64_t* ends, int64_t capacity, uint64_t* counts2, void* stream);
 
 /* Event windows handed to CUSUM+ and the rate.csv `type` code (0 accepted, 2 shorter than
  * minpoints, 3 longer than maxpoints, 4 padding leaves the trace or overlaps a neighbour;

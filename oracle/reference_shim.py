@@ -44,7 +44,8 @@ def _install_stubs() -> None:
         _stub("matplotlib", use=lambda *a, **k: None)
         _stub("matplotlib.figure", Figure=object)
         _stub("matplotlib.backends")
-        _stub("matplotlib.backends.backend_tkagg", FigureCanvasTkAgg=object, NavigationToolbar2Tk=object)
+        _stub("matplotlib.backends.backend_tkagg", FigureCanvasTkAgg=object, NavigationToolbar2Tk=object,
+              NavigationToolbar2TkAgg=object)
         _stub("matplotlib.pyplot")
         _stub("pylab")
     try:
@@ -68,7 +69,7 @@ def load(script: str) -> types.ModuleType:
     if not available():
         raise FileNotFoundError(f"reference not present at {REFERENCE_ROOT}")
     _install_stubs()
-    name = "ref_" + script.replace("-", "_").replace(".py", "")
+    name = "ref_" + script.replace("-", "_").replace(".py", "").replace(os.sep, "_")
     spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, script))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
@@ -109,6 +110,16 @@ def ref_filter_data(data, samplerate, cutoff, order):
     pt = load("plot-trace.py")
     app = make_app(samplerate, cutoff, order, data)
     pt.App.filter_data(app)
+    return app.filtered_data
+
+
+def ref_filter_data_edge(data, fc_khz, fs_khz, poles):
+    """legacy/bessel-filter.py:124-131 (App.filter_data of the step-response tool): edge pad by `poles`,
+    scipy-default filtfilt (odd extension), [poles:-poles].  The tool's entries hold kHz."""
+    bf = load(os.path.join("legacy", "bessel-filter.py"))
+    app = SimpleNamespace(fc_entry=_Entry(repr(float(fc_khz))), fs_entry=_Entry(repr(float(fs_khz))),
+                          poles=_Entry(str(int(poles))), perfect_data=data)
+    bf.App.filter_data(app)
     return app.filtered_data
 
 

@@ -119,12 +119,12 @@ def filter_data(data, samplerate, cutoff, order, padding=1000):
 
 
 def filter_data_edge(data, samplerate, cutoff, poles):
-    """legacy/bessel-filter.py:124-131 — edge pad by `poles`, then scipy-default filtfilt
-    (padtype='odd', padlen=3*ntaps); the reference keeps the edge pad in its output."""
+    """legacy/bessel-filter.py:124-131 — edge pad by `poles`, scipy-default filtfilt
+    (padtype='odd', padlen=3*ntaps) and `[poles:-poles]`: the result has the length of `data`."""
     Wn = 2.0 * float(cutoff) / float(samplerate)
     b, a = bessel(int(poles), Wn, "low")
     padded = np.pad(data, pad_width=int(poles), mode="edge")
-    return filtfilt(b, a, padded, method="pad", padlen=None)
+    return filtfilt(b, a, padded, method="pad", padlen=None)[int(poles):-int(poles)]
 
 
 def lfilter_causal(data, samplerate, cutoff, order, steady=True):

@@ -18,7 +18,7 @@ block = 1 << 16
 kw = dict(threshold=5.0, hysteresis=1.0, baseline_block=block, baseline_min=4700.0, baseline_max=5300.0,
           cusum_delta=400.0, cusum_h=10.0)
 lo, hi = pipeline.shard_bounds(n, world, rank, block)
-halo = pipeline.required_halo(1e5, 8, synth.FS, max_event=4096, block=block)
+halo = pipeline.required_halo(1e5, 8, synth.FS, max_event=100_000 + 2 * 100, block=block)    # maxpoints + 2 * event_padding (the analyzer's defaults)
 a, b = max(0, lo - halo), min(n, hi + halo)
 an = pipeline.TraceAnalyzer(b - a, S, 1e5, 8, lo_halo=lo - a, hi_halo=b - hi, group=dist.group.WORLD, device=dev, **kw)
 r = an.run(torch.from_numpy(codes[a:b]).to(dev))

@@ -23,8 +23,27 @@ from cusumtools_b200 import synth  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def edge_fixture():
+    """fixture 5: the odd-extension boundary mode of legacy/bessel-filter.py:124-131 on the tool's own 26-sample
+    step (generate_step) and on a 3 000-sample noisy step, orders 2 / 4 / 8."""
+    rng = np.random.default_rng(7)
+    step = np.zeros(26)
+    step[13:] = 1.0
+    noisy = np.concatenate((np.zeros(1500), np.ones(1500))) + 0.05 * rng.standard_normal(3000)
+    out = {"step": step, "noisy": noisy, "fc_khz": 100.0, "fs_khz": 1000.0,
+           "versions": np.array([np.__version__, scipy.__version__])}
+    for poles in (2, 4, 8):
+        out[f"step_{poles}"] = ref.ref_filter_data_edge(step, 100.0, 1000.0, poles)
+        out[f"noisy_{poles}"] = ref.ref_filter_data_edge(noisy, 100.0, 1000.0, poles)
+    np.savez_compressed(os.path.join(HERE, "edge_fixture.npz"), **out)
+
+
 def main():
     assert ref.available(), "reference not mounted"
+    if "--only-edge" in sys.argv:
+        edge_fixture()
+        return
+    edge_fixture()
     rng = np.random.default_rng(42)
     settings = synth.CHIMERA_SETTINGS
     fs = np.floor(np.squeeze(settings["ADCSAMPLERATE"]))

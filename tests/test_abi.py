@@ -36,20 +36,18 @@ def test_binding_covers_header():
 def test_version_and_struct_layout():
     from cusumtools_b200 import _lib
     L = _lib.lib()
-    assert L.ct_version() == 1
-    assert L.ct_filter_tile() == 32 * L.ct_filter_chunk()
-    # struct: 2 int32 + (4*5 + 20 + 100 + 5 + 1) floats
-    assert ctypes.sizeof(_lib.CtFilterCoef) == 8 + 4 * (20 + 20 + 100 + 5 + 1)
+    assert L.ct_version() == 2
+    assert L.ct_filter_seq_tile() == 64
+    # struct: 1 int32 + (4*5 + 5 + 1) floats
+    assert ctypes.sizeof(_lib.CtFilterCoef) == 4 + 4 * (20 + 5 + 1)
 
 
 def test_argument_errors_are_reported_without_gpu():
     from cusumtools_b200 import _lib
     L = _lib.lib()
     coef = _lib.CtFilterCoef()
-    coef.nsec, coef.tile_c = 4, L.ct_filter_chunk()
-    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 4096, 512, 0, None, None, 0, None, None)
-    assert rc == -1 and b"null" in L.ct_last_error()
-    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 0, 238, 0, None, None, 0, None, None)
+    coef.nsec = 4
+    rc = L.ct_filtfilt_u16(None, 10, 1000, 0.0, 0xFFFC, 1.0, 0.0, ctypes.byref(coef), 238, 0, None, None, 0, None, None)
     assert rc == -1 and b"bad argument" in L.ct_last_error()
     assert L.ct_filtfilt_workspace_bytes(10_000_000, 1000, 238) >= 4 * 10_001_000
     with pytest.raises(ValueError):

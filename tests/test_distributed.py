@@ -108,6 +108,17 @@ def test_event_ids_follow_rank_order():
     assert run2(_ids_job, world=3) == [(0, 321), (100, 321), (207, 321)]
 
 
+def _status_job(rank, world, group):
+    return pipeline.event_ids_and_status(10 + rank, int(rank == 1), group)
+
+
+def test_error_status_reaches_every_rank():
+    """A rank that failed passes a flag INSTEAD of raising before the collective: every rank sees it in the same
+    all_reduce that carries the event counts and takes the same decision (no rank left in a collective)."""
+    assert run2(_status_job) == [(0, 21, 1), (10, 21, 1)]
+    assert pipeline.event_ids_and_status(7, 0) == (0, 7, 0)
+
+
 def test_shard_bounds_cover_the_trace_and_align():
     for n, world, align in ((2_499_999_600, 8, 1 << 20), (10_000, 3, 4096), (4096 * 5 + 1, 2, 4096)):
         b = [pipeline.shard_bounds(n, world, r, align) for r in range(world)]

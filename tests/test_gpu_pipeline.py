@@ -73,12 +73,22 @@ def test_analyzer_with_halos_keeps_only_owned_events():
     codes, _ = synth.c1_trace(n=500_000, n_events=115, seed=12)
     lo, hi = 8192, 12288
     raw = torch.from_numpy(codes).cuda()
-    an = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=4096,
+    an = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=4096, maxpoints=4000,
                                 cusum_delta=400.0, cusum_h=10.0, **KW)
     r = an.run(raw)
     y = r.detect_trace.cpu().numpy()
     assert y.size == len(codes) and r.filtered.numel() == len(codes) - lo - hi and r.lo_halo == lo
-    check(r, oracle_chain(y, len(codes) - lo - hi, 4096, lo=lo))
+    check(r, oracle_chain(y, len(codes) - lo - hi, 4096, lo=lo, maxp=4000))
+
+
+def test_short_halos_are_rejected():
+    """A halo must cover the warm-up of both filter passes and one maximal event window: events of
+    4k-100k samples straddling a shard boundary would otherwise be dropped or mistyped."""
+    with pytest.raises(ValueError, match="shorter than"):
+        pipeline.TraceAnalyzer(500_000, S, 1e5, 8, lo_halo=8192, hi_halo=0, baseline_block=4096, **KW)
+    with pytest.raises(ValueError, match="shorter than"):
+        pipeline.TraceAnalyzer(500_000, S, 1e5, 8, lo_halo=0, hi_halo=65536, baseline_block=4096, **KW)
+    pipeline.TraceAnalyzer(500_000, S, 1e5, 8, lo_halo=0, hi_halo=65536, baseline_block=4096, maxpoints=50_000, **KW)
 
 
 def test_no_valid_baseline_block_raises():
@@ -161,7 +171,8 @@ def test_analyzer_filter_with_estimated_median_matches_the_oracle_at_the_trace_e
     from oracle import trace_oracle as to
     codes, _ = synth.c1_trace(n=n, n_events=min(1000, (n - 4000) // synth.EVENT_PERIOD), seed=n % 97)
     raw = torch.from_numpy(codes).cuda()
-    an = pipeline.TraceAnalyzer(n, S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=65536, fused_count=(n % 2 == 0), **KW)
+    an = pipeline.TraceAnalyzer(n, S, 1e5, 8, lo_halo=lo, hi_halo=hi, baseline_block=65536, maxpoints=4000,
+                                fused_count=(n % 2 == 0), **KW)
     r = an.run(raw)
     own = codes[lo:n - hi]
     srt = np.sort(own & np.uint16(filters.chimera_bitmask(S)))
