@@ -341,6 +341,9 @@ ct_detect_pass2(const uint2* __restrict__ masks, const uint4* __restrict__ runin
 }
 
 // ---------------------------------- block statistics ---------------------------------
+// oracle/events_oracle.py::block_stats: a sample counts when its whole aligned 64-sample chunk (the last chunk of
+// the trace may be shorter) lies inside [bmin, bmax].  Sixteen lanes own a chunk (a float4 each): the chunk's
+// verdict is a 16-lane vote, the sums are exact integers (order independent).
 constexpr int kStatChunk = 8192;
 __global__ void __launch_bounds__(256)
 ct_block_stats_kernel(const float* __restrict__ y, long long n, long long block, long long chunks_per_block,
@@ -352,27 +355,36 @@ ct_block_stats_kernel(const float* __restrict__ y, long long n, long long block,
     long long b1 = b0 + kStatChunk;
     const long long bend = (kb + 1) * block < n ? (kb + 1) * block : n;
     if (b1 > bend) b1 = bend;
+    const int lane = ct_lane();
+    const unsigned half_mask = 0xffffu << (lane & 16);           // the 16 lanes that share a 64-sample chunk
     long long c = 0, a = 0, b = 0;
-    auto tally = [&](float v) {
-        if (v >= bmin && v <= bmax) {
-            float d = __fmul_rn(__fsub_rn(v, c0), scale);
-            long long q = (long long)__float2ll_rn(d);
-            c += 1; a += q; b += q * q;
-        }
-    };
-    if ((reinterpret_cast<uintptr_t>(y + b0) & 15) == 0 && b1 - b0 == kStatChunk) {
-        // 8192 samples = 2048 float4 = 8 independent 16-byte loads per thread
-        const uint4* y4 = reinterpret_cast<const uint4*>(y + b0);
-        uint4 q[8];
+    const bool aligned = (reinterpret_cast<uintptr_t>(y + b0) & 15) == 0;
+    // 8192 samples = 32 rounds of 256 threads x 4 consecutive samples (64-sample chunks: 16 adjacent lanes)
+    for (long long wb = b0 + (long long)(threadIdx.x & ~31) * 4; wb < b1; wb += 1024) {      // warp-uniform trip count (full-warp votes)
+        const long long p0 = wb + lane * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        int have = 0;
+        if (aligned && p0 + 4 <= b1) {
+            const uint4 q = ct_ldg_stream(y + p0);
+            v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+            have = 4;
+        } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) q[u] = ct_ldg_stream(y4 + threadIdx.x + u * 256);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            tally(__uint_as_float(q[u].x)); tally(__uint_as_float(q[u].y));
-            tally(__uint_as_float(q[u].z)); tally(__uint_as_float(q[u].w));
+            for (int e = 0; e < 4; ++e) if (p0 + e < b1) { v[e] = y[p0 + e]; have = e + 1; }
         }
-    } else {
-        for (long long p = b0 + threadIdx.x; p < b1; p += 256) tally(y[p]);
+        bool ok = true;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (e < have) ok = ok && v[e] >= bmin && v[e] <= bmax;
+        const unsigned votes = __ballot_sync(CT_FULL, ok);
+        if ((votes & half_mask) == half_mask) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (e < have) {
+                    const long long q = (long long)__float2ll_rn(__fmul_rn(__fsub_rn(v[e], c0), scale));
+                    c += 1; a += q; b += q * q;
+                }
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -380,7 +392,7 @@ ct_block_stats_kernel(const float* __restrict__ y, long long n, long long block,
         a += __shfl_xor_sync(CT_FULL, a, o);
         b += __shfl_xor_sync(CT_FULL, b, o);
     }
-    if (ct_lane() == 0 && c) {
+    if (lane == 0 && c) {
         atomicAdd(reinterpret_cast<unsigned long long*>(cnt + kb), (unsigned long long)c);
         atomicAdd(reinterpret_cast<unsigned long long*>(s1 + kb), (unsigned long long)a);
         atomicAdd(reinterpret_cast<unsigned long long*>(s2 + kb), (unsigned long long)b);
@@ -587,6 +599,7 @@ int64_t ct_detect_workspace_bytes(int64_t n) {
 int ct_block_stats_f32(const float* y, int64_t n, int64_t block, float bmin, float bmax, float c0,
                        int shift, int64_t* cnt, int64_t* s1, int64_t* s2, void* stream) {
     if (!y || !cnt || !s1 || !s2 || n < 0 || block <= 0) { ct_set_error("block_stats: bad argument"); return CT_ERR_ARG; }
+    if (block % 64) { ct_set_error("block_stats: the baseline block must be a multiple of 64 samples (the chunk of the in-window rule)"); return CT_ERR_ARG; }
     long long nb = (n + block - 1) / block;
     cudaStream_t st = (cudaStream_t)stream;
     if (nb == 0) return CT_OK;

@@ -44,6 +44,7 @@ constexpr int kG = 8;               // 8-sample slots per tile
 constexpr int kRuns = 64;           // runs per warp (32 lanes x 2 halves)
 constexpr int kStage = 8192;        // bytes per shared-memory stage / output half-tile: 64 rows x 128 B
 constexpr int kWarps = 4;           // warps per CTA, one per SM sub-partition; 3 CTAs per SM (16 KB of shared memory per warp)
+constexpr int kPfDist = 4;          // backward pass: scratch units are prefetched into L2 this many slot pairs ahead
 constexpr int kCtasPerSm = 3;       // 12 warps per SM: three per scheduler, up to 168 registers each
 
 typedef float2 f2;
@@ -229,41 +230,45 @@ static __device__ void out_store_guarded(const SeqArgs& a, unsigned outb, int hb
 }
 
 // ------------------------------------------------------------------ baseline block sums + chunk extrema (BWD epilogue)
+// oracle/events_oracle.py::block_stats: q = rint((v - c0) 2^s) summed over the samples whose whole aligned 64-sample
+// chunk lies inside [st_min, st_max].  A chunk is one tile row of a run, so a lane tallies its own chunks: the sums of
+// the chunk in 32/64-bit partials, its extrema on the side (they are also what the detector wants), one verdict per
+// chunk - no per-sample compare or select.
 struct StatAcc { int c; long long s1, s2; };
-static __device__ __forceinline__ void tally(const SeqArgs& a, StatAcc& acc, float v) {
-    const bool in = v >= a.st_min && v <= a.st_max;
-    // (v - c0) * 2^s in one FFMA: scaling by a power of two commutes with the rounding of the difference
-    const int q = in ? __float2int_rn(__fmaf_rn(v, a.st_scale, a.st_nc0s)) : 0;
-    acc.c += in ? 1 : 0; acc.s1 += q; acc.s2 += (long long)q * q;
-}
-// Per-slot partial tallies: 32-bit count / sum (8 samples, |q| < 2^23: fused blocks are >= 2^16 samples), folded
-// into the 64-bit accumulators once per slot.
-static __device__ __forceinline__ void tally_slot(const SeqArgs& a, StatAcc& a0, StatAcc& a1, const f2 (&y)[8]) {
-    int c0 = 0, c1 = 0, s0 = 0, s1 = 0;
-    long long q0 = 0, q1 = 0;
+struct ChunkAcc { int s1a, s1b; long long s2a, s2b; };      // chunk partials of the two halves
+static __device__ __forceinline__ void tally_slot(const SeqArgs& a, ChunkAcc& k, const f2 (&y)[8]) {
+    const f2 sc = splat(a.st_scale), nc = splat(a.st_nc0s);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const bool in0 = y[e].x >= a.st_min && y[e].x <= a.st_max, in1 = y[e].y >= a.st_min && y[e].y <= a.st_max;
-        const int u0 = in0 ? __float2int_rn(__fmaf_rn(y[e].x, a.st_scale, a.st_nc0s)) : 0;
-        const int u1 = in1 ? __float2int_rn(__fmaf_rn(y[e].y, a.st_scale, a.st_nc0s)) : 0;
-        c0 += in0 ? 1 : 0; c1 += in1 ? 1 : 0; s0 += u0; s1 += u1;
-        q0 += (long long)u0 * u0; q1 += (long long)u1 * u1;
+        // (v - c0) * 2^s in one FFMA: scaling by a power of two commutes with the rounding of the difference
+        const f2 t = fma2(y[e], sc, nc);
+        const int u0 = __float2int_rn(t.x), u1 = __float2int_rn(t.y);
+        k.s1a += u0; k.s1b += u1;
+        k.s2a += (long long)u0 * u0; k.s2b += (long long)u1 * u1;
     }
-    a0.c += c0; a0.s1 += s0; a0.s2 += q0;
-    a1.c += c1; a1.s1 += s1; a1.s2 += q1;
+}
+// trace ends: sample by sample, only positions inside [0, n_out)
+static __device__ __forceinline__ void tally_one(const SeqArgs& a, int& s1, long long& s2, float v) {
+    const int q = __float2int_rn(__fmaf_rn(v, a.st_scale, a.st_nc0s));
+    s1 += q; s2 += (long long)q * q;
 }
 
 static __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 static __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// Work distribution: groups are handed out in order from a global counter (a warp that shares its scheduler with
+// Work distribution: groups are handed out from a global counter (a warp that shares its scheduler with
 // fewer or faster neighbours simply takes more of them; neighbouring groups are in flight together, which keeps
 // their DRAM pages and L2 lines warm), or by static round robin when the caller gave no counter.
 static __device__ __forceinline__ long long next_group(const SeqArgs& a, long long static_next, int lane, bool first) {
     if (!a.next_group) return first ? a.g_first + static_next : static_next;
     unsigned long long v = 0;
     if (lane == 0) v = atomicAdd(a.next_group, 1ULL);
-    return a.g_first + (long long)__shfl_sync(CT_FULL, v, 0);
+    const long long i = (long long)__shfl_sync(CT_FULL, v, 0), span = a.ngroups - a.g_first;
+    if (i >= span) return a.ngroups;
+    // the last two groups (the right end of the trace: guarded, slow EDGE code) go out FIRST so that they run beside
+    // the bulk of the work instead of after it; everything else in ascending order
+    const long long ne = span < 2 ? span : 2;
+    return i < ne ? a.ngroups - 1 - i : a.g_first + (i - ne);
 }
 
 // =============================== forward pass ========================================
@@ -550,6 +555,17 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
         if (!EDGE) {
             ldg_vec<F>(y1 + scratch_off<D>(s0, to, jp, TO), xa);
             ldg_vec<F>(y1 + scratch_off<D>(s1, to, jp, TO), xb);
+            // the register pipeline is two pairs deep (about a microsecond of work): it hides an L2 hit, not a DRAM
+            // access under load, so the units of the pair kPfDist further on are pulled into L2 now (both halves of
+            // a pair are contiguous: 256 F bytes, one line per lane)
+            const int ip = i + kPfDist;
+            if (ip < npairs && lane < 2 * F) {
+                const int tp = ip >> 2, jpp = 3 - (ip & 3);
+                const bool wp = tp < wt;
+                const int top = wp ? wt - 1 - tp : TO - 1 - (tp - wt);
+                const float* pf = y1 + scratch_off<D>(run0 + (wp ? 1 : 0), top, jpp, TO) + lane * 32;
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
+            }
         } else {
             // units beyond the scratch are never dereferenced; positions beyond the forward output are replaced by `hold` below
             if (s0 < a.scratch_runs) ldg_vec<F>(y1 + scratch_off<D>(s0, to, jp, TO), xa);
@@ -573,6 +589,8 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
         const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
         const long long tpos0 = a.base + (warm ? r0 + 1 : r0) * a.R + (long long)to * kK;   // position of the tile's first sample, half 0
         float mn0 = __int_as_float(0x7f800000), mx0 = __int_as_float(0xff800000), mn1 = mn0, mx1 = mx0;
+        ChunkAcc ck; ck.s1a = ck.s1b = 0; ck.s2a = ck.s2b = 0;     // the tile row of each run is one chunk of the in-window rule
+        int have0 = EDGE ? 0 : kK, have1 = have0;                    // samples of the chunk that exist (trace ends)
 #pragma unroll 1
         for (int jq = 0; jq < 4; ++jq) {
             const int jp = 3 - jq;
@@ -608,8 +626,8 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
                 if (store) {
                     out_write_slot(outb, lane, jj, x);
                     if (!EDGE) {
-                        if (STATS) tally_slot(a, acc0, acc1, x);
-                        if (SUMM) {
+                        if (STATS) tally_slot(a, ck, x);
+                        if (STATS || SUMM) {
 #pragma unroll
                             for (int e = 0; e < 8; e += 2) {
                                 mn0 = fmin3(mn0, x[e].x, x[e + 1].x); mx0 = fmax3(mx0, x[e].x, x[e + 1].x);
@@ -621,12 +639,12 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             if (p0 + e >= 0 && p0 + e < a.n_out) {
-                                if (STATS) tally(a, acc0, x[e].x);
-                                mn0 = fminf(mn0, x[e].x); mx0 = fmaxf(mx0, x[e].x);
+                                if (STATS) tally_one(a, ck.s1a, ck.s2a, x[e].x);
+                                mn0 = fminf(mn0, x[e].x); mx0 = fmaxf(mx0, x[e].x); ++have0;
                             }
                             if (p1 + e >= 0 && p1 + e < a.n_out) {
-                                if (STATS) tally(a, acc1, x[e].y);
-                                mn1 = fminf(mn1, x[e].y); mx1 = fmaxf(mx1, x[e].y);
+                                if (STATS) tally_one(a, ck.s1b, ck.s2b, x[e].y);
+                                mn1 = fminf(mn1, x[e].y); mx1 = fmaxf(mx1, x[e].y); ++have1;
                             }
                         }
                     }
@@ -650,6 +668,10 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
                     __syncwarp();
                 }
             }
+        }
+        if (STATS && store) {                              // the chunk's verdict: every existing sample inside the window
+            if (have0 > 0 && mn0 >= a.st_min && mx0 <= a.st_max) { acc0.c += have0; acc0.s1 += ck.s1a; acc0.s2 += ck.s2a; }
+            if (have1 > 0 && mn1 >= a.st_min && mx1 <= a.st_max) { acc1.c += have1; acc1.s1 += ck.s1b; acc1.s2 += ck.s2b; }
         }
         if (SUMM && store) {
             // tiles descend: the newest chunk is the lowest one of its group of four

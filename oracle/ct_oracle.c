@@ -30,6 +30,8 @@ void orc_lfilter(const double *b, const double *a, int ntaps, const double *x, i
     }
 }
 
+/* oracle/events_oracle.py::block_stats: a sample counts when its whole aligned 64-sample chunk (the last chunk of
+ * the trace may be shorter) lies inside [bmin, bmax]; block % 64 == 0. */
 void orc_block_stats(const float *y, int64_t n, int64_t block, float bmin, float bmax,
                      float c0, int shift, int64_t *cnt, int64_t *s1, int64_t *s2)
 {
@@ -38,10 +40,14 @@ void orc_block_stats(const float *y, int64_t n, int64_t block, float bmin, float
     for (int64_t k = 0; k < nb; ++k) {
         int64_t c = 0, a = 0, b = 0;
         int64_t e = (k + 1) * block < n ? (k + 1) * block : n;
-        for (int64_t i = k * block; i < e; ++i) {
-            float v = y[i];
-            if (v >= bmin && v <= bmax) {
-                float d = (v - c0) * scale;
+        for (int64_t i0 = k * block; i0 < e; i0 += 64) {
+            int64_t i1 = i0 + 64 < e ? i0 + 64 : e;
+            int ok = 1;
+            for (int64_t i = i0; i < i1; ++i)
+                if (!(y[i] >= bmin && y[i] <= bmax)) { ok = 0; break; }
+            if (!ok) continue;
+            for (int64_t i = i0; i < i1; ++i) {
+                float d = (y[i] - c0) * scale;
                 int64_t q = (int64_t)rintf(d);
                 c += 1; a += q; b += q * q;
             }

@@ -33,25 +33,65 @@ def stats_shift(half_width: float, block: int) -> int:
     return s
 
 
+STATS_CHUNK = 64
+
+
 def block_stats(y, block, bmin, bmax, c0, shift):
-    """Per-block count / sum / sum of squares of q = rint((y - c0) * 2^shift) over the
-    samples with bmin <= y <= bmax.  Returns three int64 arrays of length ceil(N/block)."""
+    """Per-block count / sum / sum of squares of q = rint((y - c0) * 2^shift) over the baseline samples of the
+    block.  A sample counts when its whole CHUNK - the aligned group of 64 samples it belongs to, counted from
+    sample 0 (the last chunk of the trace may be shorter) - lies inside [bmin, bmax]: a chunk that holds an event
+    edge or an excursion is left out as a whole.  `block` is a multiple of 64.  Returns three int64 arrays of
+    length ceil(N/block)."""
     y = np.asarray(y, dtype=np.float32)
     n = y.size
+    assert block % STATS_CHUNK == 0
     nb = (n + block - 1) // block
     cnt = np.zeros(nb, dtype=np.int64)
     s1 = np.zeros(nb, dtype=np.int64)
     s2 = np.zeros(nb, dtype=np.int64)
     scale = np.float32(2.0 ** shift)
+    lo, hi = np.float32(bmin), np.float32(bmax)
     for k in range(nb):
         seg = y[k * block:(k + 1) * block]
-        m = (seg >= np.float32(bmin)) & (seg <= np.float32(bmax))
-        d = (seg[m] - np.float32(c0)).astype(np.float32) * scale
+        nch = (seg.size + STATS_CHUNK - 1) // STATS_CHUNK
+        ok = np.zeros(seg.size, dtype=bool)
+        for c in range(nch):
+            ch = seg[c * STATS_CHUNK:(c + 1) * STATS_CHUNK]
+            if ch.min() >= lo and ch.max() <= hi:
+                ok[c * STATS_CHUNK:(c + 1) * STATS_CHUNK] = True
+        d = (seg[ok] - np.float32(c0)).astype(np.float32) * scale
         q = np.rint(d).astype(np.int64)
         cnt[k] = q.size
         s1[k] = q.sum()
         s2[k] = (q * q).sum()
     return cnt, s1, s2
+
+
+def block_stats_fast(y, block, bmin, bmax, c0, shift):
+    """`block_stats`, vectorised over chunks (same definition; tests assert the identity)."""
+    y = np.asarray(y, dtype=np.float32)
+    n = y.size
+    assert block % STATS_CHUNK == 0
+    nb = (n + block - 1) // block
+    nfull = n // STATS_CHUNK
+    lo, hi = np.float32(bmin), np.float32(bmax)
+    ch = y[:nfull * STATS_CHUNK].reshape(nfull, STATS_CHUNK)
+    ok = (ch.min(axis=1) >= lo) & (ch.max(axis=1) <= hi)
+    q = np.rint((ch - np.float32(c0)).astype(np.float32) * np.float32(2.0 ** shift)).astype(np.int64)
+    q[~ok] = 0
+    c_cnt = np.where(ok, STATS_CHUNK, 0).astype(np.int64)
+    c_s1, c_s2 = q.sum(axis=1), (q * q).sum(axis=1)
+    tail = y[nfull * STATS_CHUNK:]
+    if tail.size:
+        t_ok = tail.min() >= lo and tail.max() <= hi
+        tq = np.rint((tail - np.float32(c0)).astype(np.float32) * np.float32(2.0 ** shift)).astype(np.int64) if t_ok else np.zeros(0, np.int64)
+        c_cnt = np.append(c_cnt, tq.size); c_s1 = np.append(c_s1, tq.sum()); c_s2 = np.append(c_s2, (tq * tq).sum())
+    cpb = block // STATS_CHUNK
+    pad = nb * cpb - c_cnt.size
+    if pad:
+        z = np.zeros(pad, np.int64)
+        c_cnt, c_s1, c_s2 = np.append(c_cnt, z), np.append(c_s1, z), np.append(c_s2, z)
+    return (c_cnt.reshape(nb, cpb).sum(axis=1), c_s1.reshape(nb, cpb).sum(axis=1), c_s2.reshape(nb, cpb).sum(axis=1))
 
 
 def baseline_from_stats(cnt, s1, s2, c0, shift, min_count=16):

@@ -71,6 +71,23 @@ for cutoff in cutoffs:
             assert rc == 0, L.ct_last_error()
         return f
 
+    if os.environ.get("CT_CLOCKS"):
+        # sustained loops with nvidia-smi sampling: do the kernels hold the clock they show in a 5-launch burst?
+        import subprocess, time
+        for name, fn in (("forward", fwd), ("backward+sums+extrema", bwd(C.byref(stats), mm.data_ptr()))):
+            pr = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,clocks_event_reasons.sw_power_cap,"
+                                   "clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown",
+                                   "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            time.sleep(0.2)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(300):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            pr.terminate()
+            rows = [r.strip() for r in pr.stdout.read().splitlines() if r.strip()]
+            print(f"  sustained {name}: {e0.elapsed_time(e1) / 300:.3f} ms per launch over 300 launches; nvidia-smi samples "
+                  f"(sm MHz, mem MHz, W, power cap, hw slowdown, thermal): first {rows[:2]} ... mid {rows[len(rows)//2:len(rows)//2+3]} ... last {rows[-2:]}", flush=True)
     t_f = timed(fwd)
     report("forward pass", t_f, 2.0 + 4.0 / D)
     t_b = timed(bwd(None, None))

