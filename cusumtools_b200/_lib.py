@@ -19,11 +19,11 @@ CT_MAX_SECTIONS = 5
 class CtFilterCoef(C.Structure):
     _fields_ = [
         ("nsec", C.c_int32),
+        ("order", C.c_int32),
         ("na1", C.c_float * CT_MAX_SECTIONS),
         ("na2", C.c_float * CT_MAX_SECTIONS),
-        ("n1", C.c_float * CT_MAX_SECTIONS),
-        ("n2", C.c_float * CT_MAX_SECTIONS),
         ("ss", C.c_float * CT_MAX_SECTIONS),
+        ("fir", C.c_float * (2 * CT_MAX_SECTIONS + 1)),
         ("gain", C.c_float),
     ]
 

@@ -36,6 +36,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -159,29 +160,30 @@ static __device__ __forceinline__ long long scratch_off(long long run, int to, i
 }
 
 // ------------------------------------------------------------------ the cascade
-// one step for the sample pair u (both halves); the last section's output carries gain and offset
+// H(z) = g (1 + z^-1)^N / prod_s (1 - na1_s z^-1 - na2_s z^-2).  The all-pole sections run at every sample (2 FMA per
+// section and sample, the section output IS its state); the numerator is one binomial FIR with the gain folded in,
+// evaluated only where its output is needed (forward pass: at the kept positions, 9 taps per D samples) or only over
+// the taps that see a non-zero input (backward pass: the zero-stuffed scratch, again 9 taps per D samples).  For the
+// quarter-rate scratch that is 10.25 instead of 16 FMA per sample and pass - and, with the zeros at Nyquist applied
+// last / first, 4x less rounding noise than the section-by-section form (0.005 pA against the float64 reference).
+template <int NSEC> struct Coefs { f2 na1[NSEC], na2[NSEC], cf[2 * NSEC + 1], off; };
 template <int NSEC>
-__device__ __forceinline__ f2 cascade_step(f2 u, f2 (&v1)[NSEC], f2 (&v2)[NSEC], const f2 (&na1)[NSEC], const f2 (&na2)[NSEC],
-                                           const f2 (&c1)[NSEC], const f2 (&c2)[NSEC], const f2 gl, const f2 off) {
+__device__ __forceinline__ void load_coef(const CtFilterCoef& k, float out_gain, float offset, Coefs<NSEC>& c) {
 #pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        const f2 vn = fma2(na1[s], v1[s], fma2(na2[s], v2[s], u));
-        const f2 yo = fma2(c1[s], v1[s], fma2(c2[s], v2[s], s == NSEC - 1 ? fma2(gl, u, off) : u));
-        v2[s] = v1[s]; v1[s] = vn;
-        u = yo;
-    }
-    return u;
+    for (int s = 0; s < NSEC; ++s) { c.na1[s] = splat(k.na1[s]); c.na2[s] = splat(k.na2[s]); }
+#pragma unroll
+    for (int i = 0; i <= 2 * NSEC; ++i) c.cf[i] = splat(k.fir[i] * out_gain);
+    c.off = splat(offset);
 }
 template <int NSEC>
-__device__ __forceinline__ void load_coef(const CtFilterCoef& k, float out_gain, f2 (&na1)[NSEC], f2 (&na2)[NSEC], f2 (&c1)[NSEC],
-                                          f2 (&c2)[NSEC], f2& gl) {
+__device__ __forceinline__ f2 allpole_step(f2 u, f2 (&v1)[NSEC], f2 (&v2)[NSEC], const Coefs<NSEC>& c) {
 #pragma unroll
     for (int s = 0; s < NSEC; ++s) {
-        na1[s] = splat(k.na1[s]); na2[s] = splat(k.na2[s]);
-        const float g = (s == NSEC - 1) ? k.gain * out_gain : 1.f;   // the overall gain rides on the last section's output
-        c1[s] = splat((k.na1[s] + k.n1[s]) * g); c2[s] = splat((k.na2[s] + k.n2[s]) * g);
+        const f2 vn = fma2(c.na1[s], v1[s], fma2(c.na2[s], v2[s], u));
+        v2[s] = v1[s]; v1[s] = vn;
+        u = vn;
     }
-    gl = splat(k.gain * out_gain);
+    return u;
 }
 
 // ------------------------------------------------------------------ exact-median window count (optional, FWD)
@@ -276,9 +278,7 @@ static __device__ __forceinline__ long long next_group(const SeqArgs& a, long lo
 template <int NSEC, typename InT, int MODE, bool COUNT, bool EDGE>
 __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap* in_map, const CUtensorMap* out_map,
                                           const long long g, const int lane, const unsigned stage0, const unsigned bar0,
-                                          const unsigned outb, unsigned& phase,
-                                          const f2 (&na1)[NSEC], const f2 (&na2)[NSEC], const f2 (&c1)[NSEC], const f2 (&c2)[NSEC],
-                                          const f2 gl, const f2 off2) {
+                                          const unsigned outb, unsigned& phase, const Coefs<NSEC>& cf) {
     constexpr bool U16 = sizeof(InT) == 2;
     constexpr int SPT = U16 ? 1 : 2;             // stages per tile (a stage row is 128 bytes)
     constexpr int SLOTS = kG / SPT;              // slots per stage
@@ -292,7 +292,9 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
     const unsigned m2 = a.mask | (a.mask << 16);
     const f2 kmagic = splat(-(8388608.f + (float)a.isub));
 
-    f2 v1[NSEC], v2[NSEC];
+    constexpr int TAPS = 2 * NSEC + 1;              // binomial FIR taps (orders below 2 NSEC have zero tails)
+    constexpr int HIST = TAPS - 1 > 8 ? 16 : 8;     // all-pole outputs of the previous slot(s) the FIR reaches back into
+    f2 v1[NSEC], v2[NSEC], ahist[HIST];
     {   // runs that begin in the left pad start from the steady state of the pad value (scipy: zi * x[0])
         float p0 = 0.f, p1 = 0.f;
         if (EDGE) {
@@ -301,6 +303,8 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
         }
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(p0 * k.ss[s], p1 * k.ss[s]); v2[s] = v1[s]; }
+#pragma unroll
+        for (int i = 0; i < HIST; ++i) ahist[i] = v1[NSEC - 1];
     }
     CwAcc cw;
     if (COUNT) {
@@ -425,8 +429,25 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
 #pragma unroll
                     for (int e = 0; e < 8; ++e) x[e] = __fadd2_rn(make_float2(__uint_as_float(wa[e]), __uint_as_float(wb[e])), nsub);
                 }
+                f2 ap[8];                                  // all-pole output of the slot
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl, off2);
+                for (int e = 0; e < 8; ++e) ap[e] = allpole_step<NSEC>(x[e], v1, v2, cf);
+                if (store) {
+                    // numerator (+ gain, + offset in the final-output mode) at the positions that are kept
+#pragma unroll
+                    for (int e = 0; e < 8; e += D) {
+                        f2 y = MODE == 0 ? fma2(cf.cf[0], ap[e], cf.off) : __fmul2_rn(cf.cf[0], ap[e]);
+#pragma unroll
+                        for (int t2 = 1; t2 < TAPS; ++t2) y = fma2(cf.cf[t2], e - t2 >= 0 ? ap[e - t2 >= 0 ? e - t2 : 0] : ahist[HIST + e - t2], y);
+                        x[e] = y;
+                    }
+                }
+                if (HIST == 16) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ahist[i] = ahist[8 + i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ahist[HIST - 8 + i] = ap[i];
                 if (store) {
                     if (MODE == 0) {
                         out_write_slot(outb, lane, jj, x);
@@ -504,9 +525,8 @@ ct_filter_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     const long long gw = (long long)blockIdx.x * kWarps + wib;
     const long long nw = (long long)gridDim.x * kWarps;
 
-    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC], gl;
-    load_coef<NSEC>(k, a.scale, na1, na2, c1, c2, gl);
-    const f2 off2 = splat(a.offset);
+    Coefs<NSEC> cf;
+    load_coef<NSEC>(k, a.scale, a.offset, cf);
     unsigned phase = 0;
     for (long long g = next_group(a, gw, lane, true); g < a.ngroups; g = next_group(a, g + nw, lane, false)) {
         // interior groups (every stage and output piece of all 64 runs inside the data, the counted range too) run guard-free
@@ -514,8 +534,8 @@ ct_filter_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         bool interior = a.tma_in && p_lo >= 0 && p_hi <= a.n_in;
         if (MODE == 0) interior = interior && a.tma_out && p_hi <= a.n_out;
         if (COUNT) interior = interior && p_lo + a.Hw >= a.cw_p0 && p_hi <= a.cw_p1;
-        if (interior) fwd_group<NSEC, InT, MODE, COUNT, false>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, na1, na2, c1, c2, gl, off2);
-        else fwd_group<NSEC, InT, MODE, COUNT, true>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, na1, na2, c1, c2, gl, off2);
+        if (interior) fwd_group<NSEC, InT, MODE, COUNT, false>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, cf);
+        else fwd_group<NSEC, InT, MODE, COUNT, true>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, cf);
     }
     if (MODE == 0 && lane == 0) bulk_wait_read<0>();         // shared memory must outlive the last tile store
 }
@@ -525,9 +545,7 @@ ct_filter_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
 // r + 1) only to warm the recursion up.  The scratch holds D * (forward output) at every D-th position.
 template <int NSEC, int D, bool STATS, bool SUMM, bool EDGE>
 __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap* out_map, const long long g,
-                                          const int lane, const unsigned outb, const float hold,
-                                          const f2 (&na1)[NSEC], const f2 (&na2)[NSEC], const f2 (&c1)[NSEC], const f2 (&c2)[NSEC],
-                                          const f2 gl, const f2 off2) {
+                                          const int lane, const unsigned outb, const float hold_d, const Coefs<NSEC>& cf) {
     constexpr int F = 16 / D;
     const float* y1 = reinterpret_cast<const float*>(a.in);
     const long long run0 = g * kRuns;
@@ -535,16 +553,26 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
     const int ntiles = (a.Hw + a.R) / kK, wt = a.Hw / kK, TO = a.R / kK;
     const int npairs = ntiles * 4;
 
-    f2 v1[NSEC], v2[NSEC];
-    {   // runs whose first processed position lies beyond the data start from the steady state of `hold`
-        // (scipy: zi * y[-1], _signaltools.py:4910-4913); the cascade's own gain/offset do not enter the state
+    constexpr int TAPS = 2 * NSEC + 1;              // binomial FIR taps
+    constexpr int PER = 8 / D;                      // kept samples per slot
+    constexpr int NW = (8 + TAPS - 1 + D - 1) / D;  // window of kept samples the FIR of one slot reaches: positions [0, 8 + TAPS - 1)
+    f2 v1[NSEC], v2[NSEC], zw[NW];
+    {   // Runs whose first processed position lies beyond the data start from the steady state of the held value
+        // (scipy: zi * y[-1], _signaltools.py:4910-4913).  Beyond the data the scratch is the zero-stuffed constant
+        // hold_d, whose mean is hold_d / D: the FIR's DC output times the all-pole steady-state factors.
         float h0 = 0.f, h1 = 0.f;
         if (EDGE) {
-            h0 = a.base + r0 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
-            h1 = a.base + r1 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold : 0.f;
+            h0 = a.base + r0 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold_d : 0.f;
+            h1 = a.base + r1 * a.R + a.R + a.Hw - 1 >= a.n_in ? hold_d : 0.f;
         }
+        float sum = 0.f;
 #pragma unroll
-        for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(h0 * k.ss[s], h1 * k.ss[s]); v2[s] = v1[s]; }
+        for (int i = 0; i < TAPS; ++i) sum += cf.cf[i].x;
+        const float w0 = h0 * sum * (1.f / (float)D), w1 = h1 * sum * (1.f / (float)D);
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(w0 * k.ss[s], w1 * k.ss[s]); v2[s] = v1[s]; }
+#pragma unroll
+        for (int i = 0; i < NW; ++i) zw[i] = make_float2(h0, h1);
     }
     // pair i (0 .. npairs-1) in processing order: tile t = i / 4, pair jp = 3 - i % 4 (descending positions)
     auto fetch = [&](int i, Vec<F>& xa, Vec<F>& xb) {
@@ -605,24 +633,36 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
 #pragma unroll
             for (int sl = 1; sl >= 0; --sl) {              // upper slot of the pair first
                 const int jj = jp * 2 + sl;
-                f2 x[8];
+                // the slot's kept samples enter the window at positions 0, D, ..; the entries above came down from the
+                // slots processed before (higher positions)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if (e % D == 0) x[e] = make_float2(ca.v[sl * (8 / D) + e / D], cb.v[sl * (8 / D) + e / D]);
-                    else x[e] = make_float2(0.f, 0.f);     // zero stuffing: the images sit where this very filter has no gain
-                }
+                for (int i = NW - 1; i >= PER; --i) zw[i] = zw[i - PER];
+#pragma unroll
+                for (int i = 0; i < PER; ++i) zw[i] = make_float2(ca.v[sl * PER + i], cb.v[sl * PER + i]);
                 if (EDGE) {
                     const long long q0 = tpos0 + jj * 8, q1 = q0 + 32LL * a.R;
-                    if (q1 + 8 > a.n_in) {                 // (q0 < q1) beyond the forward output: held value, at full rate
+                    if (q1 + 8 > a.n_in) {                 // (q0 < q1) beyond the forward output: the held value
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            if (q0 + e >= a.n_in) x[e].x = hold;
-                            if (q1 + e >= a.n_in) x[e].y = hold;
+                        for (int i = 0; i < PER; ++i) {
+                            if (q0 + i * D >= a.n_in) zw[i].x = hold_d;
+                            if (q1 + i * D >= a.n_in) zw[i].y = hold_d;
                         }
                     }
                 }
+                f2 x[8];
 #pragma unroll
-                for (int ee = 0; ee < 8; ++ee) { const int e = 7 - ee; x[e] = cascade_step<NSEC>(x[e], v1, v2, na1, na2, c1, c2, gl, off2); }
+                for (int ee = 0; ee < 8; ++ee) {
+                    const int e = 7 - ee;
+                    // numerator over the zero-stuffed scratch: only the taps that meet a kept position, e <= i D <= e + TAPS - 1
+                    f2 w = make_float2(0.f, 0.f);
+                    bool first = true;
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) {
+                        const int t2 = i * D - e;
+                        if (t2 >= 0 && t2 < TAPS) { w = first ? __fmul2_rn(cf.cf[t2], zw[i]) : fma2(cf.cf[t2], zw[i], w); first = false; }
+                    }
+                    x[e] = __fadd2_rn(allpole_step<NSEC>(w, v1, v2, cf), cf.off);
+                }
                 if (store) {
                     out_write_slot(outb, lane, jj, x);
                     if (!EDGE) {
@@ -717,19 +757,19 @@ ct_filter_bwd_kernel(const __grid_constant__ CUtensorMap out_map, SeqArgs a, CtF
     const long long nw = (long long)gridDim.x * kWarps;
     const int TO = a.R / kK;
 
-    f2 na1[NSEC], na2[NSEC], c1[NSEC], c2[NSEC], gl;
-    load_coef<NSEC>(k, a.scale, na1, na2, c1, c2, gl);
-    const f2 off2 = splat(a.offset);
-    // the forward output is held constant beyond n_in: its last kept sample (the output is flat at the end of the pad)
+    Coefs<NSEC> cf;
+    load_coef<NSEC>(k, a.scale, a.offset, cf);
+    // the forward output is held constant beyond n_in (scipy: the backward pass starts from zi * y[-1]): as a scratch
+    // entry, i.e. D times its last kept sample (the output is flat at the end of the pad)
     const long long last = (a.n_in - 1 - a.base) / D * D;                  // relative to the run grid
     const int lo = (int)(last % a.R);
-    const float hold = y1[scratch_off<D>(last / a.R, lo / kK, (lo % kK) >> 4, TO) + (lo & 15) / D] * (1.f / (float)D);
+    const float hold_d = y1[scratch_off<D>(last / a.R, lo / kK, (lo % kK) >> 4, TO) + (lo & 15) / D];
 
     for (long long g = next_group(a, gw, lane, true); g < a.ngroups; g = next_group(a, g + nw, lane, false)) {
         const long long p_lo = a.base + g * kRuns * a.R, p_hi = a.base + (g + 1) * kRuns * a.R;
         const bool interior = a.tma_out && p_lo >= 0 && p_hi + a.Hw <= a.n_in && p_hi <= a.n_out && (g + 1) * kRuns < a.scratch_runs;
-        if (interior) bwd_group<NSEC, D, STATS, SUMM, false>(a, k, &out_map, g, lane, outb, hold, na1, na2, c1, c2, gl, off2);
-        else bwd_group<NSEC, D, STATS, SUMM, true>(a, k, &out_map, g, lane, outb, hold, na1, na2, c1, c2, gl, off2);
+        if (interior) bwd_group<NSEC, D, STATS, SUMM, false>(a, k, &out_map, g, lane, outb, hold_d, cf);
+        else bwd_group<NSEC, D, STATS, SUMM, true>(a, k, &out_map, g, lane, outb, hold_d, cf);
     }
     if (lane == 0) bulk_wait_read<0>();                    // shared memory must outlive the last tile store
 }
@@ -839,11 +879,11 @@ int dispatch_bwd(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap& om,
 // held value after the data is then not the settled output.
 double cascade_gain(const CtFilterCoef& k, double w) {
     const double cr = cos(w), ci = -sin(w), c2r = cos(2 * w), c2i = -sin(2 * w);   // z^-1, z^-2
-    double mag = fabs((double)k.gain);
+    // |1 + z^-1|^order = (2 |cos(w/2)|)^order
+    double mag = fabs((double)k.gain) * pow(2.0 * fabs(cos(0.5 * w)), (double)k.order);
     for (int s = 0; s < k.nsec; ++s) {
-        const double nr = 1.0 + k.n1[s] * cr + k.n2[s] * c2r, ni = k.n1[s] * ci + k.n2[s] * c2i;
         const double dr = 1.0 - k.na1[s] * cr - k.na2[s] * c2r, di = -k.na1[s] * ci - k.na2[s] * c2i;
-        mag *= sqrt((nr * nr + ni * ni) / (dr * dr + di * di));
+        mag /= sqrt(dr * dr + di * di);
     }
     return mag;
 }
@@ -872,7 +912,8 @@ int pick_decimation(const CtFilterCoef& k, long long pad, int Hw) {
 // half-occupied SM).  Hw <= R always.
 int pick_run(long long n, int Hw) {
     const long long target_runs = (long long)ct_sm_count() * kWarps * kRuns;
-    long long R = 4096;
+    static const long long r_max = [] { const char* e = getenv("CT_SEQ_RMAX"); const long long v = e ? atoll(e) : 0; return v >= 256 ? v : 4096; }();
+    long long R = r_max;
     while (R > 256 && (n + R - 1) / R < target_runs) R >>= 1;
     while (R < Hw) R <<= 1;
     return (int)R;

@@ -32,18 +32,26 @@ def make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
 
 
 def _make_coef(design: BesselDesign) -> _lib.CtFilterCoef:
+    """H(z) = gain (1 + z^-1)^order / prod (1 - na1 z^-1 - na2 z^-2): the kernel runs the all-pole sections at every
+    sample and the numerator as ONE binomial FIR (with the gain folded in) only where it is needed.  The gain is
+    evaluated from the float32-rounded denominators, so the float32 cascade's DC gain is exactly 1."""
     k = _lib.CtFilterCoef()
     k.nsec = design.nsec
-    dc = 1.0  # DC gain of the cascade up to (not including) the current section
+    order = 0
+    inv = 1.0           # DC gain of the all-pole sections up to and including the current one
     for s in range(design.nsec):
         a1, a2 = design.sections[s]
-        fo = bool(design.first_order[s])
-        n1, n2 = (1.0, 0.0) if fo else (2.0, 1.0)
-        k.na1[s], k.na2[s], k.n1[s], k.n2[s] = -a1, -a2, n1, n2
-        k.ss[s] = dc / (1.0 + a1 + a2)
-        dc *= (1.0 + n1 + n2) / (1.0 + a1 + a2)
-    k.gain = design.gain
-    peak = 65536.0 * dc  # largest un-normalised intermediate for a full-scale step
+        k.na1[s], k.na2[s] = -a1, -a2
+        den = 1.0 - float(k.na1[s]) - float(k.na2[s])          # from the values the kernel will use
+        inv /= den
+        k.ss[s] = inv
+        order += 1 if bool(design.first_order[s]) else 2
+    k.order = order
+    gain = 1.0 / (inv * 2.0 ** order)
+    k.gain = gain
+    for i in range(order + 1):
+        k.fir[i] = gain * math.comb(order, i)
+    peak = 65536.0 * inv  # largest un-normalised intermediate for a full-scale step
     if not math.isfinite(peak) or peak > 1e36:
         raise ValueError("cutoff/samplerate too low for the float32 cascade (intermediate overflow)")
     return k

@@ -28,15 +28,17 @@ extern "C" {
 
 /* Filter coefficients as the kernel consumes them (built on the host in float64 by
  * cusumtools_b200/design.py from the same Bessel design the reference requests with
- * scipy.signal.bessel(order, Wn, 'low') at plot-trace.py:317).
- *   section s: v[n] = x[n] + na1*v[n-1] + na2*v[n-2];  y[n] = v[n] + n1*v[n-1] + n2*v[n-2]
- *   ss  = steady-state value of v for a unit constant at the cascade input
- *   gain = overall scale making the DC gain exactly 1 (applied in the last section)   */
+ * scipy.signal.bessel(order, Wn, 'low') at plot-trace.py:317):
+ *   H(z) = gain (1 + z^-1)^order / prod_s (1 - na1[s] z^-1 - na2[s] z^-2)
+ *   fir[k] = gain * C(order, k), k = 0..order (zero beyond): the numerator as one binomial FIR
+ *   ss[s]  = steady-state output of all-pole section s for a unit constant at the cascade input
+ *   gain   = prod_s (1 - na1[s] - na2[s]) / 2^order, evaluated from the float32-rounded na1/na2: DC gain exactly 1 */
 typedef struct CtFilterCoef {
     int32_t nsec;
+    int32_t order;
     float na1[CT_MAX_SECTIONS], na2[CT_MAX_SECTIONS];
-    float n1[CT_MAX_SECTIONS], n2[CT_MAX_SECTIONS];
     float ss[CT_MAX_SECTIONS];
+    float fir[2 * CT_MAX_SECTIONS + 1];
     float gain;
 } CtFilterCoef;
 

@@ -90,6 +90,14 @@ for cutoff in cutoffs:
                   f"(sm MHz, mem MHz, W, power cap, hw slowdown, thermal): first {rows[:2]} ... mid {rows[len(rows)//2:len(rows)//2+3]} ... last {rows[-2:]}", flush=True)
     t_f = timed(fwd)
     report("forward pass", t_f, 2.0 + 4.0 / D)
+    cnt9 = torch.zeros(9, dtype=torch.int64, device="cuda")
+
+    def fwd_count():
+        rc = L.ct_filter_forward_u16(raw.data_ptr(), n, 1000, est, mask, 0.0, C.byref(coef), H, 0, 0, max(0, int(c1) - 12), 4, 0, n,
+                                     cnt9.data_ptr(), 0, 0, ws.data_ptr(), wsb, st)
+        assert rc == 0, L.ct_last_error()
+
+    report("forward pass + fused exact-median window count", timed(fwd_count), 2.0 + 4.0 / D)
     t_b = timed(bwd(None, None))
     report("backward pass", t_b, 4.0 + 4.0 / D)
     t_bs = timed(bwd(C.byref(stats), None))

@@ -38,8 +38,8 @@ def test_version_and_struct_layout():
     L = _lib.lib()
     assert L.ct_version() == 2
     assert L.ct_filter_seq_tile() == 64
-    # struct: 1 int32 + (4*5 + 5 + 1) floats
-    assert ctypes.sizeof(_lib.CtFilterCoef) == 4 + 4 * (20 + 5 + 1)
+    # struct: 2 int32 + (3*5 + 11 + 1) floats
+    assert ctypes.sizeof(_lib.CtFilterCoef) == 8 + 4 * (15 + 11 + 1)
 
 
 def test_argument_errors_are_reported_without_gpu():
