@@ -106,6 +106,21 @@ class ChimeraSeries:
             o += len(p.codes)
         return host, pieces[0].settings
 
+    def reader(self, start_s=None, end_s=None) -> "WindowReader":
+        """The window as a random-access source of raw codes for the streamed analysis
+        (pipeline.StreamingAnalyzer.run_from_file): nothing is read until a range is asked for."""
+        pieces = self.window(start_s, end_s)
+        if not all(_settings_equal(p.settings, pieces[0].settings) for p in pieces):
+            raise ValueError("files in the window have different gain settings: use load_pA()")
+        fs = self.samplerate
+        start_index = int(float(start_s) * fs) if start_s is not None else 0
+        spans, o = [], 0
+        for p in pieces:                         # (window offset, file, first sample inside the file, samples)
+            first = start_index - int(self.file_start_index[p.file_index]) if p is pieces[0] else 0
+            spans.append((o, self.sorted_files[p.file_index], first, len(p.codes)))
+            o += len(p.codes)
+        return WindowReader(spans, o, pieces[0].settings)
+
     def load_codes(self, start_s=None, end_s=None, device="cuda"):
         """`host_codes` copied to the device.  Returns (uint16 tensor, settings)."""
         host, settings = self.host_codes(start_s, end_s)
@@ -127,6 +142,49 @@ class ChimeraSeries:
             _lib.check(rc, "ct_dequant_u16")
             o += raw.numel()
         return out
+
+
+class WindowReader:
+    """Raw uint16 codes of a window of a `.log` series (plot-trace.py:230-269 slicing), readable range by range
+    straight into caller memory (pinned slabs): `os.preadv` copies from the page cache / disk into the destination
+    in one step and releases the GIL, so several threads can fill disjoint parts of a slab at once."""
+
+    def __init__(self, spans, n: int, settings):
+        self.spans, self.n, self.settings = spans, int(n), settings
+        self._fds: dict = {}
+
+    def _fd(self, path: str) -> int:
+        fd = self._fds.get(path)
+        if fd is None:
+            fd = self._fds[path] = os.open(path, os.O_RDONLY)
+        return fd
+
+    def read_into(self, dst: np.ndarray, a: int, b: int) -> None:
+        """dst[0 : b - a] = window samples [a, b) (dst: contiguous uint16/int16 array of at least b - a entries)."""
+        mv = memoryview(dst.view(np.uint8).reshape(-1))
+        for off, path, first, cnt in self.spans:
+            lo, hi = max(a, off), min(b, off + cnt)
+            if hi <= lo:
+                continue
+            pos, want = 2 * (first + lo - off), 2 * (hi - lo)
+            out = mv[2 * (lo - a):2 * (lo - a) + want]
+            got = 0
+            while got < want:
+                r = os.preadv(self._fd(path), [out[got:]], pos + got)
+                if r <= 0:
+                    raise IOError(f"short read from {path}")
+                got += r
+
+    def close(self) -> None:
+        for fd in self._fds.values():
+            os.close(fd)
+        self._fds = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def load_chimera(path: str, start_s=None, end_s=None, device="cuda"):

@@ -522,6 +522,99 @@ class StreamResult:
     redone: str = ""                # "", "first" (first sub-shard redone with the exact pad) or "whole" (fallback)
 
 
+class _HostFeed:
+    """Pieces of a trace that already sits in (pinned) host memory: every copy is queued up front."""
+
+    def __init__(self, host_codes: torch.Tensor):
+        self.host = host_codes
+
+    def start(self, an: "StreamingAnalyzer", pieces, cur) -> None:
+        self.events = []
+        an.copy_stream.wait_stream(cur)                        # the previous step may still read raw_dev
+        with torch.cuda.stream(an.copy_stream):
+            for a, b in pieces:
+                if b > a:
+                    an.raw_dev[a:b].copy_(self.host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(an.copy_stream)
+                self.events.append(ev)
+
+    def wait(self, i: int, cur) -> None:
+        cur.wait_event(self.events[i])
+
+    def finish(self) -> None:
+        pass
+
+    def whole(self, an: "StreamingAnalyzer") -> torch.Tensor:
+        return self.host
+
+
+class _FileFeed:
+    """Pieces read from the `.log` series on a worker thread (loader.WindowReader: several reader threads fill
+    disjoint parts of a pinned slab with preadv, GIL released), each handed to the copy engine as soon as it is in
+    memory; `slabs` pinned slabs rotate, so reading piece i+1 overlaps the host->device copy of piece i and the
+    kernels of piece i-1 (plot-trace.py:230-299 reads the whole window before anything else happens)."""
+
+    def __init__(self, reader, threads: int = 8, slabs: int = 3):
+        self.reader, self.threads, self.nslabs = reader, int(threads), int(slabs)
+        self.error = None
+
+    def start(self, an: "StreamingAnalyzer", pieces, cur) -> None:
+        import threading
+        need = max((b - a for a, b in pieces), default=1)
+        pool = getattr(an, "_slabs", None)
+        if pool is None or len(pool) != self.nslabs or pool[0].numel() < need:
+            pool = an._slabs = [torch.empty(need, dtype=an.raw_dev.dtype, pin_memory=True) for _ in range(self.nslabs)]
+        self.slabs = pool
+        self.ready = [threading.Event() for _ in pieces]
+        self.events = [None] * len(pieces)
+        an.copy_stream.wait_stream(cur)
+        self.thread = threading.Thread(target=self._run, args=(an, list(pieces)), daemon=True)
+        self.thread.start()
+
+    def _run(self, an, pieces) -> None:
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            with torch.cuda.device(an.device), ThreadPoolExecutor(self.threads) as pool:
+                slab_ev = [None] * self.nslabs
+                for i, (a, b) in enumerate(pieces):
+                    j = i % self.nslabs
+                    if slab_ev[j] is not None:
+                        slab_ev[j].synchronize()               # the slab's previous copy has left host memory
+                    if b > a:
+                        dst = self.slabs[j].numpy()
+                        cuts = np.linspace(a, b, self.threads + 1).astype(np.int64)
+                        futs = [pool.submit(self.reader.read_into, dst[int(c0) - a:], int(c0), int(c1))
+                                for c0, c1 in zip(cuts[:-1], cuts[1:]) if c1 > c0]
+                        for f in futs:
+                            f.result()
+                    with torch.cuda.stream(an.copy_stream):
+                        if b > a:
+                            an.raw_dev[a:b].copy_(self.slabs[j][:b - a], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(an.copy_stream)
+                    slab_ev[j] = self.events[i] = ev
+                    self.ready[i].set()
+        except BaseException as e:                              # surfaces in wait()
+            self.error = e
+            for r in self.ready:
+                r.set()
+
+    def wait(self, i: int, cur) -> None:
+        self.ready[i].wait()
+        if self.error is not None:
+            raise self.error
+        cur.wait_event(self.events[i])
+
+    def finish(self) -> None:
+        self.thread.join()
+
+    def whole(self, an: "StreamingAnalyzer") -> torch.Tensor:
+        host = torch.empty(an.n_ext, dtype=an.raw_dev.dtype, pin_memory=True)
+        self.reader.read_into(host.numpy(), 0, an.n_ext)
+        return host
+
+
 class StreamingAnalyzer:
     """Stages 1-3 over a trace that is still in pinned host memory, overlapped with its own
     host->device copy: the owned range is cut into time sub-shards (the multi-GPU sharding of
@@ -621,35 +714,44 @@ class StreamingAnalyzer:
         return nk
 
     def run_from_host(self, host_codes: torch.Tensor) -> StreamResult:
-        with torch.cuda.device(self.device):
-            return self._run_from_host(host_codes)
-
-    def _run_from_host(self, host_codes: torch.Tensor) -> StreamResult:
         """`host_codes`: CPU (ideally pinned) uint16/int16 tensor [lo_halo | owned | hi_halo].  One
         host synchronisation per sub-shard (its event count), all hidden under the copy except the last."""
         if host_codes.numel() != self.n_ext or host_codes.dtype not in (torch.uint16, torch.int16) or host_codes.is_cuda:
             raise ValueError("host_codes must be a CPU uint16/int16 tensor of the planned length")
-        if self.raw_dev is None or self.raw_dev.dtype != host_codes.dtype:
-            self.raw_dev = torch.empty(self.n_ext, dtype=host_codes.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            return self._run_stream(_HostFeed(host_codes), host_codes.dtype)
+
+    def run_from_file(self, reader, threads: int = 8, slabs: int = 3) -> StreamResult:
+        """The same with the codes still in the `.log` files: `reader` = loader.ChimeraSeries(...).reader(start_s,
+        end_s) over [lo_halo | owned | hi_halo].  A worker thread reads the pieces into rotating pinned slabs and
+        queues their host->device copies; file reads, PCIe and kernels overlap (the from-file path of SURVEY.md 8d/f4)."""
+        if int(reader.n) != self.n_ext:
+            raise ValueError(f"analyzer was planned for {self.n_ext} samples, the window holds {reader.n}")
+        with torch.cuda.device(self.device):
+            return self._run_stream(_FileFeed(reader, threads, slabs), torch.uint16)
+
+    def _run_stream(self, feed, dtype) -> StreamResult:
+        if self.raw_dev is None or self.raw_dev.dtype != dtype:
+            self.raw_dev = torch.empty(self.n_ext, dtype=dtype, device=self.device)
         L = _lib.lib()
         cur = torch.cuda.current_stream(self.device)
         a0, b_end = self.lo_halo, self.lo_halo + self.n_own
         # ---- the copy, cut where each sub-shard's extended range is complete
         ends = [eb for (_, _, _, eb) in self.sub]
         ends[-1] = self.n_ext
-        arrivals = []
-        self.copy_stream.wait_stream(cur)                      # the previous step may still read raw_dev
-        with torch.cuda.stream(self.copy_stream):
-            prev = 0
-            for e in ends:
-                if e > prev:
-                    self.raw_dev[prev:e].copy_(host_codes[prev:e], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
-                arrivals.append((prev, e, ev))
-                prev = max(prev, e)
+        arrivals, prev = [], 0
+        for e in ends:
+            arrivals.append((prev, max(prev, e)))
+            prev = max(prev, e)
+        feed.start(self, arrivals, cur)
+        try:
+            return self._consume(feed, arrivals, L, cur, a0, b_end)
+        finally:
+            feed.finish()
+
+    def _consume(self, feed, arrivals, L, cur, a0, b_end) -> StreamResult:
         # ---- median estimate from the first piece
-        cur.wait_event(arrivals[0][2])
+        feed.wait(0, cur)
         first = self.raw_dev[a0:max(a0 + 1, min(arrivals[0][1], b_end))]
         plan = median_estimate(self.n_own, self.mask, _median_kernels(first, self.mask)[0], self.group, self.device,
                                n_sampled=first.numel())
@@ -680,8 +782,8 @@ class StreamingAnalyzer:
                 failed = True
                 return 0
 
-        for i, (pa, pe, ev) in enumerate(arrivals):
-            cur.wait_event(ev)
+        for i, (pa, pe) in enumerate(arrivals):
+            feed.wait(i, cur)
             ca, cb = max(pa, a0), min(pe, b_end)
             if plan.exact is None and cb > ca:           # exact-median window count of this piece's owned codes
                 rc = L.ct_count_window_u16(self.raw_dev[ca:cb].data_ptr(), cb - ca, self.mask, plan.lo, plan.step,
@@ -706,7 +808,7 @@ class StreamingAnalyzer:
         start = reserve - max(first_rows, 0)
         first_id, total, any_failed = event_ids_and_status(0 if failed else rows - start, int(failed), self.group, self.device)
         if any_failed:
-            return self._run_whole(host_codes)
+            return self._run_whole(feed.whole(self))
         cur.synchronize()
         bl.dev["have_thresholds"] = True
         bl._checked = True

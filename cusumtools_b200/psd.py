@@ -172,14 +172,13 @@ def segment_share(n: int, nperseg: int, world: int, rank: int) -> tuple[int, int
 
 
 def reduce_sums(acc: torch.Tensor, nseg: int, group=None):
-    """Sum the per-rank periodogram sums and segment counts over `group` (the one collective
-    of the PSD stage: L/2+1 float64 values + one integer); returns (acc numpy, nseg)."""
+    """Sum the per-rank periodogram sums and segment counts over `group`: the one collective of the PSD stage,
+    L/2+1 float64 values with the integer count riding as one more (exact below 2^53); returns (acc numpy, nseg)."""
     if group is not None:
         import torch.distributed as dist
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-        t = torch.tensor([int(nseg)], dtype=torch.int64, device=acc.device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        nseg = int(t.item())
+        packed = torch.cat((acc, torch.tensor([float(int(nseg))], dtype=torch.float64, device=acc.device)))
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        acc, nseg = packed[:-1], int(round(float(packed[-1].item())))
     return acc.cpu().numpy(), int(nseg)
 
 

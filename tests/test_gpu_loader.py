@@ -92,3 +92,39 @@ def test_filter_data_on_bin_trace_takes_the_median_pad(tmp_path):
     y = filters.bessel_filtfilt(torch.from_numpy(x).cuda(), 4166666.0, 1e5, 8).cpu().numpy()
     want = to.filter_data(x.astype(np.float64), 4166666.0, 1e5, 8)
     assert np.abs(y - want).max() < 0.05
+
+
+def test_streaming_from_file_equals_streaming_from_host(tmp_path):
+    """plot-trace.py:230-299 reads the window of a multi-file `.log` series before anything else happens; here the
+    files are read piece by piece on a worker thread into rotating pinned slabs while earlier pieces are already
+    being copied and analysed.  Same sub-shards, same kernels: the result equals the run from one host buffer."""
+    import scipy.io as sio
+    from cusumtools_b200 import pipeline
+    codes, _ = synth.c1_trace(n=3_000_000, n_events=700, seed=21)
+    cuts = [0, 1_100_000, 1_900_001, len(codes)]
+    stamps = ["20210301_120000", "20210301_120001", "20210301_120002"]
+    for i, st in enumerate(stamps):
+        base = os.path.join(str(tmp_path), "pore_" + st)
+        codes[cuts[i]:cuts[i + 1]].tofile(base + ".log")
+        sio.savemat(base + ".mat", synth.CHIMERA_SETTINGS)
+    series = loader.ChimeraSeries(os.path.join(str(tmp_path), "pore_" + stamps[1] + ".log"))
+    fs = series.samplerate
+    start_s, end_s = 100_000 / fs + 1e-9, 2_900_000 / fs + 1e-9
+    rd = series.reader(start_s, end_s)
+    lo, hi = int(start_s * fs), int(end_s * fs)
+    assert rd.n == hi - lo
+    kw = dict(threshold=5.0, hysteresis=1.0, baseline_block=65536, baseline_min=4700.0, baseline_max=5300.0,
+              cusum_delta=400.0, cusum_h=10.0)
+    an = pipeline.StreamingAnalyzer(rd.n, rd.settings, 1e5, 8, shards=5, **kw)
+    from_file = an.run_from_file(rd, threads=3, slabs=2)
+    tf = {k: v.copy() for k, v in from_file.tables.items()}
+    yf = from_file.filtered.clone()
+    from_host = an.run_from_host(torch.from_numpy(codes[lo:hi].copy()).pin_memory())
+    assert from_file.median_codes == from_host.median_codes and from_file.total_events == from_host.total_events > 600
+    valid = np.arange(tf["mean"].shape[1])[None, :] < tf["n_levels"][:, None]      # level rows are defined up to n_levels
+    for k in tf:
+        if k in ("mean", "std"):
+            assert np.array_equal(tf[k][valid], from_host.tables[k][valid]), k
+        else:
+            assert np.array_equal(tf[k], from_host.tables[k]), k
+    assert torch.equal(yf, from_host.filtered)
