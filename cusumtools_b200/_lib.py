@@ -75,6 +75,7 @@ SIGNATURES = {
     "ct_welch_single_workspace_bytes": (_i64, [_i64]),
     "ct_welch_single_f32": (C.c_int, [_vp, _i64, C.c_double, C.c_int32, _vp, _i64, _vp, _vp]),
     "ct_event_extrema_f32": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ct_event_columns": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_int, _vp, _vp, _vp]),
     "ct_intra_crossings_f32": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp]),
     "ct_cusum_batch_dev": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _f32, _f32, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "ct_cusum_batch": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _f32, _f32, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

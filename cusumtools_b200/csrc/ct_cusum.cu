@@ -560,7 +560,84 @@ __global__ void __launch_bounds__(256) ct_event_extrema_kernel(const float* __re
     }
 }
 
+// ---- derived per-event statistics (the non-level columns of events.csv) ------------------------------
+// mosaicConverter.py:72-154 derives them from the level list of an event; here one thread per event reads its rows
+// of the level table (float64 means / stds from the exact integer sums, int32 edges) and leaves
+//   cols[e][0..10] = baseline before, baseline after, effective baseline, sub-level duration (samples),
+//                    average blockage, max blockage, its level's length (samples), min blockage, its level's
+//                    length, residual (rms of trace minus step fit), max deviation from the effective baseline
+// and the event's final type (0 accepted, 5 CUSUM+ found no sub-level, 6 level overflow; other codes pass through).
+// Conventions: cusumtools_b200/writer.py (blockage = sign(baseline) (baseline - level); in-event statistics run over
+// the sub-levels 1 .. L-2; ties keep the first level).  Sums run level by level in index order.
+constexpr int kEventCols = 12;
+__global__ void ct_event_columns_kernel(const int* __restrict__ n_levels, const int* __restrict__ edges,
+                                        const double* __restrict__ mean, const double* __restrict__ sd,
+                                        const int* __restrict__ type, const unsigned char* __restrict__ overflow,
+                                        const float* __restrict__ xmin, const float* __restrict__ xmax, long long nev,
+                                        const long long* __restrict__ nev_dev, int ML, double* __restrict__ cols,
+                                        int* __restrict__ type_out) {
+    if (nev_dev) { const long long d = *nev_dev; nev = d < nev ? d : nev; }
+    for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < nev; ev += (long long)gridDim.x * blockDim.x) {
+        const int L = n_levels[ev];
+        int t = type ? type[ev] : 0;
+        if (t == 0 && overflow[ev]) t = 6;
+        if (t == 0 && L < 3) t = 5;
+        type_out[ev] = t;
+        double* c = cols + ev * kEventCols;
+        if (t != 0) {
+#pragma unroll
+            for (int i = 0; i < kEventCols; ++i) c[i] = 0.0;
+            continue;
+        }
+        const int* ed = edges + ev * (ML + 1);
+        const double* mu = mean + ev * ML;
+        const double* sg = sd + ev * ML;
+        const double before = mu[0], after = mu[L - 1];
+        const double eff = 0.5 * (before + after);
+        const double sgn = eff >= 0.0 ? 1.0 : -1.0;
+        double tot = 0.0, res = 0.0, dur = 0.0, wsum = 0.0;
+        double bmax = -1.0 / 0.0, bmin = 1.0 / 0.0, lmax = 0.0, lmin = 0.0;
+        for (int k = 0; k < L; ++k) {
+            const double len = (double)(ed[k + 1] - ed[k]);
+            tot += len;
+            res += len * sg[k] * sg[k];
+            if (k >= 1 && k < L - 1) {
+                dur += len;
+                wsum += len * mu[k];
+                const double b = sgn * (eff - mu[k]);
+                if (b > bmax) { bmax = b; lmax = len; }
+                if (b < bmin) { bmin = b; lmin = len; }
+            }
+        }
+        c[0] = before; c[1] = after; c[2] = eff; c[3] = dur;
+        c[4] = sgn * (eff - wsum / dur);
+        c[5] = bmax; c[6] = lmax; c[7] = bmin; c[8] = lmin;
+        c[9] = sqrt(res / tot);
+        c[10] = fmax(fabs((double)xmax[ev] - eff), fabs((double)xmin[ev] - eff));
+        c[11] = 0.0;
+    }
+}
+
 }  // namespace
+
+extern "C" int ct_event_columns(const int32_t* n_levels, const int32_t* edges, const double* level_mean, const double* level_std,
+                                const int32_t* type, const uint8_t* overflow, const float* xmin, const float* xmax,
+                                int64_t n_events, const int64_t* n_events_dev, int max_levels, double* cols12, int32_t* type_out,
+                                void* stream) {
+    if (!n_levels || !edges || !level_mean || !level_std || !overflow || !xmin || !xmax || !cols12 || !type_out || n_events < 0 ||
+        max_levels < 2) {
+        ct_set_error("event_columns: bad argument"); return CT_ERR_ARG;
+    }
+    if (n_events == 0) return CT_OK;
+    long long grid = (n_events + 255) / 256;
+    const long long cap = (long long)ct_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    CT_COUNT_LAUNCH();
+    ct_event_columns_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        n_levels, edges, level_mean, level_std, type, overflow, xmin, xmax, n_events, (const long long*)n_events_dev, max_levels,
+        cols12, type_out);
+    return ct_check_launch("ct_event_columns_kernel");
+}
 
 extern "C" int64_t ct_cusum_workspace_bytes(int64_t n_events) { return 24 + 4 * (n_events > 0 ? n_events : 0) + 8; }
 

@@ -25,8 +25,11 @@ fixed here (SURVEY.md Appendix A.4 lists the open points):
   consumer draws at readevents.py:1363-1366); at most `max_crossings` pairs are listed per event,
   the count is complete.  No step-response fit: `rc_const1_us` = `rc_const2_us` = 0.
 
-Everything here is O(events) host arithmetic on tables that came from the device; the only
-device work is the per-event extrema kernel (ct_event_extrema_f32).
+The derived per-event statistics (baselines, blockages, area, residual, max deviation, final type) are computed on
+the device, one thread per event from the level table (ct_event_columns, after ct_event_extrema_f32); this module
+formats them.  Callers that only have host arrays (tests, converters) get the same columns from the NumPy statement
+of the definition in `event_columns_host`.  List columns are kept as padded 2-D arrays (`RaggedColumn`) and turned
+into `%.16g;` strings column by column when a file is written: no per-event Python loop anywhere.
 """
 from __future__ import annotations
 
@@ -63,6 +66,98 @@ def event_extrema(y: torch.Tensor, win_start: torch.Tensor, win_end: torch.Tenso
     return lo, hi
 
 
+def event_columns(levels, types, xmin: torch.Tensor, xmax: torch.Tensor, n_events_dev=None):
+    """Device side of the derived columns: (cols float64 [E, 12], type int32 [E]) CUDA tensors from a
+    `cusum.LevelTable` (+ rate.csv type codes, per-event extrema); see ct_event_columns in the C header."""
+    E = int(levels.n_levels.numel())
+    dev = levels.n_levels.device
+    cols = torch.empty((E, 12), dtype=torch.float64, device=dev)
+    tout = torch.empty(E, dtype=torch.int32, device=dev)
+    if E:
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ct_event_columns(levels.n_levels.data_ptr(), levels.edges.data_ptr(), levels.mean.data_ptr(),
+                                             levels.std.data_ptr(), types.data_ptr() if types is not None else None,
+                                             levels.overflow.data_ptr(), xmin.data_ptr(), xmax.data_ptr(), E,
+                                             n_events_dev.data_ptr() if n_events_dev is not None else None,
+                                             int(levels.max_levels), cols.data_ptr(), tout.data_ptr(), _stream_ptr(cols))
+        _lib.check(rc, "ct_event_columns")
+    return cols, tout
+
+
+def event_columns_host(types, n_levels, edges, level_mean, level_std, overflow, xmin, xmax):
+    """NumPy statement of ct_event_columns (same conventions, same level-by-level summation order): the definition
+    for callers without device tensors, and what the GPU test compares the kernel with."""
+    types = np.asarray(types, np.int32).copy()
+    nl = np.asarray(n_levels, np.int64)
+    E = nl.size
+    edges = np.asarray(edges, np.int64).reshape(E, -1)
+    mu = np.asarray(level_mean, np.float64).reshape(E, -1)
+    sd = np.asarray(level_std, np.float64).reshape(E, -1)
+    ML = mu.shape[1] if E else 0
+    types[(types == 0) & (np.asarray(overflow) != 0)] = TYPE_LEVEL_OVERFLOW
+    types[(types == 0) & (nl < 3)] = TYPE_NO_SUBLEVEL
+    cols = np.zeros((E, 12))
+    ok = types == 0
+    rows = np.nonzero(ok)[0]
+    if rows.size:
+        L = nl[rows]
+        before, after = mu[rows, 0], mu[rows, L - 1]
+        eff = 0.5 * (before + after)
+        sgn = np.where(eff >= 0, 1.0, -1.0)
+        tot = np.zeros(rows.size); res = np.zeros(rows.size); dur = np.zeros(rows.size); wsum = np.zeros(rows.size)
+        bmax = np.full(rows.size, -np.inf); bmin = np.full(rows.size, np.inf)
+        lmax = np.zeros(rows.size); lmin = np.zeros(rows.size)
+        for k in range(ML):                              # level by level, the kernel's order
+            valid = k < L
+            length = np.where(valid, edges[rows, k + 1] - edges[rows, k], 0).astype(np.float64)
+            m, s_ = np.where(valid, mu[rows, k], 0.0), np.where(valid, sd[rows, k], 0.0)
+            tot = tot + length
+            res = res + length * s_ * s_
+            inner = valid & (k >= 1) & (k < L - 1)
+            dur = np.where(inner, dur + length, dur)
+            wsum = np.where(inner, wsum + length * m, wsum)
+            b = sgn * (eff - m)
+            up, dn = inner & (b > bmax), inner & (b < bmin)
+            bmax, lmax = np.where(up, b, bmax), np.where(up, length, lmax)
+            bmin, lmin = np.where(dn, b, bmin), np.where(dn, length, lmin)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            avg = sgn * (eff - wsum / dur)
+            resid = np.sqrt(res / tot)
+        xm, xM = np.asarray(xmin, np.float64)[rows], np.asarray(xmax, np.float64)[rows]
+        dev_ = np.maximum(np.abs(xM - eff), np.abs(xm - eff))
+        cols[rows] = np.stack((before, after, eff, dur, avg, bmax, lmax, bmin, lmin, resid, dev_, np.zeros(rows.size)), axis=1)
+    return cols, types
+
+
+class RaggedColumn:
+    """A list column of events.csv (one vector of `lengths[i]` values per event) as a padded 2-D array: indexing and
+    iteration give the per-event vectors; `strings()` gives the ';'-joined `%.16g` text column by column."""
+
+    def __init__(self, data: np.ndarray, lengths: np.ndarray):
+        self.data, self.lengths = np.asarray(data, np.float64), np.asarray(lengths, np.int64)
+
+    def __len__(self) -> int:
+        return int(self.lengths.size)
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            return self.data[i, :self.lengths[i]].copy()
+        return RaggedColumn(self.data[i], self.lengths[i])
+
+    def __iter__(self):
+        return (self.data[i, :self.lengths[i]] for i in range(len(self)))
+
+    def strings(self) -> np.ndarray:
+        out = np.full(len(self), "", dtype=object)
+        for k in range(self.data.shape[1] if len(self) else 0):      # mosaicConverter.py:139-148 ('%.16g;' joined, last ';' cut)
+            sel = self.lengths > k
+            if not sel.any():
+                break
+            txt = np.char.mod("%.16g", self.data[sel, k]).astype(object)
+            out[sel] = txt if k == 0 else out[sel] + ";" + txt
+        return out
+
+
 @dataclass
 class EventTable:
     """Column-oriented event table (numpy).  `rate` holds every detected event, `events`
@@ -82,7 +177,7 @@ def _fmt_list(v) -> str:
 def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level_std, overflow, xmin, xmax,
                       samplerate: float, threshold: float, baseline_mean, baseline_std, baseline_block: int,
                       padding: int, first_id: int = 0, time_offset_s: float = 0.0, index_offset: int = 0,
-                      block_offset: int = 0, intra_count=None, intra_pairs=None) -> EventTable:
+                      block_offset: int = 0, intra_count=None, intra_pairs=None, columns=None) -> EventTable:
     """Per-event columns from the detector / CUSUM+ tables (numpy arrays, one row per detected
     event).  `index_offset` is the global sample index of the shard's first owned sample,
     `first_id` the global id of its first event (multi-GPU: pipeline.AnalysisResult)."""
@@ -95,8 +190,10 @@ def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level
     sd = np.asarray(level_std, np.float64).reshape(E, -1)
     ML = mu.shape[1] if E else 0
     fs = float(samplerate)
-    types[(types == 0) & (np.asarray(overflow) != 0)] = TYPE_LEVEL_OVERFLOW
-    types[(types == 0) & (nl < 3)] = TYPE_NO_SUBLEVEL
+    if columns is None:
+        cols, types = event_columns_host(types, nl, edges, mu, sd, overflow, xmin, xmax)
+    else:
+        cols, types = np.asarray(columns[0], np.float64).reshape(E, 12), np.asarray(columns[1], np.int32).copy()
     ids = first_id + np.arange(E, dtype=np.int64)
     t_start = time_offset_s + (index_offset + starts) / fs
     t_end = time_offset_s + (index_offset + ends) / fs
@@ -109,8 +206,7 @@ def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level
         ic = np.asarray(intra_count, np.int64)
         ip = np.asarray(intra_pairs, np.int64).reshape(E, -1)
         kmax = ip.shape[1] // 2
-        for i in np.nonzero(ic > 0)[0]:
-            crossing_txt[i] = ";".join("%.16g" % (v * (1e6 / fs)) for v in ip[i, :2 * min(int(ic[i]), kmax)])
+        crossing_txt = RaggedColumn(ip * (1e6 / fs), 2 * np.minimum(ic, kmax)).strings()
     rate = {"id": ids, "type": types, "start_time_s": t_start, "end_time_s": t_end,
             "intra_crossing_times_us": crossing_txt,
             "local_stdev": np.asarray(baseline_std, np.float64)[blk] if E else np.zeros(0),
@@ -121,39 +217,22 @@ def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level
     L = nl[ok]
     col = np.arange(ML)[None, :]
     valid = col < L[:, None]                       # levels of the window
-    inner = (col >= 1) & (col < (L - 1)[:, None])  # sub-levels (between first and last changepoint)
     length = np.where(valid, edges[ok, 1:ML + 1] - edges[ok, :ML], 0).astype(np.float64)
     m = np.where(valid, mu[ok], 0.0)
     s = np.where(valid, sd[ok], 0.0)
-    rows = np.arange(n)
-    before = m[rows, 0]
-    after = m[rows, np.maximum(L - 1, 0)]
-    eff = 0.5 * (before + after)
+    c = cols[ok]
+    before, after, eff, dur_in, avg_block = c[:, 0], c[:, 1], c[:, 2], c[:, 3], c[:, 4]
     sgn = np.where(eff >= 0, 1.0, -1.0)
-    block = sgn[:, None] * (eff[:, None] - m)      # blockage of every level
-    inner_len = np.where(inner, length, 0.0)
-    dur_in = inner_len.sum(axis=1)
+    block = sgn[:, None] * (eff[:, None] - m)      # blockage of every level; the first / last entries are the baselines
+    rows = np.arange(n)
+    if n:
+        block[rows, 0] = before - eff              # mosaicConverter.py:131-132
+        block[rows, np.maximum(L - 1, 0)] = after - eff
+    us = 1e6 / fs
     with np.errstate(invalid="ignore", divide="ignore"):
-        mean_in = (inner_len * m).sum(axis=1) / dur_in
-        avg_block = sgn * (eff - mean_in)
-        big = np.where(inner, block, -np.inf); small = np.where(inner, block, np.inf)
-        imax = big.argmax(axis=1) if n else np.zeros(0, np.int64)
-        imin = small.argmin(axis=1) if n else np.zeros(0, np.int64)
-        max_block, min_block = block[rows, imax], block[rows, imin]
-        residual = np.sqrt((length * s * s).sum(axis=1) / length.sum(axis=1))
         aeff = np.abs(eff)
-        xmin = np.asarray(xmin, np.float64)[ok]; xmax = np.asarray(xmax, np.float64)[ok]
-        max_dev = np.maximum(np.abs(xmax - eff), np.abs(xmin - eff))
-        us = 1e6 / fs
-        lists = {k: np.empty(n, dtype=object) for k in ("level_current_pA", "level_duration_us", "blockages_pA", "stdev_pA")}
-        for i in range(n):
-            k = int(L[i])
-            bl = block[i, :k].copy()
-            bl[0] = before[i] - eff[i]; bl[k - 1] = after[i] - eff[i]      # mosaicConverter.py:131-132
-            lists["level_current_pA"][i] = m[i, :k].copy()
-            lists["level_duration_us"][i] = length[i, :k] * us
-            lists["blockages_pA"][i] = bl
-            lists["stdev_pA"][i] = s[i, :k].copy()
+        lists = {"level_current_pA": RaggedColumn(m, L), "level_duration_us": RaggedColumn(length * us, L),
+                 "blockages_pA": RaggedColumn(np.where(valid, block, 0.0), L), "stdev_pA": RaggedColumn(s, L)}
         ts = t_start[ok]
         delay = np.empty(n)
         if n:
@@ -163,12 +242,12 @@ def build_event_table(*, starts, ends, types, n_levels, edges, level_mean, level
                   "duration_us": (ends[ok] - starts[ok]) * us, "threshold": np.full(n, float(threshold)),
                   "baseline_before_pA": before, "baseline_after_pA": after, "effective_baseline_pA": eff,
                   "area_pC": avg_block * dur_in / fs, "average_blockage_pA": avg_block,
-                  "relative_average_blockage": avg_block / aeff, "max_blockage_pA": max_block,
-                  "relative_max_blockage": max_block / aeff, "max_blockage_duration_us": length[rows, imax] * us,
+                  "relative_average_blockage": avg_block / aeff, "max_blockage_pA": c[:, 5],
+                  "relative_max_blockage": c[:, 5] / aeff, "max_blockage_duration_us": c[:, 6] * us,
                   "n_levels": L - 1, "intra_crossings": ic[ok], "rc_const1_us": np.zeros(n),
-                  "rc_const2_us": np.zeros(n), "residual_pA": residual, "max_deviation_pA": max_dev,
-                  "min_blockage_pA": min_block, "relative_min_blockage": min_block / aeff,
-                  "min_blockage_duration_us": length[rows, imin] * us, **lists}
+                  "rc_const2_us": np.zeros(n), "residual_pA": c[:, 9], "max_deviation_pA": c[:, 10],
+                  "min_blockage_pA": c[:, 7], "relative_min_blockage": c[:, 7] / aeff,
+                  "min_blockage_duration_us": c[:, 8] * us, **lists}
     return EventTable(events=events, rate=rate)
 
 
@@ -176,8 +255,9 @@ def event_table_from_result(an, r, *, samplerate: float, time_offset_s: float = 
     """Event table of one `pipeline.TraceAnalyzer.run` result (device -> host, then
     `build_event_table`)."""
     lo, hi = event_extrema(r.detect_trace, r.win_start, r.win_end)
+    cols = event_columns(r.levels, r.types, lo, hi) if r.levels is not None else None
     tabs = an.tables_to_host(r)
-    return build_event_table(starts=tabs["starts"], ends=tabs["ends"], types=tabs["types"], n_levels=tabs["n_levels"],
+    return build_event_table(columns=None if cols is None else (cols[0].cpu().numpy(), cols[1].cpu().numpy()), starts=tabs["starts"], ends=tabs["ends"], types=tabs["types"], n_levels=tabs["n_levels"],
                              edges=tabs["edges"], level_mean=tabs["mean"], level_std=tabs["std"],
                              overflow=tabs["overflow"], xmin=lo.cpu().numpy(), xmax=hi.cpu().numpy(),
                              samplerate=samplerate, threshold=an.threshold, baseline_mean=r.baseline.mean,
@@ -196,7 +276,14 @@ def event_table_from_stream(san, rs, *, samplerate: float, time_offset_s: float 
     w0 = torch.from_numpy(np.clip(t["starts"] - pad, 0, n)).to(dev)
     w1 = torch.from_numpy(np.clip(t["ends"] + pad, 0, n)).to(dev)
     lo, hi = event_extrema(rs.filtered, w0, w1)
-    return build_event_table(starts=t["starts"], ends=t["ends"], types=t["types"], n_levels=t["n_levels"],
+    cols = None
+    if "mean" in t:          # the level table went to the host sub-shard by sub-shard: one upload for the derived columns
+        from .cusum import LevelTable
+        lv = LevelTable(*(torch.from_numpy(np.ascontiguousarray(t[k])).to(dev) for k in ("n_levels", "edges", "mean", "std", "overflow")),
+                        int(t["mean"].shape[1]))
+        c, ty = event_columns(lv, torch.from_numpy(np.ascontiguousarray(t["types"])).to(dev), lo, hi)
+        cols = (c.cpu().numpy(), ty.cpu().numpy())
+    return build_event_table(columns=cols, starts=t["starts"], ends=t["ends"], types=t["types"], n_levels=t["n_levels"],
                              edges=t["edges"], level_mean=t["mean"], level_std=t["std"], overflow=t["overflow"],
                              xmin=lo.cpu().numpy(), xmax=hi.cpu().numpy(), samplerate=samplerate,
                              threshold=float(san.kw.get("threshold", 5.0)), baseline_mean=rs.baseline.mean,
@@ -207,10 +294,10 @@ def event_table_from_stream(san, rs, *, samplerate: float, time_offset_s: float 
 
 def _write_csv(path: str, columns, table: dict) -> None:
     import pandas as pd
-    df = pd.DataFrame({c: table[c] for c in columns}, columns=columns)
-    for c in ("level_current_pA", "level_duration_us", "blockages_pA", "stdev_pA"):
-        if c in df.columns and df[c].dtype == object:
-            df[c] = [_fmt_list(v) for v in df[c]]
+    df = pd.DataFrame({c: (np.zeros(len(table[c])) if isinstance(table[c], RaggedColumn) else table[c]) for c in columns}, columns=columns)
+    for c in columns:
+        if isinstance(table[c], RaggedColumn):
+            df[c] = table[c].strings()
     df.to_csv(path, index=False, encoding="utf-8")
 
 

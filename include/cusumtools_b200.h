@@ -208,6 +208,17 @@ int ct_intra_crossings_f32(const float* y, int64_t n_total, const int64_t* win_s
 int ct_event_extrema_f32(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                          int64_t n_events, const int64_t* n_events_dev, float* xmin, float* xmax, void* stream);
 
+/* Derived per-event statistics: the non-level columns of events.csv that mosaicConverter.py:72-154 computes from an
+ * event's level list (readevents.py:1470-1508 names them), one thread per event from the level table of ct_cusum_batch:
+ *   cols12[e] = { baseline_before, baseline_after, effective_baseline, sub-level duration (samples), average_blockage,
+ *                 max_blockage, length of its level (samples), min_blockage, length of its level, residual,
+ *                 max_deviation, 0 }                                (pA; conventions: cusumtools_b200/writer.py)
+ *   type_out[e] = type[e], or 5 (accepted but CUSUM+ found no sub-level) / 6 (level overflow); rows of events with
+ *   type_out != 0 are zero.  xmin / xmax: ct_event_extrema_f32.  type and n_events_dev may be NULL.                */
+int ct_event_columns(const int32_t* n_levels, const int32_t* edges, const double* level_mean, const double* level_std,
+                     const int32_t* type, const uint8_t* overflow, const float* xmin, const float* xmax, int64_t n_events,
+                     const int64_t* n_events_dev, int max_levels, double* cols12, int32_t* type_out, void* stream);
+
 /* ---- stage 4: Welch PSD ------------------------------------------------------------
  * Replaces scipy.signal.welch(x, fs, nperseg=L) as called at plot-trace.py:442,
  * noise-fit.py:92 (use_abs != 0: welch(|x|)), legacy/minimal_psd.py:255: periodic Hann,

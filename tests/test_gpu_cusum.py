@@ -108,3 +108,27 @@ def test_full_c3_checksum_properties():
     want = c_twin.cusum_batch(x[:offsets[5000]], offsets[:5001], 400.0, 10.0, 16)
     assert np.array_equal(a.edges[:5000].cpu().numpy(), want[1])
     assert np.array_equal(a.std[:5000].cpu().numpy(), want[3])
+
+
+def test_event_columns_kernel_matches_the_numpy_statement():
+    """The non-level columns of events.csv (mosaicConverter.py:72-154: baselines, blockages, area inputs, residual,
+    max deviation, final type) computed one thread per event on the device against writer.event_columns_host."""
+    from cusumtools_b200 import pipeline, writer
+    codes, _ = synth.c1_trace(n=1_500_000, n_events=350, seed=12)
+    S = synth.CHIMERA_SETTINGS
+    for ml in (16, 3):                        # 3: every two-level event overflows the table (type 6)
+        an = pipeline.TraceAnalyzer(len(codes), S, 1e5, 8, threshold=5.0, hysteresis=1.0, baseline_block=65536,
+                                    baseline_min=4700.0, baseline_max=5300.0, cusum_delta=400.0, cusum_h=10.0, max_levels=ml)
+        r = an.run(torch.from_numpy(codes).cuda())
+        lo, hi = writer.event_extrema(r.detect_trace, r.win_start, r.win_end)
+        cols, typ = writer.event_columns(r.levels, r.types, lo, hi)
+        want_c, want_t = writer.event_columns_host(r.types.cpu().numpy(), r.levels.n_levels.cpu().numpy(), r.levels.edges.cpu().numpy(),
+                                                   r.levels.mean.cpu().numpy(), r.levels.std.cpu().numpy(),
+                                                   r.levels.overflow.cpu().numpy(), lo.cpu().numpy(), hi.cpu().numpy())
+        assert np.array_equal(typ.cpu().numpy(), want_t)
+        assert (want_t == 0).sum() > 300 if ml == 16 else (want_t == 6).sum() > 300
+        assert np.allclose(cols.cpu().numpy(), want_c, rtol=1e-12, atol=1e-9)
+        tab = writer.event_table_from_result(an, r, samplerate=synth.FS)
+        assert len(tab) == int((want_t == 0).sum())
+        if ml == 16:
+            assert abs(np.median(tab.events["max_blockage_pA"]) - 1600) < 100
