@@ -5,10 +5,10 @@
 // definition of record is oracle/events_oracle.py::cusum_event, the two-sided CUSUM of
 // SURVEY.md Appendix C with every reduction in exact integer arithmetic, so changepoints
 // are bit-identical to the sequential definition whatever the scan order:
-//   q_k  = rint((x_k - x_0) * 64)                      (int32, |q| < 2^22)
-//   Sq, Sqq = prefix sums of q, q^2 from the anchor    (warp scans: int32 / int64)
-//   m, v = running mean / population variance          (float64 from the exact sums)
-//   s+-  = rint(1024 * (+-delta/v) (q - m -+ delta/2)) (float32 ops, individually rounded)
+//   q_k  = rint((x_k - x_0) * 64)                      (int32)
+//   d_k  = q_k - q_anchor ; Sd, Sdd = prefix sums of d, d^2 from the anchor   (exact integers: scan-order independent)
+//   m, v = running mean / population variance          (float32 from the exact sums: deviations from the anchor are small)
+//   s+-  = rint(1024 * (+-delta/v) (d - m -+ delta/2)) (float32 ops, individually rounded; 1/v correctly rounded)
 //   S+-  = prefix sums of s+-, g+- = S+- - running min (warp sum scan + warp min scan)
 // A jump is detected at the first k with g+ > H or g- > H; the new level starts after the
 // last index at which the winning g was 0; the anchor moves to k and the block is redone
@@ -20,27 +20,20 @@ namespace {
 
 constexpr int kE = 8;                 // samples per lane per block
 constexpr int kBlk = 32 * kE;         // 256
-constexpr float kQ = 64.0f, kQMax = 4194303.0f, kSScale = 1024.0f, kSMax = 2097152.0f;
+constexpr float kQ = 64.0f, kSScale = 1024.0f, kSMax = 2097152.0f;
 constexpr int kBig = 0x3fffffff;
 
-// rc[cnt] = the oracle's refined reciprocal of the sample count: rc32 = 1.0f/(float)cnt (IEEE
-// float32 division), rc = (double)rc32, rc = rc * (2.0 - (double)cnt * rc).  It only depends
-// on cnt, so it is tabulated once per device with the very same operations and the hot loop
-// replaces a division and four float64 operations per sample by one (L1-resident) load.
+// rc[cnt] = 1.0f / (float)cnt (IEEE division), the oracle's reciprocal of the sample count: it only depends on cnt,
+// so it is tabulated once per device and the hot loop replaces a division by one (L1-resident) load.
 constexpr int kRcTab = 1 << 16;
-__global__ void ct_cusum_rc_table(double* tab) {
+__global__ void ct_cusum_rc_table(float* tab) {
     const int cnt = blockIdx.x * blockDim.x + threadIdx.x;
     if (cnt >= kRcTab) return;
-    double rc = 0.0;
-    if (cnt > 0) {
-        rc = (double)__fdiv_rn(1.0f, (float)cnt);
-        rc = __dmul_rn(rc, __dsub_rn(2.0, __dmul_rn((double)cnt, rc)));
-    }
-    tab[cnt] = rc;
+    tab[cnt] = cnt > 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
 }
 
 struct CusumArgs {
-    const double* rctab;
+    const float* rctab;
     const float* y; long long ntot;
     const long long* w0; const long long* w1; const int* type; long long nev;
     const long long* nev_dev;          // event count read from device memory (NULL: use nev)
@@ -81,9 +74,25 @@ __device__ __forceinline__ void warp_excl_summin2(int sp, int mp, int sn, int mn
     if (lane == 0) { exsp = 0; exmp = kBig; exsn = 0; exmn = kBig; }
 }
 __device__ __forceinline__ int quantise(float x, float x0) {
-    float d = __fmul_rn(__fsub_rn(x, x0), kQ);
-    d = fminf(fmaxf(d, -kQMax), kQMax);
-    return __float2int_rn(d);
+    return __float2int_rn(__fmul_rn(__fsub_rn(x, x0), kQ));      // (the conversion saturates at the int32 range)
+}
+// The increments of both tests from the exact sums of the deviations d = q - q_anchor over [k0, k]
+// (oracle/events_oracle.py::cusum_increments, operation for operation, all float32).
+struct SeqOut { int sp, sn; };
+__device__ __forceinline__ float cusum_mean(long long Sd, float rc) { return __fmul_rn(__ll2float_rn(Sd), rc); }
+__device__ __forceinline__ SeqOut cusum_tail(long long Sdd, float m, float rc, float t, float dq, float hq) {
+    const float v = __fsub_rn(__fmul_rn(__ll2float_rn(Sdd), rc), __fmul_rn(m, m));
+    // branch-free: evaluate with a harmless divisor when the variance carries no information, then mask
+    const bool ok = v > 0.f;
+    const float r = __fmul_rn(dq, __frcp_rn(ok ? v : 1.f));
+    float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
+    float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
+    fa = fminf(fmaxf(fa, -kSMax), kSMax);
+    fb = fminf(fmaxf(fb, -kSMax), kSMax);
+    SeqOut o;
+    o.sp = ok ? __float2int_rn(fa) : 0;
+    o.sn = ok ? __float2int_rn(fb) : 0;
+    return o;
 }
 // highest index k in [lo, hi] among the lane-held candidates (cand = per-lane best or -1)
 __device__ __forceinline__ int warp_max(int v) {
@@ -111,6 +120,7 @@ __device__ void warp_event(const CusumArgs& a, const long long ev, const int lan
         if (lane == 0) ed[0] = 0;
         int nedge = 1, overflow = 0;
         int k0 = 0;
+        int qa = 0;                         // q at the anchor (x0 itself for the first level)
         long long cSq = 0, cSqq = 0;
         int mp = kBig, mn = kBig;           // running min of S+-, relative to the block start
         int argp = 0, argn = 0;             // last index at which g+- was 0
@@ -154,7 +164,7 @@ __device__ void warp_event(const CusumArgs& a, const long long ev, const int lan
 #pragma unroll
                 for (int e = 0; e < kE; ++e) {
                     const int k = r0 + e;
-                    const int qv = (k >= k0 && k < n) ? q[e] : 0;
+                    const int qv = (k >= k0 && k < n) ? q[e] - qa : 0;       // deviation from the anchor sample
                     aq += qv; aqq += (long long)qv * qv;
                     pq[e] = aq; pqq[e] = aqq;
                 }
@@ -171,27 +181,11 @@ __device__ void warp_event(const CusumArgs& a, const long long ev, const int lan
                     int sp = 0, sn = 0;
                     if (k > k0 && k < n) {
                         const int cnt = k - k0 + 1;
-                        const double Sq = (double)(cSq + exq + pq[e]);
-                        const double Sqq = (double)(cSqq + exqq + pqq[e]);
-                        double rc;
-                        if (cnt < kRcTab) rc = __ldg(a.rctab + cnt);
-                        else {
-                            rc = (double)__fdiv_rn(1.0f, (float)cnt);
-                            rc = __dmul_rn(rc, __dsub_rn(2.0, __dmul_rn((double)cnt, rc)));
-                        }
-                        const double m = __dmul_rn(Sq, rc);
-                        const double vv = __dmul_rn(__dsub_rn(Sqq, __dmul_rn(Sq, m)), rc);
-                        const float v = __double2float_rn(vv);
-                        if (v > 0.f) {
-                            const float r = __fdiv_rn(dq, v);
-                            const float t = __fsub_rn((float)q[e], __double2float_rn(m));
-                            float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
-                            float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
-                            fa = fminf(fmaxf(fa, -kSMax), kSMax);
-                            fb = fminf(fmaxf(fb, -kSMax), kSMax);
-                            sp = __float2int_rn(fa);
-                            sn = __float2int_rn(fb);
-                        }
+                        const float rc = cnt < kRcTab ? __ldg(a.rctab + cnt) : __fdiv_rn(1.0f, (float)cnt);
+                        const float m = cusum_mean(cSq + exq + pq[e], rc);
+                        const float t = __fsub_rn((float)(q[e] - qa), m);
+                        const SeqOut o = cusum_tail(cSqq + exqq + pqq[e], m, rc, t, dq, hq);
+                        sp = o.sp; sn = o.sn;
                     }
                     ap += sp; an += sn;
                     lp[e] = ap; ln[e] = an;
@@ -248,6 +242,7 @@ __device__ void warp_event(const CusumArgs& a, const long long ev, const int lan
                 if (lane == 0) ed[nedge] = jmin + 1;
                 ++nedge;
                 k0 = kdet; cSq = 0; cSqq = 0; mp = kBig; mn = kBig; argp = kdet; argn = kdet;
+                qa = quantise(a.y[p0 + kdet], x0);
                 // restart at the lane chunk (32-byte grid) that holds the new anchor: nothing before
                 // it is needed again, so no block position is spent on samples behind the anchor
                 const int nrs = rs + ((kdet - rs) & ~(kE - 1));
@@ -331,25 +326,11 @@ constexpr int kSeqMax = 16384;         // longest window a single lane takes
 constexpr int kSeqMinEvents = 16384;   // below this one event per lane cannot fill the GPU: warps take everything
 constexpr unsigned char kRawSums = 0x80;   // overflow[] bit: level rows hold raw integer sums (finalize pending)
 
-struct SeqOut { int sp, sn; };
-
-// The increments of both tests from the running sums.  Split in two: the mean and the sample's deviation t
-// are needed for every sample; the variance, the IEEE division and the two products only matter when an
-// increment can change a statistic (see the quiet-sample shortcut in the kernel).
-__device__ __forceinline__ SeqOut seq_increments_tail(double Sqd, double m, double rc, long long Sqq, float t, float dq, float hq) {
-    const double vv = __dmul_rn(__dsub_rn((double)Sqq, __dmul_rn(Sqd, m)), rc);
-    const float v = __double2float_rn(vv);
-    // branch-free: evaluate with a harmless divisor when the variance carries no information, then mask
-    const bool ok = v > 0.f;
-    const float r = __fdiv_rn(dq, ok ? v : 1.f);
-    float fa = __fmul_rn(__fmul_rn(r, __fsub_rn(t, hq)), kSScale);
-    float fb = __fmul_rn(__fmul_rn(-r, __fadd_rn(t, hq)), kSScale);
-    fa = fminf(fmaxf(fa, -kSMax), kSMax);
-    fb = fminf(fmaxf(fb, -kSMax), kSMax);
-    SeqOut o;
-    o.sp = ok ? __float2int_rn(fa) : 0;
-    o.sn = ok ? __float2int_rn(fb) : 0;
-    return o;
+// sums of q, q^2 (relative to x0: what the level statistics are made of) over the cnt samples from the anchor, from
+// the sums of the deviations d = q - qa
+__device__ __forceinline__ void level_sums(long long Sd, long long Sdd, int cnt, int qa, long long& Sq, long long& Sqq) {
+    Sq = Sd + (long long)cnt * qa;
+    Sqq = Sdd + 2LL * qa * Sd + (long long)cnt * ((long long)qa * qa);
 }
 
 __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(CusumArgs a) {
@@ -368,9 +349,9 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
     long long ev = 0, p0 = 0;
     int n = 0, gk = 0;                   // window length; relative index of the current 8-sample group
     float x0 = 0.f, nx0 = 0.f;           // the window's first sample and -64 x0 (quantisation: (x - x0) * 64, one FFMA)
-    int k0 = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0, overflow = 0;
-    long long Sq = 0, Sqq = 0;           // sums over [k0, k]
-    long long Lp = 0, Lpp = 0;           // sums over [e0, k0): the part of the open level before the anchor
+    int k0 = 0, qa = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0, overflow = 0;
+    long long Sd = 0, Sdd = 0;           // sums of d = q - qa, d^2 over [k0, k] (qa = q at the anchor k0)
+    long long Lp = 0, Lpp = 0;           // sums of q, q^2 over [e0, k0): the part of the open level before the anchor
     float nx[kS];                        // the lane's next group of samples (software prefetch)
 #pragma unroll
     for (int e = 0; e < kS; ++e) nx[e] = 0.f;
@@ -409,8 +390,8 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
                     else {
                         n = (int)nn;
                         gk = -(int)(p0 & (kS - 1));
-                        k0 = 0; gp = gn = 0; rp = rn = 0; nedge = 1; e0 = 0; overflow = 0;
-                        Sq = Sqq = 0; Lp = Lpp = 0;
+                        k0 = 0; qa = 0; gp = gn = 0; rp = rn = 0; nedge = 1; e0 = 0; overflow = 0;
+                        Sd = Sdd = 0; Lp = Lpp = 0;
                         a.edges[ev * (ML + 1)] = 0;
                         load_group(p0 + gk, nx);
                         x0 = a.y[p0];
@@ -437,21 +418,20 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
             // committed and the group takes the per-sample path.
             bool done = false;
             if (__all_sync(__activemask(), gk >= 0 && gk + kS <= n && !overflow && (gp | gn) == 0)) {
-                const double* rcp = a.rctab + (gk - k0 + 1);             // counts gk-k0+1 .. gk-k0+kS <= kSeqMax < kRcTab
-                double rcv[kS];
+                const float* rcp = a.rctab + (gk - k0 + 1);              // counts gk-k0+1 .. gk-k0+kS <= kSeqMax < kRcTab
+                float rcv[kS];
 #pragma unroll
                 for (int e = 0; e < kS; ++e) rcv[e] = __ldg(rcp + e);
-                long long S1 = Sq, S2 = Sqq;
+                long long S1 = Sd, S2 = Sdd;
                 bool allq = true;
 #pragma unroll
                 for (int e = 0; e < kS; ++e) {
-                    const int q = __float2int_rn(fminf(fmaxf(__fmaf_rn(xv[e], kQ, nx0), -kQMax), kQMax));
-                    S1 += q; S2 += (long long)q * q;
-                    const double m = __dmul_rn((double)S1, rcv[e]);
-                    const float t = __fsub_rn((float)q, __double2float_rn(m));
+                    const int d = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0)) - qa;
+                    S1 += d; S2 += (long long)d * d;
+                    const float t = __fsub_rn((float)d, cusum_mean(S1, rcv[e]));
                     allq = allq && fabsf(t) <= hq;
                 }
-                if (__all_sync(__activemask(), allq)) { Sq = S1; Sqq = S2; rp = rn = gk + kS - 1; done = true; }
+                if (__all_sync(__activemask(), allq)) { Sd = S1; Sdd = S2; rp = rn = gk + kS - 1; done = true; }
             }
             if (!done)
 #pragma unroll
@@ -459,12 +439,12 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
                 const int k = gk + e;
                 if ((unsigned)k >= nlim) continue;       // before the window (k < 0 wraps), behind it, or frozen by overflow
                 // == quantise(xv[e], x0): scaling by 2^6 commutes with the rounding of the difference
-                const int q = __float2int_rn(fminf(fmaxf(__fmaf_rn(xv[e], kQ, nx0), -kQMax), kQMax));
-                Sq += q; Sqq += (long long)q * q;
-                const double rc = __ldg(a.rctab + (k - k0 + 1));      // k - k0 + 1 <= kSeqMax < kRcTab
-                const double Sqd = (double)Sq;
-                const double m = __dmul_rn(Sqd, rc);
-                const float t = __fsub_rn((float)q, __double2float_rn(m));
+                const int q = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0));
+                const int d = q - qa;
+                Sd += d; Sdd += (long long)d * d;
+                const float rc = __ldg(a.rctab + (k - k0 + 1));       // k - k0 + 1 <= kSeqMax < kRcTab
+                const float m = cusum_mean(Sd, rc);
+                const float t = __fsub_rn((float)d, m);
                 // Quiet sample: both statistics are 0 and |t| <= delta/2, so both increments are <= 0 whatever the
                 // variance is (r > 0 or masked; t - hq <= 0 and t + hq >= 0 survive every rounding and the clamps) and
                 // the statistics stay 0 with their argmin at k: exactly what the full evaluation would leave.  On the
@@ -472,7 +452,7 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
                 // at a sample agree (warp-uniform branch), the full evaluation is always valid.
                 const bool quiet = (gp | gn) == 0 && fabsf(t) <= hq;
                 if (__all_sync(__activemask(), quiet)) { rp = k; rn = k; continue; }
-                const SeqOut s = seq_increments_tail(Sqd, m, rc, Sqq, t, dq, hq);
+                const SeqOut s = cusum_tail(Sdd, m, rc, t, dq, hq);
                 gp = max(gp + s.sp, 0); rp = gp == 0 ? k : rp;
                 gn = max(gn + s.sn, 0); rn = gn == 0 ? k : rn;
                 if (max(gp, gn) > H) {
@@ -484,22 +464,27 @@ __global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(Cu
                         const long long qj = quantise(a.y[p0 + j], x0);
                         T += qj; TT += qj * qj;
                     }
+                    long long Sq, Sqq;
+                    level_sums(Sd, Sdd, k - k0 + 1, qa, Sq, Sqq);
                     const long long row = ev * ML + (nedge - 1);
                     reinterpret_cast<long long*>(a.mean)[row] = Lp + Sq - T;      // level [e0, edge)
                     reinterpret_cast<long long*>(a.sd)[row] = Lpp + Sqq - TT;
                     a.edges[ev * (ML + 1) + nedge] = edge;
                     ++nedge;
                     e0 = edge; Lp = T - q; Lpp = TT - (long long)q * q;
-                    k0 = k; Sq = q; Sqq = (long long)q * q; gp = gn = 0; rp = rn = k;
+                    k0 = k; qa = q; Sd = 0; Sdd = 0; gp = gn = 0; rp = rn = k;
                 }
             }
             gk += kS;
             if (gk >= n || overflow) {
+                long long Sq = 0, Sqq = 0;
                 if (overflow) {                          // the rest of the window belongs to the last level
                     long long T = 0, TT = 0;
 #pragma unroll 1
                     for (int j = e0; j < n; ++j) { const long long qj = quantise(a.y[p0 + j], x0); T += qj; TT += qj * qj; }
-                    Lp = T; Lpp = TT; Sq = 0; Sqq = 0;
+                    Lp = T; Lpp = TT;
+                } else {
+                    level_sums(Sd, Sdd, n - k0, qa, Sq, Sqq);
                 }
                 const long long row = ev * ML + (nedge - 1);
                 reinterpret_cast<long long*>(a.mean)[row] = Lp + Sq;              // level [e0, n)
@@ -659,13 +644,13 @@ static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_star
     cudaMemsetAsync(workspace, 0, 24, st);
     if (n_events == 0) return CT_OK;
     // library-owned per-device reciprocal table (built once with the oracle's operations)
-    static double* tabs[64] = {nullptr};
+    static float* tabs[64] = {nullptr};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) { ct_set_error("cusum: unsupported device ordinal"); return CT_ERR_UNSUPPORTED; }
     if (!tabs[dev]) {
-        double* t = nullptr;
-        if (cudaMalloc(&t, sizeof(double) * kRcTab) != cudaSuccess) { ct_set_error("cusum: table allocation failed"); return CT_ERR_CUDA; }
+        float* t = nullptr;
+        if (cudaMalloc(&t, sizeof(float) * kRcTab) != cudaSuccess) { ct_set_error("cusum: table allocation failed"); return CT_ERR_CUDA; }
         CT_COUNT_LAUNCH();
         ct_cusum_rc_table<<<kRcTab / 256, 256, 0, st>>>(t);
         int rc0 = ct_check_launch("ct_cusum_rc_table"); if (rc0) return rc0;

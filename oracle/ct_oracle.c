@@ -83,15 +83,16 @@ int64_t orc_detect(const float *y, int64_t n, int64_t block, const int32_t *sign
 }
 
 #define CQ 64.0f
-#define CQMAX 4194303.0f
 #define CSSCALE 1024.0f
 #define CSMAX 2097152.0f
 
 static inline int64_t quantise(float x, float x0)
 {
     float d = (x - x0) * CQ;
-    d = fminf(fmaxf(d, -CQMAX), CQMAX);
-    return (int64_t)rintf(d);
+    d = rintf(d);
+    if (!(d > -2147483648.0f)) return d != d ? 0 : -2147483648LL;     /* the conversion saturates at the int32 range */
+    if (d >= 2147483648.0f) return 2147483647LL;
+    return (int64_t)d;
 }
 
 /* One event.  edges[0..max_levels], returns number of levels; *overflow set if truncated. */
@@ -106,22 +107,23 @@ static int cusum_event(const float *x, int64_t n, float delta, float h, int max_
     edges[nedge++] = 0;
     *overflow = 0;
     int64_t k0 = 0;
-    int64_t q0 = quantise(x[0], x0);
-    int64_t Sq = q0, Sqq = q0 * q0;
+    int64_t qa = quantise(x[0], x0);
+    uint64_t Sd = 0, Sdd = 0;                        /* two's-complement sums of d and d^2 (d = q - q_anchor) */
     int64_t gp = 0, gn = 0, rp = 0, rn = 0;
     for (int64_t k = 1; k < n; ++k) {
-        int64_t qk = quantise(x[k], x0);
-        Sq += qk; Sqq += qk * qk;
+        int64_t d = quantise(x[k], x0) - qa;
+        Sd += (uint64_t)d; Sdd += (uint64_t)d * (uint64_t)d;
         int64_t cnt = k - k0 + 1;
-        double rc = (double)(1.0f / (float)cnt);
-        rc = rc * (2.0 - (double)cnt * rc);
-        double m = (double)Sq * rc;
-        double vv = ((double)Sqq - (double)Sq * m) * rc;
-        float v = (float)vv;
+        float rc = 1.0f / (float)cnt;
+        float m = (float)(int64_t)Sd * rc;
+        float p1 = (float)(int64_t)Sdd * rc;
+        float p2 = m * m;
+        float v = p1 - p2;
         int64_t sp = 0, sn = 0;
         if (v > 0.0f) {
-            float r = dq / v;
-            float t = (float)qk - (float)m;
+            float ri = 1.0f / v;
+            float r = dq * ri;
+            float t = (float)d - m;
             float a = (r * (t - hq)) * CSSCALE;
             float b = ((-r) * (t + hq)) * CSSCALE;
             a = fminf(fmaxf(a, -CSMAX), CSMAX);
@@ -135,7 +137,7 @@ static int cusum_event(const float *x, int64_t n, float delta, float h, int max_
             int64_t jmin = gp >= gn ? rp : rn;
             if (nedge >= max_levels) { *overflow = 1; break; }
             edges[nedge++] = (int32_t)(jmin + 1);
-            k0 = k; Sq = qk; Sqq = qk * qk; gp = gn = 0; rp = rn = k;
+            k0 = k; qa += d; Sd = 0; Sdd = 0; gp = gn = 0; rp = rn = k;
         }
     }
     edges[nedge++] = (int32_t)n;

@@ -233,52 +233,47 @@ def event_windows(starts, ends, n, padding, minpoints, maxpoints):
 
 # ------------------------------------------------------------------- stage 3: CUSUM+
 CUSUM_Q = np.float32(64.0)          # samples are quantised to 1/64 pA
-CUSUM_QMAX = np.float32(4194303.0)  # |q| <= 2^22 - 1
 CUSUM_SSCALE = np.float32(1024.0)   # log-likelihood increments quantised to 2^-10
 CUSUM_SMAX = np.float32(2097152.0)   # |s| <= 2^21 fixed-point units (2048 nats per sample)
 
 
 def cusum_quantise(x):
-    """q_k = rint((x_k - x_0) * 64), saturated to +-(2^22 - 1); int64 array."""
+    """q_k = rint((x_k - x_0) * 64) as int32 (the conversion saturates at the int32 range); int64 array."""
     x = np.asarray(x, dtype=np.float32)
     d = (x - x[0]).astype(np.float32) * CUSUM_Q
-    d = np.minimum(np.maximum(d, -CUSUM_QMAX), CUSUM_QMAX)
-    return np.rint(d).astype(np.int64)
+    return np.clip(np.rint(d), -2147483648.0, 2147483647.0).astype(np.int64)
 
 
 def cusum_increments(q, k0, delta):
-    """Fixed-point log-likelihood-ratio increments s+_k, s-_k for k in (k0, n) with the
-    running mean / population variance taken over q[k0..k].
-
-    Per sample, in this exact order of individually rounded operations:
-      cnt  = k - k0 + 1
-      rc32 = 1.0f / (float)cnt ;  rc = (double)rc32 ; rc = rc * (2.0 - (double)cnt * rc)
-      m    = (double)Sq * rc
-      vv   = ((double)Sqq - (double)Sq * m) * rc          (population variance, q^2 units)
-      v    = (float)vv ;  if !(v > 0): s+ = s- = 0
-      r    = dq / v                                        (dq = delta*64 as float32)
-      t    = (float)q_k - (float)m
+    """Fixed-point log-likelihood-ratio increments s+_k, s-_k for k in (k0, n) with the running mean / population
+    variance of the current level taken over q[k0..k].  The sums are exact integers of the
+    deviations from the anchor sample, d_j = q_j - q_k0 (small numbers, so that float32 carries everything that
+    follows; order independent, so a parallel scan gives the same values); per sample, in this exact order of
+    individually rounded float32 operations:
+      cnt  = k - k0 + 1 ;  rc = 1.0f / (float)cnt
+      m    = (float)Sd * rc                                (Sd = sum of d over [k0, k], int64 -> float32, RN)
+      v    = (float)Sdd * rc - m * m                       (three operations; Sdd = sum of d^2)
+      if !(v > 0): s+ = s- = 0
+      r    = dq * (1.0f / v)                               (dq = delta*64; correctly rounded reciprocal)
+      t    = (float)d_k - m
       s+   = rint(clamp(( r) * (t - dq/2) * 1024))
       s-   = rint(clamp((-r) * (t + dq/2) * 1024))
     """
     q = np.asarray(q, dtype=np.int64)
-    seg = q[k0:]
-    Sq = np.cumsum(seg)[1:]
-    Sqq = np.cumsum(seg * seg)[1:]
+    seg = q[k0:] - q[k0]
+    Sd = np.cumsum(seg)[1:]
+    Sdd = np.cumsum(seg * seg)[1:]
     cnt = np.arange(2, seg.size + 1, dtype=np.int64)
     dq = np.float32(np.float32(delta) * CUSUM_Q)
     hq = np.float32(dq * np.float32(0.5))
-    rc32 = (np.float32(1.0) / cnt.astype(np.float32)).astype(np.float32)
-    rc = rc32.astype(np.float64)
-    rc = rc * (2.0 - cnt.astype(np.float64) * rc)
-    Sqd = Sq.astype(np.float64)
-    m = Sqd * rc
-    vv = (Sqq.astype(np.float64) - Sqd * m) * rc
-    v = vv.astype(np.float32)
+    one = np.float32(1.0)
+    rc = (one / cnt.astype(np.float32)).astype(np.float32)
+    m = (Sd.astype(np.float32) * rc).astype(np.float32)
+    v = ((Sdd.astype(np.float32) * rc).astype(np.float32) - (m * m).astype(np.float32)).astype(np.float32)
     ok = v > 0
-    vs = np.where(ok, v, np.float32(1.0)).astype(np.float32)
-    r = (dq / vs).astype(np.float32)
-    t = (seg[1:].astype(np.float32) - m.astype(np.float32)).astype(np.float32)
+    vs = np.where(ok, v, one).astype(np.float32)
+    r = (dq * (one / vs).astype(np.float32)).astype(np.float32)
+    t = (seg[1:].astype(np.float32) - m).astype(np.float32)
     sp = (r * (t - hq).astype(np.float32)).astype(np.float32) * CUSUM_SSCALE
     sn = ((-r) * (t + hq).astype(np.float32)).astype(np.float32) * CUSUM_SSCALE
     sp = np.minimum(np.maximum(sp, -CUSUM_SMAX), CUSUM_SMAX)
@@ -381,25 +376,26 @@ def cusum_event_sequential(x, delta, h, max_levels=32):
     H = int(np.rint(np.float32(h) * CUSUM_SSCALE))
     dq = np.float32(np.float32(delta) * CUSUM_Q)
     hq = np.float32(dq * np.float32(0.5))
+    one = np.float32(1.0)
     edges = [0]
     overflow = False
     k0 = 0
-    Sq, Sqq = int(q[0]), int(q[0]) ** 2
+    qa = int(q[0])
+    Sd = Sdd = 0
     gp = gn = 0
     rp = rn = 0   # last index at which g was (re)set to zero
     k = 1
     while k < n:
-        Sq += int(q[k]); Sqq += int(q[k]) ** 2
+        d = int(q[k]) - qa
+        Sd += d; Sdd += d * d
         cnt = k - k0 + 1
-        rc = np.float64(np.float32(1.0) / np.float32(cnt))
-        rc = rc * (np.float64(2.0) - np.float64(cnt) * rc)
-        m = np.float64(Sq) * rc
-        vv = (np.float64(Sqq) - np.float64(Sq) * m) * rc
-        v = np.float32(vv)
+        rc = np.float32(one / np.float32(cnt))
+        m = np.float32(np.float32(Sd) * rc)
+        v = np.float32(np.float32(np.float32(Sdd) * rc) - np.float32(m * m))
         sp = sn = 0
         if v > 0:
-            r = np.float32(dq / v)
-            t = np.float32(np.float32(q[k]) - np.float32(m))
+            r = np.float32(dq * np.float32(one / v))
+            t = np.float32(np.float32(d) - m)
             a = np.float32(np.float32(r * np.float32(t - hq)) * CUSUM_SSCALE)
             b = np.float32(np.float32((-r) * np.float32(t + hq)) * CUSUM_SSCALE)
             a = min(max(a, -CUSUM_SMAX), CUSUM_SMAX)
@@ -418,7 +414,7 @@ def cusum_event_sequential(x, delta, h, max_levels=32):
                 break
             edges.append(jmin + 1)
             k0 = k
-            Sq, Sqq = int(q[k]), int(q[k]) ** 2
+            qa = int(q[k]); Sd = Sdd = 0
             gp = gn = 0
             rp = rn = k
         k += 1
