@@ -23,17 +23,7 @@ constexpr int kBlk = 32 * kE;         // 256
 constexpr float kQ = 64.0f, kSScale = 1024.0f, kSMax = 2097152.0f;
 constexpr int kBig = 0x3fffffff;
 
-// rc[cnt] = 1.0f / (float)cnt (IEEE division), the oracle's reciprocal of the sample count: it only depends on cnt,
-// so it is tabulated once per device and the hot loop replaces a division by one (L1-resident) load.
-constexpr int kRcTab = 1 << 16;
-__global__ void ct_cusum_rc_table(float* tab) {
-    const int cnt = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cnt >= kRcTab) return;
-    tab[cnt] = cnt > 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
-}
-
 struct CusumArgs {
-    const float* rctab;
     const float* y; long long ntot;
     const long long* w0; const long long* w1; const int* type; long long nev;
     const long long* nev_dev;          // event count read from device memory (NULL: use nev)
@@ -181,7 +171,7 @@ __device__ void warp_event(const CusumArgs& a, const long long ev, const int lan
                     int sp = 0, sn = 0;
                     if (k > k0 && k < n) {
                         const int cnt = k - k0 + 1;
-                        const float rc = cnt < kRcTab ? __ldg(a.rctab + cnt) : __fdiv_rn(1.0f, (float)cnt);
+                        const float rc = __fdiv_rn(1.0f, (float)cnt);
                         const float m = cusum_mean(cSq + exq + pq[e], rc);
                         const float t = __fsub_rn((float)(q[e] - qa), m);
                         const SeqOut o = cusum_tail(cSqq + exqq + pqq[e], m, rc, t, dq, hq);
@@ -303,26 +293,32 @@ __global__ void __launch_bounds__(128, 4) ct_cusum_warp_kernel(CusumArgs a) {
 // =====================================================================================
 // Thread-per-event kernel (the production path for windows up to kSeqMax samples).
 //
-// The definition (oracle/events_oracle.py::cusum_event_sequential) is a per-sample
-// recurrence; evaluating it literally, one event per LANE, needs no prefix scans, no
-// validity masks, no block re-runs after a detection and no second pass for the level
-// statistics: ~3x fewer instructions per sample than the warp-cooperative kernel above.
-// Lanes fetch their next event from the shared counter as soon as they finish one (warp
-// aggregated), so a warp stays full whatever the event lengths.  Each lane streams its own
-// event with 256-bit loads (one 32-byte sector per instruction; the L1 keeps the line for
-// the lane's next loads).  Level sums are exact integers: the sums of the samples between
-// the changepoint and the detection index are re-read at the (rare) detections, and the
-// float64 mean / std are produced by ct_cusum_finalize from the integer sums the lanes
-// leave (bit-cast) in the mean / std arrays.
+// The definition (oracle/events_oracle.py::cusum_event_sequential) is a per-sample recurrence; evaluating it
+// literally, one event per LANE, needs no prefix scans, no validity masks, no block re-runs after a detection and
+// no second pass for the level statistics.  What decides the speed is how the 32 private sample streams of a warp
+// reach the lanes and how many instructions the plateaus of an event cost:
+//  * every lane's window is cut into PIECES of 32 samples on the 128-byte line grid of the trace.  A warp moves the
+//    next piece of all its 32 lanes with 8 cp.async instructions (8 lanes x 16 bytes = one whole line per event,
+//    global -> shared memory without registers, one round ahead), into rows of 144 bytes (bank-conflict-free 128-bit
+//    reads of a lane's own row); the 16 spare bytes of a row carry the piece's header (event, index of its first
+//    sample, window length, line), written by the fetch cursor of the lane, which runs one round ahead of the
+//    evaluation and takes the next event from the shared counter (warp aggregated) when its window is used up;
+//  * the reciprocal table of the sample count (1.0f / cnt, IEEE) lives in shared memory, built by the CTA;
+//  * the warp is convergent throughout: votes are over all 32 lanes, lanes without a sample at a position vote "yes"
+//    and commit nothing.
+// Level sums are exact integers: the sums of the samples between the changepoint and the detection index are
+// re-read at the (rare) detections, and the float64 mean / std are produced by ct_cusum_finalize from the integer
+// sums the lanes leave (bit-cast) in the mean / std arrays.
 // =====================================================================================
-#ifndef CT_CUSUM_SEQ_GROUP
-#define CT_CUSUM_SEQ_GROUP 8
-#endif
-#ifndef CT_CUSUM_SEQ_CTAS
-#define CT_CUSUM_SEQ_CTAS 3
-#endif
-constexpr int kS = CT_CUSUM_SEQ_GROUP;   // samples a lane processes per (unrolled) group: 4 or 8
+constexpr int kS = 8;                  // samples a lane processes per (unrolled) group
+constexpr int kPiece = 32;             // samples per piece = one 128-byte line
+constexpr int kRowB = 144;             // bytes per shared-memory row: 128 of samples + 16 of header
+constexpr int kStageB = 32 * kRowB;    // one round of a warp
+constexpr int kStages = 2;
+constexpr int kSeqWarps = 16;          // warps per CTA, one CTA per SM
 constexpr int kSeqMax = 16384;         // longest window a single lane takes
+constexpr int kSeqTab = kSeqMax + 16;  // entries of the reciprocal table
+constexpr int kSeqSmem = kSeqTab * 4 + kSeqWarps * kStages * kStageB;
 constexpr int kSeqMinEvents = 16384;   // below this one event per lane cannot fill the GPU: warps take everything
 constexpr unsigned char kRawSums = 0x80;   // overflow[] bit: level rows hold raw integer sums (finalize pending)
 
@@ -332,170 +328,211 @@ __device__ __forceinline__ void level_sums(long long Sd, long long Sdd, int cnt,
     Sq = Sd + (long long)cnt * qa;
     Sqq = Sdd + 2LL * qa * Sd + (long long)cnt * ((long long)qa * qa);
 }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+}
 
-__global__ void __launch_bounds__(256, CT_CUSUM_SEQ_CTAS) ct_cusum_seq_kernel(CusumArgs a) {
+__global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* rct = reinterpret_cast<float*>(smem);
     const int lane = ct_lane();
+    unsigned char* wbuf = smem + kSeqTab * 4 + (threadIdx.x >> 5) * (kStages * kStageB);
+    for (int i = threadIdx.x; i < kSeqTab; i += blockDim.x) rct[i] = i > 0 ? __fdiv_rn(1.0f, (float)i) : 0.f;
+    __syncthreads();
     const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
     const float dq = __fmul_rn(a.delta, kQ);
     const float hq = __fmul_rn(dq, 0.5f);
-    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & (4 * kS - 1)) == 0;
     long long nev = a.nev;
     if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
     const int ML = a.max_levels;
-    const long long seq_limit = nev < kSeqMinEvents ? 0 : kSeqMax;
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;      // cp.async moves 16-byte units
+    const long long seq_limit = (nev < kSeqMinEvents || !aligned) ? 0 : kSeqMax;
+    const long long full_lines = a.ntot >> 5;
 
-    // per-lane event state
-    bool active = false, exhausted = false;
-    long long ev = 0, p0 = 0;
-    int n = 0, gk = 0;                   // window length; relative index of the current 8-sample group
-    float x0 = 0.f, nx0 = 0.f;           // the window's first sample and -64 x0 (quantisation: (x - x0) * 64, one FFMA)
-    int k0 = 0, qa = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0, overflow = 0;
-    long long Sd = 0, Sdd = 0;           // sums of d = q - qa, d^2 over [k0, k] (qa = q at the anchor k0)
-    long long Lp = 0, Lpp = 0;           // sums of q, q^2 over [e0, k0): the part of the open level before the anchor
-    float nx[kS];                        // the lane's next group of samples (software prefetch)
-#pragma unroll
-    for (int e = 0; e < kS; ++e) nx[e] = 0.f;
-    auto load_group = [&](long long pa, float (&x)[kS]) {
-        if (aligned && pa >= 0 && pa + kS <= a.ntot) {
-            const uint4* p4 = reinterpret_cast<const uint4*>(a.y + pa);
-#pragma unroll
-            for (int u = 0; u < kS / 4; ++u) {
-                const uint4 w = __ldg(p4 + u);
-                x[4 * u] = __uint_as_float(w.x); x[4 * u + 1] = __uint_as_float(w.y);
-                x[4 * u + 2] = __uint_as_float(w.z); x[4 * u + 3] = __uint_as_float(w.w);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < kS; ++e) { const long long p = pa + e; x[e] = (p >= 0 && p < a.ntot) ? a.y[p] : 0.f; }
-        }
-    };
-
-    for (;;) {
-        // ---- lanes without an event fetch the next ones (one atomic per warp)
-        const unsigned need = __ballot_sync(CT_FULL, !active && !exhausted);
-        if (need) {
+    // ---- fetch cursor (one round ahead of the evaluation)
+    bool exhausted = false;
+    int f_ev = 0, f_n = 0, f_kb = 0, f_left = 0;
+    unsigned f_line = 0;
+    auto fetch = [&](int stage) {
+        unsigned need = __ballot_sync(CT_FULL, f_left == 0 && !exhausted);
+        while (need) {                                       // lanes whose window is used up take the next events
             const int leader = __ffs(need) - 1;
             long long base = 0;
             if (lane == leader) base = (long long)atomicAdd(a.counter, (unsigned long long)__popc(need));
             base = __shfl_sync(CT_FULL, base, leader);
-            if (!active && !exhausted) {
-                ev = base + __popc(need & ((1u << lane) - 1u));
+            if (f_left == 0 && !exhausted) {
+                const long long ev = base + __popc(need & ((1u << lane) - 1u));
                 if (ev >= nev) exhausted = true;
                 else {
-                    p0 = a.w0[ev];
+                    const long long p0 = a.w0[ev];
                     const long long nn = a.w1[ev] - p0;
                     const bool bad = nn <= 0 || p0 < 0 || a.w1[ev] > a.ntot || nn > 0x3fffffffLL || (a.type && a.type[ev] != 0);
                     if (bad) { a.n_levels[ev] = 0; a.overflow[ev] = 0; }
                     else if (nn > seq_limit) a.pending[atomicAdd(a.counter + 1, 1ULL)] = (int)ev;
                     else {
-                        n = (int)nn;
-                        gk = -(int)(p0 & (kS - 1));
-                        k0 = 0; qa = 0; gp = gn = 0; rp = rn = 0; nedge = 1; e0 = 0; overflow = 0;
-                        Sd = Sdd = 0; Lp = Lpp = 0;
+                        f_ev = (int)ev; f_n = (int)nn;
+                        f_kb = -(int)(p0 & (kPiece - 1));
+                        f_line = (unsigned)(p0 >> 5);
+                        f_left = (f_n - f_kb + kPiece - 1) >> 5;
                         a.edges[ev * (ML + 1)] = 0;
-                        load_group(p0 + gk, nx);
-                        x0 = a.y[p0];
-                        nx0 = __fmul_rn(x0, -kQ);
-                        active = true;
                     }
                 }
             }
+            need = __ballot_sync(CT_FULL, f_left == 0 && !exhausted);
         }
-        if (__ballot_sync(CT_FULL, active) == 0) {
-            if (__ballot_sync(CT_FULL, !exhausted) == 0) break;
-            continue;
+        unsigned char* st = wbuf + stage * kStageB;
+        const bool has = f_left > 0;
+        *reinterpret_cast<int4*>(st + lane * kRowB + 128) = make_int4(has ? f_ev : -1, f_kb, f_n, (int)f_line);
+        const unsigned myline = has ? f_line : 0xffffffffu;
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(st) + (lane >> 3) * kRowB + (lane & 7) * 16;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {                     // 4 rows per instruction, one 128-byte line each
+            const unsigned L = __shfl_sync(CT_FULL, myline, it * 4 + (lane >> 3));
+            const long long g = ((long long)L << 5) + ((lane & 7) << 2);
+            int bytes = 16;
+            if ((long long)L >= full_lines) {                // the trace's last (partial) line, or no piece at all
+                const long long rem = a.ntot - g;
+                bytes = (L == 0xffffffffu || rem <= 0) ? 0 : (rem >= 4 ? 16 : (int)rem * 4);
+            }
+            cp_async16(dst0 + it * 4 * kRowB, bytes ? a.y + g : a.y, bytes);
         }
-        if (active) {
-            // ---- one group of 8 consecutive samples of this lane's event (the next group is already on its way)
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (has) { ++f_line; f_kb += kPiece; --f_left; }
+    };
+
+    // ---- per-lane event state
+    bool running = false;                // inside an event that has not been closed
+    long long p0 = 0;
+    int ev = 0, n = 0;
+    float x0 = 0.f, nx0 = 0.f;           // the window's first sample and -64 x0 (quantisation: (x - x0) * 64, one FFMA)
+    int k0 = 0, qa = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0;
+    long long Sd = 0, Sdd = 0;           // sums of d = q - qa, d^2 over [k0, k] (qa = q at the anchor k0)
+    long long Lp = 0, Lpp = 0;           // sums of q, q^2 over [e0, k0): the part of the open level before the anchor
+
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) fetch(s);
+    int stage = 0;
+    for (;;) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(kStages - 1) : "memory");
+        __syncwarp();
+        const float* row = reinterpret_cast<const float*>(wbuf + stage * kStageB + lane * kRowB);
+        const int4 hdr = *reinterpret_cast<const int4*>(row + kPiece);
+        const bool hev = hdr.x >= 0;
+        if (__ballot_sync(CT_FULL, hev) == 0) break;         // the cursors ran dry: every later round is empty as well
+        const int kb = hdr.y;                                 // window index of the piece's first sample
+        if (hev && kb <= 0) {                                 // first piece of the lane's next event
+            ev = hdr.x; n = hdr.z;
+            p0 = ((long long)(unsigned)hdr.w << 5) - kb;
+            x0 = row[-kb];
+            nx0 = __fmul_rn(x0, -kQ);
+            k0 = 0; qa = 0; gp = gn = 0; rp = rn = 0; nedge = 1; e0 = 0;
+            Sd = Sdd = 0; Lp = Lpp = 0;
+            running = true;
+        }
+#pragma unroll 1
+        for (int g = 0; g < kPiece / kS; ++g) {
+            const int gk = kb + g * kS;
+            const bool act = hev && running && gk < n && gk + kS > 0;
+            if (!__any_sync(CT_FULL, act)) continue;
             float xv[kS];
-#pragma unroll
-            for (int e = 0; e < kS; ++e) xv[e] = nx[e];
-            if (gk + kS < n) load_group(p0 + gk + kS, nx);
-            const unsigned nlim = overflow ? 0u : (unsigned)n;
+            {
+                const float4 u = *reinterpret_cast<const float4*>(row + g * kS);
+                const float4 v = *reinterpret_cast<const float4*>(row + g * kS + 4);
+                xv[0] = u.x; xv[1] = u.y; xv[2] = u.z; xv[3] = u.w; xv[4] = v.x; xv[5] = v.y; xv[6] = v.z; xv[7] = v.w;
+            }
+            unsigned nlim = act ? (unsigned)n : 0u;
             // ---- quiet group: the whole group lies inside the window, both statistics are 0 and every sample of
-            // it is quiet (see below) in EVERY lane that is at a group: then only the running sums move.  The
-            // attempt costs ~20 instructions per sample with one vote per group; if it fails nothing has been
-            // committed and the group takes the per-sample path.
+            // it is quiet (see below) in EVERY lane that has the group: then only the running sums move.  One vote
+            // per group; if it fails nothing has been committed and the group takes the per-sample path.
             bool done = false;
-            if (__all_sync(__activemask(), gk >= 0 && gk + kS <= n && !overflow && (gp | gn) == 0)) {
-                const float* rcp = a.rctab + (gk - k0 + 1);              // counts gk-k0+1 .. gk-k0+kS <= kSeqMax < kRcTab
-                float rcv[kS];
-#pragma unroll
-                for (int e = 0; e < kS; ++e) rcv[e] = __ldg(rcp + e);
+            if (__all_sync(CT_FULL, !act || (gk >= 0 && gk + kS <= n && (gp | gn) == 0))) {
+                const float* rcp = rct + (act ? gk - k0 + 1 : 1);        // counts gk-k0+1 .. gk-k0+kS <= kSeqMax
                 long long S1 = Sd, S2 = Sdd;
                 bool allq = true;
 #pragma unroll
                 for (int e = 0; e < kS; ++e) {
                     const int d = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0)) - qa;
                     S1 += d; S2 += (long long)d * d;
-                    const float t = __fsub_rn((float)d, cusum_mean(S1, rcv[e]));
+                    const float t = __fsub_rn((float)d, cusum_mean(S1, rcp[e]));
                     allq = allq && fabsf(t) <= hq;
                 }
-                if (__all_sync(__activemask(), allq)) { Sd = S1; Sdd = S2; rp = rn = gk + kS - 1; done = true; }
+                if (__all_sync(CT_FULL, allq || !act)) {
+                    if (act) { Sd = S1; Sdd = S2; rp = rn = gk + kS - 1; }
+                    done = true;
+                }
             }
             if (!done)
 #pragma unroll
             for (int e = 0; e < kS; ++e) {
                 const int k = gk + e;
-                if ((unsigned)k >= nlim) continue;       // before the window (k < 0 wraps), behind it, or frozen by overflow
+                const bool valid = (unsigned)k < nlim;   // inside the window (k < 0 wraps) of an open event
                 // == quantise(xv[e], x0): scaling by 2^6 commutes with the rounding of the difference
                 const int q = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0));
-                const int d = q - qa;
+                const int d = valid ? q - qa : 0;
                 Sd += d; Sdd += (long long)d * d;
-                const float rc = __ldg(a.rctab + (k - k0 + 1));       // k - k0 + 1 <= kSeqMax < kRcTab
+                const float rc = rct[valid ? k - k0 + 1 : 1];
                 const float m = cusum_mean(Sd, rc);
                 const float t = __fsub_rn((float)d, m);
                 // Quiet sample: both statistics are 0 and |t| <= delta/2, so both increments are <= 0 whatever the
                 // variance is (r > 0 or masked; t - hq <= 0 and t + hq >= 0 survive every rounding and the clamps) and
                 // the statistics stay 0 with their argmin at k: exactly what the full evaluation would leave.  On the
-                // plateaus of an event almost every sample is quiet; the shortcut is taken when all the lanes that are
-                // at a sample agree (warp-uniform branch), the full evaluation is always valid.
-                const bool quiet = (gp | gn) == 0 && fabsf(t) <= hq;
-                if (__all_sync(__activemask(), quiet)) { rp = k; rn = k; continue; }
+                // plateaus of an event almost every sample is quiet; the shortcut is taken when all the lanes agree
+                // (warp-uniform branch), the full evaluation is always valid.
+                const bool quiet = !valid || ((gp | gn) == 0 && fabsf(t) <= hq);
+                if (__all_sync(CT_FULL, quiet)) { if (valid) { rp = k; rn = k; } continue; }
                 const SeqOut s = cusum_tail(Sdd, m, rc, t, dq, hq);
+                if (!valid) continue;
                 gp = max(gp + s.sp, 0); rp = gp == 0 ? k : rp;
                 gn = max(gn + s.sn, 0); rn = gn == 0 ? k : rn;
                 if (max(gp, gn) > H) {
-                    if (nedge >= ML) { overflow = 1; continue; }
+                    if (nedge >= ML) {                       // level table full: the rest of the window is the last level
+                        long long T = 0, TT = 0;
+#pragma unroll 1
+                        for (int j = e0; j < n; ++j) { const long long qj = quantise(a.y[p0 + j], x0); T += qj; TT += qj * qj; }
+                        const long long r_ = (long long)ev * ML + (nedge - 1);
+                        reinterpret_cast<long long*>(a.mean)[r_] = T;
+                        reinterpret_cast<long long*>(a.sd)[r_] = TT;
+                        a.edges[(long long)ev * (ML + 1) + nedge] = n;
+                        a.n_levels[ev] = nedge;
+                        a.overflow[ev] = (unsigned char)(1 | kRawSums);
+                        running = false; nlim = 0u;
+                        continue;
+                    }
                     const int edge = ((gp >= gn) ? rp : rn) + 1;
                     long long T = 0, TT = 0;             // sums over [edge, k]
 #pragma unroll 1
                     for (int j = edge; j <= k; ++j) {
-                        const long long qj = quantise(a.y[p0 + j], x0);
+                        const long long qj = quantise(j >= kb ? row[j - kb] : a.y[p0 + j], x0);
                         T += qj; TT += qj * qj;
                     }
                     long long Sq, Sqq;
                     level_sums(Sd, Sdd, k - k0 + 1, qa, Sq, Sqq);
-                    const long long row = ev * ML + (nedge - 1);
-                    reinterpret_cast<long long*>(a.mean)[row] = Lp + Sq - T;      // level [e0, edge)
-                    reinterpret_cast<long long*>(a.sd)[row] = Lpp + Sqq - TT;
-                    a.edges[ev * (ML + 1) + nedge] = edge;
+                    const long long r_ = (long long)ev * ML + (nedge - 1);
+                    reinterpret_cast<long long*>(a.mean)[r_] = Lp + Sq - T;       // level [e0, edge)
+                    reinterpret_cast<long long*>(a.sd)[r_] = Lpp + Sqq - TT;
+                    a.edges[(long long)ev * (ML + 1) + nedge] = edge;
                     ++nedge;
                     e0 = edge; Lp = T - q; Lpp = TT - (long long)q * q;
                     k0 = k; qa = q; Sd = 0; Sdd = 0; gp = gn = 0; rp = rn = k;
                 }
             }
-            gk += kS;
-            if (gk >= n || overflow) {
-                long long Sq = 0, Sqq = 0;
-                if (overflow) {                          // the rest of the window belongs to the last level
-                    long long T = 0, TT = 0;
-#pragma unroll 1
-                    for (int j = e0; j < n; ++j) { const long long qj = quantise(a.y[p0 + j], x0); T += qj; TT += qj * qj; }
-                    Lp = T; Lpp = TT;
-                } else {
-                    level_sums(Sd, Sdd, n - k0, qa, Sq, Sqq);
-                }
-                const long long row = ev * ML + (nedge - 1);
-                reinterpret_cast<long long*>(a.mean)[row] = Lp + Sq;              // level [e0, n)
-                reinterpret_cast<long long*>(a.sd)[row] = Lpp + Sqq;
-                a.edges[ev * (ML + 1) + nedge] = n;
+            if (act && running && gk + kS >= n) {            // the window ends in this group: level [e0, n)
+                long long Sq, Sqq;
+                level_sums(Sd, Sdd, n - k0, qa, Sq, Sqq);
+                const long long r_ = (long long)ev * ML + (nedge - 1);
+                reinterpret_cast<long long*>(a.mean)[r_] = Lp + Sq;
+                reinterpret_cast<long long*>(a.sd)[r_] = Lpp + Sqq;
+                a.edges[(long long)ev * (ML + 1) + nedge] = n;
                 a.n_levels[ev] = nedge;
-                a.overflow[ev] = (unsigned char)(overflow | kRawSums);
-                active = false;
+                a.overflow[ev] = kRawSums;
+                running = false;
             }
         }
+        __syncwarp();                                         // every lane is done with the rows of this stage
+        fetch(stage);
+        stage = stage + 1 == kStages ? 0 : stage + 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // float64 level mean / population std from the integer sums the lanes left in the arrays
@@ -643,22 +680,7 @@ static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_star
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(workspace, 0, 24, st);
     if (n_events == 0) return CT_OK;
-    // library-owned per-device reciprocal table (built once with the oracle's operations)
-    static float* tabs[64] = {nullptr};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) { ct_set_error("cusum: unsupported device ordinal"); return CT_ERR_UNSUPPORTED; }
-    if (!tabs[dev]) {
-        float* t = nullptr;
-        if (cudaMalloc(&t, sizeof(float) * kRcTab) != cudaSuccess) { ct_set_error("cusum: table allocation failed"); return CT_ERR_CUDA; }
-        CT_COUNT_LAUNCH();
-        ct_cusum_rc_table<<<kRcTab / 256, 256, 0, st>>>(t);
-        int rc0 = ct_check_launch("ct_cusum_rc_table"); if (rc0) return rc0;
-        cudaStreamSynchronize(st);          // one-time: other streams may use the table next
-        tabs[dev] = t;
-    }
     CusumArgs a;
-    a.rctab = tabs[dev];
     a.y = y; a.ntot = n_total; a.w0 = (const long long*)win_start; a.w1 = (const long long*)win_end; a.type = type;
     a.nev = n_events; a.nev_dev = (const long long*)n_events_dev; a.delta = delta; a.h = h; a.max_levels = max_levels; a.n_levels = n_levels; a.edges = edges;
     a.mean = level_mean; a.sd = level_std; a.overflow = overflow; a.counter = (unsigned long long*)workspace;
@@ -667,13 +689,14 @@ static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_star
     cudaMemsetAsync(edges, 0xff, (size_t)n_events * (size_t)(max_levels + 1) * sizeof(int32_t), st);
     const int sms = ct_sm_count();
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_cusum_seq_kernel, 256, 0);
-    if (occ < 1) occ = 1;
-    long long grid = (long long)sms * occ;
-    long long want = (n_events + 255) / 256;
+    if (cudaFuncSetAttribute(ct_cusum_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmem) != cudaSuccess) {
+        ct_set_error("cusum: cannot reserve %d bytes of shared memory", kSeqSmem); return CT_ERR_CUDA;
+    }
+    long long grid = sms;                                    // persistent: one CTA per SM
+    long long want = (n_events + kSeqWarps * 32 - 1) / (kSeqWarps * 32);
     if (grid > want) grid = want;
     CT_COUNT_LAUNCH();
-    ct_cusum_seq_kernel<<<(unsigned)grid, 256, 0, st>>>(a);
+    ct_cusum_seq_kernel<<<(unsigned)grid, kSeqWarps * 32, kSeqSmem, st>>>(a);
     int rc = ct_check_launch("ct_cusum_seq_kernel"); if (rc) return rc;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ct_cusum_warp_kernel, 128, 0);
     if (occ < 1) occ = 1;

@@ -10,7 +10,7 @@ for r in rows:
     if len(r) >= 8 and r[0].isdigit():
         try: n = int(r[7])
         except ValueError: continue
-        out.append((n, fname, int(r[0]), r[1].strip()[:100], int(r[4] or 0))); tot += n
+        out.append((n, fname, int(r[0]), r[1].strip()[:100], int(r[4]) if r[4].isdigit() else 0)); tot += n
 stall = sum(o[4] for o in out)
 print("total warp-instructions", tot)
 for n, f, ln, src, st in sorted(out, reverse=True)[:top]:
