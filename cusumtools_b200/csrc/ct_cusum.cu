@@ -31,6 +31,7 @@ struct CusumArgs {
     int* n_levels; int* edges; double* mean; double* sd; unsigned char* overflow;
     unsigned long long* counter;       // [0] event fetch counter, [1] pending count, [2] pending fetch counter
     int* pending;                      // events left to the warp-cooperative kernel
+    const int* order;                  // hand-out order of the thread-per-event kernel (longest windows first); NULL: index order
 };
 
 // fused exclusive scan of an int32 and an int64 lane total (one shuffle round trip per step)
@@ -361,9 +362,10 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
             if (lane == leader) base = (long long)atomicAdd(a.counter, (unsigned long long)__popc(need));
             base = __shfl_sync(CT_FULL, base, leader);
             if (f_left == 0 && !exhausted) {
-                const long long ev = base + __popc(need & ((1u << lane) - 1u));
-                if (ev >= nev) exhausted = true;
+                const long long slot = base + __popc(need & ((1u << lane) - 1u));
+                if (slot >= nev) exhausted = true;
                 else {
+                    const long long ev = a.order ? a.order[slot] : slot;
                     const long long p0 = a.w0[ev];
                     const long long nn = a.w1[ev] - p0;
                     const bool bad = nn <= 0 || p0 < 0 || a.w1[ev] > a.ntot || nn > 0x3fffffffLL || (a.type && a.type[ev] != 0);
@@ -383,18 +385,18 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
         unsigned char* st = wbuf + stage * kStageB;
         const bool has = f_left > 0;
         *reinterpret_cast<int4*>(st + lane * kRowB + 128) = make_int4(has ? f_ev : -1, f_kb, f_n, (int)f_line);
-        const unsigned myline = has ? f_line : 0xffffffffu;
+        // valid samples of the lane's line (32 except on the trace's last line; 0 without a piece: nothing is read)
+        int avail = 0;
+        if (has) avail = (long long)f_line < full_lines ? kPiece : (int)(a.ntot - ((long long)f_line << 5));
+        const unsigned myline = has ? f_line : 0u;
         const unsigned dst0 = (unsigned)__cvta_generic_to_shared(st) + (lane >> 3) * kRowB + (lane & 7) * 16;
+        const char* src0 = reinterpret_cast<const char*>(a.y) + (lane & 7) * 16;
+        const int c4 = (lane & 7) * 4;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {                     // 4 rows per instruction, one 128-byte line each
             const unsigned L = __shfl_sync(CT_FULL, myline, it * 4 + (lane >> 3));
-            const long long g = ((long long)L << 5) + ((lane & 7) << 2);
-            int bytes = 16;
-            if ((long long)L >= full_lines) {                // the trace's last (partial) line, or no piece at all
-                const long long rem = a.ntot - g;
-                bytes = (L == 0xffffffffu || rem <= 0) ? 0 : (rem >= 4 ? 16 : (int)rem * 4);
-            }
-            cp_async16(dst0 + it * 4 * kRowB, bytes ? a.y + g : a.y, bytes);
+            const int A = __shfl_sync(CT_FULL, avail, it * 4 + (lane >> 3));
+            cp_async16(dst0 + it * 4 * kRowB, src0 + ((unsigned long long)L << 7), min(max(A - c4, 0), 4) * 4);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (has) { ++f_line; f_kb += kPiece; --f_left; }
@@ -441,29 +443,44 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                 xv[0] = u.x; xv[1] = u.y; xv[2] = u.z; xv[3] = u.w; xv[4] = v.x; xv[5] = v.y; xv[6] = v.z; xv[7] = v.w;
             }
             unsigned nlim = act ? (unsigned)n : 0u;
-            // ---- quiet group: the whole group lies inside the window, both statistics are 0 and every sample of
-            // it is quiet (see below) in EVERY lane that has the group: then only the running sums move.  One vote
-            // per group; if it fails nothing has been committed and the group takes the per-sample path.
-            bool done = false;
-            if (__all_sync(CT_FULL, !act || (gk >= 0 && gk + kS <= n && (gp | gn) == 0))) {
-                const float* rcp = rct + (act ? gk - k0 + 1 : 1);        // counts gk-k0+1 .. gk-k0+kS <= kSeqMax
-                long long S1 = Sd, S2 = Sdd;
-                bool allq = true;
+            // ---- quiet prefix.  A sample is QUIET when both statistics are 0 and its deviation from the running mean
+            // is within +-delta/2: both increments are then <= 0 whatever the variance is (r > 0 or masked; t - hq <= 0
+            // and t + hq >= 0 survive every rounding and the clamps), so the statistics stay 0 with their argmin at the
+            // sample - exactly what the full evaluation would leave; only the running sums move.  On the plateaus of an
+            // event almost every sample is quiet.  All lanes evaluate the group as if it were quiet (straight-line
+            // code, 13 instructions per sample); `first` is the first position at which that is not known to hold for
+            // the lane (statistics not 0, before the window: 0; a deviation outside the band or the window's end: there),
+            // one warp reduction gives the prefix every lane may commit, the per-sample path takes the rest.
+            int dv[kS];
+            long long S1 = Sd, S2 = Sdd;
+            unsigned nq = 0;
+            {
+                const bool att = act && gk >= 0 && (gp | gn) == 0;
+                const float* rcp = rct + (att ? gk - k0 + 1 : 1);        // counts gk-k0+1 .. gk-k0+kS <= kSeqMax + kS
 #pragma unroll
                 for (int e = 0; e < kS; ++e) {
-                    const int d = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0)) - qa;
-                    S1 += d; S2 += (long long)d * d;
-                    const float t = __fsub_rn((float)d, cusum_mean(S1, rcp[e]));
-                    allq = allq && fabsf(t) <= hq;
+                    dv[e] = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0)) - qa;
+                    S1 += dv[e]; S2 += (long long)dv[e] * dv[e];
+                    const float t = __fsub_rn((float)dv[e], cusum_mean(S1, rcp[e]));
+                    if (!(fabsf(t) <= hq)) nq |= 1u << e;
                 }
-                if (__all_sync(CT_FULL, allq || !act)) {
-                    if (act) { Sd = S1; Sdd = S2; rp = rn = gk + kS - 1; }
-                    done = true;
-                }
+                nq |= 1u << min(max(n - gk, 0), kS);                    // the window's end (bit 8: the whole group is inside)
+                if (!att) nq = 1u;
+                if (!act) nq = 1u << kS;
             }
-            if (!done)
+            const int F = (int)__reduce_min_sync(CT_FULL, (unsigned)(__ffs(nq) - 1));
+            if (F == kS) {
+                if (act) { Sd = S1; Sdd = S2; rp = rn = gk + kS - 1; }
+            } else {
+                if (F > 0 && act) {
+#pragma unroll
+                    for (int e = 0; e < kS - 1; ++e)
+                        if (e < F) { Sd += dv[e]; Sdd += (long long)dv[e] * dv[e]; }
+                    rp = rn = gk + F - 1;
+                }
 #pragma unroll
             for (int e = 0; e < kS; ++e) {
+                if (e < F) continue;
                 const int k = gk + e;
                 const bool valid = (unsigned)k < nlim;   // inside the window (k < 0 wraps) of an open event
                 // == quantise(xv[e], x0): scaling by 2^6 commutes with the rounding of the difference
@@ -473,11 +490,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                 const float rc = rct[valid ? k - k0 + 1 : 1];
                 const float m = cusum_mean(Sd, rc);
                 const float t = __fsub_rn((float)d, m);
-                // Quiet sample: both statistics are 0 and |t| <= delta/2, so both increments are <= 0 whatever the
-                // variance is (r > 0 or masked; t - hq <= 0 and t + hq >= 0 survive every rounding and the clamps) and
-                // the statistics stay 0 with their argmin at k: exactly what the full evaluation would leave.  On the
-                // plateaus of an event almost every sample is quiet; the shortcut is taken when all the lanes agree
-                // (warp-uniform branch), the full evaluation is always valid.
+                // quiet in every lane: the shortcut again (warp-uniform branch); the full evaluation is always valid
                 const bool quiet = !valid || ((gp | gn) == 0 && fabsf(t) <= hq);
                 if (__all_sync(CT_FULL, quiet)) { if (valid) { rp = k; rn = k; } continue; }
                 const SeqOut s = cusum_tail(Sdd, m, rc, t, dq, hq);
@@ -516,6 +529,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                     k0 = k; qa = q; Sd = 0; Sdd = 0; gp = gn = 0; rp = rn = k;
                 }
             }
+            }
             if (act && running && gk + kS >= n) {            // the window ends in this group: level [e0, n)
                 long long Sq, Sqq;
                 level_sums(Sd, Sdd, n - k0, qa, Sq, Sqq);
@@ -533,6 +547,60 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
         stage = stage + 1 == kStages ? 0 : stage + 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// ---- hand-out order: longest windows first -------------------------------------------------------------------
+// Lanes take their next event from a shared counter, so the run ends when the lane that drew the last long window is
+// done with it while its 31 neighbours idle.  Handing the windows out by decreasing length class (256 samples per
+// class; a counting sort in two small kernels, the order inside a class is irrelevant: results are per event) leaves
+// only the shortest windows for the end.
+constexpr int kLenClasses = 64;
+__device__ __forceinline__ int len_class(long long len) {
+    if (len <= 0 || len > kSeqMax) return 0;                 // not for the lanes: dealt with at once
+    const int c = (int)((len - 1) >> 8);
+    return kLenClasses - 1 - (c < kLenClasses - 2 ? c : kLenClasses - 2);
+}
+__global__ void __launch_bounds__(256) ct_cusum_order_count(const long long* __restrict__ w0, const long long* __restrict__ w1,
+                                                             long long nev, const long long* __restrict__ nev_dev,
+                                                             unsigned* __restrict__ cls_count) {
+    __shared__ unsigned h[kLenClasses];
+    if (nev_dev) { const long long d = *nev_dev; nev = d < nev ? d : nev; }
+    if (threadIdx.x < kLenClasses) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long ev = (long long)blockIdx.x * blockDim.x + threadIdx.x; ev < nev; ev += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&h[len_class(w1[ev] - w0[ev])], 1u);
+    __syncthreads();
+    if (threadIdx.x < kLenClasses && h[threadIdx.x]) atomicAdd(&cls_count[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) ct_cusum_order_fill(const long long* __restrict__ w0, const long long* __restrict__ w1,
+                                                            long long nev, const long long* __restrict__ nev_dev,
+                                                            const unsigned* __restrict__ cls_count, unsigned* __restrict__ cls_fill,
+                                                            int* __restrict__ order) {
+    __shared__ unsigned base[kLenClasses], h[kLenClasses], off[kLenClasses];
+    if (nev_dev) { const long long d = *nev_dev; nev = d < nev ? d : nev; }
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        for (int c = 0; c < kLenClasses; ++c) { base[c] = acc; acc += cls_count[c]; }
+    }
+    constexpr int kChunk = 256 * 16;
+    for (long long c0 = (long long)blockIdx.x * kChunk; c0 < nev; c0 += (long long)gridDim.x * kChunk) {
+        __syncthreads();
+        if (threadIdx.x < kLenClasses) h[threadIdx.x] = 0;
+        __syncthreads();
+        int cls[16]; unsigned pos[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const long long ev = c0 + i * 256 + threadIdx.x;
+            cls[i] = -1;
+            if (ev < nev) { cls[i] = len_class(w1[ev] - w0[ev]); pos[i] = atomicAdd(&h[cls[i]], 1u); }
+        }
+        __syncthreads();
+        if (threadIdx.x < kLenClasses && h[threadIdx.x]) off[threadIdx.x] = base[threadIdx.x] + atomicAdd(&cls_fill[threadIdx.x], h[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (cls[i] >= 0) order[off[cls[i]] + pos[i]] = (int)(c0 + i * 256 + threadIdx.x);
+    }
 }
 
 // float64 level mean / population std from the integer sums the lanes left in the arrays
@@ -661,7 +729,11 @@ extern "C" int ct_event_columns(const int32_t* n_levels, const int32_t* edges, c
     return ct_check_launch("ct_event_columns_kernel");
 }
 
-extern "C" int64_t ct_cusum_workspace_bytes(int64_t n_events) { return 24 + 4 * (n_events > 0 ? n_events : 0) + 8; }
+// workspace: [0, 24) counters, [32, 544) class counts / fill counters of the hand-out order, then the pending list and
+// the order (int32 per event each)
+constexpr long long kWsHead = 32 + 2 * 4 * kLenClasses;
+static long long ws_list_bytes(int64_t n_events) { return ((4 * (n_events > 0 ? n_events : 0)) + 15) & ~15LL; }
+extern "C" int64_t ct_cusum_workspace_bytes(int64_t n_events) { return kWsHead + 2 * ws_list_bytes(n_events); }
 
 static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                         const int32_t* type, int64_t n_events, const int64_t* n_events_dev, float delta, float h,
@@ -678,13 +750,28 @@ static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_star
         ct_set_error("cusum: workspace too small or unaligned"); return CT_ERR_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(workspace, 0, 24, st);
+    cudaMemsetAsync(workspace, 0, kWsHead, st);
     if (n_events == 0) return CT_OK;
     CusumArgs a;
     a.y = y; a.ntot = n_total; a.w0 = (const long long*)win_start; a.w1 = (const long long*)win_end; a.type = type;
     a.nev = n_events; a.nev_dev = (const long long*)n_events_dev; a.delta = delta; a.h = h; a.max_levels = max_levels; a.n_levels = n_levels; a.edges = edges;
     a.mean = level_mean; a.sd = level_std; a.overflow = overflow; a.counter = (unsigned long long*)workspace;
-    a.pending = reinterpret_cast<int*>((unsigned long long*)workspace + 3);
+    a.pending = reinterpret_cast<int*>((char*)workspace + kWsHead);
+    a.order = nullptr;
+    if (n_events >= kSeqMinEvents) {                         // (below that the warps take every event)
+        unsigned* cls_count = reinterpret_cast<unsigned*>((char*)workspace + 32);
+        unsigned* cls_fill = cls_count + kLenClasses;
+        int* order = reinterpret_cast<int*>((char*)workspace + kWsHead + ws_list_bytes(n_events));
+        long long og = (n_events + 256 * 16 - 1) / (256 * 16);
+        if (og > 4LL * ct_sm_count()) og = 4LL * ct_sm_count();
+        CT_COUNT_LAUNCH();
+        ct_cusum_order_count<<<(unsigned)og, 256, 0, st>>>(a.w0, a.w1, n_events, a.nev_dev, cls_count);
+        int rc0 = ct_check_launch("ct_cusum_order_count"); if (rc0) return rc0;
+        CT_COUNT_LAUNCH();
+        ct_cusum_order_fill<<<(unsigned)og, 256, 0, st>>>(a.w0, a.w1, n_events, a.nev_dev, cls_count, cls_fill, order);
+        rc0 = ct_check_launch("ct_cusum_order_fill"); if (rc0) return rc0;
+        a.order = order;
+    }
     // rows of events nobody processes (rejected types) keep edges == -1
     cudaMemsetAsync(edges, 0xff, (size_t)n_events * (size_t)(max_levels + 1) * sizeof(int32_t), st);
     const int sms = ct_sm_count();
