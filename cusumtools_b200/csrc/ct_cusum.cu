@@ -316,9 +316,12 @@ constexpr int kPiece = 32;             // samples per piece = one 128-byte line
 constexpr int kRowB = 144;             // bytes per shared-memory row: 128 of samples + 16 of header
 constexpr int kStageB = 32 * kRowB;    // one round of a warp
 constexpr int kStages = 2;
-constexpr int kSeqWarps = 16;          // warps per CTA, one CTA per SM
+#ifndef CT_CUSUM_SEQ_WARPS
+#define CT_CUSUM_SEQ_WARPS 20
+#endif
+constexpr int kSeqWarps = CT_CUSUM_SEQ_WARPS;   // warps per CTA, one CTA per SM
 constexpr int kSeqMax = 16384;         // longest window a single lane takes
-constexpr int kSeqTab = kSeqMax + 16;  // entries of the reciprocal table
+constexpr int kSeqTab = 8192 + 16;     // entries of the reciprocal table in shared memory
 constexpr int kSeqSmem = kSeqTab * 4 + kSeqWarps * kStages * kStageB;
 constexpr int kSeqMinEvents = 16384;   // below this one event per lane cannot fill the GPU: warps take everything
 constexpr unsigned char kRawSums = 0x80;   // overflow[] bit: level rows hold raw integer sums (finalize pending)
@@ -455,8 +458,9 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
             long long S1 = Sd, S2 = Sdd;
             unsigned nq = 0;
             {
-                const bool att = act && gk >= 0 && (gp | gn) == 0;
-                const float* rcp = rct + (att ? gk - k0 + 1 : 1);        // counts gk-k0+1 .. gk-k0+kS <= kSeqMax + kS
+                // (counts beyond the shared-memory table - a plateau of more than 8 192 samples - take the per-sample path)
+                const bool att = act && gk >= 0 && (gp | gn) == 0 && gk - k0 + kS < kSeqTab;
+                const float* rcp = rct + (att ? gk - k0 + 1 : 1);
 #pragma unroll
                 for (int e = 0; e < kS; ++e) {
                     dv[e] = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0)) - qa;
@@ -478,16 +482,17 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                         if (e < F) { Sd += dv[e]; Sdd += (long long)dv[e] * dv[e]; }
                     rp = rn = gk + F - 1;
                 }
-#pragma unroll
-            for (int e = 0; e < kS; ++e) {
-                if (e < F) continue;
+                // (rolled: the evaluation and the changepoint bookkeeping exist once, the code stays in the instruction cache)
+#pragma unroll 1
+            for (int e = F; e < kS; ++e) {
                 const int k = gk + e;
                 const bool valid = (unsigned)k < nlim;   // inside the window (k < 0 wraps) of an open event
-                // == quantise(xv[e], x0): scaling by 2^6 commutes with the rounding of the difference
-                const int q = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0));
+                // == quantise(x, x0): scaling by 2^6 commutes with the rounding of the difference
+                const int q = __float2int_rn(__fmaf_rn(row[g * kS + e], kQ, nx0));
                 const int d = valid ? q - qa : 0;
                 Sd += d; Sdd += (long long)d * d;
-                const float rc = rct[valid ? k - k0 + 1 : 1];
+                const int cnt = valid ? k - k0 + 1 : 1;
+                const float rc = cnt < kSeqTab ? rct[cnt] : __fdiv_rn(1.0f, (float)cnt);
                 const float m = cusum_mean(Sd, rc);
                 const float t = __fsub_rn((float)d, m);
                 // quiet in every lane: the shortcut again (warp-uniform branch); the full evaluation is always valid
