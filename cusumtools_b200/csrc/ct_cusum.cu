@@ -455,17 +455,19 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
             // the lane (statistics not 0, before the window: 0; a deviation outside the band or the window's end: there),
             // one warp reduction gives the prefix every lane may commit, the per-sample path takes the rest.
             int dv[kS];
-            long long S1 = Sd, S2 = Sdd;
+            int s32 = (int)Sd;                                           // (the attempt needs the sum to fit: 32-bit adds and conversions)
             unsigned nq = 0;
             {
-                // (counts beyond the shared-memory table - a plateau of more than 8 192 samples - take the per-sample path)
-                const bool att = act && gk >= 0 && (gp | gn) == 0 && gk - k0 + kS < kSeqTab;
+                // (counts beyond the shared-memory table - a plateau of more than 8 192 samples - and sums beyond 2^30
+                // take the per-sample path)
+                const bool att = act && gk >= 0 && (gp | gn) == 0 && gk - k0 + kS < kSeqTab &&
+                                 (unsigned long long)(Sd + (1LL << 30)) < (1ULL << 31);
                 const float* rcp = rct + (att ? gk - k0 + 1 : 1);
 #pragma unroll
                 for (int e = 0; e < kS; ++e) {
                     dv[e] = __float2int_rn(__fmaf_rn(xv[e], kQ, nx0)) - qa;
-                    S1 += dv[e]; S2 += (long long)dv[e] * dv[e];
-                    const float t = __fsub_rn((float)dv[e], cusum_mean(S1, rcp[e]));
+                    s32 += dv[e];                                        // |d| < 2^23 (the definition's domain): no overflow
+                    const float t = __fsub_rn((float)dv[e], __fmul_rn(__int2float_rn(s32), rcp[e]));
                     if (!(fabsf(t) <= hq)) nq |= 1u << e;
                 }
                 nq |= 1u << min(max(n - gk, 0), kS);                    // the window's end (bit 8: the whole group is inside)
@@ -474,7 +476,12 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
             }
             const int F = (int)__reduce_min_sync(CT_FULL, (unsigned)(__ffs(nq) - 1));
             if (F == kS) {
-                if (act) { Sd = S1; Sdd = S2; rp = rn = gk + kS - 1; }
+                if (act) {
+                    Sd = s32;
+#pragma unroll
+                    for (int e = 0; e < kS; ++e) Sdd += (long long)dv[e] * dv[e];
+                    rp = rn = gk + kS - 1;
+                }
             } else {
                 if (F > 0 && act) {
 #pragma unroll
@@ -492,7 +499,8 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                 const int d = valid ? q - qa : 0;
                 Sd += d; Sdd += (long long)d * d;
                 const int cnt = valid ? k - k0 + 1 : 1;
-                const float rc = cnt < kSeqTab ? rct[cnt] : __fdiv_rn(1.0f, (float)cnt);
+                float rc = rct[min(cnt, kSeqTab - 1)];
+                if (cnt >= kSeqTab) rc = __fdiv_rn(1.0f, (float)cnt);    // (a plateau beyond the table: rare)
                 const float m = cusum_mean(Sd, rc);
                 const float t = __fsub_rn((float)d, m);
                 // quiet in every lane: the shortcut again (warp-uniform branch); the full evaluation is always valid
