@@ -322,7 +322,8 @@ constexpr int kStages = 2;
 constexpr int kSeqWarps = CT_CUSUM_SEQ_WARPS;   // warps per CTA, one CTA per SM
 constexpr int kSeqMax = 16384;         // longest window a single lane takes
 constexpr int kSeqTab = 8192 + 16;     // entries of the reciprocal table in shared memory
-constexpr int kSeqSmem = kSeqTab * 4 + kSeqWarps * kStages * kStageB;
+constexpr int kSeqTabLead = 8;         // zero entries in front of it (the positions of a group before the window's first sample)
+constexpr int kSeqSmem = (kSeqTab + kSeqTabLead) * 4 + kSeqWarps * kStages * kStageB;
 constexpr int kSeqMinEvents = 16384;   // below this one event per lane cannot fill the GPU: warps take everything
 constexpr unsigned char kRawSums = 0x80;   // overflow[] bit: level rows hold raw integer sums (finalize pending)
 
@@ -338,10 +339,10 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, int by
 
 __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float* rct = reinterpret_cast<float*>(smem);
+    float* rct = reinterpret_cast<float*>(smem) + kSeqTabLead;           // rct[-kSeqTabLead .. 0] = 0, rct[c] = 1.0f / c
     const int lane = ct_lane();
-    unsigned char* wbuf = smem + kSeqTab * 4 + (threadIdx.x >> 5) * (kStages * kStageB);
-    for (int i = threadIdx.x; i < kSeqTab; i += blockDim.x) rct[i] = i > 0 ? __fdiv_rn(1.0f, (float)i) : 0.f;
+    unsigned char* wbuf = smem + (kSeqTab + kSeqTabLead) * 4 + (threadIdx.x >> 5) * (kStages * kStageB);
+    for (int i = (int)threadIdx.x - kSeqTabLead; i < kSeqTab; i += blockDim.x) rct[i] = i > 0 ? __fdiv_rn(1.0f, (float)i) : 0.f;
     __syncthreads();
     const int H = __float2int_rn(__fmul_rn(a.h, kSScale));
     const float dq = __fmul_rn(a.delta, kQ);
@@ -451,16 +452,24 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
             // and t + hq >= 0 survive every rounding and the clamps), so the statistics stay 0 with their argmin at the
             // sample - exactly what the full evaluation would leave; only the running sums move.  On the plateaus of an
             // event almost every sample is quiet.  All lanes evaluate the group as if it were quiet (straight-line
-            // code, 13 instructions per sample); `first` is the first position at which that is not known to hold for
-            // the lane (statistics not 0, before the window: 0; a deviation outside the band or the window's end: there),
-            // one warp reduction gives the prefix every lane may commit, the per-sample path takes the rest.
+            // code on 32-bit sums); the first position at which that is not known to hold for a lane (statistics not 0:
+            // position 0; a deviation outside the band: there) goes through one warp reduction, which gives the prefix
+            // every lane may commit; the per-sample path takes the rest.  The positions of a group that lie outside the
+            // lane's window do not break the prefix: before the window they hold the first sample (deviation 0, the
+            // table's zero entries make the mean 0), behind it they are masked and left out of the sums.
+            if (__any_sync(CT_FULL, act && gk < 0)) {
+#pragma unroll
+                for (int e = 0; e < kS - 1; ++e)
+                    if (gk + e < 0) xv[e] = x0;
+            }
+            const int endc = n - gk;                                     // positions of the group inside the window (>= kS: all)
             int dv[kS];
             int s32 = (int)Sd;                                           // (the attempt needs the sum to fit: 32-bit adds and conversions)
             unsigned nq = 0;
             {
                 // (counts beyond the shared-memory table - a plateau of more than 8 192 samples - and sums beyond 2^30
                 // take the per-sample path)
-                const bool att = act && gk >= 0 && (gp | gn) == 0 && gk - k0 + kS < kSeqTab &&
+                const bool att = act && (gp | gn) == 0 && gk - k0 + kS < kSeqTab &&
                                  (unsigned long long)(Sd + (1LL << 30)) < (1ULL << 31);
                 const float* rcp = rct + (att ? gk - k0 + 1 : 1);
 #pragma unroll
@@ -470,25 +479,26 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                     const float t = __fsub_rn((float)dv[e], __fmul_rn(__int2float_rn(s32), rcp[e]));
                     if (!(fabsf(t) <= hq)) nq |= 1u << e;
                 }
-                nq |= 1u << min(max(n - gk, 0), kS);                    // the window's end (bit 8: the whole group is inside)
+                if (endc < kS) nq &= (1u << endc) - 1u;
+                nq |= 1u << kS;
                 if (!att) nq = 1u;
                 if (!act) nq = 1u << kS;
             }
             const int F = (int)__reduce_min_sync(CT_FULL, (unsigned)(__ffs(nq) - 1));
-            if (F == kS) {
-                if (act) {
+            if (F > 0 && act) {
+                if (F == kS && endc >= kS) {
                     Sd = s32;
 #pragma unroll
                     for (int e = 0; e < kS; ++e) Sdd += (long long)dv[e] * dv[e];
-                    rp = rn = gk + kS - 1;
-                }
-            } else {
-                if (F > 0 && act) {
+                } else {
+                    const int lim = min(F, endc);
 #pragma unroll
-                    for (int e = 0; e < kS - 1; ++e)
-                        if (e < F) { Sd += dv[e]; Sdd += (long long)dv[e] * dv[e]; }
-                    rp = rn = gk + F - 1;
+                    for (int e = 0; e < kS; ++e)
+                        if (e < lim) { Sd += dv[e]; Sdd += (long long)dv[e] * dv[e]; }
                 }
+                rp = rn = max(gk + F - 1, 0);
+            }
+            if (F < kS) {
                 // (rolled: the evaluation and the changepoint bookkeeping exist once, the code stays in the instruction cache)
 #pragma unroll 1
             for (int e = F; e < kS; ++e) {
