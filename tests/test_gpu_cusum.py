@@ -132,3 +132,55 @@ def test_event_columns_kernel_matches_the_numpy_statement():
         assert len(tab) == int((want_t == 0).sum())
         if ml == 16:
             assert abs(np.median(tab.events["max_blockage_pA"]) - 1600) < 100
+
+
+def _windows_case(seed, n_events, ntot_pad, max_levels=8, unaligned=False):
+    """>= 16384 windows (so that the thread-per-event kernel takes them) with every shape of window it has special code
+    for: lengths 1, 2, 31, 32, 33 and other short ones, plateaus longer than the shared-memory reciprocal table (8192),
+    windows longer than a lane takes (16384: left to the warps), a window ending on the last sample of a trace whose
+    length is not a multiple of the 128-byte line, a window starting at sample 0, rejected types, level overflow."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(40, 400, n_events)
+    lens[:12] = [1, 2, 31, 32, 33, 63, 64, 65, 9000, 12000, 17000, 20000]
+    rng.shuffle(lens)
+    gaps = rng.integers(0, 70, n_events)
+    w0 = np.cumsum(lens + gaps) - lens - gaps[0]            # first window starts at sample 0
+    w1 = w0 + lens
+    ntot = int(w1[-1]) + ntot_pad
+    y = (5000 + 24 * rng.standard_normal(ntot)).astype(np.float32)
+    for e in range(n_events):
+        L = int(lens[e]); a = int(w0[e])
+        if L >= 40:
+            k = int(rng.integers(0, 4))
+            cuts = np.linspace(a + 5, a + L - 5, k + 2).astype(np.int64)
+            for i in range(k + 1):
+                if i % 2 == 0 and k > 0:
+                    y[cuts[i]:cuts[i + 1]] -= np.float32(600 + 400 * (i % 3))
+        if e % 97 == 0 and L > 200:                           # many jumps: more levels than the table holds
+            for j in range(12):
+                y[a + 10 + 15 * j:a + L] += np.float32(900 * (-1) ** j)
+    typ = np.zeros(n_events, np.int32); typ[rng.integers(0, n_events, 50)] = 2
+    return y, w0.astype(np.int64), w1.astype(np.int64), typ, max_levels
+
+
+@pytest.mark.parametrize("ntot_pad,unaligned", [(0, False), (13, False), (5, True)])
+def test_thread_per_event_kernel_window_shapes(ntot_pad, unaligned):
+    y, w0, w1, typ, ml = _windows_case(31 + ntot_pad, 20000, ntot_pad)
+    buf = torch.empty(y.size + 8, dtype=torch.float32, device="cuda")
+    yt = buf[1:1 + y.size] if unaligned else buf[:y.size]     # unaligned: no 16-byte copies, every window goes to the warps
+    yt.copy_(torch.from_numpy(y))
+    t = cusum.cusum_levels(yt, torch.from_numpy(w0).cuda(), torch.from_numpy(w1).cuda(), delta=400.0, h=10.0,
+                           max_levels=ml, types=torch.from_numpy(typ).cuda())
+    torch.cuda.synchronize()
+    flat = np.concatenate([y[a:b] for a, b in zip(w0, w1)])
+    offs = np.concatenate(([0], np.cumsum(w1 - w0)))
+    want = c_twin.cusum_batch(flat, offs, 400.0, 10.0, ml)
+    keep = typ == 0
+    nl = t.n_levels.cpu().numpy()
+    assert np.all(nl[~keep] == 0)
+    assert np.array_equal(nl[keep], want[0][keep])
+    assert np.array_equal(t.edges.cpu().numpy()[keep], want[1][keep])
+    assert np.array_equal(t.mean.cpu().numpy()[keep], want[2][keep])
+    assert np.array_equal(t.std.cpu().numpy()[keep], want[3][keep])
+    assert np.array_equal(t.overflow.cpu().numpy()[keep], want[4][keep])
+    assert want[4][keep].sum() > 5 and (want[0][keep] >= 3).sum() > 5000
