@@ -51,10 +51,11 @@ def cusum_levels(y: torch.Tensor, win_start: torch.Tensor, win_end: torch.Tensor
     L = _lib.lib()
     wsb = int(L.ct_cusum_workspace_bytes(E))
     ws = torch.empty((wsb + 7) // 8, dtype=torch.int64, device=dev)
-    rc = L.ct_cusum_batch(y.data_ptr(), y.numel(), win_start.data_ptr(), win_end.data_ptr(),
-                                   types.data_ptr() if types is not None else None, E, float(delta), float(h),
-                                   int(max_levels), nl.data_ptr(), ed.data_ptr(), mu.data_ptr(), sd.data_ptr(),
-                                   ov.data_ptr(), ws.data_ptr(), wsb, _stream_ptr(y))
+    with torch.cuda.device(dev):        # the library launches on the current device
+        rc = L.ct_cusum_batch(y.data_ptr(), y.numel(), win_start.data_ptr(), win_end.data_ptr(),
+                              types.data_ptr() if types is not None else None, E, float(delta), float(h),
+                              int(max_levels), nl.data_ptr(), ed.data_ptr(), mu.data_ptr(), sd.data_ptr(),
+                              ov.data_ptr(), ws.data_ptr(), wsb, _stream_ptr(y))
     _lib.check(rc, "ct_cusum_batch")
     return LevelTable(nl, ed, mu, sd, ov, int(max_levels))
 

@@ -47,8 +47,9 @@ def welch_sums(x: torch.Tensor, nperseg: int, *, use_abs: bool = False, shift: f
     if shift is None:
         shift = float(x[: min(x.numel(), 1 << 16)].abs().mean().item() if use_abs else x[: min(x.numel(), 1 << 16)].mean().item()) if x.numel() else 0.0
     nseg = C.c_int64(0)
-    rc = lib.ct_welch_f32(x.data_ptr(), x.numel(), L, float(shift), int(bool(use_abs)), batch, ws.data_ptr(), wsb,
-                          acc.data_ptr(), C.byref(nseg), _stream_ptr(x))
+    with torch.cuda.device(x.device):   # the library launches on the current device
+        rc = lib.ct_welch_f32(x.data_ptr(), x.numel(), L, float(shift), int(bool(use_abs)), batch, ws.data_ptr(), wsb,
+                              acc.data_ptr(), C.byref(nseg), _stream_ptr(x))
     _lib.check(rc, "ct_welch_f32")
     return acc, int(nseg.value)
 
@@ -79,7 +80,8 @@ def welch_single_sums(x: torch.Tensor, *, use_abs: bool = False) -> torch.Tensor
     acc = torch.empty(n // 2 + 1, dtype=torch.float64, device=x.device)
     xm = x.abs() if use_abs else x
     mean = float(xm.sum(dtype=torch.float64).item()) / n         # scipy's detrend='constant' of the segment
-    rc = lib.ct_welch_single_f32(x.data_ptr(), n, mean, int(bool(use_abs)), ws.data_ptr(), wsb, acc.data_ptr(), _stream_ptr(x))
+    with torch.cuda.device(x.device):
+        rc = lib.ct_welch_single_f32(x.data_ptr(), n, mean, int(bool(use_abs)), ws.data_ptr(), wsb, acc.data_ptr(), _stream_ptr(x))
     _lib.check(rc, "ct_welch_single_f32")
     return acc
 
