@@ -36,3 +36,20 @@ static __device__ __forceinline__ void ct_stg_stream(void* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// -DCT_BOUNDS_CHECK: every hand-computed offset into a workspace / table is checked against the extent the host
+// passed along (compute-sanitizer is not available on every pool); a violation prints the site and traps.  The
+// production build compiles the checks away.
+#ifdef CT_BOUNDS_CHECK
+#define CT_CHECK_RANGE(off, count, limit, what)                                                                     \
+    do {                                                                                                            \
+        const long long ct_o_ = (long long)(off), ct_l_ = (long long)(limit);                                       \
+        if (ct_o_ < 0 || ct_o_ + (long long)(count) > ct_l_) {                                                      \
+            printf("CT_BOUNDS_CHECK %s: offset %lld + %d beyond %lld (block %d thread %d)\n", what, ct_o_, (int)(count), ct_l_, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                                              \
+            asm volatile("trap;");                                                                                  \
+        }                                                                                                           \
+    } while (0)
+#else
+#define CT_CHECK_RANGE(off, count, limit, what) do { } while (0)
+#endif

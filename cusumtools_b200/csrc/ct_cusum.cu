@@ -544,6 +544,8 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                     long long Sq, Sqq;
                     level_sums(Sd, Sdd, k - k0 + 1, qa, Sq, Sqq);
                     const long long r_ = (long long)ev * ML + (nedge - 1);
+                    CT_CHECK_RANGE(r_, 1, a.nev * ML, "cusum, level row");
+                    CT_CHECK_RANGE(p0 + edge, k - edge + 1, a.ntot, "cusum, re-read of the samples behind a changepoint");
                     reinterpret_cast<long long*>(a.mean)[r_] = Lp + Sq - T;       // level [e0, edge)
                     reinterpret_cast<long long*>(a.sd)[r_] = Lpp + Sqq - TT;
                     a.edges[(long long)ev * (ML + 1) + nedge] = edge;
@@ -622,7 +624,10 @@ __global__ void __launch_bounds__(256) ct_cusum_order_fill(const long long* __re
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (cls[i] >= 0) order[off[cls[i]] + pos[i]] = (int)(c0 + i * 256 + threadIdx.x);
+            if (cls[i] >= 0) {
+                CT_CHECK_RANGE(off[cls[i]] + pos[i], 1, nev, "cusum, hand-out order");
+                order[off[cls[i]] + pos[i]] = (int)(c0 + i * 256 + threadIdx.x);
+            }
     }
 }
 

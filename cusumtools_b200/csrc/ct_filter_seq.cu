@@ -61,6 +61,7 @@ struct SeqArgs {
     long long ngroups;     // groups [g_first, ngroups) are processed
     long long g_first;
     long long scratch_runs;// runs the scratch holds
+    long long scratch_floats, summ_count;   // extents of the scratch (floats) and of the chunk-extrema array (float2), for CT_BOUNDS_CHECK
     long long base;        // position of run 0 (<= 0): aligns groups with baseline blocks
     unsigned long long* next_group;   // work counter (zeroed by the host): warps fetch groups g_first + counter++ (NULL: static round robin)
     int R, Hw;             // run length, warm-up (multiples of kK, Hw <= R)
@@ -482,7 +483,9 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
                             float oa[F], ob[F];
 #pragma unroll
                             for (int i = 0; i < F; ++i) { oa[i] = keep[i].x; ob[i] = keep[i].y; }
-                            float* dst = a.out + scratch_off<D>(run0 + lane, t - wt, jj >> 1, TO);
+                            const long long so = scratch_off<D>(run0 + lane, t - wt, jj >> 1, TO);
+                            CT_CHECK_RANGE(so, 33 * F, a.scratch_floats, "forward pass, scratch store");
+                            float* dst = a.out + so;
                             stg_vec<F>(dst, oa);
                             stg_vec<F>(dst + 32 * F, ob);
                         }
@@ -581,6 +584,8 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
         const int to = warm ? wt - 1 - t : TO - 1 - (t - wt);
         const long long s0 = warm ? r0 + 1 : r0, s1 = warm ? r1 + 1 : r1;
         if (!EDGE) {
+            CT_CHECK_RANGE(scratch_off<D>(s0, to, jp, TO), F, a.scratch_floats, "backward pass, scratch load (half 0)");
+            CT_CHECK_RANGE(scratch_off<D>(s1, to, jp, TO), F, a.scratch_floats, "backward pass, scratch load (half 1)");
             ldg_vec<F>(y1 + scratch_off<D>(s0, to, jp, TO), xa);
             ldg_vec<F>(y1 + scratch_off<D>(s1, to, jp, TO), xb);
             // the register pipeline is two pairs deep (about a microsecond of work): it hides an L2 hit, not a DRAM
@@ -596,8 +601,8 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
             }
         } else {
             // units beyond the scratch are never dereferenced; positions beyond the forward output are replaced by `hold` below
-            if (s0 < a.scratch_runs) ldg_vec<F>(y1 + scratch_off<D>(s0, to, jp, TO), xa);
-            if (s1 < a.scratch_runs) ldg_vec<F>(y1 + scratch_off<D>(s1, to, jp, TO), xb);
+            if (s0 < a.scratch_runs) { CT_CHECK_RANGE(scratch_off<D>(s0, to, jp, TO), F, a.scratch_floats, "backward pass (edge), scratch load"); ldg_vec<F>(y1 + scratch_off<D>(s0, to, jp, TO), xa); }
+            if (s1 < a.scratch_runs) { CT_CHECK_RANGE(scratch_off<D>(s1, to, jp, TO), F, a.scratch_floats, "backward pass (edge), scratch load"); ldg_vec<F>(y1 + scratch_off<D>(s1, to, jp, TO), xb); }
         }
     };
     StatAcc acc0, acc1;
@@ -718,6 +723,8 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
             sb0[3] = sb0[2]; sb0[2] = sb0[1]; sb0[1] = sb0[0]; sb0[0] = make_float2(mn0, mx0);
             sb1[3] = sb1[2]; sb1[2] = sb1[1]; sb1[1] = sb1[0]; sb1[0] = make_float2(mn1, mx1);
             if ((to & 3) == 0) {
+                CT_CHECK_RANGE(r0 * TO + to, 4, a.summ_count, "backward pass, chunk extrema (half 0)");
+                CT_CHECK_RANGE(r1 * TO + to, 4, a.summ_count, "backward pass, chunk extrema (half 1)");
                 float2* d0 = a.summ + (r0 * TO + to);
                 float2* d1 = a.summ + (r1 * TO + to);
                 const float f0[8] = {sb0[0].x, sb0[0].y, sb0[1].x, sb0[1].y, sb0[2].x, sb0[2].y, sb0[3].x, sb0[3].y};
@@ -996,6 +1003,7 @@ int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, f
     a.in = in; a.n_in = n; a.mask = mask; a.Hw = p.Hw; a.R = p.R; a.base = p.base;
     if (in_kind == 0) split_sub(a, sub, pad_x); else { a.fsub = sub; a.pad_x = pad_x; }
     a.out = reinterpret_cast<float*>(workspace);
+    a.scratch_floats = (ct_filtfilt_workspace_bytes(n, pad, H) - 256) / 4;
     if (counts9 && part != 1 && in_kind == 0) {
         if (!cw_step || (cw_step & (cw_step - 1))) { ct_set_error("filter: window step must be a power of two"); return CT_ERR_ARG; }
         a.cw_lo = cw_lo; a.cw_sh = __builtin_ctz(cw_step); a.cw_out = (unsigned long long*)counts9;
@@ -1047,6 +1055,8 @@ int ct_filter_backward_seq(int64_t n, int64_t pad, float sub, float scale, float
     b.offset = offset - scale * (sub - floorf(sub));      // see split_sub: the kernel subtracted floor(sub)
     b.Hw = p.Hw; b.R = p.R; b.base = p.base; b.scratch_runs = p.ng_fwd * kRuns; b.ngroups = p.ng_bwd;
     b.summ = reinterpret_cast<float2*>(summaries);
+    b.scratch_floats = (ct_filtfilt_workspace_bytes(n, pad, H) - 256) / 4;
+    b.summ_count = ct_filter_summary_count(n, pad, H);
     if (summaries && (reinterpret_cast<uintptr_t>(summaries) & 31)) { ct_set_error("filter: chunk extrema must be 32-byte aligned"); return CT_ERR_ARG; }
     if (stats) {
         if (stats->block <= 0 || stats->block % p.G || stats->origin != origin || !stats->cnt || !stats->s1 || !stats->s2) {
