@@ -177,8 +177,10 @@ int ct_event_windows(const int64_t* starts, const int64_t* ends, const uint64_t*
  * offsets inside the window, edges[0] = 0, edges[n_levels] = length, unused = -1),
  * level mean / population std in pA (float64), overflow flag (more jumps than
  * max_levels-1).  workspace: ct_cusum_workspace_bytes(n_events) bytes of device scratch
- * (8-byte aligned).  Windows of up to 16384 samples are segmented one event per lane, longer
- * ones (and batches too small to fill the GPU that way) one event per warp.                */
+ * (16-byte aligned; the library keeps no device state of its own).  Windows of up to 16384
+ * samples are segmented one event per lane (y 16-byte aligned, batches of >= 16384 events),
+ * everything else one event per warp.  Domain of the definition: |y - y[win_start[e]]| < 65536 pA
+ * inside a window (samples are quantised to 1/64 pA relative to the window's first sample).   */
 int64_t ct_cusum_workspace_bytes(int64_t n_events);
 int ct_cusum_batch(const float* y, int64_t n_total, const int64_t* win_start, const int64_t* win_end,
                    const int32_t* type, int64_t n_events, float delta, float h, int max_levels,
