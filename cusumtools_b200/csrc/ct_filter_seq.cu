@@ -105,6 +105,16 @@ static __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                  :: "l"(map), "r"(x), "r"(y), "r"(src) : "memory");
 }
+// the same with an L2 eviction policy (write-once output: evict_first keeps it from displacing lines that are still being filled)
+static __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, int x, int y, unsigned src, unsigned long long pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                 :: "l"(map), "r"(x), "r"(y), "r"(src), "l"(pol) : "memory");
+}
+static __device__ __forceinline__ unsigned long long l2_stream_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> static __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
@@ -148,6 +158,17 @@ template <> __device__ __forceinline__ void stg_vec<8>(float* p, const float* f)
                  :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
 }
 template <> __device__ __forceinline__ void stg_vec<16>(float* p, const float* f) { stg_vec<8>(p, f); stg_vec<8>(p + 8, f + 8); }
+// 32-byte store that asks L2 to keep the line (evict_last): small pieces of the same line arrive tens of microseconds
+// apart (chunk extrema: 32 bytes per run every four tiles) and should leave for DRAM as one line, not as four sectors.
+static __device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+static __device__ __forceinline__ void stg8_keep(float* p, const float* f, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "l"(pol) : "memory");
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]), "l"(pol) : "memory");
+}
 
 // ------------------------------------------------------------------ scratch layout
 // Unit = the kept samples of one PAIR of slots (16 positions) of one run: F = 16/D floats.  Units of the 32
@@ -710,8 +731,9 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(out_map, to * kK, (int)run0, outb);
-                        tma_store_2d(out_map, to * kK + 32, (int)run0, outb + (unsigned)kStage);
+                        const unsigned long long pol = l2_stream_policy();
+                        tma_store_2d_hint(out_map, to * kK, (int)run0, outb, pol);
+                        tma_store_2d_hint(out_map, to * kK + 32, (int)run0, outb + (unsigned)kStage, pol);
                         bulk_commit();
                     }
                 }
@@ -749,8 +771,9 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
                 float2* d1 = a.summ + (r1 * TO + to);
                 const float f0[8] = {sb0[0].x, sb0[0].y, sb0[1].x, sb0[1].y, sb0[2].x, sb0[2].y, sb0[3].x, sb0[3].y};
                 const float f1[8] = {sb1[0].x, sb1[0].y, sb1[1].x, sb1[1].y, sb1[2].x, sb1[2].y, sb1[3].x, sb1[3].y};
-                stg_vec<8>(reinterpret_cast<float*>(d0), f0);
-                stg_vec<8>(reinterpret_cast<float*>(d1), f1);
+                const unsigned long long keep = l2_keep_policy();
+                stg8_keep(reinterpret_cast<float*>(d0), f0, keep);
+                stg8_keep(reinterpret_cast<float*>(d1), f1, keep);
             }
         }
     }
