@@ -632,7 +632,17 @@ __global__ void __launch_bounds__(256) ct_cusum_order_fill(const long long* __re
 }
 
 // float64 level mean / population std from the integer sums the lanes left in the arrays
-// (oracle/events_oracle.py::level_stats, operation for operation); one thread per event.
+// (oracle/events_oracle.py::level_stats, operation for operation).
+__device__ __forceinline__ void finalize_level(const CusumArgs& a, long long i, double x0, int e0, int e1) {
+    const double len = (double)(e1 - e0);
+    const double ad = (double)reinterpret_cast<const long long*>(a.mean)[i];
+    const double bd = (double)reinterpret_cast<const long long*>(a.sd)[i];
+    a.mean[i] = __dadd_rn(x0, __ddiv_rn(__ddiv_rn(ad, len), 64.0));
+    double var = __dsub_rn(bd, __ddiv_rn(__dmul_rn(ad, ad), len));
+    if (var < 0.0) var = 0.0;
+    a.sd[i] = __ddiv_rn(__dsqrt_rn(__ddiv_rn(var, len)), 64.0);
+}
+// One thread per event (any max_levels).
 __global__ void ct_cusum_finalize_kernel(CusumArgs a) {
     long long nev = a.nev;
     if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
@@ -643,17 +653,34 @@ __global__ void ct_cusum_finalize_kernel(CusumArgs a) {
         const int* ed = a.edges + ev * (ML + 1);
         const int nl = a.n_levels[ev];
         const double x0 = (double)a.y[a.w0[ev]];
-        for (int lv = 0; lv < nl; ++lv) {
-            const long long i = ev * ML + lv;
-            const double len = (double)(ed[lv + 1] - ed[lv]);
-            const double ad = (double)reinterpret_cast<const long long*>(a.mean)[i];
-            const double bd = (double)reinterpret_cast<const long long*>(a.sd)[i];
-            a.mean[i] = __dadd_rn(x0, __ddiv_rn(__ddiv_rn(ad, len), 64.0));
-            double var = __dsub_rn(bd, __ddiv_rn(__dmul_rn(ad, ad), len));
-            if (var < 0.0) var = 0.0;
-            a.sd[i] = __ddiv_rn(__dsqrt_rn(__ddiv_rn(var, len)), 64.0);
-        }
+        for (int lv = 0; lv < nl; ++lv) finalize_level(a, ev * ML + lv, x0, ed[lv], ed[lv + 1]);
         a.overflow[ev] = f & (unsigned char)~kRawSums;
+    }
+}
+// One thread per table entry when max_levels divides the warp (the rows of the level table are then read and written
+// as whole lines: 0.06 instead of 0.17 ms for 600 k events); an event's threads sit in one warp, so its flag is
+// cleared once they have all read it.
+__global__ void __launch_bounds__(256) ct_cusum_finalize_rows_kernel(CusumArgs a) {
+    long long nev = a.nev;
+    if (a.nev_dev) { const long long d = *a.nev_dev; nev = d < nev ? d : nev; }
+    const int ML = a.max_levels;
+    const long long total = nev * ML;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < total; i0 += stride) {
+        const long long i = i0 + threadIdx.x;
+        const bool in = i < total;
+        const long long ev = in ? i / ML : 0;
+        const int lv = (int)(i - ev * ML);
+        unsigned char f = 0;
+        int nl = 0;
+        if (in) { f = a.overflow[ev]; nl = a.n_levels[ev]; }
+        const bool raw = in && (f & kRawSums);
+        if (raw && lv < nl) {
+            const int* ed = a.edges + ev * (ML + 1);
+            finalize_level(a, i, (double)a.y[a.w0[ev]], ed[lv], ed[lv + 1]);
+        }
+        __syncwarp();
+        if (raw && lv == 0) a.overflow[ev] = f & (unsigned char)~kRawSums;
     }
 }
 
@@ -821,10 +848,16 @@ static int cusum_launch(const float* y, int64_t n_total, const int64_t* win_star
     CT_COUNT_LAUNCH();
     ct_cusum_warp_kernel<<<(unsigned)grid, 128, 0, st>>>(a);
     rc = ct_check_launch("ct_cusum_warp_kernel"); if (rc) return rc;
-    grid = (n_events + 255) / 256;
-    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
     CT_COUNT_LAUNCH();
-    ct_cusum_finalize_kernel<<<(unsigned)grid, 256, 0, st>>>(a);
+    if (max_levels <= 32 && 32 % max_levels == 0) {
+        grid = (n_events * max_levels + 255) / 256;
+        if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+        ct_cusum_finalize_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(a);
+    } else {
+        grid = (n_events + 255) / 256;
+        if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+        ct_cusum_finalize_kernel<<<(unsigned)grid, 256, 0, st>>>(a);
+    }
     return ct_check_launch("ct_cusum_finalize_kernel");
 }
 
