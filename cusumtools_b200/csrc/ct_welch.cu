@@ -728,6 +728,25 @@ static int bluestein_logm(long long n) {
 
 extern "C" {
 
+// CTAs of `threads` threads resident on the GPU at once (the register-resident kernels use up to 128 registers)
+static int resident_ctas(int threads) {
+    int per_sm = 65536 / (128 * threads);
+    if (per_sm < 1) per_sm = 1;
+    return ct_sm_count() * per_sm;
+}
+// Number of CTAs the segments of a batch are split over per unit (row pair / column group).
+static int pick_split(int units, int nseg, int resident) {
+    int best = 1;
+    double best_cost = 1e300;
+    for (int s = 1; s <= nseg && s <= 64; ++s) {
+        const long long grid = (long long)units * s;
+        const double waves = (double)((grid + resident - 1) / resident);
+        const double cost = waves * ((double)((nseg + s - 1) / s) + 0.5);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
 int64_t ct_welch_workspace_bytes(int32_t nperseg, int32_t batch) {
     if (nperseg < 256 || (nperseg & (nperseg - 1))) return -1;
     if (nperseg <= (1 << 14)) return 256;                      // whole-segment kernel: no intermediate
@@ -766,16 +785,15 @@ int ct_welch_f32(const float* x, int64_t n, int32_t nperseg, float shift, int32_
     a.Y = (cpx*)workspace;
     a.segsum = (double*)((char*)workspace + (size_t)batch * N * 8);
     const int N1 = 1 << logn1, N2 = 1 << logn2;
-    const int target = 2 * ct_sm_count();
     for (long long s0 = 0; s0 < nseg; s0 += batch) {
         a.seg0 = s0; a.nseg = (int)((nseg - s0 < batch) ? nseg - s0 : batch);
         cudaMemsetAsync(a.segsum, 0, (size_t)a.nseg * 8, st);
         // enough CTAs to fill the GPU: the segments of the batch are split over rsplit CTAs per row pair
         // (and over ssplit CTAs per column group); more segments per CTA amortise its set-up
-        a.rsplit = 1;
-        while ((N1 / 2 + 1) * a.rsplit < target && a.rsplit * 2 <= a.nseg) a.rsplit *= 2;
-        a.ssplit = 1;
-        while ((N2 / kFastCols) * a.ssplit < target && a.ssplit * 2 <= a.nseg) a.ssplit *= 2;
+        // (chosen against the wave quantisation: the CTAs of a launch run in ceil(grid / resident) waves, and a CTA
+        // costs its segments plus about half a segment of set-up)
+        a.rsplit = pick_split(N1 / 2 + 1, a.nseg, resident_ctas(2 * (N2 / 8)));
+        a.ssplit = pick_split(N2 / kFastCols, a.nseg, resident_ctas((N1 / 8) * kFastCols));
         int rc = cols_fast(a, st); if (rc) return rc;
         rc = rows_fast(a, st); if (rc) return rc;
     }
