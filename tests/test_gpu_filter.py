@@ -196,3 +196,44 @@ def test_large_trace_properties():
     want = to.filter_data(x, synth.FS, 1e5, 8)[5000:-5000]
     got = y[lo:hi].cpu().numpy()
     assert np.abs(got - want).max() < ABS_TOL
+
+
+def test_integration_stub_binds_the_c_abi_directly():
+    """a maintainer's own ctypes binding of ct_filtfilt_u16 (own CDLL handle, own mirror of
+    CtFilterCoef, argtypes as written there) gives the package's result bit for bit."""
+    import ctypes as C
+    from cusumtools_b200 import _lib
+
+    class Coef(C.Structure):
+        _fields_ = [("nsec", C.c_int32), ("order", C.c_int32), ("na1", C.c_float * 5), ("na2", C.c_float * 5),
+                    ("ss", C.c_float * 5), ("fir", C.c_float * 11), ("gain", C.c_float)]
+
+    L = C.CDLL(_lib.LIB_PATH)
+    L.ct_last_error.restype = C.c_char_p
+    assert L.ct_version() == 2
+    L.ct_filtfilt_u16.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_uint16, C.c_float, C.c_float,
+                                  C.POINTER(Coef), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.ct_filtfilt_workspace_bytes.restype = C.c_int64
+    L.ct_filtfilt_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int]
+    S = synth.CHIMERA_SETTINGS
+    codes, _ = synth.c1_trace(n=700_001, n_events=100, seed=21)
+    raw = torch.from_numpy(codes).cuda()
+    want = filters.dequant_filtfilt(raw, S, 1e5, 8)
+    design = bessel_lowpass(8, 2 * 1e5 / synth.FS)
+    theirs = filters.make_coef(design)
+    assert C.sizeof(Coef) == C.sizeof(theirs)
+    coef = Coef.from_buffer_copy(bytes(theirs))
+    H = filters.warmup_samples(design)
+    mask = filters.chimera_bitmask(S)
+    alpha, _ = filters.chimera_affine(S)
+    c1, c2 = filters.code_median(raw, mask)
+    median_code = 0.5 * (c1 + c2)
+    pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), S)))
+    out = torch.empty(raw.numel(), dtype=torch.float32, device="cuda")
+    wsb = L.ct_filtfilt_workspace_bytes(raw.numel(), 1000, H)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    rc = L.ct_filtfilt_u16(raw.data_ptr(), raw.numel(), 1000, median_code, mask, alpha, pad_value, C.byref(coef), H, 0,
+                           out.data_ptr(), ws.data_ptr(), wsb, None, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, L.ct_last_error().decode()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
