@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
     int k0 = 0, qa = 0, gp = 0, gn = 0, rp = 0, rn = 0, nedge = 1, e0 = 0;
     long long Sd = 0, Sdd = 0;           // sums of d = q - qa, d^2 over [k0, k] (qa = q at the anchor k0)
     long long Lp = 0, Lpp = 0;           // sums of q, q^2 over [e0, k0): the part of the open level before the anchor
+    long long ZpS = 0, ZpSS = 0, ZnS = 0, ZnSS = 0;   // sums of d, d^2 over [k0, last zero of g+ / g-] (valid while that g > 0)
 
 #pragma unroll
     for (int s = 0; s < kStages; ++s) fetch(s);
@@ -518,6 +519,10 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                 if (__all_sync(CT_FULL, quiet)) { if (valid) { rp = k; rn = k; } continue; }
                 const SeqOut s = cusum_tail(Sdd, m, rc, t, dq, hq);
                 if (!valid) continue;
+                // sums up to the last zero of each statistic (a statistic that is 0 now was last 0 at k - 1): what a
+                // detection needs to cut the level at the changepoint without re-reading the samples behind it
+                if (gp == 0) { ZpS = Sd - d; ZpSS = Sdd - (long long)d * d; }
+                if (gn == 0) { ZnS = Sd - d; ZnSS = Sdd - (long long)d * d; }
                 gp = max(gp + s.sp, 0); rp = gp == 0 ? k : rp;
                 gn = max(gn + s.sn, 0); rn = gn == 0 ? k : rn;
                 if (max(gp, gn) > H) {
@@ -534,23 +539,19 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
                         running = false; nlim = 0u;
                         continue;
                     }
-                    const int edge = ((gp >= gn) ? rp : rn) + 1;
-                    long long T = 0, TT = 0;             // sums over [edge, k]
-#pragma unroll 1
-                    for (int j = edge; j <= k; ++j) {
-                        const long long qj = quantise(j >= kb ? row[j - kb] : a.y[p0 + j], x0);
-                        T += qj; TT += qj * qj;
-                    }
-                    long long Sq, Sqq;
-                    level_sums(Sd, Sdd, k - k0 + 1, qa, Sq, Sqq);
+                    const bool pwin = gp >= gn;
+                    const int edge = (pwin ? rp : rn) + 1;
+                    const long long zs = pwin ? ZpS : ZnS, zss = pwin ? ZpSS : ZnSS;     // sums of d, d^2 over [k0, edge)
+                    long long Aq, Aqq, Bq, Bqq;
+                    level_sums(zs, zss, edge - k0, qa, Aq, Aqq);                                      // [k0, edge) in q units
+                    level_sums(Sd - zs - d, Sdd - zss - (long long)d * d, k - edge, qa, Bq, Bqq);     // [edge, k)
                     const long long r_ = (long long)ev * ML + (nedge - 1);
                     CT_CHECK_RANGE(r_, 1, a.nev * ML, "cusum, level row");
-                    CT_CHECK_RANGE(p0 + edge, k - edge + 1, a.ntot, "cusum, re-read of the samples behind a changepoint");
-                    reinterpret_cast<long long*>(a.mean)[r_] = Lp + Sq - T;       // level [e0, edge)
-                    reinterpret_cast<long long*>(a.sd)[r_] = Lpp + Sqq - TT;
+                    reinterpret_cast<long long*>(a.mean)[r_] = Lp + Aq;           // level [e0, edge)
+                    reinterpret_cast<long long*>(a.sd)[r_] = Lpp + Aqq;
                     a.edges[(long long)ev * (ML + 1) + nedge] = edge;
                     ++nedge;
-                    e0 = edge; Lp = T - q; Lpp = TT - (long long)q * q;
+                    e0 = edge; Lp = Bq; Lpp = Bqq;
                     k0 = k; qa = q; Sd = 0; Sdd = 0; gp = gn = 0; rp = rn = k;
                 }
             }
