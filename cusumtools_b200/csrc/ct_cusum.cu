@@ -396,11 +396,19 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 1) ct_cusum_seq_kernel(CusumAr
         const unsigned dst0 = (unsigned)__cvta_generic_to_shared(st) + (lane >> 3) * kRowB + (lane & 7) * 16;
         const char* src0 = reinterpret_cast<const char*>(a.y) + (lane & 7) * 16;
         const int c4 = (lane & 7) * 4;
+        if (__all_sync(CT_FULL, avail == kPiece)) {          // the usual round: 32 whole lines
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {                     // 4 rows per instruction, one 128-byte line each
-            const unsigned L = __shfl_sync(CT_FULL, myline, it * 4 + (lane >> 3));
-            const int A = __shfl_sync(CT_FULL, avail, it * 4 + (lane >> 3));
-            cp_async16(dst0 + it * 4 * kRowB, src0 + ((unsigned long long)L << 7), min(max(A - c4, 0), 4) * 4);
+            for (int it = 0; it < 8; ++it) {                 // 4 rows per instruction, one 128-byte line each
+                const unsigned L = __shfl_sync(CT_FULL, myline, it * 4 + (lane >> 3));
+                cp_async16(dst0 + it * 4 * kRowB, src0 + ((unsigned long long)L << 7), 16);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const unsigned L = __shfl_sync(CT_FULL, myline, it * 4 + (lane >> 3));
+                const int A = __shfl_sync(CT_FULL, avail, it * 4 + (lane >> 3));
+                cp_async16(dst0 + it * 4 * kRowB, src0 + ((unsigned long long)L << 7), min(max(A - c4, 0), 4) * 4);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (has) { ++f_line; f_kb += kPiece; --f_left; }
