@@ -663,7 +663,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison at the benchmarked size")
     ap.add_argument("--no-file", action="store_true", help="skip the from-file leg (writes the trace to --file-dir first)")
     ap.add_argument("--file-dir", default=None, help="directory for the from-file leg's temporary .log series (default: the system temp dir)")
-    ap.add_argument("--file-threads", type=int, default=8, help="reader threads of the from-file leg")
+    ap.add_argument("--file-threads", type=int, default=max(1, min(16, os.cpu_count() or 8)),
+                    help="reader threads of the from-file leg (default: the host cores, at most 16: 17.4 against 15.8 Gsamples/s with 8)")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
