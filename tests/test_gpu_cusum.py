@@ -184,3 +184,27 @@ def test_thread_per_event_kernel_window_shapes(ntot_pad, unaligned):
     assert np.array_equal(t.std.cpu().numpy()[keep], want[3][keep])
     assert np.array_equal(t.overflow.cpu().numpy()[keep], want[4][keep])
     assert want[4][keep].sum() > 5 and (want[0][keep] >= 3).sum() > 5000
+
+
+@pytest.mark.parametrize("delta,h,noise", [(400.0, 10.0, 33.0), (50.0, 2.0, 24.0), (800.0, 40.0, 60.0), (120.0, 1.0, 5.0)])
+def test_thread_per_event_kernel_on_ramps(delta, h, noise):
+    """17 000 windows (the thread-per-event kernel) whose level changes are RAMPS of 0-20 samples, as on a filtered trace:
+    the statistics stay non-zero for many samples, several changepoints follow each other, and with a small delta nearly
+    every sample takes the full evaluation.  Bit-exact against the C twin."""
+    rng = np.random.default_rng(int(delta + h))
+    n_events = 17000
+    lens = rng.integers(60, 500, n_events)
+    offs = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    x = 5000 + noise * rng.standard_normal(int(offs[-1]))
+    for e in range(n_events):
+        a, n = int(offs[e]), int(lens[e])
+        for c in np.sort(rng.integers(10, n - 10, int(rng.integers(0, 4)))):
+            depth = float(rng.choice([-1600.0, -800.0, 600.0, 1200.0]))
+            ramp = int(rng.integers(0, 20))
+            prof = np.ones(n - c) if ramp == 0 else np.minimum(1.0, (np.arange(n - c) + 1) / ramp)
+            x[a + c:a + n] += depth * prof
+    x = x.astype(np.float32)
+    got = run_gpu(x, offs, delta, h, max_levels=12)
+    want = c_twin.cusum_batch(x, offs, delta, h, 12)
+    assert_same(got, want)
+    assert (want[0] >= 3).sum() > 3000
