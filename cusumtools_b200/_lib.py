@@ -50,6 +50,9 @@ SIGNATURES = {
     "ct_filtfilt_stats_granule": (_i64, [_i64, _i64, C.c_int]),
     "ct_filter_forward_u16": (C.c_int, [_vp, _i64, _i64, _f32, _u16, _f32, C.POINTER(CtFilterCoef), C.c_int, _i64, C.c_int,
                                         _u32, _u32, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "ct_median_verify": (C.c_int, [_vp, C.c_int, _i64, _i64, _u32, _u32, _f32, _vp, _vp]),
+    "ct_filter_forward_ends_u16": (C.c_int, [_vp, _i64, _i64, _f32, _u16, _vp, C.POINTER(CtFilterCoef), C.c_int, _i64, _vp, _i64,
+                                             _vp]),
     "ct_filter_backward": (C.c_int, [_i64, _i64, _f32, _f32, _f32, C.POINTER(CtFilterCoef), C.c_int, _i64, _vp, _vp, _i64,
                                      C.POINTER(CtFilterStats), _vp, _vp]),
     "ct_filtfilt_u16": (C.c_int, [_vp, _i64, _i64, _f32, _u16, _f32, _f32, C.POINTER(CtFilterCoef),

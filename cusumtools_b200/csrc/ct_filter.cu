@@ -18,31 +18,36 @@ __global__ void ct_hist_sampled_kernel(const uint16_t* __restrict__ raw, long lo
 
 constexpr int kWin = 8;
 // out[0] = #codes < lo ; out[1+i] = #codes == lo + i*step (step = power of two, lo a multiple of it).
-// Eight 8-bit in-register counters in two 32-bit words: with d = code - lo (negative below the
-// window) the increment is 1 << (8 * d/step) through PTX shl.b32, which CLAMPS shift amounts >= 32 to
-// "all bits out" (result 0), so codes below or above the window add nothing without any compare; the
-// sign bit of d is the "below" count.  ~10 integer operations per code.
+// Eight 8-bit in-register counters in two 32-bit words: with a = 8 (code - lo) / step (negative below the window) the
+// increment is 1 << a through PTX shl.b32, which CLAMPS shift amounts >= 32 to "all bits out" (result 0), so codes below
+// or above the window add nothing without any compare; the sign bit of a is the "below" count.
+// Round 2 (second half): the round-1 form ran 6.5 instructions per code, ALL on the ALU pipe (SHF / LEA.HI / LOP3 / IADD3,
+// one warp instruction per two cycles and scheduler): ALU-bound at 0.72 of the DRAM rate (ncu: math_pipe_throttle 1.8 per
+// issue).  Now the word is masked and shifted once, a = e * k8 + c and the sign a * 2 >> 32 are IMAD / IMAD.HI (FMA pipe:
+// the multipliers are kernel arguments so that ptxas cannot turn them back into shifts), which leaves 3.5 ALU instructions
+// per code; and a warp reads 2 KB contiguous per batch instead of four 512-byte pieces 4.8 MB apart
+// (scripts/ubench/count_bw.cu: 4.6 -> 5.7 TB/s on 2^30 codes).
 static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
     unsigned r;
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
     return r;
 }
-// WIDE = false: only the first four window codes are counted (one counter word: 7 instead of 10 operations per code).
+// WIDE = false: only the first four window codes are counted (one counter word).
 template <bool WIDE>
 __global__ void __launch_bounds__(256)
 ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned mask, unsigned lo,
-                       unsigned step, unsigned long long* __restrict__ out /*[1+kWin]*/) {
+                       unsigned step, unsigned k8, unsigned two, unsigned long long* __restrict__ out /*[1+kWin]*/) {
     const int sh = __ffs(step) - 1;
+    const unsigned nlo8 = 0u - (lo >> sh) * 8u;
     unsigned long long tot[1 + kWin];
 #pragma unroll
     for (int i = 0; i <= kWin; ++i) tot[i] = 0;
     unsigned below = 0, c0 = 0, c1 = 0;
-    auto tally = [&](unsigned code) {                      // code already masked
-        const unsigned d = code - lo;
-        below += d >> 31;                                  // codes and lo are < 2^16: negative iff code < lo
-        const unsigned amt = sh >= 3 ? d >> (sh - 3) : d << (3 - sh);   // 8 * (d / step): d is a multiple of step
-        c0 += shl_clamp(1u, amt);
-        if (WIDE) c1 += shl_clamp(1u, amt - 32u);
+    auto tally = [&](unsigned e) {                         // e = (code & mask) >> sh
+        const unsigned a = e * k8 + nlo8;                  // |a| < 2^20
+        below = __umulhi(a, two) + below;                  // a >> 31
+        c0 += shl_clamp(1u, a);
+        if (WIDE) c1 += shl_clamp(1u, e * k8 + (nlo8 - 32u));
     };
     auto flush = [&]() {
         tot[0] += below; below = 0;
@@ -51,52 +56,56 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
         c0 = 0; c1 = 0;
     };
     const unsigned m2 = mask | (mask << 16);
+    auto tally_word = [&](unsigned w) {
+        const unsigned p = (w & m2) >> sh;                 // the low bits of the high code are masked: nothing leaks down
+        tally(p & 0xffffu); tally(p >> 16);
+    };
     const long long nvec = n / 8;
     const uint4* v = reinterpret_cast<const uint4*>(raw);
     const bool aligned = (reinterpret_cast<uintptr_t>(raw) & 15) == 0;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
     if (aligned) {
-        long long i = tid;
+        // a warp reads 2 KB contiguous per batch (4 x 512 bytes), a CTA 16 KB; CTAs stride over the trace in 16 KB pieces;
+        // the next batch is on its way while this one is tallied
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const long long per_cta = 256 * 4;                 // uint4 per piece
+        const long long npieces = nvec / per_cta;
+        long long pc = blockIdx.x;
         int rounds = 0;
-        // four independent 16-byte loads per batch, the next batch on its way while this one is tallied
         uint4 q[4], nq[4];
-        bool have = i + 3 * nth < nvec;
+        bool have = pc < npieces;
         if (have) {
+            const uint4* b = v + pc * per_cta + warp * 128 + lane;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) q[u] = ct_ldg_stream(v + i + u * nth);
+            for (int u = 0; u < 4; ++u) q[u] = ct_ldg_stream(b + u * 32);
         }
         while (have) {
-            const long long inext = i + 4 * nth;
-            const bool more = inext + 3 * nth < nvec;
+            const long long pn = pc + gridDim.x;
+            const bool more = pn < npieces;
             if (more) {
+                const uint4* b = v + pn * per_cta + warp * 128 + lane;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) nq[u] = ct_ldg_stream(v + inext + u * nth);
+                for (int u = 0; u < 4; ++u) nq[u] = ct_ldg_stream(b + u * 32);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned ww[4] = {q[u].x & m2, q[u].y & m2, q[u].z & m2, q[u].w & m2};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { tally(ww[j] & 0xffffu); tally(ww[j] >> 16); }
-            }
+            for (int u = 0; u < 4; ++u) { tally_word(q[u].x); tally_word(q[u].y); tally_word(q[u].z); tally_word(q[u].w); }
             if (++rounds == 7) { flush(); rounds = 0; }     // 32 tallies per round: an 8-bit counter holds 7 rounds
 #pragma unroll
             for (int u = 0; u < 4; ++u) q[u] = nq[u];
-            i = inext;
+            pc = pn;
             have = more;
         }
         flush();
-        for (; i < nvec; i += nth) {
-            const uint4 q = ct_ldg_stream(v + i);
-            const unsigned ww[4] = {q.x & m2, q.y & m2, q.z & m2, q.w & m2};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { tally(ww[j] & 0xffffu); tally(ww[j] >> 16); }
+        for (long long i = npieces * per_cta + tid; i < nvec; i += nth) {
+            const uint4 qq = ct_ldg_stream(v + i);
+            tally_word(qq.x); tally_word(qq.y); tally_word(qq.z); tally_word(qq.w);
             flush();
         }
-        for (long long k = nvec * 8 + tid; k < n; k += nth) { tally(raw[k] & mask); flush(); }
+        for (long long k = nvec * 8 + tid; k < n; k += nth) { tally((unsigned)(raw[k] & mask) >> sh); flush(); }
     } else {
         int since = 0;
-        for (long long k = tid; k < n; k += nth) { tally(raw[k] & mask); if (++since == 128) { flush(); since = 0; } }
+        for (long long k = tid; k < n; k += nth) { tally((unsigned)(raw[k] & mask) >> sh); if (++since == 128) { flush(); since = 0; } }
     }
     flush();
 #pragma unroll
@@ -107,7 +116,25 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
         if (ct_lane() == 0 && sum) atomicAdd(&out[i], sum);
     }
 }
-
+// The host side of the exact median (pipeline.median_verify) on the device: the two middle order statistics from the
+// window counts, the pad of the filter ends (median - subtracted estimate) and whether the window held them.
+__global__ void ct_median_verify_kernel(const unsigned long long* __restrict__ c, int nbins, long long k1, long long k2,
+                                        unsigned lo, unsigned step, float sub_code, CtMedianResult* __restrict__ r) {
+    if (threadIdx.x) return;
+    const unsigned long long below = c[0];
+    unsigned long long cum = below;
+    unsigned c1 = 0, c2 = 0;
+    bool have1 = false, have2 = false;
+    for (int i = 0; i < nbins; ++i) {
+        cum += c[1 + i];
+        if (!have1 && cum >= (unsigned long long)k1 + 1) { c1 = lo + (unsigned)i * step; have1 = true; }
+        if (!have2 && cum >= (unsigned long long)k2 + 1) { c2 = lo + (unsigned)i * step; have2 = true; }
+    }
+    const bool ok = below <= (unsigned long long)k1 && have1 && have2;
+    r->code1 = ok ? c1 : 0; r->code2 = ok ? c2 : 0;
+    r->pad_x = ok ? 0.5f * ((float)c1 + (float)c2) - sub_code : 0.f;
+    r->status = ok ? 0u : ((unsigned long long)k1 < below ? 1u : 2u);
+}
 
 }  // namespace
 
@@ -118,7 +145,7 @@ int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float s
 int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float pad_x,
                           const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t cw_lo, uint32_t cw_step,
                           int64_t cw_begin, int64_t cw_end, uint64_t* counts9, int64_t from_pos, int64_t to_pos,
-                          void* workspace, int64_t workspace_bytes, cudaStream_t st);
+                          void* workspace, int64_t workspace_bytes, const float* pad_x_dev, cudaStream_t st);
 int ct_filter_backward_seq(int64_t n, int64_t pad, float sub, float scale, float offset, const CtFilterCoef* coef, int H,
                            int64_t origin, float* out, const void* workspace, int64_t workspace_bytes,
                            const CtFilterStats* stats, float* summaries, cudaStream_t st);
@@ -131,8 +158,29 @@ int ct_filter_forward_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub
                           int64_t to_pos, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!raw || !coef || n <= 0 || pad < 0 || H < 0 || origin < 0) { ct_set_error("filter_forward: bad argument"); return CT_ERR_ARG; }
     return ct_filter_forward_seq(raw, 0, n, pad, sub_code, mask, pad_x, coef, H, origin, part, window_lo, window_step,
-                                 count_begin, count_end, counts9, from_pos, to_pos, workspace, workspace_bytes,
+                                 count_begin, count_end, counts9, from_pos, to_pos, workspace, workspace_bytes, nullptr,
                                  (cudaStream_t)stream);
+}
+
+int ct_filter_forward_ends_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub_code, uint16_t mask,
+                               const float* pad_x_dev, const CtFilterCoef* coef, int H, int64_t origin, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+    if (!raw || !coef || !pad_x_dev || n <= 0 || pad < 0 || H < 0 || origin < 0) {
+        ct_set_error("filter_forward_ends: bad argument"); return CT_ERR_ARG;
+    }
+    return ct_filter_forward_seq(raw, 0, n, pad, sub_code, mask, 0.f, coef, H, origin, 1, 0, 1, 0, 0, nullptr, 0, 0, workspace,
+                                 workspace_bytes, pad_x_dev, (cudaStream_t)stream);
+}
+
+int ct_median_verify(const uint64_t* counts9, int nbins, int64_t k1, int64_t k2, uint32_t lo, uint32_t step, float sub_code,
+                     CtMedianResult* result, void* stream) {
+    if (!counts9 || !result || nbins < 1 || nbins > 8 || k1 < 0 || k2 < k1 || step < 1) {
+        ct_set_error("median_verify: bad argument"); return CT_ERR_ARG;
+    }
+    CT_COUNT_LAUNCH();
+    ct_median_verify_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(counts9), nbins,
+                                                                k1, k2, lo, step, sub_code, result);
+    return ct_check_launch("ct_median_verify_kernel");
 }
 
 int ct_filter_backward(int64_t n, int64_t pad, float sub_code, float scale, float offset, const CtFilterCoef* coef, int H,
@@ -180,7 +228,9 @@ int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t
 
 static int count_window(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step, uint64_t* counts9,
                         bool wide, void* stream) {
-    if (!raw || !counts9 || n < 0 || step < 1) { ct_set_error("count_window: bad argument"); return CT_ERR_ARG; }
+    if (!raw || !counts9 || n < 0 || step < 1 || (step & (step - 1)) || (lo & (step - 1))) {
+        ct_set_error("count_window: bad argument (step must be a power of two and lo a multiple of it)"); return CT_ERR_ARG;
+    }
     if (n == 0) return CT_OK;
     long long blocks = (long long)ct_sm_count() * 8;
     long long want = (n / 8 + 255) / 256 + 1;
@@ -188,10 +238,10 @@ static int count_window(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t 
     CT_COUNT_LAUNCH();
     if (wide)
         ct_count_window_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-            raw, n, mask, lo, step, reinterpret_cast<unsigned long long*>(counts9));
+            raw, n, mask, lo, step, 8u, 2u, reinterpret_cast<unsigned long long*>(counts9));
     else
         ct_count_window_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-            raw, n, mask, lo, step, reinterpret_cast<unsigned long long*>(counts9));
+            raw, n, mask, lo, step, 8u, 2u, reinterpret_cast<unsigned long long*>(counts9));
     return ct_check_launch("ct_count_window_kernel");
 }
 

@@ -67,10 +67,11 @@ struct SeqArgs {
     int R, Hw;             // run length, warm-up (multiples of kK, Hw <= R)
     int isub; unsigned mask; float fsub;   // uint16: x' = (code & mask) - isub; float: x' = x - fsub
     float pad_x;           // FWD: x' in the pad and beyond
+    const float* pad_x_dev;// FWD, optional: added to pad_x on the device (the exact median arrives without a host round trip); 0 there: nothing to do
     float scale, offset;   // gain / offset folded into the last section (FWD scratch: D, 0)
     int tma_in, tma_out;   // tensor maps usable (alignment)
     // optional fused window count for the exact median (ct_count_window_u16 semantics), FWD uint16 only
-    unsigned cw_lo; int cw_sh; unsigned long long* cw_out; long long cw_p0, cw_p1;
+    unsigned cw_k, cw_c; unsigned long long* cw_out; long long cw_p0, cw_p1;   // a = pat * cw_k + cw_c, see cw_tally2
     // optional fused baseline block statistics of the final output (ct_block_stats_f32 semantics)
     long long st_origin, st_block; float st_min, st_max, st_scale, st_nc0s;
     long long* st_cnt; long long* st_s1; long long* st_s2;
@@ -209,24 +210,35 @@ __device__ __forceinline__ f2 allpole_step(f2 u, f2 (&v1)[NSEC], f2 (&v2)[NSEC],
 }
 
 // ------------------------------------------------------------------ exact-median window count (optional, FWD)
+// counts[0] = #codes < lo, counts[1 + i] = #codes == lo + i*step for i < 4 (ct_count_window4_u16 semantics), tallied from
+// the float bit patterns the conversion has produced anyway: pat = 0x4B000000 + code, so a = pat*k + c with k = 8 / step and
+// c = -(0x4B000000 + lo) k (mod 2^32) is 8 (code - lo) / step: its sign bit is the "below" count and 1 << a (PTX shl.b32
+// CLAMPS amounts >= 32: nothing for codes above the window or below it) the increment of four 8-bit in-register counters.
+// Three and a half instructions per code (IMAD, LEA.HI, SHF.L, half an IADD3): the pass is issue-bound once the tally rides
+// on it, so every instruction per code costs 0.1 ms per 2.5 G samples (round-2 form: 8.5 per code, eight window codes).
 static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
     unsigned r;
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
     return r;
 }
-struct CwAcc { unsigned tot[9], below, c0, c1; int since; };
-static __device__ __forceinline__ void cw_tally(unsigned code, const SeqArgs& a, CwAcc& w) {
-    const unsigned d = code - a.cw_lo;
-    w.below += d >> 31;
-    const unsigned amt = a.cw_sh >= 3 ? d >> (a.cw_sh - 3) : d << (3 - a.cw_sh);
-    w.c0 += shl_clamp(1u, amt);
-    w.c1 += shl_clamp(1u, amt - 32u);
+struct CwAcc { unsigned tot[5], below, c0; int since; };
+static __device__ __forceinline__ unsigned cw_amount(unsigned pat, const SeqArgs& a) { return pat * a.cw_k + a.cw_c; }
+static __device__ __forceinline__ void cw_tally2(unsigned pat0, unsigned pat1, const SeqArgs& a, CwAcc& w) {
+    const unsigned a0 = cw_amount(pat0, a), a1 = cw_amount(pat1, a);
+    w.below += a0 >> 31;
+    w.below += a1 >> 31;
+    w.c0 += shl_clamp(1u, a0) + shl_clamp(1u, a1);
+}
+static __device__ __forceinline__ void cw_tally1(unsigned pat, const SeqArgs& a, CwAcc& w) {
+    const unsigned a0 = cw_amount(pat, a);
+    w.below += a0 >> 31;
+    w.c0 += shl_clamp(1u, a0);
 }
 static __device__ __forceinline__ void cw_flush(CwAcc& w) {
     w.tot[0] += w.below; w.below = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { w.tot[1 + i] += (w.c0 >> (8 * i)) & 0xffu; w.tot[5 + i] += (w.c1 >> (8 * i)) & 0xffu; }
-    w.c0 = 0; w.c1 = 0; w.since = 0;
+    for (int i = 0; i < 4; ++i) w.tot[1 + i] += (w.c0 >> (8 * i)) & 0xffu;
+    w.c0 = 0; w.since = 0;
 }
 
 // ------------------------------------------------------------------ output half-tiles (shared by FWD-final and BWD)
@@ -300,7 +312,7 @@ static __device__ __forceinline__ long long next_group(const SeqArgs& a, long lo
 template <int NSEC, typename InT, int MODE, bool COUNT, bool EDGE>
 __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& k, const CUtensorMap* in_map, const CUtensorMap* out_map,
                                           const long long g, const int lane, const unsigned stage0, const unsigned bar0,
-                                          const unsigned outb, unsigned& phase, const Coefs<NSEC>& cf) {
+                                          const unsigned outb, unsigned& phase, const Coefs<NSEC>& cf, const float pad_x) {
     constexpr bool U16 = sizeof(InT) == 2;
     constexpr int SPT = U16 ? 1 : 2;             // stages per tile (a stage row is 128 bytes)
     constexpr int SLOTS = kG / SPT;              // slots per stage
@@ -320,8 +332,8 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
     {   // runs that begin in the left pad start from the steady state of the pad value (scipy: zi * x[0])
         float p0 = 0.f, p1 = 0.f;
         if (EDGE) {
-            p0 = a.base + (run0 + lane) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
-            p1 = a.base + (run0 + lane + 32) * a.R - a.Hw < 0 ? a.pad_x : 0.f;
+            p0 = a.base + (run0 + lane) * a.R - a.Hw < 0 ? pad_x : 0.f;
+            p1 = a.base + (run0 + lane + 32) * a.R - a.Hw < 0 ? pad_x : 0.f;
         }
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) { v1[s] = make_float2(p0 * k.ss[s], p1 * k.ss[s]); v2[s] = v1[s]; }
@@ -331,8 +343,8 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
     CwAcc cw;
     if (COUNT) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) cw.tot[i] = 0;
-        cw.below = cw.c0 = cw.c1 = 0; cw.since = 0;
+        for (int i = 0; i < 5; ++i) cw.tot[i] = 0;
+        cw.below = cw.c0 = 0; cw.since = 0;
     }
 
     // stage q covers the positions base + (run0 + r) R + off(q) + [0, SAMP), r = 0..63
@@ -363,7 +375,7 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
                     const long long p = a.base + (run0 + r) * a.R + off + col;
                     InT v;
                     if (U16) v = (p >= 0 && p < a.n_in) ? in[p] : (InT)0;
-                    else v = (p >= 0 && p < a.n_in) ? in[p] : (InT)(a.fsub + a.pad_x);
+                    else v = (p >= 0 && p < a.n_in) ? in[p] : (InT)(a.fsub + pad_x);
                     const unsigned addr = buf + swz(r, col / EPC) + (unsigned)(col % EPC) * (unsigned)sizeof(InT);
                     if (U16) asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory");
                     else asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"((float)v) : "memory");
@@ -404,39 +416,38 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
                     const uint4 rb = lds128(row0 + 32 * 128 + (unsigned)((j ^ sw) << 4));
                     const unsigned wa[4] = {ra.x & m2, ra.y & m2, ra.z & m2, ra.w & m2};
                     const unsigned wb[4] = {rb.x & m2, rb.y & m2, rb.z & m2, rb.w & m2};
+                    unsigned pl[4][2], ph[4][2];           // 2^23 + code as float bit patterns (byte permute): [word][run]
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
-                        // 2^23 + code as a float (byte permute), minus (2^23 + isub): exact
-                        const f2 lo = make_float2(__uint_as_float(__byte_perm(wa[w], 0x4B000000u, 0x7410)),
-                                                  __uint_as_float(__byte_perm(wb[w], 0x4B000000u, 0x7410)));
-                        const f2 hi = make_float2(__uint_as_float(__byte_perm(wa[w], 0x4B000000u, 0x7432)),
-                                                  __uint_as_float(__byte_perm(wb[w], 0x4B000000u, 0x7432)));
-                        x[2 * w] = __fadd2_rn(lo, kmagic);
-                        x[2 * w + 1] = __fadd2_rn(hi, kmagic);
+                        pl[w][0] = __byte_perm(wa[w], 0x4B000000u, 0x7410); pl[w][1] = __byte_perm(wb[w], 0x4B000000u, 0x7410);
+                        ph[w][0] = __byte_perm(wa[w], 0x4B000000u, 0x7432); ph[w][1] = __byte_perm(wb[w], 0x4B000000u, 0x7432);
+                        // minus (2^23 + isub): exact
+                        x[2 * w] = __fadd2_rn(make_float2(__uint_as_float(pl[w][0]), __uint_as_float(pl[w][1])), kmagic);
+                        x[2 * w + 1] = __fadd2_rn(make_float2(__uint_as_float(ph[w][0]), __uint_as_float(ph[w][1])), kmagic);
                     }
                     if (edge) {                            // x' = pad_x in the pad and beyond it
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const long long p0 = lo0 + jj * 8 + e, p1 = lo1 + jj * 8 + e;
-                            if (!(p0 >= 0 && p0 < a.n_in)) x[e].x = a.pad_x;
-                            if (!(p1 >= 0 && p1 < a.n_in)) x[e].y = a.pad_x;
+                            if (!(p0 >= 0 && p0 < a.n_in)) x[e].x = pad_x;
+                            if (!(p1 >= 0 && p1 < a.n_in)) x[e].y = pad_x;
                         }
                     }
                     if (COUNT && store) {                  // every code of [cw_p0, cw_p1) is tallied exactly once
                         if (!cw_part) {
 #pragma unroll
                             for (int w = 0; w < 4; ++w) {
-                                cw_tally(wa[w] & 0xffffu, a, cw); cw_tally(wa[w] >> 16, a, cw);
-                                cw_tally(wb[w] & 0xffffu, a, cw); cw_tally(wb[w] >> 16, a, cw);
+                                cw_tally2(pl[w][0], ph[w][0], a, cw);
+                                cw_tally2(pl[w][1], ph[w][1], a, cw);
                             }
                         } else {
 #pragma unroll 1
                             for (int w = 0; w < 4; ++w) {
                                 const long long pa0 = lo0 + jj * 8 + 2 * w, pb0 = lo1 + jj * 8 + 2 * w;
-                                if (pa0 >= a.cw_p0 && pa0 < a.cw_p1) cw_tally(wa[w] & 0xffffu, a, cw);
-                                if (pa0 + 1 >= a.cw_p0 && pa0 + 1 < a.cw_p1) cw_tally(wa[w] >> 16, a, cw);
-                                if (pb0 >= a.cw_p0 && pb0 < a.cw_p1) cw_tally(wb[w] & 0xffffu, a, cw);
-                                if (pb0 + 1 >= a.cw_p0 && pb0 + 1 < a.cw_p1) cw_tally(wb[w] >> 16, a, cw);
+                                if (pa0 >= a.cw_p0 && pa0 < a.cw_p1) cw_tally1(pl[w][0], a, cw);
+                                if (pa0 + 1 >= a.cw_p0 && pa0 + 1 < a.cw_p1) cw_tally1(ph[w][0], a, cw);
+                                if (pb0 >= a.cw_p0 && pb0 < a.cw_p1) cw_tally1(pl[w][1], a, cw);
+                                if (pb0 + 1 >= a.cw_p0 && pb0 + 1 < a.cw_p1) cw_tally1(ph[w][1], a, cw);
                             }
                         }
                         if (++cw.since == 15) cw_flush(cw);   // 16 tallies per slot: an 8-bit counter holds 15 slots
@@ -519,7 +530,7 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
     if (COUNT) {                                           // (a lane tallies < 2^32 codes per group)
         cw_flush(cw);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
+        for (int i = 0; i < 5; ++i) {
             unsigned v = cw.tot[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CT_FULL, v, o);
@@ -535,6 +546,12 @@ ct_filter_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
     constexpr int kPerWarp = 2 * kStage + (MODE == 0 ? 2 * kStage : 0);
     const int lane = ct_lane();
     const int wib = threadIdx.x >> 5;
+    float pad_x = a.pad_x;
+    if (a.pad_x_dev) {                                       // the end groups re-run with the exact median's pad: a no-op when
+        const float d = __ldg(a.pad_x_dev);                  // the estimate was the median
+        if (d == 0.f) return;
+        pad_x += d;
+    }
     const unsigned sbase = smem_u32(smem);
     const unsigned stage0 = sbase + (unsigned)wib * kPerWarp;
     const unsigned outb = stage0 + 2 * kStage;
@@ -558,8 +575,8 @@ ct_filter_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_co
         bool interior = a.tma_in && p_lo >= 0 && p_hi <= a.n_in;
         if (MODE == 0) interior = interior && a.tma_out && p_hi <= a.n_out;
         if (COUNT) interior = interior && p_lo + a.Hw >= a.cw_p0 && p_hi <= a.cw_p1;
-        if (interior) fwd_group<NSEC, InT, MODE, COUNT, false>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, cf);
-        else fwd_group<NSEC, InT, MODE, COUNT, true>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, cf);
+        if (interior) fwd_group<NSEC, InT, MODE, COUNT, false>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, cf, pad_x);
+        else fwd_group<NSEC, InT, MODE, COUNT, true>(a, k, &in_map, &out_map, g, lane, stage0, bar0, outb, phase, cf, pad_x);
     }
     if (MODE == 0 && lane == 0) bulk_wait_read<0>();         // shared memory must outlive the last tile store
 }
@@ -1041,17 +1058,19 @@ void split_sub(SeqArgs& a, float sub, float pad_x) {
 int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, float sub, uint16_t mask, float pad_x,
                           const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t cw_lo, uint32_t cw_step,
                           int64_t cw_begin, int64_t cw_end, uint64_t* counts9, int64_t from_pos, int64_t to_pos,
-                          void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                          void* workspace, int64_t workspace_bytes, const float* pad_x_dev, cudaStream_t st) {
     int rc = check_ws(workspace, workspace_bytes, n, pad, H); if (rc) return rc;
     const Plan p = make_plan(n, pad, H, origin);
     SeqArgs a; init_args(a);
     a.in = in; a.n_in = n; a.mask = mask; a.Hw = p.Hw; a.R = p.R; a.base = p.base;
     if (in_kind == 0) split_sub(a, sub, pad_x); else { a.fsub = sub; a.pad_x = pad_x; }
     a.out = reinterpret_cast<float*>(workspace);
+    a.pad_x_dev = part == 1 ? pad_x_dev : nullptr;
     a.scratch_floats = (ct_filtfilt_workspace_bytes(n, pad, H) - 256) / 4;
     if (counts9 && part != 1 && in_kind == 0) {
         if (!cw_step || (cw_step & (cw_step - 1))) { ct_set_error("filter: window step must be a power of two"); return CT_ERR_ARG; }
-        a.cw_lo = cw_lo; a.cw_sh = __builtin_ctz(cw_step); a.cw_out = (unsigned long long*)counts9;
+        if (cw_step > 8) { ct_set_error("filter: the fused window count needs a window step <= 8 (ADC of 13 bits or more)"); return CT_ERR_UNSUPPORTED; }
+        a.cw_k = 8u / cw_step; a.cw_c = 0u - (0x4B000000u + cw_lo) * a.cw_k; a.cw_out = (unsigned long long*)counts9;
         a.cw_p0 = cw_begin < 0 ? 0 : cw_begin; a.cw_p1 = cw_end > n ? n : cw_end;
     }
     const int D = pick_decimation(*coef, pad, p.Hw);
@@ -1152,7 +1171,7 @@ int ct_filtfilt_seq(const void* in, int in_kind, int64_t n, int64_t pad, float s
     }
     const int64_t origin = stats ? stats->origin : 0;
     int rc = ct_filter_forward_seq(in, in_kind, n, pad, sub, mask, 0.f, coef, H, origin, 0, 0, 1, 0, 0, nullptr, 0, 0, workspace,
-                                   workspace_bytes, st);
+                                   workspace_bytes, nullptr, st);
     if (rc) return rc;
     return ct_filter_backward_seq(n, pad, in_kind == 0 ? sub : 0.f, scale, offset, coef, H, origin, out, workspace, workspace_bytes,
                                   stats, nullptr, st);

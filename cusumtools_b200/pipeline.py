@@ -246,7 +246,7 @@ class TraceAnalyzer:
                  minpoints: int = 8, maxpoints: int = 100_000, cusum_delta: float | None = None,
                  cusum_h: float | None = None, max_levels: int = cusum.DEFAULT_MAX_LEVELS,
                  event_capacity: int | None = None, group=None, device="cuda", fuse_stats: bool = True,
-                 fused_count: bool = False, intra_threshold: float = 0.0, intra_hysteresis: float = 0.0,
+                 fused_count: bool = True, intra_threshold: float = 0.0, intra_hysteresis: float = 0.0,
                  max_crossings: int = 8, halos_clipped_by_trace_ends: bool = False):
         self.n_ext, self.lo_halo, self.hi_halo = int(n_ext), int(lo_halo), int(hi_halo)
         self.n_own = self.n_ext - self.lo_halo - self.hi_halo
@@ -280,7 +280,7 @@ class TraceAnalyzer:
         # baseline block sums ride on the filter's epilogue when the block is a whole number of its warp groups
         self.fuse_stats = (bool(fuse_stats) and self.block >= 65536
                            and self.block % filters.stats_granule(self.n_ext, self.padding, self.design) == 0)
-        self.fused_count = bool(fused_count)     # tally the exact-median window inside the forward pass (measured slower)
+        self.fused_count = bool(fused_count)     # the exact-median window tally rides on the forward pass (+0.35 ms against 0.79 ms as its own kernel on C2)
         self.filter_ws = None
         self.minmax = None                         # (min, max) of every 64-sample chunk of y, left by the backward pass
         self.H = max(1, self.design.impulse_tail(filters.DEFAULT_HALO_EPS))
@@ -297,6 +297,7 @@ class TraceAnalyzer:
         self.w1 = torch.empty(cap, dtype=torch.int64, device=dev)
         self.typ = torch.empty(cap, dtype=torch.int32, device=dev)
         self.scalars = torch.zeros(4, dtype=torch.int64, device=dev)     # n_starts, n_ends, n_kept, first kept index
+        self.median_result = torch.zeros(4, dtype=torch.int32, device=dev)   # CtMedianResult: code1, code2, pad_x (float bits), status
         if self.intra_threshold > 0:
             self.ic = torch.zeros(cap, dtype=torch.int32, device=dev)
             self.ip = torch.full((cap, 2 * self.max_crossings), -1, dtype=torch.int32, device=dev)
@@ -339,7 +340,7 @@ class TraceAnalyzer:
         with torch.cuda.device(self.device):
             return self._run(raw_ext, stage_hook, _arrivals, _fixed)
 
-    def _run(self, raw_ext: torch.Tensor, stage_hook=None, _arrivals=None, _fixed=None) -> AnalysisResult:
+    def _run(self, raw_ext: torch.Tensor, stage_hook=None, _arrivals=None, _fixed=None, _host_median: bool = False) -> AnalysisResult:
         """One pass of stages 1-3.  `stage_hook(name)` (optional) is called after the launches of each
         stage have been enqueued: 'median', 'filter', 'baseline', 'detect', 'cusum' (profiling only).
         `_fixed = (MedianPlan, pad_x, (c1, c2))` (StreamingAnalyzer) skips the median stages: the filter
@@ -378,47 +379,65 @@ class TraceAnalyzer:
         fused = plan.exact is None and _fixed is None
         pieces = [(0, 0, self.n_ext)] if _arrivals is None else [(2, a, b) for a, b in zip(_arrivals[0][:-1], _arrivals[0][1:])]
         pad_first = float(_fixed[1]) if _fixed is not None else 0.0
-        narrow = fused and _arrivals is None and self.group is None
+        # the estimate of a resident trace comes from a sample of ALL of it (s.e. < 0.1 code step), on every rank the same:
+        # four window codes around it are enough for the first attempt (a miss falls back to the eight-code kernel)
+        narrow = fused and _arrivals is None
         if narrow:
             plan.lo = max(0, plan.est - plan.step)
+        ride = narrow and self.fused_count and plan.step <= 8       # the tally rides on the forward pass (3.5 instructions per code)
         for i, (part, a, b) in enumerate(pieces):
             if _arrivals is not None:
                 cur.wait_event(_arrivals[1][i])
             rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask, pad_first,
                                          C.byref(coef), self.H, origin, part, plan.lo, plan.step, lo, lo + n_own,
-                                         counts.data_ptr() if (fused and self.fused_count) else None, a, b,
+                                         counts.data_ptr() if ride else None, a, b,
                                          self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
             _lib.check(rc, "ct_filter_forward_u16")
-            if fused and not self.fused_count:     # the window count of this piece's owned codes, as its own (ALU-bound) kernel
+            if fused and not ride:                 # the window count of this piece's owned codes as its own kernel
                 ca, cb = max(a, lo), min(b, lo + n_own)
                 if cb > ca:
-                    # the estimate of a resident trace comes from a sample of ALL of it (s.e. < 0.1 code step): four
-                    # window codes around it are enough for the first attempt and cost 7 instead of 10 operations per code
                     count = L.ct_count_window4_u16 if narrow else L.ct_count_window_u16
                     rc = count(raw_ext[ca:cb].data_ptr(), cb - ca, self.mask, plan.lo, plan.step, counts.data_ptr(), st)
                     _lib.check(rc, "ct_count_window_u16")
-        # ---- median, phase 2: exact order statistics (one small read; retries only if the window missed)
-        if _fixed is not None:
-            c1, c2 = _fixed[2]
-        else:
-            c1, c2 = median_search(n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
-                                   first_counts=counts if fused else None)
-        self.last_median = (c1, c2)
-        pad_x = 0.5 * (c1 + c2) - plan.est if _fixed is None else 0.0
-        if pad_x != 0.0:        # the pad holds median - estimate: redo the groups at the two ends of the trace
-            rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask,
-                                         float(pad_x), C.byref(coef), self.H, origin, 1, 0, 1, 0, 0, None, 0, 0,
-                                         self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
-            _lib.check(rc, "ct_filter_forward_u16")
+        # everything the backward launch needs that does not depend on the exact median is prepared BEFORE the host waits
+        # for the counts: the GPU idles from the end of the forward pass to the backward launch
         bl = detect.new_baseline(self.n_det, self.block, self.bmin, self.bmax, self.device) if self.fuse_stats else None
         stats = detect.stats_args(bl, origin=0) if bl is not None else None
         offset = float(filters.scale_codes_host(np.array([plan.est], dtype=np.uint16), self.settings)[0])
+        # ---- median, phase 2: exact order statistics
+        on_device = narrow and not _host_median
+        if on_device:
+            # no host round trip between the passes: one thread turns the (summed) counts into the two middle codes and the
+            # pad of the filter ends, the end groups re-run with it (their CTAs return at once when the estimate was the
+            # median), and the backward pass follows; the codes reach the host with the step's one synchronisation.  If
+            # the window missed them (status != 0) the step is redone the host-driven way.
+            _all_reduce_(counts, self.group)
+            res = self.median_result
+            rc = L.ct_median_verify(counts.data_ptr(), 4, plan.k1, plan.k2, plan.lo, plan.step, float(plan.est),
+                                    res.data_ptr(), st)
+            _lib.check(rc, "ct_median_verify")
+            rc = L.ct_filter_forward_ends_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask,
+                                              res[2:].data_ptr(), C.byref(coef), self.H, origin,
+                                              self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
+            _lib.check(rc, "ct_filter_forward_ends_u16")
+            c1 = c2 = None
+        else:
+            if _fixed is not None:
+                c1, c2 = _fixed[2]
+            else:
+                c1, c2 = median_search(n_own, self.mask, hist_fn, count_fn, self.group, self.device, plan=plan,
+                                       first_counts=counts if fused else None)
+            pad_x = 0.5 * (c1 + c2) - plan.est if _fixed is None else 0.0
+            if pad_x != 0.0:        # the pad holds median - estimate: redo the groups at the two ends of the trace
+                rc = L.ct_filter_forward_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask,
+                                             float(pad_x), C.byref(coef), self.H, origin, 1, 0, 1, 0, 0, None, 0, 0,
+                                             self.filter_ws.data_ptr(), self.filter_ws.numel(), st)
+                _lib.check(rc, "ct_filter_forward_u16")
         y = self.y
         rc = L.ct_filter_backward(self.n_ext, self.padding, float(plan.est), float(alpha), offset, C.byref(coef), self.H, origin,
                                   y.data_ptr(), self.filter_ws.data_ptr(), self.filter_ws.numel(),
                                   C.byref(stats) if stats is not None else None, self.minmax.data_ptr(), st)
         _lib.check(rc, "ct_filter_backward")
-        pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), self.settings)))
         yd = y
         st = filters._stream_ptr(y)
         hook("filter")
@@ -453,11 +472,18 @@ class TraceAnalyzer:
                                        self.intra_hysteresis, max_pairs=self.max_crossings, n_events_dev=sc[2:],
                                        out=(self.ic, self.ip))
             hook("cusum")
-            host = torch.cat((sc[:4], bl.dev["status"].to(torch.int64))).cpu().numpy()   # the step's one sync
+            tail = (self.median_result.to(torch.int64),) if on_device else ()
+            host = torch.cat((sc[:4], bl.dev["status"].to(torch.int64)) + tail).cpu().numpy()   # the step's one sync
+            if on_device:
+                if int(host[8]) != 0:                # the four-code window missed the median (every rank sees the same counts)
+                    return self._run(raw_ext, stage_hook, _arrivals, _fixed, _host_median=True)
+                c1, c2 = int(host[5]), int(host[6])
             ns, ne, nk, i0 = int(host[0]), int(host[1]), int(host[2]), int(host[3])
             if max(ns, ne) <= self.cap:
                 break
             self._alloc_events(max(ns, ne))          # more events than planned: grow and redo stages 2-3
+        self.last_median = (c1, c2)
+        pad_value = float(np.median(filters.scale_codes_host(np.array([c1, c2], dtype=np.uint16), self.settings)))
         status = int(host[4]) != 0
         if _fixed is None:
             # the error decision is collective: the flag rides with the event counts, then every rank raises

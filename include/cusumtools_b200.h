@@ -93,7 +93,7 @@ int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, con
  *     filtfilt(code - m) + m == filtfilt(code - c) + c      for ANY constant c,
  * provided the pad holds m - c instead of 0.  So the forward pass may subtract an estimate c
  * (`sub_code`) with pad_x = 0; it can tally, on the side, the window counts that pin the exact
- * median m (counts9: as ct_count_window_u16, zeroed by the caller); if m != c the caller re-runs
+ * median m (counts9: as ct_count_window4_u16 - the first four window codes, window_step <= 8 -, zeroed by the caller); if m != c the caller re-runs
  * only the groups the pad influences (`part` = 1, pad_x = m - c) and then runs the backward
  * pass with the same sub_code and offset = value(sub_code).  `origin` (>= 0) aligns the run grid with
  * baseline blocks counted from that output sample; both passes must get the same value.  Only codes at
@@ -109,6 +109,24 @@ int ct_filter_forward_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub
                           const CtFilterCoef* coef, int H, int64_t origin, int part, uint32_t window_lo,
                           uint32_t window_step, int64_t count_begin, int64_t count_end, uint64_t* counts9, int64_t from_pos,
                           int64_t to_pos, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same step without a host round trip between the passes (the GPU would idle from the end of the forward pass until
+ * the host has turned the counts into the median and launched the rest):
+ *   ct_median_verify: ONE thread evaluates the counts (uint64[1 + nbins]: #codes < lo, #codes == lo + i*step; summed over
+ *     the ranks by the caller if there are several) for the order statistics k1 <= k2 (0-based ranks of the two middle
+ *     codes) and leaves them in `result` (device memory) with pad_x = (code1 + code2) / 2 - sub_code;
+ *     status 0 = found, 1 = the window lies above the median, 2 = below (code / pad fields 0: the caller re-counts);
+ *   ct_filter_forward_ends_u16: `part` = 1 of ct_filter_forward_u16 with the pad read from `result->pad_x` on the device;
+ *     its CTAs return at once when it is 0 (the estimate was the median). */
+typedef struct CtMedianResult {
+    uint32_t code1, code2;   /* the two middle order statistics of the masked codes */
+    float pad_x;             /* median - sub_code */
+    uint32_t status;
+} CtMedianResult;
+int ct_median_verify(const uint64_t* counts9, int nbins, int64_t k1, int64_t k2, uint32_t lo, uint32_t step, float sub_code,
+                     CtMedianResult* result, void* stream);
+int ct_filter_forward_ends_u16(const uint16_t* raw, int64_t n, int64_t pad, float sub_code, uint16_t mask,
+                               const float* pad_x_dev, const CtFilterCoef* coef, int H, int64_t origin, void* workspace,
+                               int64_t workspace_bytes, void* stream);
 int ct_filter_backward(int64_t n, int64_t pad, float sub_code, float scale, float offset, const CtFilterCoef* coef, int H,
                        int64_t origin, float* out, const void* workspace, int64_t workspace_bytes, const CtFilterStats* stats,
                        float* chunk_minmax, void* stream);

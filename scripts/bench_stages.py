@@ -7,7 +7,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 29
 S = synth.CHIMERA_SETTINGS
 raw = synth.device_trace(n, "cuda", seed=1234)
 an = pipeline.TraceAnalyzer(n, S, 1e5, 8, threshold=5.0, hysteresis=1.0, baseline_block=1 << 20, baseline_min=4700.0,
-                            baseline_max=5300.0, cusum_delta=400.0, cusum_h=10.0, fuse_stats=bool(int(os.environ.get('FUSE', '1'))), fused_count=bool(int(os.environ.get('FUSEC', '0'))))
+                            baseline_max=5300.0, cusum_delta=400.0, cusum_h=10.0, fuse_stats=bool(int(os.environ.get('FUSE', '1'))), fused_count=bool(int(os.environ.get('FUSEC', '1'))))
 for rep in range(4):
     marks = {}
     def hook(name):
