@@ -57,6 +57,7 @@ class MedianPlan:
     est: int                    # estimated median code (a multiple of step)
     lo: int                     # first code of the 8-code verification window
     exact: tuple[int, int] | None = None     # already exact (small traces: full histogram)
+    se: float = float("inf")    # standard error of the estimate in code steps: sqrt(sampled) / (2 x samples at the estimate)
 
 
 def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n_sampled: int | None = None) -> MedianPlan:
@@ -90,8 +91,12 @@ def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n
         want = torch.tensor([k1 + 1, k2 + 1], dtype=torch.int64, device=cdf.device)
         c1, c2 = (int(v) for v in torch.searchsorted(cdf, want).tolist())
         return MedianPlan(n, k1, k2, step, shift, c1, max(0, c1 - 3 * step), exact=(c1, c2))
-    est = (int(torch.searchsorted(cdf, (cdf[-1:] + 1) // 2).item()) >> shift) * step
-    return MedianPlan(n, k1, k2, step, shift, est, max(0, est - 3 * step))
+    idx = torch.searchsorted(cdf, (cdf[-1:] + 1) // 2).clamp_(max=hist.numel() - 1)
+    i, dens, total = (int(v) for v in torch.cat((idx, hist[idx], cdf[-1:])).tolist())      # one read: 24 bytes
+    est = (i >> shift) * step
+    # the sample median of m samples with density f at the median has s.e. 1 / (2 f sqrt(m)); f = dens / m per code step
+    se = 0.5 * float(np.sqrt(max(total, 1))) / max(dens, 1)
+    return MedianPlan(n, k1, k2, step, shift, est, max(0, est - 3 * step), se=se)
 
 
 def median_verify(plan: MedianPlan, counts9, group=None):
@@ -381,7 +386,8 @@ class TraceAnalyzer:
         pad_first = float(_fixed[1]) if _fixed is not None else 0.0
         # the estimate of a resident trace comes from a sample of ALL of it (s.e. < 0.1 code step), on every rank the same:
         # four window codes around it are enough for the first attempt (a miss falls back to the eight-code kernel)
-        narrow = fused and _arrivals is None
+        # (a wide distribution - a drifting baseline - makes the estimate uncertain: the eight-code window then)
+        narrow = fused and _arrivals is None and plan.se <= 0.25
         if narrow:
             plan.lo = max(0, plan.est - plan.step)
         ride = narrow and self.fused_count and plan.step <= 8       # the tally rides on the forward pass (3.5 instructions per code)
@@ -406,6 +412,7 @@ class TraceAnalyzer:
         offset = float(filters.scale_codes_host(np.array([plan.est], dtype=np.uint16), self.settings)[0])
         # ---- median, phase 2: exact order statistics
         on_device = narrow and not _host_median
+        self.last_median_route = "device" if on_device else ("host after a device miss" if _host_median else "host")
         if on_device:
             # no host round trip between the passes: one thread turns the (summed) counts into the two middle codes and the
             # pad of the filter ends, the end groups re-run with it (their CTAs return at once when the estimate was the

@@ -365,3 +365,39 @@ def test_config_c1_end_to_end_against_the_cpu_path():
     nl = ref["lv"][0][same]
     lvl_err = max(np.abs(gm[i, :nl[i]] - ref["lv"][2][same][i, :nl[i]]).max() for i in range(0, len(nl), 10))
     assert lvl_err < 1.0                                 # pA; a changepoint moved by one sample shifts a level mean slightly
+
+
+def _exact_pair(codes):
+    from cusumtools_b200 import filters
+    srt = np.sort(codes & np.uint16(filters.chimera_bitmask(S)))
+    return int(srt[(codes.size - 1) // 2]), int(srt[codes.size // 2])
+
+
+def test_median_routes_drift_and_window_miss():
+    """The three routes of the exact median inside TraceAnalyzer.run (plot-trace.py:319: np.pad(mode='median')):
+    (a) narrow four-code window verified on the device (ct_median_verify: no host round trip between the passes),
+    (b) a drifting baseline: the estimate is uncertain (MedianPlan.se > 0.25), eight-code window and host loop,
+    (c) a distribution whose SAMPLE median sits 40 codes below the true one: the device-side verification reports a
+        miss and the step is redone the host-driven way.  Median, pad value and filtered trace are the exact ones."""
+    from cusumtools_b200 import filters
+    from oracle import trace_oracle as to
+    n = 5_000_000
+    base, _ = synth.c1_trace(n=n, n_events=600, seed=7)
+    drift = (base.astype(np.int64) + 4 * (np.arange(n) * 200 // n)).astype(np.uint16)        # +200 code steps (470 pA) over the trace
+    # (c): stride-4 sampling (n // 2^20 = 4) sees only positions 0, 4, 8, ...; they hold code A, the others mostly B = A + 40 steps
+    A = int(_exact_pair(base)[0])
+    tri = np.full(n, A + 160, dtype=np.uint16)
+    tri[::4] = A
+    tri[1::4][: n // 4 - 2] = A                        # A holds just under half of all samples: the median is B
+    seen = []
+    for name, codes in (("narrow", base), ("drift", drift), ("miss", tri)):
+        raw = torch.from_numpy(codes).cuda()
+        an = pipeline.TraceAnalyzer(n, S, 1e5, 8, baseline_block=65536, maxpoints=4000, **KW)
+        r = an.run(raw)
+        seen.append(an.last_median_route)
+        assert r.median_codes == _exact_pair(codes), name
+        assert r.pad_value == float(np.median(to.scale_raw_data(codes, S))), name
+        want = filters.dequant_filtfilt(raw, S, 1e5, 8, median_codes=r.median_codes).cpu().numpy()
+        assert np.abs(r.detect_trace.cpu().numpy() - want).max() < 0.02, name
+    assert _exact_pair(tri) == (A + 160, A + 160)
+    assert seen == ["device", "host", "host after a device miss"]
