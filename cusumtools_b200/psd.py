@@ -15,8 +15,9 @@ import torch
 from . import _lib
 from .filters import _require_cuda, _stream_ptr
 
-L2_BUDGET_BYTES = 512 << 20    # four-step intermediate of one batch of segments (bigger batches measured faster
-                               # up to ~1 GB: more segments per CTA; L2 residency of the intermediate does not matter)
+L2_BUDGET_BYTES = 1 << 30      # four-step intermediate of one batch of segments (bigger batches measured faster up to
+                               # ~1 GB: more segments per CTA - C4 16.9 ms at 512 MB, 15.9 ms at 1 GB; L2 residency of the
+                               # intermediate does not matter; two half-batches on two streams: 16.2 ms, rejected)
 
 
 def psd_length(n: int, samplerate: float, psd_length_s: float | None = None) -> int:
