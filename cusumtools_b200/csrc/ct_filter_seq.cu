@@ -210,35 +210,42 @@ __device__ __forceinline__ f2 allpole_step(f2 u, f2 (&v1)[NSEC], f2 (&v2)[NSEC],
 }
 
 // ------------------------------------------------------------------ exact-median window count (optional, FWD)
-// counts[0] = #codes < lo, counts[1 + i] = #codes == lo + i*step for i < 4 (ct_count_window4_u16 semantics), tallied from
-// the float bit patterns the conversion has produced anyway: pat = 0x4B000000 + code, so a = pat*k + c with k = 8 / step and
-// c = -(0x4B000000 + lo) k (mod 2^32) is 8 (code - lo) / step: its sign bit is the "below" count and 1 << a (PTX shl.b32
-// CLAMPS amounts >= 32: nothing for codes above the window or below it) the increment of four 8-bit in-register counters.
-// Three and a half instructions per code (IMAD, LEA.HI, SHF.L, half an IADD3): the pass is issue-bound once the tally rides
-// on it, so every instruction per code costs 0.1 ms per 2.5 G samples (round-2 form: 8.5 per code, eight window codes).
+// counts[0] = #codes < lo, counts[1 + i] = #codes == lo + i*step for i < 8 (ct_count_window_u16 semantics), tallied from
+// the float bit patterns the conversion has produced anyway: pat = 0x4B000000 + code, so a = pat*k + c with k = 4 / step and
+// c = -(0x4B000000 + lo) k (mod 2^32) is 4 (code - lo) / step: its sign bit is the "below" count and 1 << a (PTX shl.b32
+// CLAMPS amounts >= 32: nothing for codes above the window or below it) the increment of EIGHT 4-bit counters in one
+// register.  After 8 tallies (a field holds at most 8) the even and the odd fields are added to two registers of 8-bit
+// counters (5 instructions), which are emptied every 15 slots.  4.1 instructions per code (IMAD, LEA.HI, SHF.L, half an
+// IADD3, 5/8 for the spreading): the pass is issue-bound once the tally rides on it, so every instruction per code costs
+// 0.1 ms per 2.5 G samples (round-2 form: 8.5 per code).
 static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
     unsigned r;
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
     return r;
 }
-struct CwAcc { unsigned tot[5], below, c0; int since; };
+struct CwAcc { unsigned tot[9], below, c4, ce, co; int since; };
 static __device__ __forceinline__ unsigned cw_amount(unsigned pat, const SeqArgs& a) { return pat * a.cw_k + a.cw_c; }
 static __device__ __forceinline__ void cw_tally2(unsigned pat0, unsigned pat1, const SeqArgs& a, CwAcc& w) {
     const unsigned a0 = cw_amount(pat0, a), a1 = cw_amount(pat1, a);
     w.below += a0 >> 31;
     w.below += a1 >> 31;
-    w.c0 += shl_clamp(1u, a0) + shl_clamp(1u, a1);
+    w.c4 += shl_clamp(1u, a0) + shl_clamp(1u, a1);
 }
 static __device__ __forceinline__ void cw_tally1(unsigned pat, const SeqArgs& a, CwAcc& w) {
     const unsigned a0 = cw_amount(pat, a);
     w.below += a0 >> 31;
-    w.c0 += shl_clamp(1u, a0);
+    w.c4 += shl_clamp(1u, a0);
 }
-static __device__ __forceinline__ void cw_flush(CwAcc& w) {
+static __device__ __forceinline__ void cw_spread(CwAcc& w) {      // at most 8 tallies since the last call
+    w.ce += w.c4 & 0x0f0f0f0fu;
+    w.co += (w.c4 >> 4) & 0x0f0f0f0fu;
+    w.c4 = 0;
+}
+static __device__ __forceinline__ void cw_flush(CwAcc& w) {       // at most 30 spreads since the last call
     w.tot[0] += w.below; w.below = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w.tot[1 + i] += (w.c0 >> (8 * i)) & 0xffu;
-    w.c0 = 0; w.since = 0;
+    for (int i = 0; i < 4; ++i) { w.tot[1 + 2 * i] += (w.ce >> (8 * i)) & 0xffu; w.tot[2 + 2 * i] += (w.co >> (8 * i)) & 0xffu; }
+    w.ce = 0; w.co = 0; w.since = 0;
 }
 
 // ------------------------------------------------------------------ output half-tiles (shared by FWD-final and BWD)
@@ -343,8 +350,8 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
     CwAcc cw;
     if (COUNT) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) cw.tot[i] = 0;
-        cw.below = cw.c0 = 0; cw.since = 0;
+        for (int i = 0; i < 9; ++i) cw.tot[i] = 0;
+        cw.below = cw.c4 = cw.ce = cw.co = 0; cw.since = 0;
     }
 
     // stage q covers the positions base + (run0 + r) R + off(q) + [0, SAMP), r = 0..63
@@ -439,6 +446,7 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
                             for (int w = 0; w < 4; ++w) {
                                 cw_tally2(pl[w][0], ph[w][0], a, cw);
                                 cw_tally2(pl[w][1], ph[w][1], a, cw);
+                                if (w & 1) cw_spread(cw);      // 8 tallies
                             }
                         } else {
 #pragma unroll 1
@@ -448,9 +456,10 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
                                 if (pa0 + 1 >= a.cw_p0 && pa0 + 1 < a.cw_p1) cw_tally1(ph[w][0], a, cw);
                                 if (pb0 >= a.cw_p0 && pb0 < a.cw_p1) cw_tally1(pl[w][1], a, cw);
                                 if (pb0 + 1 >= a.cw_p0 && pb0 + 1 < a.cw_p1) cw_tally1(ph[w][1], a, cw);
+                                if (w & 1) cw_spread(cw);
                             }
                         }
-                        if (++cw.since == 15) cw_flush(cw);   // 16 tallies per slot: an 8-bit counter holds 15 slots
+                        if (++cw.since == 15) cw_flush(cw);   // two spreads of <= 8 per slot: an 8-bit counter holds 15 slots
                     }
                 } else {
                     const uint4 a0 = lds128(row0 + (unsigned)(((2 * j) ^ sw) << 4)), a1 = lds128(row0 + (unsigned)(((2 * j + 1) ^ sw) << 4));
@@ -530,7 +539,7 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
     if (COUNT) {                                           // (a lane tallies < 2^32 codes per group)
         cw_flush(cw);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < 9; ++i) {
             unsigned v = cw.tot[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CT_FULL, v, o);
@@ -1069,8 +1078,8 @@ int ct_filter_forward_seq(const void* in, int in_kind, int64_t n, int64_t pad, f
     a.scratch_floats = (ct_filtfilt_workspace_bytes(n, pad, H) - 256) / 4;
     if (counts9 && part != 1 && in_kind == 0) {
         if (!cw_step || (cw_step & (cw_step - 1))) { ct_set_error("filter: window step must be a power of two"); return CT_ERR_ARG; }
-        if (cw_step > 8) { ct_set_error("filter: the fused window count needs a window step <= 8 (ADC of 13 bits or more)"); return CT_ERR_UNSUPPORTED; }
-        a.cw_k = 8u / cw_step; a.cw_c = 0u - (0x4B000000u + cw_lo) * a.cw_k; a.cw_out = (unsigned long long*)counts9;
+        if (cw_step > 4) { ct_set_error("filter: the fused window count needs a window step <= 4 (ADC of 14 bits or more)"); return CT_ERR_UNSUPPORTED; }
+        a.cw_k = 4u / cw_step; a.cw_c = 0u - (0x4B000000u + cw_lo) * a.cw_k; a.cw_out = (unsigned long long*)counts9;
         a.cw_p0 = cw_begin < 0 ? 0 : cw_begin; a.cw_p1 = cw_end > n ? n : cw_end;
     }
     const int D = pick_decimation(*coef, pad, p.Hw);

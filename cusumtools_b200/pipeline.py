@@ -384,13 +384,17 @@ class TraceAnalyzer:
         fused = plan.exact is None and _fixed is None
         pieces = [(0, 0, self.n_ext)] if _arrivals is None else [(2, a, b) for a, b in zip(_arrivals[0][:-1], _arrivals[0][1:])]
         pad_first = float(_fixed[1]) if _fixed is not None else 0.0
-        # the estimate of a resident trace comes from a sample of ALL of it (s.e. < 0.1 code step), on every rank the same:
-        # four window codes around it are enough for the first attempt (a miss falls back to the eight-code kernel)
-        # (a wide distribution - a drifting baseline - makes the estimate uncertain: the eight-code window then)
-        narrow = fused and _arrivals is None and plan.se <= 0.25
+        # The estimate of a resident trace comes from a sample of ALL of it, on every rank the same; its standard error
+        # follows from the density at the estimate (MedianPlan.se, in code steps).  Up to 0.8 the eight-code window
+        # est - 3 .. est + 4 holds the median (4 sigma) and is verified on the device; the tally rides on the forward pass
+        # (4.1 instructions per code) or runs as its own kernel (four codes est - 1 .. est + 2 when se <= 0.25).  Beyond
+        # that - a drifting baseline - or from a partial trace (streaming): the host loop.
+        device_ok = fused and _arrivals is None and plan.se <= 0.8
+        ride = device_ok and self.fused_count and plan.step <= 4
+        narrow = device_ok and not ride and plan.se <= 0.25
+        nbins = 4 if narrow else 8
         if narrow:
             plan.lo = max(0, plan.est - plan.step)
-        ride = narrow and self.fused_count and plan.step <= 8       # the tally rides on the forward pass (3.5 instructions per code)
         for i, (part, a, b) in enumerate(pieces):
             if _arrivals is not None:
                 cur.wait_event(_arrivals[1][i])
@@ -411,7 +415,7 @@ class TraceAnalyzer:
         stats = detect.stats_args(bl, origin=0) if bl is not None else None
         offset = float(filters.scale_codes_host(np.array([plan.est], dtype=np.uint16), self.settings)[0])
         # ---- median, phase 2: exact order statistics
-        on_device = narrow and not _host_median
+        on_device = device_ok and not _host_median
         self.last_median_route = "device" if on_device else ("host after a device miss" if _host_median else "host")
         if on_device:
             # no host round trip between the passes: one thread turns the (summed) counts into the two middle codes and the
@@ -420,7 +424,7 @@ class TraceAnalyzer:
             # the window missed them (status != 0) the step is redone the host-driven way.
             _all_reduce_(counts, self.group)
             res = self.median_result
-            rc = L.ct_median_verify(counts.data_ptr(), 4, plan.k1, plan.k2, plan.lo, plan.step, float(plan.est),
+            rc = L.ct_median_verify(counts.data_ptr(), nbins, plan.k1, plan.k2, plan.lo, plan.step, float(plan.est),
                                     res.data_ptr(), st)
             _lib.check(rc, "ct_median_verify")
             rc = L.ct_filter_forward_ends_u16(raw_ext.data_ptr(), self.n_ext, self.padding, float(plan.est), self.mask,

@@ -93,7 +93,7 @@ int ct_filtfilt_f32(const float* x, int64_t n, int64_t pad, float pad_value, con
  *     filtfilt(code - m) + m == filtfilt(code - c) + c      for ANY constant c,
  * provided the pad holds m - c instead of 0.  So the forward pass may subtract an estimate c
  * (`sub_code`) with pad_x = 0; it can tally, on the side, the window counts that pin the exact
- * median m (counts9: as ct_count_window4_u16 - the first four window codes, window_step <= 8 -, zeroed by the caller); if m != c the caller re-runs
+ * median m (counts9: as ct_count_window_u16, window_step <= 4, zeroed by the caller); if m != c the caller re-runs
  * only the groups the pad influences (`part` = 1, pad_x = m - c) and then runs the backward
  * pass with the same sub_code and offset = value(sub_code).  `origin` (>= 0) aligns the run grid with
  * baseline blocks counted from that output sample; both passes must get the same value.  Only codes at
@@ -139,6 +139,7 @@ int ct_filter_backward(int64_t n, int64_t pad, float sub_code, float scale, floa
  * cheaper first attempt when the estimate comes from a sample of the whole trace.         */
 int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t mask,
                         uint32_t* hist65536, void* stream);
+
 int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
                         uint64_t* counts9, void* stream);
 int ct_count_window4_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,

@@ -375,15 +375,16 @@ def _exact_pair(codes):
 
 def test_median_routes_drift_and_window_miss():
     """The three routes of the exact median inside TraceAnalyzer.run (plot-trace.py:319: np.pad(mode='median')):
-    (a) narrow four-code window verified on the device (ct_median_verify: no host round trip between the passes),
-    (b) a drifting baseline: the estimate is uncertain (MedianPlan.se > 0.25), eight-code window and host loop,
+    (a) the eight-code window tallied by the forward pass and verified on the device (ct_median_verify: no host round
+        trip between the passes),
+    (b) a drifting baseline: the estimate is uncertain (MedianPlan.se > 0.8), host loop,
     (c) a distribution whose SAMPLE median sits 40 codes below the true one: the device-side verification reports a
         miss and the step is redone the host-driven way.  Median, pad value and filtered trace are the exact ones."""
     from cusumtools_b200 import filters
     from oracle import trace_oracle as to
     n = 5_000_000
     base, _ = synth.c1_trace(n=n, n_events=600, seed=7)
-    drift = (base.astype(np.int64) + 4 * (np.arange(n) * 200 // n)).astype(np.uint16)        # +200 code steps (470 pA) over the trace
+    drift = (base.astype(np.int64) + 4 * (np.arange(n) * 3000 // n)).astype(np.uint16)       # +3000 code steps (7 nA) over the trace
     # (c): stride-4 sampling (n // 2^20 = 4) sees only positions 0, 4, 8, ...; they hold code A, the others mostly B = A + 40 steps
     A = int(_exact_pair(base)[0])
     tri = np.full(n, A + 160, dtype=np.uint16)
