@@ -454,8 +454,9 @@ class SpectrumSample:
     def fit_spectrum(self) -> None:
         from scipy.optimize import curve_fit           # a 3-parameter host fit, outside the hot path
         self.p0 = [self.thermal, self.pink, self.brown]
-        popt, _ = curve_fit(psd_fit, self.f, np.log10(self.Pxx), self.p0,
-                            sigma=np.sqrt(np.arange(1, len(self.f) + 1) + np.sqrt(3) / 3), maxfev=100000)
+        with np.errstate(invalid="ignore"):            # the optimiser probes negative arguments of the log
+            popt, _ = curve_fit(psd_fit, self.f, np.log10(self.Pxx), self.p0,
+                                sigma=np.sqrt(np.arange(1, len(self.f) + 1) + np.sqrt(3) / 3), maxfev=100000)
         self.thermal, self.pink, self.brown = popt
 
 
