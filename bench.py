@@ -389,7 +389,7 @@ def run_ours(args):
         hook("psd")
         cols = {"starts": r.events.starts + (first_index), "ends": r.events.ends + (first_index), "types": r.types,
                 "n_levels": r.levels.n_levels, "edges": r.levels.edges, "mean": r.levels.mean, "std": r.levels.std}
-        g = pipeline.gather_tables(cols, group, dst=0, ragged={"edges": ("n_levels", 1), "mean": ("n_levels", 0), "std": ("n_levels", 0)})
+        g = pipeline.gather_tables(cols, group, dst=0)
         hook("gather")
         last.update(psd_segments=nseg, gathered=None if g is None else int(g["starts"].shape[0]))
         return acc, g

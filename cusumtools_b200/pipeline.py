@@ -890,67 +890,39 @@ def analyze_trace(raw: torch.Tensor, settings, cutoff: float, order: int = 8, *,
                          baseline_max=baseline_max, padding=padding)
 
 
-def gather_tables(tables: dict, group=None, dst: int = 0, ragged: dict | None = None) -> dict | None:
+def gather_tables(tables: dict, group=None, dst: int = 0) -> dict | None:
     """Gather per-rank event-table columns (tensors whose first dimension is the rank's event count) to rank
     `dst` in rank order = time order (the one data-sized collective of the path, O(events)).
     One small all_reduce exchanges the row counts; every column then travels point to point, exactly its rows,
     straight into its slice of the concatenated column on `dst` (one batched send/receive group, no padding and
     nothing sent to ranks that do not need it).  Returns the concatenated columns on `dst`, None elsewhere; with
-    `group=None` the input itself.
-
-    `ragged = {column: (lengths_column, extra)}`: row i of that 2-D column holds only `lengths[i] + extra` valid
-    leading entries (the level table: `n_levels` means / stds, `n_levels + 1` edges of up to 16 / 17).  Only those
-    travel - a third of the table for the usual 4-5 levels per event - and `dst` rebuilds the padded rows (zeros
-    behind the valid entries)."""
+    `group=None` the input itself."""
     if group is None:
         return tables
     import torch.distributed as dist
-    ragged = ragged or {}
     ws, rk = dist.get_world_size(group), dist.get_rank(group)
     first = next(iter(tables.values()))
     dev = first.device
-    masks, flat = {}, {}
-    for name, (len_col, extra) in ragged.items():        # valid-entry masks and the packed entries of this rank
-        t = tables[name]
-        m = torch.arange(t.shape[1], device=dev)[None, :] < (tables[len_col].to(torch.int64) + int(extra))[:, None]
-        masks[name], flat[name] = m, t[m]
-    rnames = list(ragged)
-    counts = torch.zeros((1 + len(rnames), ws), dtype=torch.int64, device=dev)
-    counts[0, rk] = first.shape[0]
-    for j, name in enumerate(rnames):
-        counts[1 + j, rk] = flat[name].numel()
+    counts = torch.zeros(ws, dtype=torch.int64, device=dev)
+    counts[rk] = first.shape[0]
     counts = _all_reduce_(counts, group).cpu().numpy()
-    offs = np.concatenate(([0], np.cumsum(counts[0])))
-    out, ops, packed = {}, [], {}
+    offs = np.concatenate(([0], np.cumsum(counts)))
+    out, ops = {}, []
     for name, t in tables.items():                       # same column order on every rank (dict order)
-        if name in ragged:
-            c = counts[1 + rnames.index(name)]
-            o = np.concatenate(([0], np.cumsum(c)))
-            t = flat[name]
-        else:
-            c, o = counts[0], offs
-            t = t.contiguous()
+        t = t.contiguous()
         if rk == dst:
-            full = torch.empty((int(o[-1]),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            full[int(o[rk]):int(o[rk + 1])] = t
+            full = torch.empty((int(offs[-1]),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            full[int(offs[rk]):int(offs[rk + 1])] = t
             for src in range(ws):
-                if src != dst and c[src]:
-                    ops.append(dist.P2POp(dist.irecv, full[int(o[src]):int(o[src + 1])], dist.get_global_rank(group, src), group))
-            (packed if name in ragged else out)[name] = full
-        elif c[rk]:
+                if src != dst and counts[src]:
+                    ops.append(dist.P2POp(dist.irecv, full[int(offs[src]):int(offs[src + 1])], dist.get_global_rank(group, src), group))
+            out[name] = full
+        elif counts[rk]:
             ops.append(dist.P2POp(dist.isend, t, dist.get_global_rank(group, dst), group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    if rk != dst:
-        return None
-    for name, (len_col, extra) in ragged.items():        # padded rows again (the lengths column has arrived with the rest)
-        width = tables[name].shape[1]
-        m = torch.arange(width, device=dev)[None, :] < (out[len_col].to(torch.int64) + int(extra))[:, None]
-        full = torch.zeros((int(offs[-1]), width), dtype=packed[name].dtype, device=dev)
-        full[m] = packed[name]
-        out[name] = full
-    return {name: out[name] for name in tables}
+    return out if rk == dst else None
 
 
 def shard_bounds(n: int, world: int, rank: int, align: int) -> tuple[int, int]:

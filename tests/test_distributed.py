@@ -170,28 +170,6 @@ def _gather_job(rank, world, group):
     return None if got is None else {k: v.numpy() for k, v in got.items()}
 
 
-def _gather_ragged_job(rank, world, group):
-    n = 4 + 2 * rank
-    g = torch.Generator().manual_seed(rank)
-    nl = torch.randint(1, 5, (n,), generator=g, dtype=torch.int32)
-    mean = torch.rand((n, 6), generator=g, dtype=torch.float64) + 1.0
-    edges = torch.randint(1, 100, (n, 7), generator=g, dtype=torch.int32)
-    mean[torch.arange(6)[None, :] >= nl[:, None]] = 0.0          # what lies behind the valid entries does not travel
-    edges[torch.arange(7)[None, :] > nl[:, None]] = 0
-    tabs = {"starts": torch.arange(n, dtype=torch.int64) + 1000 * rank, "n_levels": nl, "edges": edges, "mean": mean}
-    got = pipeline.gather_tables(tabs, group, dst=0, ragged={"edges": ("n_levels", 1), "mean": ("n_levels", 0)})
-    plain = pipeline.gather_tables(tabs, group, dst=0)
-    if got is None:
-        return None
-    assert list(got) == list(tabs)
-    return all(torch.equal(got[k], plain[k]) for k in tabs), int(got["starts"].shape[0])
-
-
-def test_ragged_level_columns_travel_packed_and_arrive_padded():
-    res = run2(_gather_ragged_job, world=3)
-    assert res[1] is None and res[2] is None and res[0] == (True, 4 + 6 + 8)
-
-
 def test_event_tables_are_gathered_in_rank_order():
     res = run2(_gather_job, world=3)
     assert res[1] is None and res[2] is None
