@@ -1,4 +1,5 @@
-"""The filter pair as the step runs it (forward pass; backward pass with block sums and chunk extrema), a few times,
+"""The filter pair as the step runs it (forward pass with the exact-median window tally riding on it; backward pass with
+block sums and chunk extrema), a few times,
 for ncu:  ncu --set full -k regex:ct_filter -s 4 -c 2 python scripts/prof_filter.py [n] [cutoff]"""
 import ctypes as C
 import os
@@ -30,8 +31,10 @@ mm = torch.empty(2 * int(L.ct_filter_summary_count(n, 1000, H)), dtype=torch.flo
 bl = detect.new_baseline(n, 1 << 20, 4700.0, 5300.0, "cuda")
 stats = detect.stats_args(bl, origin=0)
 est, offset = 40900.0, 5000.0
+cnt9 = torch.zeros(9, dtype=torch.int64, device="cuda")
 for _ in range(reps):
-    rc = L.ct_filter_forward_u16(raw.data_ptr(), n, 1000, est, mask, 0.0, C.byref(coef), H, 0, 0, 0, 1, 0, 0, None, 0, 0, ws.data_ptr(), wsb, st)
+    rc = L.ct_filter_forward_u16(raw.data_ptr(), n, 1000, est, mask, 0.0, C.byref(coef), H, 0, 0, int(est) - 12, 4, 0, n,
+                                 cnt9.data_ptr(), 0, 0, ws.data_ptr(), wsb, st)
     assert rc == 0, L.ct_last_error()
     rc = L.ct_filter_backward(n, 1000, est, float(alpha), offset, C.byref(coef), H, 0, out.data_ptr(), ws.data_ptr(), wsb,
                               C.byref(stats), mm.data_ptr(), st)
