@@ -223,6 +223,12 @@ static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
     return r;
 }
+#ifndef CT_FWD_UNROLL
+#define CT_FWD_UNROLL 1
+#endif
+// slots of the forward pass unrolled together: 1.98 ms with the tally at 1, 2.16 at 2, 2.38 at 4 (C2; without the tally
+// 1.53 / 1.54 / 1.65): the loop body with the tally is 235 instructions, and the instruction cache decides
+constexpr int kFwdUnroll = CT_FWD_UNROLL;
 struct CwAcc { unsigned tot[9], below, c4, ce, co; int since; };
 static __device__ __forceinline__ unsigned cw_amount(unsigned pat, const SeqArgs& a) { return pat * a.cw_k + a.cw_c; }
 static __device__ __forceinline__ void cw_tally2(unsigned pat0, unsigned pat1, const SeqArgs& a, CwAcc& w) {
@@ -414,7 +420,7 @@ __device__ __forceinline__ void fwd_group(const SeqArgs& a, const CtFilterCoef& 
                 if (lane == 0) bulk_wait_read<1>();
                 __syncwarp();
             }
-#pragma unroll 2
+#pragma unroll kFwdUnroll
             for (int j = 0; j < SLOTS; ++j) {
                 const int jj = hs * SLOTS + j;             // slot inside the tile
                 f2 x[8];
