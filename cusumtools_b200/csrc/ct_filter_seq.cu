@@ -696,7 +696,7 @@ __device__ __forceinline__ void bwd_group(const SeqArgs& a, const CtFilterCoef& 
                 __syncwarp();
             }
 #pragma unroll
-            for (int sl = 1; sl >= 0; --sl) {              // upper slot of the pair first
+            for (int sl = 1; sl >= 0; --sl) {              // upper slot of the pair first (rolled: 2.66 ms against 2.44 ms)
                 const int jj = jp * 2 + sl;
                 // the slot's kept samples enter the window at positions 0, D, ..; the entries above came down from the
                 // slots processed before (higher positions)
