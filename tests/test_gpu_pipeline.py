@@ -402,3 +402,64 @@ def test_median_routes_drift_and_window_miss():
         assert np.abs(r.detect_trace.cpu().numpy() - want).max() < 0.02, name
     assert _exact_pair(tri) == (A + 160, A + 160)
     assert seen == ["device", "host", "host after a device miss"]
+
+
+def test_device_side_pad_when_the_estimate_is_off_by_two_codes():
+    """The sampled positions (every 4th sample of a 5 M-sample trace) sit two code steps higher than the rest, so the
+    estimate is median + 2 steps: the eight-code window still holds the median, ct_median_verify leaves a NON-ZERO pad on
+    the device and ct_filter_forward_ends_u16 re-runs the end groups with it.  Median, pad value and the trace ends (where
+    the pad acts) must be the exact ones."""
+    from cusumtools_b200 import filters
+    from oracle import trace_oracle as to
+    n = 5_000_000
+    codes, _ = synth.c1_trace(n=n, n_events=600, seed=11)
+    codes = codes.copy()
+    codes[::4] += np.uint16(8)
+    raw = torch.from_numpy(codes).cuda()
+    for fused in (True, False):
+        an = pipeline.TraceAnalyzer(n, S, 1e5, 8, baseline_block=65536, maxpoints=4000, fused_count=fused, **KW)
+        r = an.run(raw)
+        assert an.last_median_route == "device"
+        assert r.median_codes == _exact_pair(codes)
+        res = an.median_result.cpu().numpy()
+        assert res[3] == 0 and res[2:3].view(np.float32)[0] != 0.0          # status ok, pad_x = median - estimate != 0
+        assert r.pad_value == float(np.median(to.scale_raw_data(codes, S)))
+        want = to.filter_data(to.scale_raw_data(codes, S), synth.FS, 1e5, 8)
+        got = r.detect_trace.cpu().numpy()
+        assert np.abs(got[:3000] - want[:3000]).max() < 0.05 and np.abs(got[-3000:] - want[-3000:]).max() < 0.05
+        assert np.abs(got - want).max() < 0.05
+
+
+def test_median_verify_entry_point_against_the_host_logic():
+    """ct_median_verify (one device thread) == pipeline.median_verify (numpy) on random window counts: found / window
+    above the median / window below it, four and eight codes, odd and even totals."""
+    import ctypes as C
+    from cusumtools_b200 import _lib, filters
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for trial in range(200):
+        nb = 4 if trial % 2 else 8
+        c = np.zeros(9, dtype=np.int64)
+        c[:1 + nb] = rng.integers(0, 50, 1 + nb)
+        above = int(rng.integers(0, 120))
+        c[0] = int(rng.integers(0, 120))
+        n = int(c.sum()) + above
+        if n == 0:
+            continue
+        k1, k2 = (n - 1) // 2, n // 2
+        lo, step, est = 4000 + 4 * int(rng.integers(0, 50)), 4, 4100.0
+        plan = pipeline.MedianPlan(n, k1, k2, step, 2, int(est), lo)
+        want, _ = pipeline.median_verify(plan, torch.from_numpy(c[:9].copy()))
+        if nb == 4 and want is not None and max(want) >= lo + 4 * step:
+            want = None                                         # the host logic always looks at eight codes
+        dev = torch.from_numpy(c).cuda()
+        res = torch.zeros(4, dtype=torch.int32, device="cuda")
+        _lib.check(L.ct_median_verify(dev.data_ptr(), nb, k1, k2, lo, step, est, res.data_ptr(), st), "ct_median_verify")
+        out = res.cpu().numpy()
+        if want is None:
+            assert out[3] in (1, 2) and out[3] == (1 if k1 < c[0] else 2) and out[0] == 0 and out[1] == 0
+        else:
+            assert out[3] == 0 and (int(out[0]), int(out[1])) == want
+            assert out[2:3].view(np.float32)[0] == np.float32(0.5 * (want[0] + want[1]) - est)
+    assert L.ct_median_verify(dev.data_ptr(), 9, 0, 0, 0, 4, 0.0, res.data_ptr(), st) != 0      # nbins out of range
