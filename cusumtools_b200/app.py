@@ -211,16 +211,15 @@ class App(_PsdMixin):
         except IOError:
             self.overlay_flag = False
             self.wildcard.set("baseline.csv not found in given directory")
+        # summary.txt: `key=value` lines matched by SUBSTRING like the reference does (so `intra_threshold` must not be
+        # taken for `threshold`): key fragment, attribute, type, whether an `intra` line is skipped
+        wanted = (("threshold", "threshold", float, True), ("hysteresis", "hysteresis", float, True),
+                  ("cutoff", "config_cutoff", int, False), ("poles", "config_order", int, False))
         with open(config_path, "r") as config:
             for line in config:
-                if "threshold" in line and "intra" not in line:
-                    self.threshold = float(re.split("=|\n", line)[1])
-                if "hysteresis" in line and "intra" not in line:
-                    self.hysteresis = float(re.split("=|\n", line)[1])
-                if "cutoff" in line:
-                    self.config_cutoff = int(re.split("=|\n", line)[1])
-                if "poles" in line:
-                    self.config_order = int(re.split("=|\n", line)[1])
+                for fragment, attr, kind, skip_intra in wanted:
+                    if fragment in line and not (skip_intra and "intra" in line):
+                        setattr(self, attr, kind(re.split("=|\n", line)[1]))
 
     def _event_spans(self):
         """The axvspan lists of plot-trace.py:350-369 in microseconds: (good, bad) lists of (start, end)."""
