@@ -176,3 +176,32 @@ def test_event_tables_are_gathered_in_rank_order():
     want = np.concatenate([np.arange(5 + 3 * r) + 1000 * r for r in range(3)])
     assert np.array_equal(res[0]["starts"], want)
     assert res[0]["mean"].shape == (want.size, 4) and np.array_equal(res[0]["mean"][:, 0], np.repeat([0.0, 1.0, 2.0], [5, 8, 11]))
+
+
+def test_standard_error_of_the_estimate_follows_the_density_at_the_median():
+    """MedianPlan.se = sqrt(samples) / (2 x samples at the estimate), in code steps: small for a trace that sits on its
+    baseline, large when the median falls where few samples are (a drifting baseline; the tail between two levels) -
+    what decides between the device-verified window and the host loop (pipeline.TraceAnalyzer._run)."""
+    rng = np.random.default_rng(5)
+    n, mask = 4_000_000, 0xFFFC
+
+    def plan_for(codes):
+        def hist_fn(stride):
+            return torch.from_numpy(np.bincount(codes[::stride] & mask, minlength=65536).astype(np.int32))
+        return pipeline.median_estimate(len(codes), mask, hist_fn)
+
+    quiet = _codes(1, n)
+    p = plan_for(quiet)
+    true = int(np.sort(quiet & mask)[(n - 1) // 2])
+    assert p.se < 0.1 and abs(p.est - true) <= 4 and p.est % 4 == 0 and p.lo == p.est - 12
+    drift = ((quiet.astype(np.int64) + 4 * (np.arange(n) * 3000 // n)) & 0xFFFF).astype(np.uint16)
+    assert plan_for(drift).se > 0.8
+    # half the samples 340 codes lower (inside events): the median lies in the lower tail of the baseline cluster
+    two = quiet.copy()
+    two[: int(0.493 * n)] -= np.uint16(4 * 340)
+    rng.shuffle(two)
+    assert 0.25 < plan_for(two).se < 0.8
+    small = _codes(2, 100_000)                              # below 2^20 samples: the full histogram is exact
+    ps = plan_for(small)
+    srt = np.sort(small & mask)
+    assert ps.exact == (int(srt[(len(small) - 1) // 2]), int(srt[len(small) // 2]))
