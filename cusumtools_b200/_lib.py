@@ -60,6 +60,7 @@ SIGNATURES = {
     "ct_filtfilt_f32": (C.c_int, [_vp, _i64, _i64, _f32, C.POINTER(CtFilterCoef), C.c_int,
                                   C.c_int, _vp, _vp, _i64, C.POINTER(CtFilterStats), _vp]),
     "ct_hist_sampled_u16": (C.c_int, [_vp, _i64, _i64, _u16, _vp, _vp]),
+    "ct_hist_rank": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "ct_count_window_u16": (C.c_int, [_vp, _i64, _u16, _u32, _u32, _vp, _vp]),
     "ct_count_window4_u16": (C.c_int, [_vp, _i64, _u16, _u32, _u32, _vp, _vp]),
     "ct_block_stats_f32": (C.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, C.c_int, _vp, _vp, _vp, _vp]),

@@ -9,13 +9,67 @@ namespace {
 // Sampled histogram (estimate) + exact window count (verification); the host replays the
 // reference's scale_raw_data on the selected code(s) so the pad value is bit-identical
 // to np.median(scale_raw_data(raw)).
-// (16 histograms side by side to spread the atomics of the few hundred codes a noisy trace visits, summed afterwards:
-// measured, the estimate stage went from 0.20 to 0.28 ms - the 4 MB of zero-fill and the sum cost more than the contention.)
-__global__ void ct_hist_sampled_kernel(const uint16_t* __restrict__ raw, long long n, long long stride,
-                                       unsigned mask, unsigned* __restrict__ hist) {
-    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * stride;
+// The samples of a trace fall on a few hundred codes, i.e. on a dozen L2 lines, and the atomics of one line are serialised
+// (1 M samples straight into the global histogram: 93 us).  Each CTA therefore tallies into a shared-memory window of 8192
+// codes around its first sample and adds the non-empty bins to the global histogram at the end; codes outside the window
+// go to the global histogram directly.  (16 global histograms side by side, summed afterwards, were slower than one:
+// the 4 MB of zero-fill and the sum cost more than the contention.)
+constexpr int kHistWin = 8192;
+__global__ void __launch_bounds__(1024) ct_hist_sampled_kernel(const uint16_t* __restrict__ raw, long long n, long long stride,
+                                                               unsigned mask, unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[kHistWin];
+    __shared__ unsigned sbase;
+    for (int i = threadIdx.x; i < kHistWin; i += blockDim.x) sh[i] = 0;
+    const long long first = (long long)blockIdx.x * blockDim.x * stride;
+    if (threadIdx.x == 0) {
+        const unsigned c = first < n ? (raw[first] & mask) : 0u;
+        sbase = c > kHistWin / 2 ? c - kHistWin / 2 : 0u;
+    }
+    __syncthreads();
+    const unsigned base = sbase;
+    long long i = first + (long long)threadIdx.x * stride;
     const long long step = (long long)gridDim.x * blockDim.x * stride;
-    for (; i < n; i += step) atomicAdd(&hist[raw[i] & mask], 1u);
+    for (; i < n; i += step) {
+        const unsigned c = raw[i] & mask, d = c - base;
+        if (d < (unsigned)kHistWin) atomicAdd(&sh[d], 1u);
+        else atomicAdd(&hist[c], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kHistWin; k += blockDim.x) {
+        const unsigned v = sh[k];
+        if (v) atomicAdd(&hist[base + k], v);       // base + k < 65536 + 4096: bins beyond 65535 stay empty (d < window => c <= 65535)
+    }
+}
+
+// Rank search in a 65 536-bin histogram on the device: out[0] = first bin whose cumulative count reaches ceil(total / 2)
+// (the sampled median), out[1] = its count (the density that gives the estimate's standard error), out[2] = total.
+// One CTA of 1024 threads, 64 bins each; replaces a cumsum / searchsorted / gather chain of ten small launches.
+template <typename T>
+__global__ void __launch_bounds__(1024) ct_hist_rank_kernel(const T* __restrict__ hist, long long* __restrict__ out) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    long long s = 0;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) s += (long long)hist[t * 64 + k];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                 // inclusive scan of the 1024 partial sums
+        const long long v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const long long total = part[1023], want = (total + 1) / 2;
+    const long long before = t ? part[t - 1] : 0;
+    if (total > 0 && before < want && part[t] >= want) {
+        long long c = before;
+        for (int k = 0; k < 64; ++k) {
+            const long long h = (long long)hist[t * 64 + k];
+            c += h;
+            if (c >= want) { out[0] = t * 64 + k; out[1] = h; out[2] = total; break; }
+        }
+    }
+    if (total == 0 && t == 0) { out[0] = 0; out[1] = 0; out[2] = 0; }
 }
 
 constexpr int kWin = 8;
@@ -219,9 +273,9 @@ int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t
     if (!raw || !hist65536 || n < 0 || stride < 1) { ct_set_error("hist: bad argument"); return CT_ERR_ARG; }
     if (n == 0) return CT_OK;
     long long ns = (n + stride - 1) / stride;
-    int threads = 256;
+    int threads = 1024;
     long long blocks = (ns + threads - 1) / threads;
-    long long cap = (long long)ct_sm_count() * 8;
+    long long cap = (long long)ct_sm_count();
     if (blocks > cap) blocks = cap;
     CT_COUNT_LAUNCH();
     ct_hist_sampled_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(raw, n, stride, mask, hist65536);
@@ -245,6 +299,14 @@ static int count_window(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t 
         ct_count_window_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
             raw, n, mask, lo, step, 8u, 2u, reinterpret_cast<unsigned long long*>(counts9));
     return ct_check_launch("ct_count_window_kernel");
+}
+
+int ct_hist_rank(const void* hist65536, int is_int64, int64_t* out3, void* stream) {
+    if (!hist65536 || !out3) { ct_set_error("hist_rank: null pointer"); return CT_ERR_ARG; }
+    CT_COUNT_LAUNCH();
+    if (is_int64) ct_hist_rank_kernel<long long><<<1, 1024, 0, (cudaStream_t)stream>>>((const long long*)hist65536, (long long*)out3);
+    else ct_hist_rank_kernel<unsigned><<<1, 1024, 0, (cudaStream_t)stream>>>((const unsigned*)hist65536, (long long*)out3);
+    return ct_check_launch("ct_hist_rank_kernel");
 }
 
 int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,

@@ -73,26 +73,44 @@ def median_estimate(n_local: int, mask: int, hist_fn, group=None, device=None, n
         if n == 0:
             raise ValueError("median of an empty trace")
         stride = max(1, (n if n_sampled is None else int(n_sampled)) // (1 << 20))  # ~1 M samples: median s.e. < 0.1 code
-        hist = hist_fn(stride).to(torch.int64)
+        hist = hist_fn(stride)
     else:
         # every rank samples with the stride of ITS share (ranks own equal shares), and the sample count rides in the
         # same all_reduce as the histogram: one collective for the phase
         stride = max(1, (int(n_local) if n_sampled is None else int(n_sampled)) * _world(group) // (1 << 20))
         h = hist_fn(stride).to(torch.int64)
         packed = _all_reduce_(torch.cat((h, torch.tensor([int(n_local)], dtype=torch.int64, device=h.device))), group)
+        hist, n = packed[:-1], None                        # (the total comes back with the rank search: one read)
+    exact = stride == 1 and n_sampled is None
+    if group is not None and (exact or not hist.is_cuda):
         n = int(packed[-1].item())
+    if exact:
         if n == 0:
             raise ValueError("median of an empty trace")
-        hist = packed[:-1]
-    k1, k2 = (n - 1) // 2, n // 2
-    # the rank search runs where the histogram lives (device): 8 bytes come back instead of 65 536 bins
-    cdf = torch.cumsum(hist, 0)
-    if stride == 1 and n_sampled is None:
+        k1, k2 = (n - 1) // 2, n // 2
+        cdf = torch.cumsum(hist.to(torch.int64), 0)
         want = torch.tensor([k1 + 1, k2 + 1], dtype=torch.int64, device=cdf.device)
         c1, c2 = (int(v) for v in torch.searchsorted(cdf, want).tolist())
         return MedianPlan(n, k1, k2, step, shift, c1, max(0, c1 - 3 * step), exact=(c1, c2))
-    idx = torch.searchsorted(cdf, (cdf[-1:] + 1) // 2).clamp_(max=hist.numel() - 1)
-    i, dens, total = (int(v) for v in torch.cat((idx, hist[idx], cdf[-1:])).tolist())      # one read: 24 bytes
+    # the rank search runs where the histogram lives: 24 (32) bytes come back instead of 65 536 bins
+    if hist.is_cuda and hist.dtype in (torch.int32, torch.int64) and hist.is_contiguous():
+        out = torch.empty(3, dtype=torch.int64, device=hist.device)
+        with torch.cuda.device(hist.device):
+            rc = _lib.lib().ct_hist_rank(hist.data_ptr(), int(hist.dtype == torch.int64), out.data_ptr(),
+                                         C.c_void_p(torch.cuda.current_stream(hist.device).cuda_stream))
+        _lib.check(rc, "ct_hist_rank")
+        vals = (torch.cat((out, packed[-1:])) if n is None else out).tolist()
+        i, dens, total = (int(v) for v in vals[:3])
+        if n is None:
+            n = int(vals[3])
+    else:                                                  # (CPU tensors: the gloo tests of the host logic)
+        hist = hist.to(torch.int64)
+        cdf = torch.cumsum(hist, 0)
+        idx = torch.searchsorted(cdf, (cdf[-1:] + 1) // 2).clamp_(max=hist.numel() - 1)
+        i, dens, total = (int(v) for v in torch.cat((idx, hist[idx], cdf[-1:])).tolist())
+    if n == 0:
+        raise ValueError("median of an empty trace")
+    k1, k2 = (n - 1) // 2, n // 2
     est = (i >> shift) * step
     # the sample median of m samples with density f at the median has s.e. 1 / (2 f sqrt(m)); f = dens / m per code step
     se = 0.5 * float(np.sqrt(max(total, 1))) / max(dens, 1)

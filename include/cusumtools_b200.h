@@ -140,6 +140,10 @@ int ct_filter_backward(int64_t n, int64_t pad, float sub_code, float scale, floa
 int ct_hist_sampled_u16(const uint16_t* raw, int64_t n, int64_t stride, uint16_t mask,
                         uint32_t* hist65536, void* stream);
 
+/* Rank search in the (summed) histogram on the device: out3[0] = first bin whose cumulative count reaches half the total
+ * (the sampled median), out3[1] = its count, out3[2] = the total.  hist65536: uint32[65536], or int64[65536] (is_int64)
+ * after an all_reduce over ranks. */
+int ct_hist_rank(const void* hist65536, int is_int64, int64_t* out3, void* stream);
 int ct_count_window_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
                         uint64_t* counts9, void* stream);
 int ct_count_window4_u16(const uint16_t* raw, int64_t n, uint16_t mask, uint32_t lo, uint32_t step,
