@@ -88,7 +88,8 @@ static __device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned amt) {
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(amt));
     return r;
 }
-// WIDE = false: only the first four window codes are counted (one counter word).
+// WIDE = false: only the first four window codes are counted (four 8-bit counters); WIDE: eight 4-bit counters in one register,
+// spread into 8-bit counters every 8 codes (the forward pass's tally, ct_filter_seq.cu).
 template <bool WIDE>
 __global__ void __launch_bounds__(256)
 ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned mask, unsigned lo,
@@ -98,18 +99,30 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
     unsigned long long tot[1 + kWin];
 #pragma unroll
     for (int i = 0; i <= kWin; ++i) tot[i] = 0;
-    unsigned below = 0, c0 = 0, c1 = 0;
+    // WIDE: eight 4-bit counters in c0 (a = 4 (code - lo) / step), spread into the 8-bit counters of ce / co after the 8
+    // codes of every 16-byte load; else four 8-bit counters in c0 (a = 8 (code - lo) / step)
+    unsigned below = 0, c0 = 0, ce = 0, co = 0;
+    const unsigned ka = WIDE ? k8 >> 1 : k8, nloa = WIDE ? 0u - (lo >> sh) * 4u : nlo8;
     auto tally = [&](unsigned e) {                         // e = (code & mask) >> sh
-        const unsigned a = e * k8 + nlo8;                  // |a| < 2^20
+        const unsigned a = e * ka + nloa;                  // |a| < 2^20
         below = __umulhi(a, two) + below;                  // a >> 31
         c0 += shl_clamp(1u, a);
-        if (WIDE) c1 += shl_clamp(1u, e * k8 + (nlo8 - 32u));
+    };
+    auto spread = [&]() {                                  // WIDE, at most 8 tallies since the last call
+        ce += c0 & 0x0f0f0f0fu; co += (c0 >> 4) & 0x0f0f0f0fu; c0 = 0;
     };
     auto flush = [&]() {
         tot[0] += below; below = 0;
+        if (WIDE) {
+            spread();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { tot[1 + i] += (c0 >> (8 * i)) & 0xffu; tot[5 + i] += (c1 >> (8 * i)) & 0xffu; }
-        c0 = 0; c1 = 0;
+            for (int i = 0; i < 4; ++i) { tot[1 + 2 * i] += (ce >> (8 * i)) & 0xffu; tot[2 + 2 * i] += (co >> (8 * i)) & 0xffu; }
+            ce = 0; co = 0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tot[1 + i] += (c0 >> (8 * i)) & 0xffu;
+            c0 = 0;
+        }
     };
     const unsigned m2 = mask | (mask << 16);
     auto tally_word = [&](unsigned w) {
@@ -145,7 +158,10 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
                 for (int u = 0; u < 4; ++u) nq[u] = ct_ldg_stream(b + u * 32);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { tally_word(q[u].x); tally_word(q[u].y); tally_word(q[u].z); tally_word(q[u].w); }
+            for (int u = 0; u < 4; ++u) {
+                tally_word(q[u].x); tally_word(q[u].y); tally_word(q[u].z); tally_word(q[u].w);
+                if (WIDE) spread();
+            }
             if (++rounds == 7) { flush(); rounds = 0; }     // 32 tallies per round: an 8-bit counter holds 7 rounds
 #pragma unroll
             for (int u = 0; u < 4; ++u) q[u] = nq[u];
@@ -161,7 +177,12 @@ ct_count_window_kernel(const uint16_t* __restrict__ raw, long long n, unsigned m
         for (long long k = nvec * 8 + tid; k < n; k += nth) { tally((unsigned)(raw[k] & mask) >> sh); flush(); }
     } else {
         int since = 0;
-        for (long long k = tid; k < n; k += nth) { tally((unsigned)(raw[k] & mask) >> sh); if (++since == 128) { flush(); since = 0; } }
+        for (long long k = tid; k < n; k += nth) {
+            tally((unsigned)(raw[k] & mask) >> sh);
+            ++since;
+            if (WIDE && (since & 7) == 0) spread();
+            if (since == 128) { flush(); since = 0; }
+        }
     }
     flush();
 #pragma unroll
